@@ -1,0 +1,68 @@
+"""ctypes binding of libupgpt_b200.so (the C ABI declared in include/upgpt_b200.h).
+
+The product path has NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_lib", "libupgpt_b200.so")
+_lib = None
+
+
+class UpgptError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("mode", C.c_int),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
+        ("a_batch_stride", C.c_longlong), ("w_batch_stride", C.c_longlong),
+        ("lda", C.c_int), ("ldw", C.c_int),
+        ("n_imgs", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("block_n", C.c_int), ("splits", C.c_int),
+        ("out32", C.c_void_p), ("ld32", C.c_int),
+        ("out16", C.c_void_p), ("ld16", C.c_int),
+        ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int), ("rows_per_group", C.c_int),
+        ("res32", C.c_void_p), ("ldres", C.c_int), ("ldT", C.c_int),
+        ("flags", C.c_uint), ("out_scale", C.c_float),
+    ]
+
+
+GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1 = 0, 1, 2, 3
+GEMM_F_GEGLU, GEMM_F_CHW = 1 << 1, 1 << 2
+
+
+def lib():
+    """Loads (building first if sources changed and nvcc is present) and returns the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH) or os.environ.get("UPGPT_REBUILD"):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise UpgptError("libupgpt_b200.so missing at %s; run `python -m upgpt_b200.build`" % _LIB_PATH)
+    l = C.CDLL(_LIB_PATH)
+    l.upgpt_last_error.restype = C.c_char_p
+    l.upgpt_launch_count.restype = C.c_longlong
+    l.upgpt_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    _lib = l
+    return l
+
+
+def check(rc, what):
+    if rc != 0:
+        raise UpgptError("%s failed (%d): %s" % (what, rc, lib().upgpt_last_error().decode()))
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)

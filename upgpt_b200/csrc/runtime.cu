@@ -1,0 +1,85 @@
+// Host runtime glue: error string, launch counter, TMA tensor-map encoding through the driver entry point
+// (no link-time dependency on libcuda).
+#include "common.cuh"
+#include "../../include/upgpt_b200.h"
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include <mutex>
+
+namespace upgpt {
+
+static thread_local char g_err[1024] = "";
+std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static void load_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_encodeTiled)fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) {
+    set_last_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return -3;
+  }
+  if (((uintptr_t)base & 15) != 0) {
+    set_last_error("tensor map base %p not 16-byte aligned", base);
+    return -3;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_last_error("tensor map stride[%d]=%llu not a multiple of 16 bytes", i, (unsigned long long)gstr[i - 1]);
+        return -3;
+      }
+    }
+    if (bx[i] == 0 || bx[i] > 256) {
+      set_last_error("tensor map box[%d]=%u out of range", i, bx[i]);
+      return -3;
+    }
+  }
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+                        es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu,%llu,%llu box %u,%u,%u,%u)", (int)r,
+                   rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+                   (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0), bx[0],
+                   rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0, rank > 3 ? bx[3] : 0);
+    return -3;
+  }
+  return 0;
+}
+
+}  // namespace upgpt
+
+extern "C" const char* upgpt_last_error(void) { return upgpt::g_err; }
+extern "C" int upgpt_abi_version(void) { return 1; }
+extern "C" long long upgpt_launch_count(void) { return upgpt::g_launches.load(); }

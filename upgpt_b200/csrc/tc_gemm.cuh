@@ -1,0 +1,49 @@
+// Parameter block of the tcgen05 GEMM / implicit-GEMM convolution kernel (tc_gemm.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_fp16.h>
+
+namespace upgpt {
+
+enum GemmFlags : uint32_t {
+  GEMM_ATOMIC = 1u << 0,   // split-K: red.add.f32 into out32 (caller zero-fills); bias/rowvec/res added by split 0
+  GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
+  GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
+  GEMM_CONV = 1u << 3,     // A rows are image pixels addressed through a 4-D (C, W, H, N) tensor map
+};
+
+struct GemmParams {
+  // ---- problem ----
+  int M_total;          // rows per batch entry
+  int N_total;          // output columns
+  int batch;            // batched GEMM count (A coord3 / B coord3 = batch index), 1 otherwise
+  int block_n;          // UMMA N per tile (multiple of 16, <= 256)
+  int num_m_tiles, num_n_tiles, num_splits;
+  int taps;             // 1 (GEMM / 1x1) or 9 (3x3)
+  int kblocks_per_tap;  // ceil(K_per_tap / 64)
+  int stages;           // smem pipeline depth
+  uint32_t a_bytes;     // bytes one A TMA box delivers (<= 16384)
+  uint32_t flags;
+  // ---- conv geometry (GEMM_CONV) ----
+  int H, W, HW;
+  int tile_rows;        // image rows per M tile (tile_imgs == 1)
+  int tile_imgs;        // whole images per M tile (HW * tile_imgs <= 128)
+  int tiles_per_img;
+  int n_imgs;           // number of images addressed by the output
+  int tap_dy[9], tap_dx[9], tap_dn[9];
+  // ---- epilogue ----
+  float* out32;         // [rows, ld32] (or CHW)
+  int ld32;
+  __half* out16;        // optional fp16 copy of the result (GEGLU: the only output)
+  int ld16;
+  const float* bias;    // [N_total] or null
+  const float* rowvec;  // [groups, ld_rowvec] added per row-group (timestep-embedding bias), or null
+  int ld_rowvec;
+  int rows_per_group;   // rows per image / per batch entry (group = row / rows_per_group)
+  const float* res32;   // residual [rows, ldres] or null
+  int ldres;
+  int ldT;              // CHW: stride between channels (>= rows_per_group)
+  float out_scale;      // applied to the accumulator before bias (1.0 default)
+};
+
+}  // namespace upgpt
