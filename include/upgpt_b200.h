@@ -70,6 +70,34 @@ typedef struct upgpt_gemm_args {
 } upgpt_gemm_args;
 int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Normalisation / operand preparation (HBM-bound elementwise + reductions)
+ *   replaces: GroupNorm32 (util.py:199-216), Normalize eps 1e-6 (attention.py:76-77, model.py:38-39), SiLU / swish
+ *   (openaimodel.py:201-203,225-227; model.py:33-35), LayerNorm (attention.py:203-205), nearest x2 upsample
+ *   (openaimodel.py:116; model.py:53), the skip concat th.cat([h, hs.pop()],1) (openaimodel.py:736), softmax (model.py:184)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* stats[b][g] = {sum, sum of squares} (double) over group g of image b of the channel-concat [x1 | x2] (x2 may be NULL). */
+int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
+                          void* stream);
+typedef struct upgpt_prep_args {
+  const float* x1; int C1;   /* fp32 NHWC [B][H][W][C1] */
+  const float* x2; int C2;   /* optional second tensor, concatenated on channels */
+  int B, H, W;
+  int groups;                /* GroupNorm groups (32) */
+  const double* stats;       /* from upgpt_groupnorm_stats, or NULL = no normalisation (plain cast) */
+  const float* gamma; const float* beta; float eps;
+  int silu;                  /* apply x*sigmoid(x) after the affine */
+  int layout;                /* 0 same; 1 nearest-x2 upsampled [B][2H][2W][C]; 2 stride-2 phases [4][B][H/2][W/2][C] */
+  int split3;                /* emit error-compensated operand planes [hi | lo | hi] (3C channels) */
+  void* out; int ldo;        /* fp16 output, ldo elements per pixel (0 = C or 3C) */
+  void* raw; int ldraw;      /* optional un-normalised fp16 copy (layout 0) */
+} upgpt_prep_args;
+int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
+int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                    void* out16, int ldo, void* stream);
+/* out16[r][i] = softmax_i(scale * x[r][i]) */
+int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n, float scale, void* out16, int ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,326 @@
+// Normalisation / operand-preparation kernels (HBM-bound, coalesced, vectorised).
+//
+//   gn_stats   : per-(image, group) sum / sum-of-squares of an NHWC fp32 tensor (optionally the channel concat of two)
+//   prep       : [GroupNorm-apply] [SiLU] fp32 NHWC -> fp16 tensor-core operand, optionally nearest-x2 upsampled,
+//                split into the 4 stride-2 phases, or emitted as error-compensated hi/lo/hi planes
+//   layernorm  : per-token LayerNorm fp32 -> fp16 operand
+//   softmax    : row softmax fp32 -> fp16 (VAE single-head attention)
+//
+// Replaces: GroupNorm32 / normalization (util.py:199-216), Normalize eps=1e-6 (attention.py:76-77, model.py:38-39),
+// nn.SiLU / nonlinearity (openaimodel.py:201-203,225-227; model.py:33-35), nn.LayerNorm (attention.py:203-205),
+// F.interpolate nearest x2 (openaimodel.py:116; model.py:53), th.cat([h, hs.pop()]) (openaimodel.py:736),
+// softmax (model.py:184).
+#include "common.cuh"
+#include "../../include/upgpt_b200.h"
+
+namespace upgpt {
+
+// ------------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics. stats[b][g] = {sum, sumsq} in double (zeroed by the launcher).
+// grid = (pixel chunks, B); thread t owns channels t, t+blockDim, ... and walks the chunk's pixels (coalesced rows).
+// ------------------------------------------------------------------------------------------------------------------
+template <int MAXC_PER_THREAD>
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW, int chunk,
+                int groups, double* __restrict__ stats) {
+  extern __shared__ double sh[];  // [groups][2]
+  const int C = C1 + C2;
+  const int cpg = C / groups;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, HW);
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  float s[MAXC_PER_THREAD], q[MAXC_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (int p = p0; p < p1; ++p) {
+    const size_t row = (size_t)b * HW + p;
+#pragma unroll
+    for (int j = 0; j < MAXC_PER_THREAD; ++j) {
+      const int c = threadIdx.x + j * 256;
+      if (c < C) {
+        const float v = c < C1 ? __ldg(x1 + row * C1 + c) : __ldg(x2 + row * C2 + (c - C1));
+        s[j] += v;
+        q[j] = fmaf(v, v, q[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXC_PER_THREAD; ++j) {
+    const int c = threadIdx.x + j * 256;
+    if (c < C) {
+      const int g = c / cpg;
+      atomicAdd(&sh[2 * g], (double)s[j]);
+      atomicAdd(&sh[2 * g + 1], (double)q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * groups + i], sh[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prep: normalise (optional) + SiLU (optional) + cast to fp16 with a layout transform.
+// grid = (pixel chunks, B); 4 channels per thread (float4 in, 8-byte out).
+// ------------------------------------------------------------------------------------------------------------------
+struct PrepParams {
+  const float* x1; int C1;
+  const float* x2; int C2;
+  int H, W;
+  int chunk;
+  int groups;
+  const double* stats;     // null -> no normalisation
+  const float* gamma; const float* beta;
+  float eps;
+  int silu;
+  int layout;              // 0 same, 1 nearest-up x2, 2 stride-2 phases
+  int split3;              // output channels = 3C: [hi | lo | hi]
+  __half* out; int ldo;    // elements per output pixel (>= C or 3C)
+  __half* raw; int ldraw;  // optional un-normalised fp16 copy (layout 0)
+  int B;
+};
+
+__global__ void __launch_bounds__(256)
+prep_kernel(const PrepParams p) {
+  extern __shared__ float shf[];  // scale[C], shift[C]
+  const int C = p.C1 + p.C2;
+  const int HW = p.H * p.W;
+  float* scale = shf;
+  float* shift = shf + C;
+  const int b = blockIdx.y;
+  if (p.stats) {
+    const int cpg = C / p.groups;
+    const double inv_n = 1.0 / ((double)cpg * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double su = p.stats[((size_t)b * p.groups + g) * 2];
+      const double sq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+      const double mean = su * inv_n;
+      double var = sq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      const float ga = p.gamma ? p.gamma[c] : 1.f;
+      const float be = p.beta ? p.beta[c] : 0.f;
+      scale[c] = rstd * ga;
+      shift[c] = be - (float)mean * rstd * ga;
+    }
+    __syncthreads();
+  }
+  const int C4 = C >> 2;
+  const int p0 = blockIdx.x * p.chunk;
+  const int p1 = min(p0 + p.chunk, HW);
+  const int total = (p1 - p0) * C4;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pp = p0 + idx / C4;
+    const int c = (idx % C4) << 2;
+    const size_t row = (size_t)b * HW + pp;
+    float4 v = c < p.C1 ? *(const float4*)(p.x1 + row * p.C1 + c) : *(const float4*)(p.x2 + row * p.C2 + (c - p.C1));
+    if (p.raw) {
+      __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
+      uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
+      *(uint2*)(p.raw + row * p.ldraw + c) = pk;
+    }
+    if (p.stats) {
+      v.x = fmaf(v.x, scale[c], shift[c]);
+      v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
+      v.z = fmaf(v.z, scale[c + 2], shift[c + 2]);
+      v.w = fmaf(v.w, scale[c + 3], shift[c + 3]);
+    }
+    if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const uint2 hi = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+    uint2 lo = make_uint2(0, 0);
+    if (p.split3) {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+      lo = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+    }
+    if (p.layout == 0) {
+      __half* o = p.out + row * p.ldo + c;
+      *(uint2*)o = hi;
+      if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+    } else if (p.layout == 1) {
+      const int y = pp / p.W, x = pp % p.W;
+      const int W2 = 2 * p.W;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          __half* o = p.out + ((size_t)b * 4 * HW + (size_t)(2 * y + i) * W2 + (2 * x + j)) * p.ldo + c;
+          *(uint2*)o = hi;
+          if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+        }
+    } else {
+      const int y = pp / p.W, x = pp % p.W;
+      const int ph = (y & 1) * 2 + (x & 1);
+      const int Ho = p.H >> 1, Wo = p.W >> 1;
+      __half* o = p.out + ((((size_t)ph * p.B + b) * Ho + (y >> 1)) * Wo + (x >> 1)) * p.ldo + c;
+      *(uint2*)o = hi;
+      if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (C <= 4*32*NV), one warp per token row, exact two-pass statistics in registers.
+// ------------------------------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int C4 = C >> 2;
+  const float4* xr = (const float4*)(x + (size_t)warp * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < C4) { v[j] = xr[i]; s += v[j].x + v[j].y + v[j].z + v[j].w; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < C4) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  __half* orow = out + (size_t)warp * ldo;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + j * 32;
+    if (i < C4) {
+      const float4 g = ((const float4*)gamma)[i], be = ((const float4*)beta)[i];
+      __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y);
+      __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
+      *(uint2*)(orow + 4 * i) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row softmax fp32 -> fp16, one CTA (256 threads) per row; scale applied to the logits first.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, int ldx, int n, float scale, __half* __restrict__ out, int ldo) {
+  __shared__ float red[8];
+  const float* xr = x + (size_t)blockIdx.x * ldx;
+  __half* orow = out + (size_t)blockIdx.x * ldo;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, xr[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += expf((xr[i] - m) * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x; i < n; i += 256) orow[i] = __float2half_rn(expf((xr[i] - m) * scale) * inv);
+}
+
+static int pick_chunk(int HW, int B) {
+  // aim for >= ~4 CTAs per SM without making chunks tiny
+  int chunk = (int)(((long long)HW * B + 591) / 592);
+  if (chunk < 4) chunk = 4;
+  if (chunk > 64) chunk = 64;
+  if (chunk > HW) chunk = HW;
+  return chunk;
+}
+
+}  // namespace upgpt
+
+using namespace upgpt;
+
+extern "C" int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups,
+                                     double* stats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int C = C1 + C2;
+  UPGPT_REQUIRE(x1 && stats && C > 0 && C % groups == 0, "groupnorm_stats: bad args (C=%d groups=%d)", C, groups);
+  UPGPT_REQUIRE(C <= 2048, "groupnorm_stats: C=%d > 2048", C);
+  UPGPT_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * B, stream));
+  const int chunk = pick_chunk(HW, B);
+  dim3 grid((HW + chunk - 1) / chunk, B);
+  const size_t sm = sizeof(double) * 2 * groups;
+  if (C <= 256) gn_stats_kernel<1><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
+  else if (C <= 512) gn_stats_kernel<2><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
+  else if (C <= 1024) gn_stats_kernel<4><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
+  else gn_stats_kernel<8><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(a && a->x1 && a->out, "prep_operand: null");
+  const int C = a->C1 + a->C2;
+  UPGPT_REQUIRE(a->C1 % 4 == 0 && a->C2 % 4 == 0 && C > 0, "prep_operand: channels must be multiples of 4");
+  UPGPT_REQUIRE(!a->stats || (a->groups > 0 && C % a->groups == 0), "prep_operand: bad groups");
+  UPGPT_REQUIRE(a->layout != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "prep_operand: stride-2 phases need even H, W");
+  UPGPT_REQUIRE(!a->raw || a->layout == 0, "prep_operand: raw copy only with layout 0");
+  PrepParams p{};
+  p.x1 = a->x1; p.C1 = a->C1; p.x2 = a->x2; p.C2 = a->C2; p.H = a->H; p.W = a->W; p.B = a->B;
+  p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+  p.layout = a->layout; p.split3 = a->split3;
+  p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 3 * C : C);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : C;
+  UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "prep_operand: ld must be a multiple of 4");
+  const int HW = a->H * a->W;
+  p.chunk = pick_chunk(HW, a->B);
+  dim3 grid((HW + p.chunk - 1) / p.chunk, a->B);
+  prep_kernel<<<grid, 256, sizeof(float) * 2 * C, stream>>>(p);
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                               void* out16, int ldo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(x && out16 && gamma && beta && C % 4 == 0 && C <= 2048, "layernorm: bad args (C=%d)", C);
+  if (ldx <= 0) ldx = C;
+  if (ldo <= 0) ldo = C;
+  UPGPT_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: ld must be multiple of 4");
+  const int warps_per_block = 8;
+  dim3 grid((rows + warps_per_block - 1) / warps_per_block);
+  __half* o = (__half*)out16;
+  if (C <= 256) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
+  else if (C <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
+  else if (C <= 1024) layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
+  else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n, float scale, void* out16, int ldo,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(x && out16 && n > 0 && rows > 0, "softmax_rows: bad args");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, ldx > 0 ? ldx : n, n, scale, (__half*)out16, ldo > 0 ? ldo : n);
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
