@@ -98,6 +98,60 @@ int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma
 /* out16[r][i] = softmax_i(scale * x[r][i]) */
 int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n, float scale, void* out16, int ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Flash-style attention on tcgen05/TMEM:  out = softmax(scale * Q K^T) V per (batch, head)
+ *   replaces: CrossAttention.forward einsum/softmax/einsum (attention.py:178-192), self (attn1) and cross (attn2)
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct upgpt_attn_args {
+  const void* q;  int ldq;   /* fp16 [B][Nq][ldq], head h at columns [h*dpad, (h+1)*dpad) */
+  const void* k;  int ldk;   /* fp16 [B][Nk][ldk], same head layout */
+  long long k_batch_stride;  /* elements between batches of K (0 = Nk*ldk) */
+  const void* vt; int ldvt;  /* fp16 V transposed [B][H*dpad][ldvt], keys contiguous (ldvt >= Nk, multiple of 8) */
+  void* out;      int ldo;   /* fp16 [B][Nq][ldo] */
+  int B, H, Nq, Nk;
+  int dpad;                  /* head dim padded with zero columns to 64 or 128 */
+  float scale;               /* dim_head ** -0.5 (attention.py:157) */
+} upgpt_attn_args;
+int upgpt_attention(const upgpt_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Boundary convolutions, timestep-embedding MLP, sampler updates, device step state, CUDA-graph helpers
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Direct k x k (k = 1 or 3, zero pad k/2) convolution for Cin = C1 + C2 <= 8. Inputs NCHW fp32 (x1 scaled by in_scale,
+ * x2 = concatenated extra channels, may be NULL); weights k-major [Cin*k*k][Cout] fp32; out NHWC (or NCHW) fp32.
+ *   replaces: DiffusionWrapper hybrid concat + input conv (ddpm.py:1567-1570, openaimodel.py:519); z/scale_factor +
+ *   post_quant_conv (ddpm.py:779, autoencoder.py:330-333); VAE Decoder.conv_in (model.py:491-495) */
+int upgpt_conv_small_cin(const float* x1, int C1, const float* x2, int C2, float in_scale, int B, int H, int W, int ksize,
+                         const float* wt_kmajor, const float* bias, int Cout, float* out, int out_nchw, void* stream);
+/* out[b] = [cos(t_b f_k) | sin(t_b f_k)]  (util.py:151-171); t is int64 on the device */
+int upgpt_timestep_embedding(const long long* t, int B, int dim, float max_period, float* out, void* stream);
+/* out[r][n] = act_out(sum_k act_in(x[r][k]) W[n][k] + bias[n]); fp32, rows <= 64 (time_embed, emb_layers, LinearProject) */
+int upgpt_linear_small_m(const float* x, int ldx, int rows, const float* w, const float* bias, int N, int K, int silu_in,
+                         int silu_out, float* out, int ldo, void* stream);
+/* DDIM update (ddim.py:189-203). coef[step] = {a_t, a_prev, sigma_t, sqrt(1-a_t), temperature}; the row index is
+ * *step_ptr when step_ptr != NULL (device int, for graph replay) else step_imm. noise may be NULL (eta = 0);
+ * otherwise noise + step*noise_step_stride holds this step's N(0,1) draws. pred_x0 may be NULL. */
+int upgpt_ddim_step(const float* x, const float* eps, const float* noise, long long noise_step_stride, const float* coef,
+                    const int* step_ptr, int step_imm, float* x_prev, float* pred_x0, long long n, void* stream);
+/* DDPM ancestral update (ddpm.py:224-237,1125-1185, clip_denoised=False). coef[step] = {sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped, t != 0}. */
+int upgpt_ddpm_step(const float* x, const float* eps, const float* noise, long long noise_step_stride, const float* coef,
+                    const int* step_ptr, int step_imm, float* x_prev, float* pred_x0, long long n, void* stream);
+/* op 0: *step = value; op 1: *step += value. Then, if t_buf: t_buf[0..B) = t_table[*step] (ddim.py:142). */
+int upgpt_step_state(int* step_ptr, int op, int value, long long* t_buf, int B, const long long* t_table, void* stream);
+/* out = a*sa + b*sb (b may be NULL): q_sample / mask blend helpers (ddpm.py:281-284, ddim.py:144-147) */
+int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream);
+/* clamp(-1,1)*0.5+0.5 -> uint8 NHWC (generate_utils.py:165-168) */
+int upgpt_to_uint8_nhwc(const float* x, int B, int C, int HW, uint8_t* out, void* stream);
+
+/* Stream capture of a sequence of upgpt_* calls into an executable CUDA graph. */
+int upgpt_capture_begin(void* stream);
+int upgpt_capture_end(void* stream, void** graph_exec_out);
+int upgpt_graph_launch(void* graph_exec, void* stream);
+int upgpt_graph_destroy(void* graph_exec);
+/* kernel nodes inside a captured graph (each launch of the graph adds this to upgpt_launch_count) */
+long long upgpt_graph_kernel_count(void* graph_exec);
+
 #ifdef __cplusplus
 }
 #endif

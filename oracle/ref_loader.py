@@ -27,6 +27,13 @@ class _RefImport:
         for k in self._saved:
             del sys.modules[k]
         sys.path.insert(0, REF_ROOT)
+        # the reference's `ldm` is a namespace package (no __init__.py) and would lose to this repo's regular `ldm`
+        # package: pin a synthetic top-level package whose search path is the reference tree.
+        import importlib.machinery
+        import importlib.util
+        spec = importlib.machinery.ModuleSpec("ldm", None, is_package=True)
+        spec.submodule_search_locations = [os.path.join(REF_ROOT, "ldm")]
+        sys.modules["ldm"] = importlib.util.module_from_spec(spec)
         if "omegaconf" not in sys.modules:
             oc, lc = types.ModuleType("omegaconf"), types.ModuleType("omegaconf.listconfig")
             lc.ListConfig = type("ListConfig", (list,), {})

@@ -47,7 +47,7 @@ def lib():
     l = C.CDLL(_LIB_PATH)
     l.upgpt_last_error.restype = C.c_char_p
     l.upgpt_launch_count.restype = C.c_longlong
-    l.upgpt_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
+    _bind(l)
     _lib = l
     return l
 
@@ -66,3 +66,54 @@ def stream_ptr(stream=None):
     import torch
     s = stream if stream is not None else torch.cuda.current_stream()
     return C.c_void_p(s.cuda_stream)
+
+
+class PrepArgs(C.Structure):
+    _fields_ = [
+        ("x1", C.c_void_p), ("C1", C.c_int), ("x2", C.c_void_p), ("C2", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
+        ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+        ("silu", C.c_int), ("layout", C.c_int), ("split3", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_int), ("raw", C.c_void_p), ("ldraw", C.c_int),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("k_batch_stride", C.c_longlong),
+        ("vt", C.c_void_p), ("ldvt", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dpad", C.c_int), ("scale", C.c_float),
+    ]
+
+
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_PROTOS = {
+    "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
+    "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
+    "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
+    "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
+    "upgpt_softmax_rows": [_vp, _i, _ll, _i, _f, _vp, _i, _vp],
+    "upgpt_attention": [C.POINTER(AttnArgs), _vp],
+    "upgpt_conv_small_cin": [_vp, _i, _vp, _i, _f, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
+    "upgpt_timestep_embedding": [_vp, _i, _i, _f, _vp, _vp],
+    "upgpt_linear_small_m": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "upgpt_ddim_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
+    "upgpt_ddpm_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
+    "upgpt_step_state": [_vp, _i, _i, _vp, _i, _vp, _vp],
+    "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
+    "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
+    "upgpt_capture_begin": [_vp],
+    "upgpt_capture_end": [_vp, C.POINTER(C.c_void_p)],
+    "upgpt_graph_launch": [_vp, _vp],
+    "upgpt_graph_destroy": [_vp],
+}
+EXPORTS = sorted(list(_PROTOS) + ["upgpt_last_error", "upgpt_abi_version", "upgpt_launch_count", "upgpt_graph_kernel_count"])
+
+
+def _bind(l):
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    l.upgpt_graph_kernel_count.argtypes = [_vp]
+    l.upgpt_graph_kernel_count.restype = C.c_longlong

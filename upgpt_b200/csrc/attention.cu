@@ -1,0 +1,300 @@
+// Flash-style multi-head attention on tcgen05 / TMEM for sm_100a.
+//
+//   O = softmax(scale * Q K^T) V        per (batch, head), Q:[Nq, d]  K:[Nk, d]  V:[Nk, d]
+//
+// One CTA owns a 128-query tile of one (batch, head) and streams 128-key tiles:
+//   warp0  : TMA producer (Q once; K tile + V^T tile per step, 2-stage ring)
+//   warp1  : TMEM allocator + tcgen05.mma issuer:  S = Q K^T  (TMEM cols [0,128)),  O += P V (TMEM cols [128,128+d))
+//   warps2-5 : online softmax, one query row per thread (TMEM lane == row, so row max / row sum need no shuffles):
+//              tcgen05.ld S -> running max -> exp2 -> P (fp16) written to smem in the 128B-swizzled K-major layout the
+//              PV MMA consumes; rescales the O accumulator in TMEM when the running max moves; final 1/l and fp16 store.
+// Operands are fp16, accumulation / softmax statistics fp32. Head dim is padded to 64 or 128 (zero columns).
+// V is consumed transposed (V^T [d][Nk], written that way by the projection GEMM's channel-major epilogue) so that every
+// tensor-core operand in the library uses the one K-major SWIZZLE_128B layout.
+//
+// Replaces CrossAttention.forward's einsum / softmax / einsum (attention.py:178-192) for both attn1 (self) and attn2
+// (keys = [text | style | SMPL] context, attention.py:213).
+#include "common.cuh"
+#include "../../include/upgpt_b200.h"
+
+namespace upgpt {
+
+struct AttnParams {
+  int Nq, Nk, H, B;
+  int dpad;            // 64 or 128
+  int num_q_tiles;
+  float scale_log2e;   // softmax scale * log2(e)
+  __half* out;         // [B][Nq][ldo], head h at columns h*dpad
+  int ldo;
+};
+
+static constexpr int kAttnThreads = 192;
+static constexpr int kTileBytes = 128 * 64 * 2;  // one [128][64] fp16 chunk
+
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int dch = p.dpad >> 6;                       // 64-wide d chunks (1 or 2)
+  const uint32_t qk_bytes = (uint32_t)dch * kTileBytes;      // Q tile or K tile
+  const uint32_t vt_chunk = (uint32_t)p.dpad * 128u;          // V^T chunk: [dpad rows][64 keys]
+  const uint32_t vt_bytes = 2u * vt_chunk;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + qk_bytes;                        // 2 stages
+  uint8_t* sV = sK + 2 * qk_bytes;                    // 2 stages
+  uint8_t* sP = sV + 2 * vt_bytes;                    // [2 chunks][128][64]
+  uint64_t* bars = (uint64_t*)(sP + 2 * kTileBytes);
+  uint64_t* bar_q = bars;
+  uint64_t* bar_kv_full = bars + 1;    // [2]
+  uint64_t* bar_kv_empty = bars + 3;   // [2]
+  uint64_t* bar_s = bars + 5;
+  uint64_t* bar_p = bars + 6;
+  uint64_t* bar_o = bars + 7;
+  uint32_t* tmem_base_smem = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.num_q_tiles;
+  const int bh = blockIdx.x / p.num_q_tiles;
+  const int h = bh % p.H, b = bh / p.H;
+  const int q0 = qt * 128;
+  const int n_kv = (p.Nk + 127) >> 7;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
+    mbar_init(bar_q, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  const uint32_t tS = tmem_base;          // 128 columns
+  const uint32_t tO = tmem_base + 128;    // dpad columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, qk_bytes);
+      for (int c = 0; c < dch; ++c) tma_load_4d(sQ + c * kTileBytes, &tmQ, bar_q, c * 64, h, q0, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&bar_kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bar_kv_full[s], qk_bytes + vt_bytes);
+        for (int c = 0; c < dch; ++c)
+          tma_load_4d(sK + s * qk_bytes + c * kTileBytes, &tmK, &bar_kv_full[s], c * 64, h, j * 128, b);
+        for (int c = 0; c < 2; ++c)
+          tma_load_3d(sV + s * vt_bytes + c * vt_chunk, &tmVt, &bar_kv_full[s], j * 128 + c * 64, h * p.dpad, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, 128);
+      const uint32_t idesc_o = make_idesc_f16(128, (uint32_t)p.dpad);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&bar_kv_full[s], (j >> 1) & 1);
+        if (j > 0) mbar_wait(bar_p, (j - 1) & 1);   // softmax finished reading S(j-1) and wrote P(j-1)
+        tc_fence_after();
+        if (j > 0) {
+          // O += P(j-1) V(j-1)
+          const int sp = (j - 1) & 1;
+          for (int c = 0; c < 2; ++c) {
+            const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
+            const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (j > 1 || c > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&bar_kv_empty[sp]);
+          tc_commit(bar_o);
+        }
+        // S(j) = Q K(j)^T
+        for (int c = 0; c < dch; ++c) {
+          const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + c * kTileBytes));
+          const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + s * qk_bytes + c * kTileBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tS, ad + 2 * k, bd + 2 * k, idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_s);
+      }
+      // tail: O += P(last) V(last)
+      {
+        const int j = n_kv;
+        mbar_wait(bar_p, (j - 1) & 1);
+        tc_fence_after();
+        const int sp = (j - 1) & 1;
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
+          const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (j > 1 || c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_o);
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue ================================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c2 = p.scale_log2e;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(bar_s, j & 1);
+      tc_fence_after();
+      const int kbase = j * 128;
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = (kbase + cc * 32 + i < p.Nk) ? __uint_as_float(v[i]) : -INFINITY;
+          m_tile = fmaxf(m_tile, sv);
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float alpha = exp2f((m_run - m_new) * c2);
+      const float mc = m_new * c2;
+      // P smem and the O accumulator are busy until PV(j-1) has completed
+      if (j > 0) {
+        mbar_wait(bar_o, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // pass 2: p = exp2(s*c - m*c), row sum, fp16 P into swizzled smem
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + cc * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int key = kbase + cc * 32 + i;
+          float p0 = (key < p.Nk) ? exp2f(fmaf(__uint_as_float(v[i]), c2, -mc)) : 0.f;
+          float p1 = (key + 1 < p.Nk) ? exp2f(fmaf(__uint_as_float(v[i + 1]), c2, -mc)) : 0.f;
+          l_tile += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[i >> 1] = *(uint32_t*)&hh;
+        }
+        // 32 keys = 4 x 16-byte units; chunk = cc / 2, unit index within the 128-byte row = (cc & 1) * 4 + u
+        uint8_t* rowp = sP + (cc >> 1) * kTileBytes + r * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = ((cc & 1) * 4 + u) ^ (r & 7);
+          *(uint4*)(rowp + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      m_run = m_new;
+      // rescale the O accumulator (skip on the first tile: PV(0) overwrites)
+      if (j > 0) {
+#pragma unroll 1
+        for (int cc = 0; cc < p.dpad / 32; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(tO + lane_off + cc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(tO + lane_off + cc * 32, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(bar_p);
+    }
+    // ---- epilogue: O / l -> fp16 ----
+    mbar_wait(bar_o, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l_run;
+    const int q = q0 + r;
+    __half* orow = p.out + ((size_t)b * p.Nq + q) * p.ldo + h * p.dpad;
+#pragma unroll 1
+    for (int cc = 0; cc < p.dpad / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_off + cc * 32, v);
+      tmem_ld_wait();
+      if (q < p.Nq) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          __half2 hh = __floats2half2_rn(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+          pk[i >> 1] = *(uint32_t*)&hh;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *(uint4*)(orow + cc * 32 + u * 8) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static bool g_attn_attr = false;
+
+}  // namespace upgpt
+
+using namespace upgpt;
+
+extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(a && a->q && a->k && a->vt && a->out, "attention: null pointer");
+  UPGPT_REQUIRE(a->dpad == 64 || a->dpad == 128, "attention: dpad must be 64 or 128 (got %d)", a->dpad);
+  UPGPT_REQUIRE(a->Nq > 0 && a->Nk > 0 && a->H > 0 && a->B > 0, "attention: bad sizes");
+  UPGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0, "attention: ld must be multiples of 8");
+  if (!g_attn_attr) {
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    g_attn_attr = true;
+  }
+  CUtensorMap tmQ, tmK, tmVt;
+  {
+    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nq, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->Nq};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap_f16(&tmQ, a->q, 4, dims, str, box, true)) return -3;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nk, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldk * 2,
+                       (uint64_t)(a->k_batch_stride > 0 ? a->k_batch_stride : (long long)a->ldk * a->Nk) * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap_f16(&tmK, a->k, 4, dims, str, box, true)) return -3;
+  }
+  {
+    // V^T: [B][H*dpad][ldvt], valid keys = Nk
+    uint64_t dims[3] = {(uint64_t)a->Nk, (uint64_t)a->H * a->dpad, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->ldvt * 2, (uint64_t)a->ldvt * 2 * a->H * a->dpad};
+    uint32_t box[3] = {64, (uint32_t)a->dpad, 1};
+    if (make_tmap_f16(&tmVt, a->vt, 3, dims, str, box, true)) return -3;
+  }
+  AttnParams p{};
+  p.Nq = a->Nq; p.Nk = a->Nk; p.H = a->H; p.B = a->B; p.dpad = a->dpad;
+  p.num_q_tiles = (a->Nq + 127) / 128;
+  p.scale_log2e = a->scale * 1.4426950408889634f;
+  p.out = (__half*)a->out; p.ldo = a->ldo;
+  const int dch = a->dpad / 64;
+  const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128;
+  const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);
+  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmVt, p);
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

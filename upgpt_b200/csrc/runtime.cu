@@ -13,6 +13,7 @@ static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_last_error(const char* fmt, ...) {
   va_list ap;

@@ -85,6 +85,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & GEMM_CONV) {
           if (p.tile_imgs > 1) {
             c1 = 0; c2 = 0; c3 = mt * p.tile_imgs;
+          } else if (p.tiles_per_row > 1) {
+            const int img = mt / p.tiles_per_img;
+            const int t = mt - img * p.tiles_per_img;
+            c1 = (t % p.tiles_per_row) * 128; c2 = t / p.tiles_per_row; c3 = img;
           } else {
             const int img = mt / p.tiles_per_img;
             c1 = 0; c2 = (mt - img * p.tiles_per_img) * p.tile_rows; c3 = img;
@@ -164,6 +168,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int img = mt * p.tile_imgs + r / p.HW;
           valid = (r < p.tile_imgs * p.HW) && (img < p.n_imgs);
           grow = (long long)mt * p.tile_imgs * p.HW + r;
+        } else if (p.tiles_per_row > 1) {
+          valid = true;                       // W % 128 == 0: every lane is a pixel
+          grow = (long long)mt * 128 + r;     // tiles enumerate the image in raster order
         } else {
           const int img = mt / p.tiles_per_img;
           const int y0 = (mt - img * p.tiles_per_img) * p.tile_rows;
@@ -346,11 +353,17 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   int m_rows_total;
   if (conv) {
     UPGPT_REQUIRE(a->H > 0 && a->W > 0 && a->n_imgs > 0, "upgpt_gemm(conv): bad geometry");
-    UPGPT_REQUIRE(a->W <= 128, "upgpt_gemm(conv): W=%d > 128 needs column tiling (not implemented)", a->W);
+    UPGPT_REQUIRE(a->W <= 128 || a->W % 128 == 0, "upgpt_gemm(conv): W=%d > 128 must be a multiple of 128", a->W);
     p.flags |= GEMM_CONV;
     p.H = a->H; p.W = a->W; p.HW = a->H * a->W; p.n_imgs = a->n_imgs;
     uint32_t box[4];
-    if (p.HW <= 64) {
+    p.tiles_per_row = 1;
+    if (a->W > 128) {
+      p.tile_imgs = 1; p.tile_rows = 1; p.tiles_per_row = a->W / 128;
+      p.tiles_per_img = p.tiles_per_row * a->H;
+      p.num_m_tiles = p.tiles_per_img * a->n_imgs;
+      box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+    } else if (p.HW <= 64) {
       p.tile_imgs = 128 / p.HW; p.tile_rows = a->H; p.tiles_per_img = 1;
       if (p.tile_imgs > a->n_imgs) p.tile_imgs = a->n_imgs;
       if (p.tile_imgs < 1) p.tile_imgs = 1;

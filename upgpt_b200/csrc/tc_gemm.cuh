@@ -29,6 +29,7 @@ struct GemmParams {
   int tile_rows;        // image rows per M tile (tile_imgs == 1)
   int tile_imgs;        // whole images per M tile (HW * tile_imgs <= 128)
   int tiles_per_img;
+  int tiles_per_row;    // > 1 when W > 128: a tile is a 128-pixel segment of one image row
   int n_imgs;           // number of images addressed by the output
   int tap_dy[9], tap_dx[9], tap_dn[9];
   // ---- epilogue ----
