@@ -1,0 +1,515 @@
+"""B200 execution engine for ldm.modules.diffusionmodules.openaimodel.UNetModel.
+
+The engine turns the module tree into a static *program*: a list of C-ABI kernel launches over pre-allocated device
+buffers (NHWC fp32 residual stream, fp16 tensor-core operands), recorded once per (batch, H, W, context length).
+Replaying the list is the eager path; capturing one replay in a CUDA graph is the fast path used by the samplers.
+
+Program per ResBlock (openaimodel.py:255-275):
+    gn_stats -> prep(GN+SiLU -> fp16) -> conv3x3[tcgen05](+bias +timestep-emb row vector) -> gn_stats -> prep
+    -> [skip 1x1 GEMM] -> conv3x3(+bias +residual)
+per SpatialTransformer (attention.py:250-261,211-215):
+    gn_stats -> prep(GN) -> proj_in GEMM -> LN -> QK GEMM + V^T GEMM -> flash attention -> to_out GEMM(+res)
+    -> LN -> Q GEMM -> flash attention over the cached context K/V -> to_out GEMM(+res)
+    -> LN -> GEGLU GEMM -> ff2 GEMM(+res, +fp16 copy) -> proj_out GEMM(+block input)
+The skip concat th.cat([h, hs.pop()]) (openaimodel.py:736) never exists in fp32: gn_stats / prep read both tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _C
+from ldm.modules.attention import SpatialTransformer
+from ldm.modules.diffusionmodules import openaimodel as om
+
+
+def default_precision():
+    return os.environ.get("UPGPT_PRECISION", "fp16")
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def pad_heads_rows(w, heads, d, dpad):
+    """[heads*d, K] -> [heads*dpad, K] with zero rows appended per head."""
+    K = w.shape[1]
+    out = w.new_zeros(heads, dpad, K)
+    out[:, :d] = w.reshape(heads, d, K)
+    return out.reshape(heads * dpad, K)
+
+
+def pad_heads_cols(w, heads, d, dpad):
+    """[N, heads*d] -> [N, heads*dpad] with zero columns appended per head."""
+    N = w.shape[0]
+    out = w.new_zeros(N, heads, dpad)
+    out[:, :, :d] = w.reshape(N, heads, d)
+    return out.reshape(N, heads * dpad)
+
+
+def geglu_half(inner):
+    for h in (128, 112, 96, 80, 64, 48, 32, 16):
+        if inner % h == 0:
+            return h
+    raise ValueError("GEGLU inner dim %d not a multiple of 16" % inner)
+
+
+def pack_geglu(w, b, inner, half):
+    """Rows [x(inner) ; gate(inner)] -> per tile [x(half) | gate(half)] so one accumulator tile holds matching columns."""
+    idx = []
+    for t in range(inner // half):
+        idx += list(range(t * half, (t + 1) * half)) + list(range(inner + t * half, inner + (t + 1) * half))
+    idx = torch.tensor(idx, device=w.device)
+    return w[idx].contiguous(), b[idx].contiguous()
+
+
+def split3_w(w):
+    """Error-compensated fp16 weights along K: [Wh | Wh | Wl] matching operand planes [Ah | Al | Ah]."""
+    wh = w.half()
+    wl = (w - wh.float()).half()
+    return torch.cat([wh, wh, wl], dim=-1)
+
+
+class _Program:
+    """Recorded list of (function, argument tuple) launches."""
+
+    def __init__(self):
+        self.calls = []
+        self.keep = []   # ctypes structs must outlive the program
+
+    def add(self, fn, *args):
+        self.calls.append((fn, args))
+
+    def add_struct(self, fn, struct):
+        self.keep.append(struct)
+        self.calls.append((fn, (C.byref(struct),)))
+
+    def run(self, stream):
+        for fn, args in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise _C.UpgptError("%s failed (%d): %s" % (fn.__name__, rc, _C.lib().upgpt_last_error().decode()))
+
+
+class EngineBase:
+    """Buffer bookkeeping + emitters shared by the U-Net and VAE engines."""
+
+    def __init__(self, device, precision):
+        self.dev = device
+        self.precision = precision
+        self.split3 = precision == "fp16x3"
+        self.L = _C.lib()
+        self.w = {}
+        self.bufs = {}
+        self._scratch_need = {}
+        self._scratch = {}
+        self._sizing = True
+        self.prog = _Program()
+
+    # ---- memory ----
+    def put(self, name, t):
+        t = t.contiguous()
+        if name in self.w and self.w[name].shape == t.shape and self.w[name].dtype == t.dtype:
+            self.w[name].copy_(t)      # keep the address: captured graphs stay valid across re-packs
+        else:
+            self.w[name] = t.to(self.dev)
+        return self.w[name]
+
+    def buf(self, name, shape, dtype=torch.float32):
+        if name not in self.bufs:
+            self.bufs[name] = torch.zeros(shape, device=self.dev, dtype=dtype)
+        return self.bufs[name]
+
+    def scratch(self, role, numel, dtype):
+        """Role-shared scratch: sized to the max request during the sizing pass; pointer handed out afterwards."""
+        key = (role, dtype)
+        if self._sizing:
+            self._scratch_need[key] = max(self._scratch_need.get(key, 0), int(numel))
+            return None
+        return self._scratch[key]
+
+    def finish_sizing(self):
+        for key, n in self._scratch_need.items():
+            self._scratch[key] = torch.zeros(n, device=self.dev, dtype=key[1])
+        self._sizing = False
+
+    @staticmethod
+    def p(t):
+        return 0 if t is None else t.data_ptr()
+
+    # ---- emitters ----
+    def e_gn_stats(self, x1, C1, x2, C2, B, HW, stats):
+        if self._sizing:
+            return
+        self.prog.add(self.L.upgpt_groupnorm_stats, self.p(x1), C1, self.p(x2), C2, B, HW, 32, self.p(stats))
+
+    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False):
+        if self._sizing:
+            return
+        a = _C.PrepArgs()
+        a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
+        a.B, a.H, a.W, a.groups = B, H, W, 32
+        a.stats, a.gamma, a.beta, a.eps = self.p(stats), self.p(gamma), self.p(beta), eps
+        a.silu, a.layout, a.split3 = int(silu), layout, int(split3)
+        a.out, a.ldo, a.raw, a.ldraw = self.p(out), 0, self.p(raw), 0
+        self.prog.add_struct(self.L.upgpt_prep_operand, a)
+
+    def e_gemm(self, **kw):
+        if self._sizing:
+            return
+        a = _C.GemmArgs()
+        for k, v in kw.items():
+            setattr(a, k, self.p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
+        self.prog.add_struct(self.L.upgpt_gemm, a)
+
+    def e_layernorm(self, x, rows, Cc, gamma, beta, out16):
+        if self._sizing:
+            return
+        self.prog.add(self.L.upgpt_layernorm, self.p(x), Cc, rows, Cc, self.p(gamma), self.p(beta), 1e-5, self.p(out16), Cc)
+
+    def e_attention(self, **kw):
+        if self._sizing:
+            return
+        a = _C.AttnArgs()
+        for k, v in kw.items():
+            setattr(a, k, self.p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
+        self.prog.add_struct(self.L.upgpt_attention, a)
+
+    # GroupNorm(+SiLU) -> fp16 operand of the (possibly concatenated) input; returns (operand, raw16)
+    def norm_operand(self, x1, C1, x2, C2, B, H, W, gname, eps, silu, want_raw=False, layout=0, split3=False):
+        Cc = C1 + C2
+        stats = self.buf("gn_stats", (B, 32, 2), torch.float64)
+        mult = 4 if layout == 1 else 1
+        op = self.scratch("op16", B * H * W * mult * Cc * (3 if split3 else 1), torch.float16)
+        raw = self.scratch("raw16", B * H * W * Cc, torch.float16) if want_raw else None
+        if gname is not None:
+            self.e_gn_stats(x1, C1, x2, C2, B, H * W, stats)
+            self.e_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu,
+                        layout, op, raw, split3)
+        else:
+            self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3)
+        return op, raw
+
+
+class UNetEngine(EngineBase):
+    def __init__(self, unet, B, H, W, ctx_len, precision=None):
+        dev = next(unet.parameters()).device
+        if dev.type != "cuda":
+            raise _C.UpgptError("UNetEngine needs the module on a CUDA device (no CPU fallback)")
+        super().__init__(dev, precision or default_precision())
+        self.B, self.H, self.W, self.ctx_len = B, H, W, ctx_len
+        self.mc = unet.model_channels
+        self.in_ch, self.out_ch = unet.in_channels, unet.out_channels
+        self.ctx_dim = unet.context_dim
+        nlevels = len(unet.channel_mult)
+        assert H % (2 ** (nlevels - 1)) == 0 and W % (2 ** (nlevels - 1)) == 0, "latent size must divide by the U-Net stride"
+        self.unet_ref = unet
+        self.weights_version = -1
+        self.graph = None
+        self._ctx_key = None
+        self.pack_weights(unet)
+        # two passes over the same emitter: sizing, then recording
+        self._emit(unet)
+        self.finish_sizing()
+        self._emit(unet)
+        self._emit_context(unet)
+
+    # ------------------------------------------------------------------------------------------------ weights
+    def _conv_w(self, w):
+        """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x3 planes in fp16x3 mode)."""
+        w = w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1])
+        return split3_w(w) if self.split3 else w.half()
+
+    def pack_weights(self, unet):
+        sd = {k: v.detach().to(self.dev, torch.float32) for k, v in unet.state_dict().items()}
+        put = self.put
+        for k in ("time_embed.0", "time_embed.2"):
+            put(k + ".weight", sd[k + ".weight"]); put(k + ".bias", sd[k + ".bias"])
+        # boundary convs
+        w0 = sd["input_blocks.0.0.weight"]
+        put("conv_in.weight", w0.permute(1, 2, 3, 0).reshape(-1, w0.shape[0]))
+        put("conv_in.bias", sd["input_blocks.0.0.bias"])
+        emb_w, emb_b, self.emb_off, off = [], [], {}, 0
+        for name, mod in unet.named_modules():
+            if isinstance(mod, om.ResBlock):
+                p = name
+                for g in (".in_layers.0", ".out_layers.0"):
+                    put(p + g + ".weight", sd[p + g + ".weight"]); put(p + g + ".bias", sd[p + g + ".bias"])
+                put(p + ".conv1.weight", self._conv_w(sd[p + ".in_layers.2.weight"])); put(p + ".conv1.bias", sd[p + ".in_layers.2.bias"])
+                put(p + ".conv2.weight", self._conv_w(sd[p + ".out_layers.3.weight"])); put(p + ".conv2.bias", sd[p + ".out_layers.3.bias"])
+                if (p + ".skip_connection.weight") in sd:
+                    ws = sd[p + ".skip_connection.weight"]
+                    put(p + ".skip.weight", ws.reshape(ws.shape[0], ws.shape[1]).half()); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
+                emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
+                self.emb_off[p] = off
+                off += mod.out_channels
+            elif isinstance(mod, (om.Downsample, om.Upsample)):
+                sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
+                w = sd[name + sub + ".weight"]
+                put(name + ".weight", w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]).half())
+                put(name + ".bias", sd[name + sub + ".bias"])
+            elif isinstance(mod, SpatialTransformer):
+                p = name
+                Cc, Hh, d = mod.in_channels, mod.n_heads, mod.d_head
+                dpad = 64 if d <= 64 else 128
+                assert d <= 128, "head dim > 128 not supported by the attention kernel"
+                put(p + ".norm.weight", sd[p + ".norm.weight"]); put(p + ".norm.bias", sd[p + ".norm.bias"])
+                wpi = sd[p + ".proj_in.weight"]
+                put(p + ".proj_in.weight", wpi.reshape(wpi.shape[0], wpi.shape[1]).half()); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
+                wpo = sd[p + ".proj_out.weight"]
+                put(p + ".proj_out.weight", wpo.reshape(wpo.shape[0], wpo.shape[1]).half()); put(p + ".proj_out.bias", sd[p + ".proj_out.bias"])
+                for bi in range(len(mod.transformer_blocks)):
+                    q = f"{p}.transformer_blocks.{bi}"
+                    for n in ("norm1", "norm2", "norm3"):
+                        put(f"{q}.{n}.weight", sd[f"{q}.{n}.weight"]); put(f"{q}.{n}.bias", sd[f"{q}.{n}.bias"])
+                    wq = pad_heads_rows(sd[q + ".attn1.to_q.weight"], Hh, d, dpad)
+                    wk = pad_heads_rows(sd[q + ".attn1.to_k.weight"], Hh, d, dpad)
+                    put(q + ".attn1.qk.weight", torch.cat([wq, wk], 0).half())
+                    put(q + ".attn1.v.weight", pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad).half())
+                    put(q + ".attn1.out.weight", pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad).half())
+                    put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
+                    put(q + ".attn2.q.weight", pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad).half())
+                    put(q + ".attn2.k.weight", pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad).half())
+                    put(q + ".attn2.v.weight", pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad).half())
+                    put(q + ".attn2.out.weight", pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad).half())
+                    put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
+                    inner = sd[q + ".ff.net.2.weight"].shape[1]
+                    half = geglu_half(inner)
+                    w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
+                    put(q + ".ff1.weight", w1.half()); put(q + ".ff1.bias", b1)
+                    put(q + ".ff2.weight", sd[q + ".ff.net.2.weight"].half()); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
+        put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
+        self.emb_total = off
+        put("out.0.weight", sd["out.0.weight"]); put("out.0.bias", sd["out.0.bias"])
+        put("out.conv.weight", self._conv_w(sd["out.2.weight"])); put("out.conv.bias", sd["out.2.bias"])
+        self.weights_version = unet._weights_version
+        self._ctx_key = None   # cached context K/V depends on the weights
+
+    # ------------------------------------------------------------------------------------------------ program
+    def _res_block(self, p, mod, x1, C1, x2, C2, B, H, W, out):
+        Cin, Cout = C1 + C2, mod.out_channels
+        HW = H * W
+        has_skip = (p + ".skip.weight") in self.w
+        op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=self.split3)
+        h32 = self.scratch("res_h", B * HW * Cout, torch.float32)
+        kmul = 3 if self.split3 else 1
+        emb = None if self._sizing else self.bufs["emb_all"][:, self.emb_off[p]:]
+        self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin * kmul, n_imgs=B, H=H, W=W,
+                    out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total)
+        op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=self.split3)
+        if has_skip:
+            skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
+            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
+                        bias=self.w.get(p + ".skip.bias"))
+            res = skip32
+        else:
+            assert x2 is None or self._sizing or C2 == 0
+            res = x1
+        self.e_gemm(a=op2, w=self.w.get(p + ".conv2.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cout * kmul, n_imgs=B, H=H, W=W,
+                    out32=out, bias=self.w.get(p + ".conv2.bias"), res32=res)
+
+    def _transformer(self, p, mod, x, Cc, B, H, W, out):
+        HW, M = H * W, B * H * W
+        Hh, d = mod.n_heads, mod.d_head
+        dpad = 64 if d <= 64 else 128
+        HD = Hh * dpad
+        L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
+        op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False)
+        tokA = self.scratch("tokA", M * Cc, torch.float32)
+        tokB = self.scratch("tokB", M * Cc, torch.float32)
+        tok16 = self.scratch("tok16", M * Cc, torch.float16)
+        qk16 = self.scratch("qk16", M * 2 * HD, torch.float16)
+        vt16 = self.scratch("vt16", B * HD * _round_up(HW, 8), torch.float16)
+        att16 = self.scratch("att16", M * HD, torch.float16)
+        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
+                    bias=self.w.get(p + ".proj_in.bias"))
+        cur, nxt = tokA, tokB
+        for bi in range(len(mod.transformer_blocks)):
+            q = f"{p}.transformer_blocks.{bi}"
+            g = lambda n: self.w.get(q + n)
+            inner = mod.transformer_blocks[bi].ff.net[2].in_features
+            ff16 = self.scratch("ff16", M * inner, torch.float16)
+            # --- self attention ---
+            self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16)
+            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc, out16=qk16)
+            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=vt16, rows_per_group=HW,
+                        ldT=_round_up(HW, 8), flags=_C.GEMM_F_CHW)
+            kptr = None if self._sizing else qk16[HD:]
+            self.e_attention(q=qk16, ldq=2 * HD, k=kptr, ldk=2 * HD, k_batch_stride=0, vt=vt16, ldvt=_round_up(HW, 8), out=att16,
+                             ldo=HD, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad, scale=float(d) ** -0.5)
+            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                        bias=g(".attn1.out.bias"), res32=cur)
+            cur, nxt = nxt, cur
+            # --- cross attention over the cached context K / V^T ---
+            self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16)
+            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qk16)
+            kc = self.buf(q + ".ctx_k", (B * L, HD), torch.float16)
+            vc = self.buf(q + ".ctx_vt", (B, HD, Lp), torch.float16)
+            self.e_attention(q=qk16, ldq=HD, k=kc, ldk=HD, k_batch_stride=0, vt=vc, ldvt=Lp, out=att16, ldo=HD, B=B, H=Hh,
+                             Nq=HW, Nk=L, dpad=dpad, scale=float(d) ** -0.5)
+            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                        bias=g(".attn2.out.bias"), res32=cur)
+            cur, nxt = nxt, cur
+            # --- GEGLU feed-forward ---
+            self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16)
+            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner),
+                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU)
+            last = bi == len(mod.transformer_blocks) - 1
+            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
+                        res32=cur, out16=tok16 if last else None)
+            cur, nxt = nxt, cur
+        self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
+                    bias=self.w.get(p + ".proj_out.bias"), res32=x)
+
+    def _emit(self, unet):
+        B, H, W = self.B, self.H, self.W
+        L_ = self.L
+        if not self._sizing:
+            self.prog = _Program()
+        # staged NCHW inputs: the latent and the c_concat channels live in separate buffers so the samplers can update
+        # the latent in place; the input conv reads both (DiffusionWrapper's th.cat never materialises)
+        self.lat_ch = min(self.in_ch, self.out_ch)
+        x_lat = self.buf("x_lat", (B, self.lat_ch, H, W))
+        x_cat = self.buf("x_cat", (B, max(self.in_ch - self.lat_ch, 1), H, W))
+        t_in = self.buf("t_in", (B,), torch.int64)
+        temb = self.buf("temb", (B, self.mc))
+        emb1 = self.buf("emb1", (B, 4 * self.mc))
+        emb = self.buf("emb", (B, 4 * self.mc))
+        emb_all = self.buf("emb_all", (B, self.emb_total))
+        eps = self.buf("eps", (B, self.out_ch, H, W))
+        if not self._sizing:
+            P = self.prog
+            P.add(L_.upgpt_timestep_embedding, t_in.data_ptr(), B, self.mc, 10000.0, temb.data_ptr())
+            P.add(L_.upgpt_linear_small_m, temb.data_ptr(), self.mc, B, self.w["time_embed.0.weight"].data_ptr(),
+                  self.w["time_embed.0.bias"].data_ptr(), 4 * self.mc, self.mc, 0, 1, emb1.data_ptr(), 4 * self.mc)
+            P.add(L_.upgpt_linear_small_m, emb1.data_ptr(), 4 * self.mc, B, self.w["time_embed.2.weight"].data_ptr(),
+                  self.w["time_embed.2.bias"].data_ptr(), 4 * self.mc, 4 * self.mc, 0, 0, emb.data_ptr(), 4 * self.mc)
+            P.add(L_.upgpt_linear_small_m, emb.data_ptr(), 4 * self.mc, B, self.w["emb_all.weight"].data_ptr(),
+                  self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 1, 0, emb_all.data_ptr(), self.emb_total)
+        # ---- input blocks ----
+        hs = []
+        h = self.buf("h_in0", (B, H * W, self.mc))
+        if not self._sizing:
+            ncat = self.in_ch - self.lat_ch
+            self.prog.add(L_.upgpt_conv_small_cin, x_lat.data_ptr(), self.lat_ch, x_cat.data_ptr() if ncat else 0, ncat, 1.0, B, H, W, 3,
+                          self.w["conv_in.weight"].data_ptr(), self.w["conv_in.bias"].data_ptr(), self.mc, h.data_ptr(), 0)
+        ch, ch_h, ch_w = self.mc, H, W
+        hs.append((h, ch, ch_h, ch_w))
+
+        def run_layers(prefix, layers, h, ch, hh, ww, skip=None):
+            """Runs one TimestepEmbedSequential; `skip` = (tensor, channels) concatenated onto the first ResBlock input."""
+            for j, mod in enumerate(layers):
+                p = f"{prefix}.{j}"
+                if isinstance(mod, om.ResBlock):
+                    out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
+                    if skip is not None:
+                        self._res_block(p, mod, h, ch, skip[0], skip[1], B, hh, ww, out)
+                        skip = None
+                    else:
+                        self._res_block(p, mod, h, ch, None, 0, B, hh, ww, out)
+                    h, ch = out, mod.out_channels
+                elif isinstance(mod, SpatialTransformer):
+                    out = self.buf(p + ".out", (B, hh * ww, ch))
+                    self._transformer(p, mod, h, ch, B, hh, ww, out)
+                    h = out
+                elif isinstance(mod, om.Downsample):
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2)
+                    hh, ww = hh // 2, ww // 2
+                    out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch, n_imgs=B,
+                                H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"))
+                    h, ch = out, mod.out_channels
+                elif isinstance(mod, om.Upsample):
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1)
+                    hh, ww = hh * 2, ww * 2
+                    out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
+                                W=ww, out32=out, bias=self.w.get(p + ".bias"))
+                    h, ch = out, mod.out_channels
+                else:
+                    raise NotImplementedError(type(mod))
+            return h, ch, hh, ww
+
+        for i in range(1, len(unet.input_blocks)):
+            h, ch, ch_h, ch_w = run_layers(f"input_blocks.{i}", unet.input_blocks[i], h, ch, ch_h, ch_w)
+            hs.append((h, ch, ch_h, ch_w))
+        h, ch, ch_h, ch_w = run_layers("middle_block", unet.middle_block, h, ch, ch_h, ch_w)
+        for i, blk in enumerate(unet.output_blocks):
+            s, sc, sh, sw = hs.pop()
+            assert (sh, sw) == (ch_h, ch_w)
+            h, ch, ch_h, ch_w = run_layers(f"output_blocks.{i}", blk, h, ch, ch_h, ch_w, skip=(s, sc))
+        # ---- out: GN + SiLU + conv3x3 -> eps (NCHW fp32) ----
+        op, _ = self.norm_operand(h, ch, None, 0, B, H, W, "out.0", 1e-5, True, split3=self.split3)
+        self.e_gemm(a=op, w=self.w.get("out.conv.weight"), mode=_C.GEMM_CONV3X3, N=self.out_ch, K=ch * (3 if self.split3 else 1),
+                    n_imgs=B, H=H, W=W, block_n=16, splits=1, out32=eps, bias=self.w.get("out.conv.bias"), flags=_C.GEMM_F_CHW)
+
+    def _emit_context(self, unet):
+        """Program that fills the per-layer context K / V^T caches (timestep-invariant: attention.py:162-163,175-176)."""
+        B, L, Lp = self.B, self.ctx_len, _round_up(self.ctx_len, 8)
+        main = self.prog
+        self.prog = _Program()
+        ctx32 = self.buf("ctx32", (B, L, self.ctx_dim))
+        ctx16 = self.buf("ctx16", (B * L, self.ctx_dim), torch.float16)
+        self.e_prep(ctx32, self.ctx_dim, None, 0, B, 1, L, None, None, None, 0.0, False, 0, ctx16)
+        for name, mod in unet.named_modules():
+            if isinstance(mod, SpatialTransformer):
+                dpad = 64 if mod.d_head <= 64 else 128
+                HD = mod.n_heads * dpad
+                for bi in range(len(mod.transformer_blocks)):
+                    q = f"{name}.transformer_blocks.{bi}"
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                                out16=self.bufs[q + ".ctx_k"])
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                                out16=self.bufs[q + ".ctx_vt"], rows_per_group=L, ldT=Lp, flags=_C.GEMM_F_CHW)
+        self.ctx_prog = self.prog
+        self.prog = main
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def set_context(self, context, force=False):
+        """Builds the cross-attention K / V^T cond-cache for `context` (B, L, ctx_dim). Skipped when unchanged."""
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        if not force and key == self._ctx_key:
+            return
+        assert tuple(context.shape) == (self.B, self.ctx_len, self.ctx_dim), (context.shape, (self.B, self.ctx_len, self.ctx_dim))
+        self.bufs["ctx32"].copy_(context)
+        self.ctx_prog.run(self._stream())
+        self._ctx_key = key
+
+    def stage_inputs(self, x, timesteps, c_concat=None):
+        """x: (B, in_ch, H, W) already concatenated, or the (B, lat_ch, H, W) latent with c_concat given separately."""
+        if c_concat is None and x.shape[1] == self.in_ch and self.in_ch > self.lat_ch:
+            self.bufs["x_lat"].copy_(x[:, :self.lat_ch])
+            self.bufs["x_cat"].copy_(x[:, self.lat_ch:])
+        else:
+            self.bufs["x_lat"].copy_(x)
+            if c_concat is not None:
+                self.bufs["x_cat"].copy_(c_concat)
+        if timesteps is not None:
+            self.bufs["t_in"].copy_(timesteps)
+
+    def run(self, use_graph=True):
+        """Executes one U-Net pass over the staged inputs; result in self.bufs['eps']."""
+        if use_graph:
+            if self.graph is None:
+                from .ops import Graph
+                self.prog.run(self._stream())   # warm-up (lazy module load, attribute setup) outside capture
+                self.graph = Graph().capture(lambda: self.prog.run(self._stream()))
+            self.graph.launch()
+        else:
+            self.prog.run(self._stream())
+        return self.bufs["eps"]
+
+    def forward(self, x, timesteps, context, use_graph=None):
+        """x (B, in_channels, H, W) fp32 NCHW (latent already concatenated with c_concat), timesteps (B,), context (B,L,D)."""
+        if use_graph is None:
+            use_graph = os.environ.get("UPGPT_NO_GRAPH", "0") != "1"
+        self.set_context(context)
+        self.stage_inputs(x, timesteps)
+        return self.run(use_graph).clone()
+
+    @property
+    def launches_per_step(self):
+        return len(self.prog.calls)
