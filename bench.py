@@ -1,0 +1,319 @@
+"""Headline benchmark: images/sec @256x256, 50-step DDIM, bs=8 per GPU, random-init U-Net + KL-f8 decode (BASELINE.json
+configs[1]), synthetic 32x32x4 latents / (B, 87, 768) context / bbox person mask.
+
+    python bench.py [--gpus N --steps K --warmup W]             # this repo's B200 path
+    python bench.py --impl reference [...]                     # the reference algorithm on the host CPU (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU, batch sharded (weak scaling)
+
+One "step" = one full pass of the hot path over one batch: 50 DDIM steps through the U-Net (one CUDA graph replay per
+step) + the VAE decode of the batch.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec @256x256, 50-step DDIM, bs=8"
+UNIT = "images/s"
+B_PER_GPU, LAT, CTX_LEN, CTX_DIM, DDIM_STEPS = 8, 32, 87, 768, 50
+GF_UNET_PER_SAMPLE_STEP = 91.03      # SURVEY.md 8(d), FlopCounterMode on the reference U-Net, 32x32 latent
+GF_VAE_PER_IMAGE = 622.19
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--eta", type=float, default=1.0, help="DDIM eta (reference default in log_images is 1.0)")
+    ap.add_argument("--precision", default=os.environ.get("UPGPT_PRECISION", "fp16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(args, rank):
+    """--impl reference: the reference's algorithm (oracle port of its PyTorch fp32 path) on the host cores.
+    Each 'step' is a bounded sample of the workload: ONE U-Net denoising step at B=8 plus ONE single-image VAE decode,
+    extrapolated to images/s of the full 50-step + decode job."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import ldm_oracle as O
+    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+    from upgpt_b200 import synth
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.models.autoencoder import AutoencoderKL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet = UNetModel(**BBOX_UNET_KW)
+    sd_u = synth.synth_state_dict(unet.state_dict(), 0)
+    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4)
+    sd_v = synth.synth_state_dict(ae.state_dict(), 0)
+    del unet, ae
+    x, mask, ctx = synth.synth_inputs(B_PER_GPU, LAT, LAT, CTX_LEN, CTX_DIM, 0)
+    t = torch.full((B_PER_GPU,), 501, dtype=torch.long)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx)
+            t_unet = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            O.decode_first_stage(sd_v, BBOX_VAE_KW, x[:1], 0.18215)
+            t_vae = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append((t_unet, t_vae))
+    tu = sum(a for a, _ in times) / len(times)
+    tv = sum(b for _, b in times) / len(times)
+    t_batch = DDIM_STEPS * tu + B_PER_GPU * tv
+    val = B_PER_GPU / t_batch
+    sample = "1 U-Net step at B=8 (%.2f s) + 1 single-image VAE decode (%.2f s) per bench step; extrapolated x50 steps, x8 decodes" % (tu, tv)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "bbox.yaml U-Net 32x32x4 latent, 87x768 context, 50-step DDIM, bs=8, + KL-f8 decode to 256x256",
+                       "host": "CPU, torch %s, %d threads" % (torch.__version__, cores)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_quick():
+    """cpu_baseline for the b200 arm (rank 0, N=1): ~10-30 s of oracle work on the host cores."""
+    import torch
+    from oracle import ldm_oracle as O
+    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+    from upgpt_b200 import synth
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.models.autoencoder import AutoencoderKL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    unet = UNetModel(**BBOX_UNET_KW); sd_u = synth.synth_state_dict(unet.state_dict(), 0); del unet
+    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4); sd_v = synth.synth_state_dict(ae.state_dict(), 0); del ae
+    x, mask, ctx = synth.synth_inputs(B_PER_GPU, LAT, LAT, CTX_LEN, CTX_DIM, 0)
+    t = torch.full((B_PER_GPU,), 501, dtype=torch.long)
+    with torch.no_grad():
+        O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x[:1], mask[:1]], 1), t[:1], ctx[:1])   # warm-up
+        t0 = time.perf_counter(); O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx); tu = time.perf_counter() - t0
+        t0 = time.perf_counter(); O.decode_first_stage(sd_v, BBOX_VAE_KW, x[:1], 0.18215); tv = time.perf_counter() - t0
+    val = B_PER_GPU / (DDIM_STEPS * tu + B_PER_GPU * tv)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 U-Net step at B=8 (%.2f s) + 1 single-image VAE decode (%.2f s), extrapolated to 50 steps + 8 decodes" % (tu, tv)}
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def build_model(dev, precision):
+    import torch
+    from ldm.util import load_config, instantiate_from_config
+    from upgpt_b200 import synth
+    os.environ["UPGPT_PRECISION"] = precision
+    cfg = load_config(os.path.join(ROOT, "configs", "deepfashion", "bbox.yaml"))
+    cfg.model.params["use_ema"] = False      # EMA shadow weights are a training artefact (saves 1.7 GB); same forward
+    model = instantiate_from_config(cfg.model)
+    sd = {k: v for k, v in model.state_dict().items() if k.startswith(("model.diffusion_model.", "first_stage_model.", "extra_cond_models."))}
+    model.load_state_dict(synth.synth_state_dict(sd, 0), strict=False)
+    return model.to(dev).eval()
+
+
+def roofline_dominant_kernel(dev, pk):
+    """Dominant kernel = tc_gemm_kernel (tcgen05 implicit-GEMM conv); its largest single class is the 224->224 3x3 conv at
+    32x32, B=8 (14 launches per U-Net step).  Timed alone with CUDA events on the launching stream, L2 flushed between launches."""
+    import torch
+    from upgpt_b200 import _C, ops
+    B, H, W, C = B_PER_GPU, LAT, LAT, 224
+    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half()
+    w = (torch.randn(C, 9, C, device=dev) * 0.02).half()
+    bias = torch.randn(C, device=dev)
+    out = torch.empty(B * H * W, C, device=dev)
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+    kw = dict(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias)
+    for _ in range(3):
+        ops.gemm(**kw)
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.gemm(**kw); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts) / len(ts)
+    flops = 2.0 * B * H * W * 9 * C * C
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8)", "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
+            "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": pk["src"] + " (burst: kernel timed alone)",
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops}
+
+
+def gpu_arm(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from upgpt_b200 import _C, ops, synth
+    from ldm.models.diffusion.ddim import DDIMSampler
+    L = _C.lib()
+    pk = peaks()
+    model = build_model(dev, args.precision)
+    B = B_PER_GPU
+    # synthetic inputs: resident copies (kernel-only `value`) and pinned host copies (`e2e`)
+    x_T, mask, ctx = synth.synth_inputs(B, LAT, LAT, CTX_LEN, CTX_DIM, 100 + rank)
+    x_dev, mask_dev, ctx_dev = x_T.to(dev), mask.to(dev), ctx.to(dev)
+    x_pin, mask_pin, ctx_pin = x_T.pin_memory(), mask.pin_memory(), ctx.pin_memory()
+    out_pin = torch.empty(B, 256, 256, 3, dtype=torch.uint8).pin_memory()
+    gathered = torch.empty(world * B, 256, 256, 3, dtype=torch.uint8, device=dev) if world > 1 else None
+    sampler = DDIMSampler(model)
+
+    def hot_path(xT, m, c):
+        cond = {"c_crossattn": c, "c_concat": [m]}
+        z, _ = sampler.sample(DDIM_STEPS, B, (4, LAT, LAT), conditioning=cond, eta=args.eta, x_T=xT, verbose=False, log_every_t=1000)
+        img = model.decode_first_stage(z)
+        frames = ops.to_uint8_nhwc(img)
+        if world > 1:   # the one collective of the path: all-gather of decoded frames over NVLink
+            dist.all_gather_into_tensor(gathered, frames)
+        return frames
+
+    def step_resident():
+        return hot_path(x_dev, mask_dev, ctx_dev)
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True); md = mask_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True)
+        frames = hot_path(xd, md, cd)
+        out_pin.copy_(frames, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = L.upgpt_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = e0.elapsed_time(e1)
+        launches = L.upgpt_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, launches
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, _, launches = timed(step_resident, args.warmup, args.steps)
+    clk = clocks.stop()
+    ms_e2e, wall_e2e, _ = timed(step_e2e, 1, args.steps)
+    ms_e2e = max(ms_e2e, wall_e2e * 1e3)   # host copies are part of the end-to-end figure: take the host clock if larger
+    n_img = world * B * args.steps
+    value = n_img / (ms * 1e-3)
+    e2e_val = n_img / (ms_e2e * 1e-3)
+    if rank == 0:
+        roof = roofline_dominant_kernel(dev, pk)
+        alg_tf_per_step = world * B * (DDIM_STEPS * GF_UNET_PER_SAMPLE_STEP + GF_VAE_PER_IMAGE) / 1e3
+        eng = next(iter(model.model.diffusion_model._engines.values()))
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate+residual (%s)" % args.precision, "data": "synthetic",
+                "config": {"workload": "configs[1]: bbox.yaml U-Net (425.29M params, random init) 32x32x4 latent, 87x768 context, "
+                                       "50-step DDIM eta=%g, bs=%d per GPU, + KL-f8 decode to 256x256 uint8" % (args.eta, B),
+                           "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
+                           "l2_policy": "inputs+weights (1.9 GB fp16/fp32 per pass) exceed the 126 MB L2; no explicit flush",
+                           "kernels_per_unet_step": eng.launches_per_step + 3, "precision_mode": args.precision},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
+                        "d2h_bytes_per_step": int(out_pin.numel())},
+                "gpu_launches": int(launches),
+                "clocks": clk,
+                "roofline": roof,
+                "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
+                               "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_quick()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        cpu_reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,8 +125,9 @@ def unet_structure(cfg):
     return inp, mid, out
 
 
-def unet_forward(sd, cfg, x, t, context):
-    """UNetModel.forward (openaimodel.py:710-742). x (B,Cin,H,W) fp32, t (B,) long, context (B,L,D)."""
+def unet_forward(sd, cfg, x, t, context, taps=None):
+    """UNetModel.forward (openaimodel.py:710-742). x (B,Cin,H,W) fp32, t (B,) long, context (B,L,D).
+    taps: optional dict filled with every layer's output (NCHW) keyed by its module path, for block-level parity."""
     heads = cfg["num_heads"]
     depth = cfg.get("transformer_depth", 1)
     inp, mid, out = unet_structure(cfg)
@@ -148,6 +149,8 @@ def unet_forward(sd, cfg, x, t, context):
             elif kind == "up":
                 h = F.interpolate(h, scale_factor=2, mode="nearest")   # Upsample (openaimodel.py:116-118)
                 h = conv(h, sd, p + ".conv")
+            if taps is not None:
+                taps[p] = h
         return h
 
     hs, h = [], x.float()

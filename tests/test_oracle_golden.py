@@ -1,0 +1,80 @@
+"""The CPU oracle (oracle/ldm_oracle.py) against the golden vectors produced by the REAL reference modules
+(oracle/make_golden.py, run in the build container).  Pins the oracle on every box, no GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ldm_oracle as O
+from oracle.make_golden import TINY_UNET_KW, TINY_VAE_KW
+from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+from upgpt_b200 import synth
+
+TOL = 2e-5   # fp32 reassociation between the reference's nn.Modules and the functional restatement
+
+
+def relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def _unet_sd(kw, seed):
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    return synth.synth_state_dict(UNetModel(**kw).state_dict(), seed)
+
+
+@pytest.mark.parametrize("tag,kw,B,H,W,L,ts,seed", [
+    ("tiny", TINY_UNET_KW, 2, 16, 16, 87, [981, 1], 0),
+    ("tinyrect", TINY_UNET_KW, 3, 16, 24, 20, [500], 1),
+    ("bbox", BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0),
+])
+def test_unet_eps_matches_reference_golden(golden, tag, kw, B, H, W, L, ts, seed):
+    sd = _unet_sd(kw, seed)
+    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed)
+    for t in ts:
+        with torch.no_grad():
+            y = O.diffusion_wrapper_hybrid(sd, kw, x, torch.full((B,), t, dtype=torch.long), [mask], [ctx])
+        ref = torch.from_numpy(golden[f"{tag}_eps_t{t}"])
+        assert y.shape == ref.shape
+        assert ref.abs().max() > 0.1, "golden eps must not be the all-zero output of a zero_module-initialised U-Net"
+        assert relerr(y, ref) < TOL
+
+
+@pytest.mark.parametrize("S,eta", [(50, 0.0), (10, 1.0)])
+def test_ddim_sampler_matches_reference_golden(golden, S, eta):
+    sd = _unet_sd(TINY_UNET_KW, 0)
+    x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, 0)
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    noises = torch.randn(S, *x.shape, generator=torch.Generator().manual_seed(123))
+    apply = lambda xx, tt: O.unet_forward(sd, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, ctx)
+    with torch.no_grad():
+        x0 = O.ddim_sample(apply, x, S, eta, sched, noises if eta > 0 else None)
+    assert relerr(x0, torch.from_numpy(golden[f"ddim_S{S}_eta{int(eta)}_x0"])) < 1e-4
+    ts, alphas, alphas_prev, sigmas, _ = O.ddim_schedule(sched["alphas_cumprod"], S, eta)
+    np.testing.assert_array_equal(ts, golden[f"ddim_S{S}_eta{int(eta)}_timesteps"])
+    np.testing.assert_allclose(np.asarray(alphas, dtype=np.float64), golden[f"ddim_S{S}_eta{int(eta)}_alphas"], rtol=0, atol=0)
+    np.testing.assert_allclose(alphas_prev, golden[f"ddim_S{S}_eta{int(eta)}_alphas_prev"], rtol=0, atol=0)
+    np.testing.assert_allclose(np.asarray(sigmas, dtype=np.float64), golden[f"ddim_S{S}_eta{int(eta)}_sigmas"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("tag,kw,hw", [("vaetiny", TINY_VAE_KW, 16), ("vaebbox", BBOX_VAE_KW, 32)])
+def test_vae_decode_matches_reference_golden(golden, tag, kw, hw):
+    from ldm.models.autoencoder import AutoencoderKL
+    sd = synth.synth_state_dict(AutoencoderKL(kw, embed_dim=4).state_dict(), 0)
+    z = synth.synth_inputs(1, hw, hw, 1, 8, 7)[0]
+    with torch.no_grad():
+        y = O.decode_first_stage(sd, kw, z, 0.18215)
+    ref = torch.from_numpy(golden[f"{tag}_img_sub"])
+    got = y[:, :, ::8, ::8] if hw == 32 else y
+    assert relerr(got, ref) < TOL
+    mean, std, amax = golden[f"{tag}_stats"]
+    assert abs(float(y.mean()) - mean) < 1e-4 * max(1.0, abs(amax)) and abs(float(y.abs().max()) - amax) < 1e-4 * amax
+
+
+def test_ddpm_step_closed_form():
+    """q_posterior / predict_start_from_noise identities (ddpm.py:224-237): with eps = true noise, x0 is recovered."""
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.randn(2, 4, 8, 8, generator=g); eps = torch.randn(2, 4, 8, 8, generator=g)
+    t = torch.tensor([500, 500])
+    xt = sched["sqrt_alphas_cumprod"][t].reshape(-1, 1, 1, 1) * x0 + sched["sqrt_one_minus_alphas_cumprod"][t].reshape(-1, 1, 1, 1) * eps
+    x_prev, x0_hat = O.ddpm_step(xt, eps, t, sched, torch.zeros_like(xt))
+    assert relerr(x0_hat, x0) < 1e-4

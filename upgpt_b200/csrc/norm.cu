@@ -22,15 +22,15 @@ namespace upgpt {
 template <int MAXC_PER_THREAD>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW, int chunk,
-                int groups, double* __restrict__ stats) {
-  extern __shared__ double sh[];  // [groups][2]
+                int groups, double* __restrict__ stats, double* __restrict__ partials, int* __restrict__ counters) {
+  extern __shared__ float shc[];  // per-channel {sum, sumsq}: [2][C]
+  __shared__ int s_last;
   const int C = C1 + C2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
+  const int nchunks = gridDim.x;
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(p0 + chunk, HW);
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
   float s[MAXC_PER_THREAD], q[MAXC_PER_THREAD];
 #pragma unroll
   for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] = 0.f; q[j] = 0.f; }
@@ -49,14 +49,44 @@ gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ 
 #pragma unroll
   for (int j = 0; j < MAXC_PER_THREAD; ++j) {
     const int c = threadIdx.x + j * 256;
-    if (c < C) {
-      const int g = c / cpg;
-      atomicAdd(&sh[2 * g], (double)s[j]);
-      atomicAdd(&sh[2 * g + 1], (double)q[j]);
-    }
+    if (c < C) { shc[c] = s[j]; shc[C + c] = q[j]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&stats[(size_t)b * 2 * groups + i], sh[i]);
+  // one thread per (group, moment): fixed-order double sum over the group's channels -> this chunk's partial
+  const int nout = 2 * groups;
+  double* my = partials + ((size_t)b * nchunks + blockIdx.x) * nout;
+  for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+    const int g = i >> 1, which = i & 1;
+    const float* src = shc + which * C + g * cpg;
+    double acc = 0.0;
+    for (int k = 0; k < cpg; ++k) acc += (double)src[k];
+    if (nchunks == 1) stats[(size_t)b * nout + i] = acc; else __stcg(my + i, acc);
+  }
+  if (nchunks == 1) return;
+  // deterministic cross-chunk reduction: the last chunk to arrive sums all partials of image b in chunk order
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&counters[b], 1);
+    s_last = prev == nchunks - 1;
+    if (s_last) counters[b] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const double* base = partials + (size_t)b * nchunks * nout;
+  for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= nchunks; k += 4) {
+      a0 += __ldcg(base + (size_t)(k + 0) * nout + i);
+      a1 += __ldcg(base + (size_t)(k + 1) * nout + i);
+      a2 += __ldcg(base + (size_t)(k + 2) * nout + i);
+      a3 += __ldcg(base + (size_t)(k + 3) * nout + i);
+    }
+    for (; k < nchunks; ++k) a0 += __ldcg(base + (size_t)k * nout + i);
+    stats[(size_t)b * nout + i] = (a0 + a1) + (a2 + a3);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -253,20 +283,31 @@ static int pick_chunk(int HW, int B) {
 
 using namespace upgpt;
 
+static double* g_gn_partials = nullptr;   // [B][chunks][2*groups] per-chunk partial moments (graph-stable address)
+static int* g_gn_counters = nullptr;
+static constexpr size_t kGnPartialDoubles = (size_t)1 << 21;   // 16 MB
+static constexpr int kGnMaxBatch = 4096;
+
 extern "C" int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups,
                                      double* stats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int C = C1 + C2;
   UPGPT_REQUIRE(x1 && stats && C > 0 && C % groups == 0, "groupnorm_stats: bad args (C=%d groups=%d)", C, groups);
-  UPGPT_REQUIRE(C <= 2048, "groupnorm_stats: C=%d > 2048", C);
-  UPGPT_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * groups * B, stream));
-  const int chunk = pick_chunk(HW, B);
+  UPGPT_REQUIRE(C <= 2048 && B <= kGnMaxBatch, "groupnorm_stats: C=%d > 2048 or B=%d too large", C, B);
+  if (!g_gn_partials) {
+    UPGPT_CHECK_CUDA(cudaMalloc(&g_gn_partials, kGnPartialDoubles * sizeof(double)));
+    UPGPT_CHECK_CUDA(cudaMalloc(&g_gn_counters, kGnMaxBatch * sizeof(int)));
+    UPGPT_CHECK_CUDA(cudaMemset(g_gn_counters, 0, kGnMaxBatch * sizeof(int)));
+  }
+  int chunk = pick_chunk(HW, B);
+  if ((HW + chunk - 1) / chunk > 256) chunk = (HW + 255) / 256;
+  while ((size_t)B * ((HW + chunk - 1) / chunk) * 2 * groups > kGnPartialDoubles) chunk *= 2;
   dim3 grid((HW + chunk - 1) / chunk, B);
-  const size_t sm = sizeof(double) * 2 * groups;
-  if (C <= 256) gn_stats_kernel<1><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
-  else if (C <= 512) gn_stats_kernel<2><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
-  else if (C <= 1024) gn_stats_kernel<4><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
-  else gn_stats_kernel<8><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats);
+  const size_t sm = sizeof(float) * 2 * C;
+  if (C <= 256) gn_stats_kernel<1><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
+  else if (C <= 512) gn_stats_kernel<2><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
+  else if (C <= 1024) gn_stats_kernel<4><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
+  else gn_stats_kernel<8><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

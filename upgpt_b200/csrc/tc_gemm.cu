@@ -36,6 +36,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bar_tfull = bar_empty + p.stages;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_base_smem = (uint32_t*)(bar_tempty + 2);
+  uint32_t* split_flag = tmem_base_smem + 1;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,7 +152,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool conv = (p.flags & GEMM_CONV) != 0;
-    const bool atomic = (p.flags & GEMM_ATOMIC) != 0;
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int bidx = tile / tiles_per_batch;
@@ -160,35 +160,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       rem -= split * tiles_mn;
       const int nt = rem / p.num_m_tiles;
       const int mt = rem - nt * p.num_m_tiles;
-      // ---- row bookkeeping ----
-      bool valid;
-      long long grow;  // global output row
-      if (conv) {
-        if (p.tile_imgs > 1) {
-          const int img = mt * p.tile_imgs + r / p.HW;
-          valid = (r < p.tile_imgs * p.HW) && (img < p.n_imgs);
-          grow = (long long)mt * p.tile_imgs * p.HW + r;
-        } else if (p.tiles_per_row > 1) {
-          valid = true;                       // W % 128 == 0: every lane is a pixel
-          grow = (long long)mt * 128 + r;     // tiles enumerate the image in raster order
+      // ---- row bookkeeping: tile row -> (valid, global output row) ----
+      auto row_of = [&](int rr, bool& ok, long long& gr) {
+        if (conv) {
+          if (p.tile_imgs > 1) {
+            const int img = mt * p.tile_imgs + rr / p.HW;
+            ok = (rr < p.tile_imgs * p.HW) && (img < p.n_imgs);
+            gr = (long long)mt * p.tile_imgs * p.HW + rr;
+          } else if (p.tiles_per_row > 1) {
+            ok = true;                          // W % 128 == 0: every lane is a pixel
+            gr = (long long)mt * 128 + rr;      // tiles enumerate the image in raster order
+          } else {
+            const int img = mt / p.tiles_per_img;
+            const int y0 = (mt - img * p.tiles_per_img) * p.tile_rows;
+            const int y = y0 + rr / p.W;
+            ok = (rr < p.tile_rows * p.W) && (y < p.H);
+            gr = (long long)img * p.HW + (long long)y0 * p.W + rr;
+          }
         } else {
-          const int img = mt / p.tiles_per_img;
-          const int y0 = (mt - img * p.tiles_per_img) * p.tile_rows;
-          const int y = y0 + r / p.W;
-          valid = (r < p.tile_rows * p.W) && (y < p.H);
-          grow = (long long)img * p.HW + (long long)y0 * p.W + r;
+          const int m = mt * 128 + rr;
+          ok = m < p.M_total;
+          gr = (long long)bidx * p.M_total + m;
         }
-      } else {
-        const int m = mt * 128 + r;
-        valid = m < p.M_total;
-        grow = (long long)bidx * p.M_total + m;
-      }
+      };
+      bool valid;
+      long long grow;  // global output row of this thread's accumulator lane
+      row_of(r, valid, grow);
       const int group = (int)(grow / p.rows_per_group);
       const int rig = (int)(grow - (long long)group * p.rows_per_group);
-      const bool extras = !atomic || split == 0;
-      const float* rv = (p.rowvec && extras) ? p.rowvec + (size_t)group * p.ld_rowvec : nullptr;
-      const float* rs = (p.res32 && extras) ? p.res32 + (size_t)grow * p.ldres : nullptr;
-      const float* bs = (p.bias && extras) ? p.bias : nullptr;
+      const float* rv = p.rowvec ? p.rowvec + (size_t)group * p.ld_rowvec : nullptr;
+      const float* rs = p.res32 ? p.res32 + (size_t)grow * p.ldres : nullptr;
+      const float* bs = p.bias;
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
@@ -218,68 +220,137 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-        for (int j0 = 0; j0 < p.block_n; j0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + (uint32_t)j0, v);
-          tmem_ld_wait();
-          if (valid) {
-            const int n0 = nt * p.block_n + j0;
-            float f[16];
+        // applies bias / row vector / residual to 16 consecutive columns of this thread's row and stores them
+        auto store_cols = [&](int n0, float (&f)[16]) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + i;
+            if (n < p.N_total) {
+              if (p.bias) f[i] += p.bias[n];
+              if (rv) f[i] += rv[n];
+              if (rs) f[i] += rs[n];
+            }
+          }
+          if (chw) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float x = __uint_as_float(v[i]) * p.out_scale;
               const int n = n0 + i;
               if (n < p.N_total) {
-                if (bs) x += bs[n];
-                if (rv) x += rv[n];
-                if (rs) x += rs[n];
+                const size_t o = ((size_t)group * p.N_total + n) * (size_t)p.ldT + rig;
+                if (p.out32) p.out32[o] = f[i];
+                if (p.out16) p.out16[o] = __float2half_rn(f[i]);
               }
-              f[i] = x;
             }
-            if (chw) {
+          } else if (n0 + 16 <= p.N_total) {
+            if (p.out32) {
+              float* dst = p.out32 + (size_t)grow * p.ld32 + n0;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int n = n0 + i;
-                if (n < p.N_total) {
-                  const size_t o = ((size_t)group * p.N_total + n) * (size_t)p.ldT + rig;
-                  if (p.out32) {
-                    if (atomic) atomicAdd(p.out32 + o, f[i]); else p.out32[o] = f[i];
-                  }
-                  if (p.out16) p.out16[o] = __float2half_rn(f[i]);
-                }
-              }
-            } else if (n0 + 16 <= p.N_total) {
-              if (p.out32) {
-                float* dst = p.out32 + (size_t)grow * p.ld32 + n0;
-                if (atomic) {
+              for (int i = 0; i < 4; ++i) ((float4*)dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            }
+            if (p.out16) {
+              __align__(16) __half o[16];
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) atomicAdd(dst + i, f[i]);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 4; ++i) ((float4*)dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                }
-              }
-              if (p.out16) {
-                __align__(16) __half o[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = __float2half_rn(f[i]);
-                uint4* dst = (uint4*)(p.out16 + (size_t)grow * p.ld16 + n0);
-                dst[0] = ((uint4*)o)[0];
-                dst[1] = ((uint4*)o)[1];
-              }
-            } else {
-              for (int i = 0; i < 16; ++i) {
-                const int n = n0 + i;
-                if (n < p.N_total) {
-                  if (p.out32) {
-                    float* dst = p.out32 + (size_t)grow * p.ld32 + n;
-                    if (atomic) atomicAdd(dst, f[i]); else *dst = f[i];
-                  }
-                  if (p.out16) p.out16[(size_t)grow * p.ld16 + n] = __float2half_rn(f[i]);
-                }
+              for (int i = 0; i < 16; ++i) o[i] = __float2half_rn(f[i]);
+              uint4* dst = (uint4*)(p.out16 + (size_t)grow * p.ld16 + n0);
+              dst[0] = ((uint4*)o)[0];
+              dst[1] = ((uint4*)o)[1];
+            }
+          } else {
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + i;
+              if (n < p.N_total) {
+                if (p.out32) p.out32[(size_t)grow * p.ld32 + n] = f[i];
+                if (p.out16) p.out16[(size_t)grow * p.ld16 + n] = __float2half_rn(f[i]);
               }
             }
           }
+        };
+        if (p.num_splits == 1) {
+          for (int j0 = 0; j0 < p.block_n; j0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + (uint32_t)j0, v);
+            tmem_ld_wait();
+            if (valid) {
+              float f[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
+              store_cols(nt * p.block_n + j0, f);
+            }
+          }
+        } else {
+          // ---- deterministic split-K: partial tile -> workspace; the last split to arrive reduces in fixed order ----
+          const size_t ws_split_stride = (size_t)p.ws_rows * p.ws_ld;
+          float* wrow = p.ws + (size_t)split * ws_split_stride + (size_t)grow * p.ws_ld + nt * p.block_n;
+          for (int j0 = 0; j0 < p.block_n; j0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_acc + (uint32_t)j0, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                __stcg((float4*)(wrow + j0) + i, make_float4(__uint_as_float(v[4 * i]) * p.out_scale, __uint_as_float(v[4 * i + 1]) * p.out_scale,
+                                                          __uint_as_float(v[4 * i + 2]) * p.out_scale, __uint_as_float(v[4 * i + 3]) * p.out_scale));
+            }
+          }
+          // the accumulator stage can be recycled now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+          __threadfence();
+          named_bar_sync(1, 128);
+          if (r == 0) {
+            int* ctr = p.counters + (bidx * tiles_mn + nt * p.num_m_tiles + mt);
+            const int prev = atomicAdd(ctr, 1);
+            const int last = prev == p.num_splits - 1;
+            if (last) *ctr = 0;   // self-reset: the counters are zero again when the kernel ends
+            *split_flag = (uint32_t)last;
+          }
+          named_bar_sync(1, 128);
+          const bool is_last = *split_flag != 0;
+          named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
+          if (is_last) {
+            // coalesced reduction: the 128 epilogue threads sweep the tile as a flat array of float4
+            __threadfence();
+            const int n4 = p.block_n >> 2;
+            for (int idx = r; idx < 128 * n4; idx += 128) {
+              const int rr = idx / n4;
+              const int c = (idx - rr * n4) << 2;
+              bool ok; long long gr;
+              row_of(rr, ok, gr);
+              const int n = nt * p.block_n + c;
+              if (!ok || n >= p.N_total) continue;
+              const float4* src = (const float4*)(p.ws + (size_t)gr * p.ws_ld + n);
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              int sp = 0;
+              for (; sp + 4 <= p.num_splits; sp += 4) {   // 4 independent loads in flight, summed in split order
+                const float4 t0 = __ldcg(src + (size_t)(sp + 0) * (ws_split_stride >> 2));
+                const float4 t1 = __ldcg(src + (size_t)(sp + 1) * (ws_split_stride >> 2));
+                const float4 t2 = __ldcg(src + (size_t)(sp + 2) * (ws_split_stride >> 2));
+                const float4 t3 = __ldcg(src + (size_t)(sp + 3) * (ws_split_stride >> 2));
+                a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+                a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
+                a.x += t2.x; a.y += t2.y; a.z += t2.z; a.w += t2.w;
+                a.x += t3.x; a.y += t3.y; a.z += t3.z; a.w += t3.w;
+              }
+              for (; sp < p.num_splits; ++sp) {
+                const float4 t0 = __ldcg(src + (size_t)sp * (ws_split_stride >> 2));
+                a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
+              }
+              if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
+              if (p.rowvec) {
+                const float4 b4 = *(const float4*)(p.rowvec + (size_t)(gr / p.rows_per_group) * p.ld_rowvec + n);
+                a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+              }
+              if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr * p.ldres + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
+              if (p.out32) *(float4*)(p.out32 + (size_t)gr * p.ld32 + n) = a;
+              if (p.out16) {
+                __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+                *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              }
+            }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
         }
       }
       tc_fence_before();
@@ -303,6 +374,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 static bool g_attr_set = false;
+static float* g_ws = nullptr;                 // split-K partial-tile workspace (allocated once: graph-stable address)
+static size_t g_ws_bytes = 0;
+static int* g_counters = nullptr;
+static constexpr int kMaxCounters = 1 << 16;
 
 static int gemm_device_setup() {
   if (g_attr_set) return 0;
@@ -311,22 +386,32 @@ static int gemm_device_setup() {
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+  g_ws_bytes = (size_t)96 << 20;
+  UPGPT_CHECK_CUDA(cudaMalloc(&g_ws, g_ws_bytes));
+  UPGPT_CHECK_CUDA(cudaMalloc(&g_counters, kMaxCounters * sizeof(int)));
+  UPGPT_CHECK_CUDA(cudaMemset(g_counters, 0, kMaxCounters * sizeof(int)));
   g_attr_set = true;
   return 0;
 }
 
-static int pick_block_n(int N, int want_ctas_per_mtile_hint) {
-  // largest tile that divides N and is a legal UMMA N (multiple of 16, <= 256); else pad with the smallest waste.
-  static const int cands[] = {256, 224, 192, 160, 128, 112, 96, 80, 64, 48, 32, 16};
-  if (N <= 256 && N % 16 == 0 && want_ctas_per_mtile_hint <= 1) return N;
-  int best = 0;
-  for (int c : cands) {
-    if (N % c == 0 && N / c >= want_ctas_per_mtile_hint) { best = c; break; }
+// Tile-width heuristic: the widest legal UMMA N (multiple of 16, <= 256) that divides N when the M tiles alone fill the
+// machine; otherwise the narrowest divisor (>= 64) whose tile count still fits in one wave, so that small-M layers
+// (weight-bandwidth bound) spread their weight stream over all SMs before split-K has to.
+static int pick_block_n(int N, int base_tiles, int num_sms) {
+  static const int cands[] = {256, 224, 192, 160, 128, 112, 96, 80, 64};
+  int widest = 0;
+  for (int c : cands) if (N % c == 0) { widest = c; break; }
+  if (!widest) {
+    int n = ((N + 15) / 16) * 16;
+    return n <= 256 ? n : 128;   // ragged N: TMA zero-fills the weight tail
   }
-  if (best) return best;
-  for (int c : cands) if (N % c == 0) return c;   // could not reach the hint; take the largest divisor
-  int n = ((N + 15) / 16) * 16;
-  return n <= 256 ? n : 128;
+  if (base_tiles * (N / widest) >= num_sms) return widest;
+  int best = widest;
+  for (int c : cands) {
+    if (N % c) continue;
+    if (base_tiles * (N / c) <= num_sms) best = c; else break;
+  }
+  return best;
 }
 
 }  // namespace upgpt
@@ -413,12 +498,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
 
   // ---- tile shape / split-K ----
   int bn = a->block_n;
-  if (bn <= 0) {
-    int hint = 1;
-    if (p.num_m_tiles * ((a->N + 255) / 256) * p.batch < g_num_sms / 2) hint = 2;
-    if (p.num_m_tiles * p.batch <= 8) hint = 4;
-    bn = pick_block_n(a->N, hint);
-  }
+  if (bn <= 0) bn = pick_block_n(a->N, p.num_m_tiles * p.batch, g_num_sms);
   UPGPT_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "upgpt_gemm: block_n=%d illegal", bn);
   if (p.flags & GEMM_GEGLU) UPGPT_REQUIRE(bn % 32 == 0 && a->N % bn == 0 && a->out16, "upgpt_gemm: GEGLU needs block_n%%32==0, N%%block_n==0, out16");
   p.block_n = bn;
@@ -428,7 +508,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   if (splits <= 0) {
     splits = 1;
     const int base_tiles = p.num_m_tiles * p.num_n_tiles * p.batch;
-    if (a->out32 && !a->out16 && !(p.flags & GEMM_GEGLU) && base_tiles * 2 <= g_num_sms && k_iters >= 8) {
+    if (!(p.flags & (GEMM_GEGLU | GEMM_CHW)) && base_tiles * 2 <= g_num_sms && k_iters >= 8) {
       splits = g_num_sms / base_tiles;
       if (splits > k_iters / 4) splits = k_iters / 4;
       if (splits < 1) splits = 1;
@@ -438,13 +518,24 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   // every split must own at least one k iteration
   while (splits > 1 && (splits - 1) * ((k_iters + splits - 1) / splits) >= k_iters) --splits;
   p.num_splits = splits;
-  if (splits > 1 && a->res32 == a->out32) splits = 1;  // in-place residual cannot be combined with the zero-fill
+  if ((p.flags & GEMM_CHW) || a->N % 4 != 0) splits = 1;
   p.num_splits = splits;
   if (splits > 1) {
-    UPGPT_REQUIRE(a->out32 && !a->out16 && !(p.flags & GEMM_GEGLU), "upgpt_gemm: split-K needs an fp32-only output");
-    p.flags |= GEMM_ATOMIC;
+    UPGPT_REQUIRE(!(p.flags & GEMM_GEGLU), "upgpt_gemm: split-K is not available with the GEGLU epilogue");
+    // deterministic split-K workspace: [splits][rows][ws_ld] fp32 partial tiles + one arrival counter per output tile
+    p.ws_ld = p.num_n_tiles * bn;
+    p.ws_rows = m_rows_total * p.batch;
+    const size_t need = (size_t)splits * p.ws_rows * p.ws_ld * sizeof(float);
+    const int n_ctr = p.num_m_tiles * p.num_n_tiles * p.batch;
+    if (need > g_ws_bytes || n_ctr > kMaxCounters) {
+      // shrink the split factor to fit the fixed workspace (its address must stay stable for captured graphs)
+      while (splits > 1 && ((size_t)splits * p.ws_rows * p.ws_ld * sizeof(float) > g_ws_bytes || n_ctr > kMaxCounters)) --splits;
+      while (splits > 1 && (splits - 1) * ((k_iters + splits - 1) / splits) >= k_iters) --splits;
+      p.num_splits = splits;
+    }
+    p.ws = g_ws;
+    p.counters = g_counters;
   }
-
   {
     const uint64_t ldw = a->ldw > 0 ? a->ldw : a->K;  // elements between taps
     const uint64_t n_stride = ldw * p.taps;            // elements between output channels
@@ -475,16 +566,6 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16;
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);
 
-  if (p.flags & GEMM_ATOMIC) {
-    // split-K partial sums are reduced with red.add.f32: zero the destination first (a memset node under capture)
-    const size_t rows = (size_t)m_rows_total * p.batch;
-    if (p.flags & GEMM_CHW) {
-      const size_t groups = (rows + p.rows_per_group - 1) / p.rows_per_group;
-      UPGPT_CHECK_CUDA(cudaMemsetAsync(p.out32, 0, groups * p.N_total * (size_t)p.ldT * 4, stream));
-    } else {
-      UPGPT_CHECK_CUDA(cudaMemset2DAsync(p.out32, (size_t)p.ld32 * 4, 0, (size_t)p.N_total * 4, rows, stream));
-    }
-  }
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);

@@ -6,7 +6,6 @@
 namespace upgpt {
 
 enum GemmFlags : uint32_t {
-  GEMM_ATOMIC = 1u << 0,   // split-K: red.add.f32 into out32 (caller zero-fills); bias/rowvec/res added by split 0
   GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
   GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
   GEMM_CONV = 1u << 3,     // A rows are image pixels addressed through a 4-D (C, W, H, N) tensor map
@@ -45,6 +44,10 @@ struct GemmParams {
   int ldres;
   int ldT;              // CHW: stride between channels (>= rows_per_group)
   float out_scale;      // applied to the accumulator before bias (1.0 default)
+  // ---- deterministic split-K ----
+  float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
+  int ws_rows, ws_ld;
+  int* counters;        // one arrival counter per (batch, n tile, m tile); zero between launches
 };
 
 }  // namespace upgpt
