@@ -44,7 +44,9 @@ def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timestep
 
 def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
     """(sigma_t, a_t, a_prev) per DDIM step (util.py:63-74); alphacums may be a tensor or array."""
-    ac = alphacums.detach().cpu().numpy() if isinstance(alphacums, torch.Tensor) else np.asarray(alphacums)
+    # Mixed torch-fp32 / numpy-float64 arithmetic exactly as the reference performs it: `alphas` stays a torch fp32
+    # tensor, `alphas_prev` is a float64 numpy array of fp32 values, and the sigma expression promotes term by term.
+    ac = alphacums.detach().float().cpu() if isinstance(alphacums, torch.Tensor) else torch.as_tensor(np.asarray(alphacums))
     alphas = ac[ddim_timesteps]
     alphas_prev = np.asarray([ac[0]] + ac[ddim_timesteps[:-1]].tolist())
     sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))

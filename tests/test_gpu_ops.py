@@ -1,0 +1,210 @@
+"""Per-kernel parity through the C ABI (ctypes) against fp32 PyTorch-on-CPU restatements of the reference ops.
+Tolerances: fp32-accumulated results of fp16 operands are compared against the same fp16-rounded operands in fp32
+(tol 1e-5..1e-4); outputs stored as fp16 carry one extra rounding (tol 2e-3 = 4 fp16 ulps of the max)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from upgpt_b200 import _C
+    _C.lib()
+    return torch.device("cuda:0")
+
+
+def relerr(got, ref):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    assert torch.isfinite(got).all()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-9))
+
+
+@pytest.mark.parametrize("M,N,K,splits,batch", [(128, 64, 64, 0, 1), (8192, 224, 224, 0, 1), (300, 448, 448, 0, 1), (696, 256, 768, 0, 1),
+                                                (128, 896, 896, 4, 1), (128, 896, 8064, 0, 1), (1024, 1024, 512, 0, 2), (1, 16, 8, 0, 1)])
+def test_gemm_plain(dev, M, N, K, splits, batch):
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(batch, M, K, generator=g) * 0.5).half(); W = (torch.randn(batch, N, K, generator=g) * 0.1).half()
+    b = torch.randn(N, generator=g); r = torch.randn(batch * M, N, generator=g)
+    ref = torch.einsum("bmk,bnk->bmn", A.float(), W.float()).reshape(batch * M, N) + b + r
+    out = torch.full((batch * M, N), float("nan"), device=dev)
+    o16 = torch.zeros(batch * M, N, device=dev, dtype=torch.half) if N % 8 == 0 else None
+    ops.gemm(a=A.to(dev), w=W.to(dev), mode=0, M=M, N=N, K=K, batch=batch, splits=splits, out32=out, out16=o16, bias=b.to(dev), res32=r.to(dev))
+    torch.cuda.synchronize()
+    assert relerr(out, ref) < 2e-5
+    if o16 is not None:
+        assert relerr(o16, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 64, 64), (8, 32, 32, 224, 224), (8, 16, 16, 448, 448), (8, 8, 8, 896, 896), (8, 4, 4, 1792, 896),
+                                            (2, 32, 24, 224, 224), (3, 4, 3, 896, 896), (2, 64, 64, 224, 224), (1, 256, 256, 128, 128), (1, 8, 8, 32, 16)])
+def test_conv3x3_implicit_gemm(dev, B, H, W, Cin, Cout):
+    """Zero padding comes from TMA out-of-bounds fill; edge cases: ragged 32x24, 4x3 (multi-image tiles), W=256 (column tiles)."""
+    from upgpt_b200 import ops, _C
+    g = torch.Generator().manual_seed(B * H + Cin)
+    x = (torch.randn(B, H, W, Cin, generator=g) * 0.5).half(); w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).half()
+    b = torch.randn(Cout, generator=g); e = torch.randn(B, Cout, generator=g)
+    ref = (F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, padding=1) + e[:, :, None, None]).permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    out = torch.full((B * H * W, Cout), float("nan"), device=dev)
+    ops.gemm(a=x.to(dev), w=w.permute(0, 2, 3, 1).contiguous().to(dev), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W, out32=out,
+             bias=b.to(dev), rowvec=e.to(dev))
+    torch.cuda.synchronize()
+    assert relerr(out, ref) < 2e-5
+
+
+def test_conv3x3_stride2_phases_and_nchw_out(dev):
+    from upgpt_b200 import ops, _C
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C, Co = 4, 16, 16, 224, 224
+    x = (torch.randn(B, H, W, C, generator=g) * 0.5); w = (torch.randn(Co, C, 3, 3, generator=g) * (9 * C) ** -0.5).half(); b = torch.randn(Co, generator=g)
+    xd = x.to(dev).reshape(B, H * W, C).contiguous()
+    ph = torch.zeros(4 * B * (H // 2) * (W // 2) * C, device=dev, dtype=torch.half)
+    ops.prep(x1=xd, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=0.0, silu=0, layout=2, split3=0, out=ph, raw=None)
+    out = torch.full((B * 64, Co), float("nan"), device=dev)
+    ops.gemm(a=ph, w=w.permute(0, 2, 3, 1).contiguous().to(dev), mode=_C.GEMM_CONV3X3_S2PHASE, N=Co, K=C, n_imgs=B, H=H // 2, W=W // 2, out32=out, bias=b.to(dev))
+    ref = F.conv2d(x.half().float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1)
+    torch.cuda.synchronize()
+    assert relerr(out, ref.permute(0, 2, 3, 1).reshape(B * 64, Co)) < 2e-5
+    # N=4 output conv written straight to NCHW (eps layout at the boundary)
+    w4 = (torch.randn(4, C, 3, 3, generator=g) * 0.02).half()
+    o = torch.full((B, 4, H, W), float("nan"), device=dev)
+    ops.gemm(a=x.half().to(dev), w=w4.permute(0, 2, 3, 1).contiguous().to(dev), mode=_C.GEMM_CONV3X3, N=4, K=C, n_imgs=B, H=H, W=W, block_n=16, out32=o,
+             flags=_C.GEMM_F_CHW)
+    torch.cuda.synchronize()
+    assert relerr(o, F.conv2d(x.half().float().permute(0, 3, 1, 2), w4.float(), padding=1)) < 2e-5
+
+
+def test_geglu_epilogue(dev):
+    from upgpt_b200 import ops, _C
+    from upgpt_b200.unet_engine import pack_geglu, geglu_half
+    g = torch.Generator().manual_seed(3)
+    M, C = 300, 224
+    inner = 4 * C; half = geglu_half(inner)
+    A = (torch.randn(M, C, generator=g) * 0.5).half(); W = (torch.randn(2 * inner, C, generator=g) * C ** -0.5).half(); b = torch.randn(2 * inner, generator=g) * 0.1
+    y = A.float() @ W.float().t() + b
+    ref = y[:, :inner] * F.gelu(y[:, inner:])     # exact erf GELU (attention.py:43)
+    wp, bp = pack_geglu(W, b, inner, half)
+    o16 = torch.zeros(M, inner, device=dev, dtype=torch.half)
+    ops.gemm(a=A.to(dev), w=wp.to(dev), mode=0, M=M, N=2 * inner, K=C, block_n=2 * half, out16=o16, bias=bp.to(dev), flags=_C.GEMM_F_GEGLU)
+    torch.cuda.synchronize()
+    assert relerr(o16, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,silu,eps", [(2, 16, 16, 224, 0, True, 1e-5), (2, 8, 8, 448, 224, True, 1e-5), (1, 32, 32, 128, 0, False, 1e-6), (3, 4, 3, 896, 896, True, 1e-5),
+                                                  (1, 128, 128, 128, 0, True, 1e-6)])
+def test_groupnorm_silu_prep(dev, B, H, W, C1, C2, silu, eps):
+    """GroupNorm32 over the channel concat of two tensors (group boundaries straddle the sources), fp32 statistics."""
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(C1 + C2)
+    x1 = torch.randn(B, H * W, C1, generator=g) * 2 + 0.5
+    x2 = torch.randn(B, H * W, C2, generator=g) - 1.0 if C2 else None
+    Cc = C1 + C2
+    gamma = 1 + 0.1 * torch.randn(Cc, generator=g); beta = 0.1 * torch.randn(Cc, generator=g)
+    xc = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.group_norm(xc.reshape(B, H, W, Cc).permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    ref = F.silu(ref) if silu else ref
+    stats = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64)
+    out = torch.zeros(B * H * W * Cc, device=dev, dtype=torch.half)
+    x1d, x2d = x1.to(dev), (x2.to(dev) if C2 else None)
+    ops.groupnorm_stats(x1d, x2d, B, H * W, stats)
+    ops.prep(x1=x1d, C1=C1, x2=x2d, C2=C2, B=B, H=H, W=W, groups=32, stats=stats, gamma=gamma.to(dev), beta=beta.to(dev), eps=eps, silu=int(silu), layout=0,
+             split3=0, out=out, raw=None)
+    torch.cuda.synchronize()
+    n = (Cc // 32) * H * W
+    mean_ref = xc.reshape(B, H * W, 32, Cc // 32).double().mean(dim=(1, 3))
+    assert float(((stats[:, :, 0].cpu() / n) - mean_ref).abs().max()) < 1e-6      # statistics themselves are fp64-accurate
+    assert relerr(out.reshape(B, H, W, Cc).permute(0, 3, 1, 2), ref) < 2e-3
+
+
+def test_prep_layouts_and_split3(dev):
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    B, H, W, C = 2, 8, 8, 64
+    x = torch.randn(B, H * W, C, generator=g)
+    xd = x.to(dev)
+    up = torch.zeros(B * 4 * H * W * C, device=dev, dtype=torch.half)
+    ops.prep(x1=xd, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=0.0, silu=0, layout=1, split3=0, out=up, raw=None)
+    ref = F.interpolate(x.reshape(B, H, W, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    assert relerr(up.reshape(B, 2 * H, 2 * W, C).permute(0, 3, 1, 2), ref) < 1e-3
+    s3 = torch.zeros(B * H * W * 3 * C, device=dev, dtype=torch.half)
+    ops.prep(x1=xd, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=0.0, silu=0, layout=0, split3=1, out=s3, raw=None)
+    o = s3.reshape(B * H * W, 3, C).float().cpu()
+    assert float((o[:, 0] + o[:, 1] - x.reshape(-1, C)).abs().max()) < 1e-6 and torch.equal(o[:, 0], o[:, 2])
+
+
+@pytest.mark.parametrize("rows,C", [(300, 224), (64, 448), (17, 896), (5, 64)])
+def test_layernorm(dev, rows, C):
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, C, generator=g) * 3 + 1; gamma = 1 + 0.1 * torch.randn(C, generator=g); beta = 0.1 * torch.randn(C, generator=g)
+    out = torch.zeros(rows, C, device=dev, dtype=torch.half)
+    ops.layernorm(x.to(dev), gamma.to(dev), beta.to(dev), out)
+    torch.cuda.synchronize()
+    assert relerr(out, F.layer_norm(x, (C,), gamma, beta, 1e-5)) < 2e-3
+
+
+@pytest.mark.parametrize("B,Hh,Nq,Nk,d", [(1, 1, 128, 128, 64), (2, 8, 1024, 1024, 28), (2, 8, 256, 256, 56), (2, 8, 64, 64, 112), (2, 8, 16, 16, 112),
+                                          (2, 8, 1024, 87, 28), (2, 8, 64, 87, 112), (1, 4, 384, 300, 16), (1, 8, 4096, 4096, 28), (1, 2, 1, 1, 8)])
+def test_flash_attention(dev, B, Hh, Nq, Nk, d):
+    """softmax(q k^T d^-1/2) v: self (Nk = Nq) and cross (87 context keys), ragged key tails masked, head dims 28/56/112 padded."""
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(Nq + Nk + d)
+    dpad = 64 if d <= 64 else 128
+    q = torch.randn(B, Hh, Nq, d, generator=g).half(); k = torch.randn(B, Hh, Nk, d, generator=g).half(); v = torch.randn(B, Hh, Nk, d, generator=g).half()
+    ref = torch.softmax(torch.einsum("bhid,bhjd->bhij", q.float(), k.float()) * d ** -0.5, -1) @ v.float()
+    HD = Hh * dpad
+    Q = torch.zeros(B, Nq, Hh, dpad, dtype=torch.half); Q[..., :d] = q.permute(0, 2, 1, 3)
+    K = torch.zeros(B, Nk, Hh, dpad, dtype=torch.half); K[..., :d] = k.permute(0, 2, 1, 3)
+    ldvt = (Nk + 7) // 8 * 8
+    Vt = torch.zeros(B, Hh, dpad, ldvt, dtype=torch.half); Vt[:, :, :d, :Nk] = v.permute(0, 1, 3, 2)
+    out = torch.full((B, Nq, Hh, dpad), float("nan"), device=dev, dtype=torch.half)
+    ops.attention(q=Q.to(dev), ldq=HD, k=K.to(dev), ldk=HD, k_batch_stride=0, vt=Vt.to(dev), ldvt=ldvt, out=out, ldo=HD, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=dpad,
+                  scale=d ** -0.5)
+    torch.cuda.synchronize()
+    assert relerr(out[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
+    assert float(out[..., d:].float().abs().max()) == 0.0      # padded head columns stay exactly zero
+
+
+def test_small_kernels(dev):
+    from upgpt_b200 import ops
+    from oracle import ldm_oracle as O
+    g = torch.Generator().manual_seed(2)
+    t = torch.tensor([981, 481, 1, 0])
+    assert relerr(ops.timestep_embedding(t.to(dev), 224), O.timestep_embedding(t, 224)) < 2e-6
+    x = torch.randn(4, 896, generator=g); w = torch.randn(300, 896, generator=g) * 0.03; b = torch.randn(300, generator=g)
+    got = ops.linear_small_m(x.to(dev), w.to(dev), b.to(dev), silu_in=True)
+    assert relerr(got, F.linear(F.silu(x), w, b)) < 1e-5
+    # boundary conv: latent (4ch) ++ mask (1ch) -> 224, NCHW in, NHWC out
+    xi = torch.randn(2, 4, 16, 24, generator=g); m = torch.randn(2, 1, 16, 24, generator=g); wc = torch.randn(224, 5, 3, 3, generator=g) * 0.1; bc = torch.randn(224, generator=g)
+    out = torch.zeros(2, 16 * 24, 224, device=dev)
+    ops.conv_small_cin(xi.to(dev), m.to(dev), wc.permute(1, 2, 3, 0).reshape(45, 224).contiguous().to(dev), bc.to(dev), 224, 3, out)
+    ref = F.conv2d(torch.cat([xi, m], 1), wc, bc, padding=1).permute(0, 2, 3, 1).reshape(2, 384, 224)
+    assert relerr(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("eta", [0.0, 1.0])
+def test_ddim_and_ddpm_update_kernels(dev, eta):
+    from upgpt_b200 import ops
+    from oracle import ldm_oracle as O
+    g = torch.Generator().manual_seed(4)
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    ts, a, ap, sg, s1m = O.ddim_schedule(sched["alphas_cumprod"], 50, eta)
+    x = torch.randn(2, 4, 32, 32, generator=g); e = torch.randn(2, 4, 32, 32, generator=g); nz = torch.randn(2, 4, 32, 32, generator=g)
+    import numpy as np
+    rows = np.stack([np.asarray(a, np.float32), np.asarray(ap, np.float32), np.asarray(sg, np.float32), np.asarray(s1m, np.float32), np.ones(50, np.float32)], 1)
+    coef = torch.from_numpy(rows).to(dev)
+    for index in (49, 17, 0):
+        ref_prev, ref_x0 = O.ddim_step(x, e, a[index], ap[index], sg[index], s1m[index], nz if eta > 0 else None)
+        xp, p0 = torch.empty(2, 4, 32, 32, device=dev), torch.empty(2, 4, 32, 32, device=dev)
+        ops.ddim_step(x.to(dev), e.to(dev), coef, xp, p0, noise=nz.to(dev) if eta > 0 else None, step_imm=index)
+        assert relerr(xp, ref_prev) < 2e-6 and relerr(p0, ref_x0) < 2e-6
+    model_rows = torch.stack([sched["sqrt_recip_alphas_cumprod"], sched["sqrt_recipm1_alphas_cumprod"], sched["posterior_mean_coef1"], sched["posterior_mean_coef2"],
+                              sched["posterior_log_variance_clipped"], (torch.arange(1000) != 0).float()], 1).contiguous().to(dev)
+    for tt in (999, 500, 0):
+        ref_prev, ref_x0 = O.ddpm_step(x, e, torch.full((2,), tt), sched, nz)
+        xp, p0 = torch.empty(2, 4, 32, 32, device=dev), torch.empty(2, 4, 32, 32, device=dev)
+        ops.ddpm_step(x.to(dev), e.to(dev), model_rows, xp, p0, noise=nz.to(dev), step_imm=tt)
+        assert relerr(xp, ref_prev) < 5e-6 and relerr(p0, ref_x0) < 5e-6

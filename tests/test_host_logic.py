@@ -1,0 +1,157 @@
+"""CPU-only tests of the host side: config protocol, module tree / state_dict layout, schedules, weight packing,
+conditioning routing, the C-ABI surface, and the no-fallback rule."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, tiny_ldm_config
+from oracle import ldm_oracle as O
+from oracle.ref_loader import BBOX_UNET_KW
+
+
+def test_bbox_yaml_loads_unchanged_and_instantiates():
+    from ldm.util import load_config, instantiate_from_config
+    cfg = load_config(os.path.join(ROOT, "configs", "deepfashion", "bbox.yaml"))
+    assert cfg.model.target == "ldm.models.diffusion.ddpm.LatentDiffusion"
+    assert cfg.model.params.unet_config.params.model_channels == 224
+    model = instantiate_from_config(cfg.model)
+    assert type(model).__name__ == "LatentDiffusion"
+    assert model.model.conditioning_key == "hybrid" and model.concat_key == "person_mask"
+    assert model.extra_cond_keys == ["styles", "smpl"] and abs(model.scale_factor - 0.18215) < 1e-12
+    unet = model.model.diffusion_model
+    assert sum(p.numel() for p in unet.parameters()) == 425290884      # "DiffusionWrapper has 425.29 M params" (inference.ipynb)
+    sd = model.state_dict()
+    for k in ("model.diffusion_model.input_blocks.1.0.in_layers.2.weight", "model.diffusion_model.out.2.bias",
+              "model.diffusion_model.middle_block.1.transformer_blocks.0.attn2.to_k.weight",
+              "model.diffusion_model.output_blocks.11.1.proj_out.weight", "first_stage_model.decoder.up.3.block.0.conv1.weight",
+              "first_stage_model.post_quant_conv.weight", "extra_cond_models.1.model.weight", "betas", "alphas_cumprod",
+              "model_ema.decay"):
+        assert k in sd, k
+    assert sd["model.diffusion_model.middle_block.1.transformer_blocks.0.attn2.to_k.weight"].shape == (896, 768)
+    # zero_module initialisation of the reference (openaimodel.py:229-231,685; attention.py:244-248)
+    assert float(sd["model.diffusion_model.out.2.weight"].abs().max()) == 0.0
+    assert float(sd["model.diffusion_model.input_blocks.1.1.proj_out.weight"].abs().max()) == 0.0
+
+
+def test_unet_structure_matches_survey_table():
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel, ResBlock
+    from ldm.modules.attention import SpatialTransformer
+    m = UNetModel(**BBOX_UNET_KW)
+    res = [x for x in m.modules() if isinstance(x, ResBlock)]
+    st = [x for x in m.modules() if isinstance(x, SpatialTransformer)]
+    assert len(res) == 22 and len(st) == 16
+    assert sorted({s.d_head for s in st}) == [28, 56, 112]
+    assert [b[0].channels for b in m.output_blocks] == [1792, 1792, 1792, 1792, 1792, 1344, 1344, 896, 672, 672, 448, 448]
+
+
+def test_ddpm_schedule_buffers_match_oracle():
+    from ldm.util import instantiate_from_config
+    model = instantiate_from_config(tiny_ldm_config())
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    for k, v in sched.items():
+        assert torch.equal(getattr(model, k), v), k
+    assert model.num_timesteps == 1000
+
+
+@pytest.mark.parametrize("S,eta", [(50, 0.0), (10, 1.0)])
+def test_ddim_schedule_matches_reference_golden(golden, S, eta):
+    from ldm.util import instantiate_from_config
+    from ldm.models.diffusion.ddim import DDIMSampler
+    model = instantiate_from_config(tiny_ldm_config())
+    s = DDIMSampler(model)
+    s.make_schedule(S, ddim_eta=eta, verbose=False)
+    tag = f"ddim_S{S}_eta{int(eta)}"
+    np.testing.assert_array_equal(s.ddim_timesteps, golden[tag + "_timesteps"])
+    np.testing.assert_array_equal(s.ddim_alphas.astype(np.float64), golden[tag + "_alphas"])
+    np.testing.assert_array_equal(s.ddim_alphas_prev, golden[tag + "_alphas_prev"])
+    np.testing.assert_allclose(s.ddim_sigmas, golden[tag + "_sigmas"], rtol=1e-12)
+    rows = s._coef_rows(False, 1.0)
+    assert rows.shape == (S, 5) and rows.dtype == torch.float32
+    assert float(rows[0, 1]) == float(np.float32(model.alphas_cumprod[0]))     # a_prev of the last step = alphas_cumprod[0]
+
+
+def test_weight_packing_helpers():
+    from upgpt_b200.unet_engine import pad_heads_rows, pad_heads_cols, pack_geglu, geglu_half, split3_w
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8 * 28, 224, generator=g)
+    wp = pad_heads_rows(w, 8, 28, 64)
+    assert wp.shape == (512, 224)
+    assert torch.equal(wp.reshape(8, 64, 224)[:, :28], w.reshape(8, 28, 224)) and float(wp.reshape(8, 64, 224)[:, 28:].abs().max()) == 0
+    wo = torch.randn(224, 8 * 28, generator=g)
+    wop = pad_heads_cols(wo, 8, 28, 64)
+    x = torch.randn(5, 8 * 28, generator=g)
+    xp = torch.zeros(5, 8, 64); xp[:, :, :28] = x.reshape(5, 8, 28)
+    torch.testing.assert_close(xp.reshape(5, 512) @ wop.t(), x @ wo.t())
+    inner = 896
+    half = geglu_half(inner)
+    assert inner % half == 0 and half % 16 == 0
+    w1, b1 = torch.randn(2 * inner, 224, generator=g), torch.randn(2 * inner, generator=g)
+    wpk, bpk = pack_geglu(w1, b1, inner, half)
+    y = x[:, :224] @ w1.t() + b1
+    ypk = (x[:, :224] @ wpk.t() + bpk).reshape(5, inner // half, 2, half)
+    torch.testing.assert_close(ypk[:, :, 0].reshape(5, inner), y[:, :inner])
+    torch.testing.assert_close(ypk[:, :, 1].reshape(5, inner), y[:, inner:])
+    w3 = split3_w(w1)
+    k = 224
+    rec = w3[:, :k].float() + w3[:, 2 * k:].float()
+    assert float((rec - w1).abs().max()) < 1e-6 and torch.equal(w3[:, :k], w3[:, k:2 * k])
+
+
+def test_conditioning_routing():
+    from upgpt_b200.sampler_engine import FusedSampler
+    c = torch.zeros(2, 87, 8); m = torch.zeros(2, 1, 4, 4)
+    cc, ct = FusedSampler.split_cond({"c_crossattn": c, "c_concat": [m]}, "hybrid")
+    assert cc is c and ct is m
+    cc, ct = FusedSampler.split_cond({"c_crossattn": [c, c], "c_concat": [m]}, "hybrid")
+    assert cc.shape == (2, 174, 8)
+    assert FusedSampler.split_cond({"c_crossattn": c}, "hybrid") is None
+    cc, ct = FusedSampler.split_cond(c, "crossattn")
+    assert cc is c and ct is None
+
+
+def test_extra_cond_assembly_shapes():
+    """c = cat(text(B,77,D), styles(B,9,D), Linear(smpl(B,1,85))) (ddpm.py:733-739) -- DummyModel/identity parts on CPU."""
+    from ldm.modules.poses.poses import DummyModel
+    from ldm.modules.encoders.modules import FrozenCLIPEmbedder, FrozenClipImageEmbedder2
+    t = torch.randn(2, 77, 768)
+    assert FrozenCLIPEmbedder().encode(t) is t
+    s = torch.randn(2, 9, 768)
+    assert FrozenClipImageEmbedder2()(s) is s and DummyModel()(s) is s
+    with pytest.raises(RuntimeError):
+        FrozenClipImageEmbedder2()(torch.randn(2, 9, 3, 224, 224))
+
+
+def test_no_cpu_fallback():
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from oracle.make_golden import TINY_UNET_KW
+    m = UNetModel(**TINY_UNET_KW)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 5, 16, 16), torch.zeros(1, dtype=torch.long), torch.zeros(1, 87, 128))
+    from ldm.util import instantiate_from_config
+    model = instantiate_from_config(tiny_ldm_config())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.decode_first_stage(torch.zeros(1, 4, 16, 16))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads (no GPU needed) and exports exactly the functions include/upgpt_b200.h declares."""
+    from upgpt_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "upgpt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(upgpt_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = _C.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_C.EXPORTS) == declared
+    assert lib.upgpt_abi_version() == 1
+    assert lib.upgpt_launch_count() == 0
+
+
+def test_lr_scheduler_stub_matches_reference_formula():
+    from ldm.lr_scheduler import LambdaLinearScheduler
+    s = LambdaLinearScheduler(warm_up_steps=[100], f_min=[1.0], f_max=[1.0], f_start=[1e-6], cycle_lengths=[10 ** 13])
+    assert abs(s(0) - 1e-6) < 1e-12 and abs(s(50) - (1e-6 + (1 - 1e-6) * 0.5)) < 1e-9 and s(1000) == 1.0
