@@ -69,6 +69,8 @@ typedef struct upgpt_gemm_args {
   float out_scale;          /* accumulator scale before bias (0 = 1.0) */
 } upgpt_gemm_args;
 int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
+/* bring-up instrumentation: CTA c of every following upgpt_gemm stamps %globaltimer (ns) into buf[c*16 + slot]; NULL = off */
+int upgpt_debug_set_gemm_timestamps(long long* buf);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Normalisation / operand preparation (HBM-bound elementwise + reductions)
@@ -123,8 +125,9 @@ int upgpt_attention(const upgpt_attn_args* args, void* stream);
  *   post_quant_conv (ddpm.py:779, autoencoder.py:330-333); VAE Decoder.conv_in (model.py:491-495) */
 int upgpt_conv_small_cin(const float* x1, int C1, const float* x2, int C2, float in_scale, int B, int H, int W, int ksize,
                          const float* wt_kmajor, const float* bias, int Cout, float* out, int out_nchw, void* stream);
-/* out[b] = [cos(t_b f_k) | sin(t_b f_k)]  (util.py:151-171); t is int64 on the device */
-int upgpt_timestep_embedding(const long long* t, int B, int dim, float max_period, float* out, void* stream);
+/* out[b] = [cos(t_b f_k) | sin(t_b f_k)]  (util.py:151-171); t is int64 on the device. freqs: optional device table of the
+ * dim/2 fp32 frequencies (pass the host-computed torch table for bit-identical arguments), NULL = computed on the device */
+int upgpt_timestep_embedding(const long long* t, int B, int dim, float max_period, const float* freqs, float* out, void* stream);
 /* out[r][n] = act_out(sum_k act_in(x[r][k]) W[n][k] + bias[n]); fp32, rows <= 64 (time_embed, emb_layers, LinearProject) */
 int upgpt_linear_small_m(const float* x, int ldx, int rows, const float* w, const float* bias, int N, int K, int silu_in,
                          int silu_out, float* out, int ldo, void* stream);

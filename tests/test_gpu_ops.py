@@ -40,7 +40,7 @@ def test_gemm_plain(dev, M, N, K, splits, batch):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 32, 32, 64, 64), (8, 32, 32, 224, 224), (8, 16, 16, 448, 448), (8, 8, 8, 896, 896), (8, 4, 4, 1792, 896),
-                                            (2, 32, 24, 224, 224), (3, 4, 3, 896, 896), (2, 64, 64, 224, 224), (1, 256, 256, 128, 128), (1, 8, 8, 32, 16)])
+                                            (2, 32, 24, 224, 224), (3, 4, 3, 896, 896), (2, 64, 64, 224, 224), (1, 256, 256, 128, 128), (1, 64, 192, 128, 128), (1, 8, 8, 32, 16)])
 def test_conv3x3_implicit_gemm(dev, B, H, W, Cin, Cout):
     """Zero padding comes from TMA out-of-bounds fill; edge cases: ragged 32x24, 4x3 (multi-image tiles), W=256 (column tiles)."""
     from upgpt_b200 import ops, _C
@@ -165,7 +165,8 @@ def test_flash_attention(dev, B, Hh, Nq, Nk, d):
                   scale=d ** -0.5)
     torch.cuda.synchronize()
     assert relerr(out[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
-    assert float(out[..., d:].float().abs().max()) == 0.0      # padded head columns stay exactly zero
+    if d < dpad:
+        assert float(out[..., d:].float().abs().max()) == 0.0      # padded head columns stay exactly zero
 
 
 def test_small_kernels(dev):

@@ -1,0 +1,43 @@
+"""In-kernel %globaltimer timeline of tc_gemm_kernel (CTA 0 and the slowest CTA): where does the time go?"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from upgpt_b200 import _C, ops
+dev = torch.device("cuda:0")
+L = _C.lib()
+names = ["start", "setup done", "prod first issue", "prod last issue", "mma first full", "mma second full", "mma last full", "mma tile committed",
+         "epi tfull", "epi stores issued", "all joined", "dealloc done", "c0 tmem loaded", "c0 staged", "c0 barrier", "c0 flushed"]
+ts = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
+
+def run(name, fn, cold):
+    fn(); fn(); torch.cuda.synchronize()
+    if cold: flush.zero_()
+    ts.zero_(); torch.cuda.synchronize()
+    L.upgpt_debug_set_gemm_timestamps(ts.data_ptr())
+    fn(); torch.cuda.synchronize()
+    L.upgpt_debug_set_gemm_timestamps(None)
+    t = ts.cpu().reshape(148, 16)
+    act = t[:, 0] > 0
+    t0 = t[act, 0].min()
+    end = t[act, 11]
+    slow = int(torch.nonzero(act)[end.argmax()][0]) if act.any() else 0
+    print(f"--- {name} [{'cold' if cold else 'warm'}]: {int(act.sum())} CTAs, kernel span {(t[act, 11].max() - t0).item() / 1e3:.2f} us")
+    for c in (0, slow):
+        row = t[c]
+        print(f"  CTA {c}: " + ", ".join(f"{n}={(row[i] - t0).item() / 1e3:.2f}" for i, n in enumerate(names) if row[i] > 0))
+
+M, N, K = 128, 896, 896
+a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)
+for cold in (False, True):
+    run("gemm M128 N896 K896 bn64", lambda: ops.gemm(a=a, w=w, mode=0, M=M, N=N, K=K, block_n=64, splits=1, out32=out), cold)
+B, H, W, C = 8, 32, 32, 224
+x = (torch.randn(B, H, W, C, device=dev) * 0.5).half(); wc = (torch.randn(C, 9, C, device=dev) * 0.02).half()
+outc = torch.empty(B * H * W, C, device=dev); bias = torch.randn(C, device=dev)
+for cold in (False, True):
+    run("conv 224->224 @32 B8", lambda: ops.gemm(a=x, w=wc, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=outc, bias=bias), cold)
+M2 = 8192
+a2 = (torch.randn(M2, 224, device=dev) * 0.5).half(); w2 = (torch.randn(224, 224, device=dev) * 0.02).half(); out2 = torch.empty(M2, 224, device=dev); r2 = torch.randn(M2, 224, device=dev)
+for cold in (False, True):
+    run("gemm M8192 N224 K224 +res", lambda: ops.gemm(a=a2, w=w2, mode=0, M=M2, N=224, K=224, out32=out2, res32=r2), cold)

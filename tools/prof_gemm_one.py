@@ -1,0 +1,26 @@
+"""A few tc_gemm launches for `ncu --set full` (shape chosen by argv: conv224 | gemm_small | gemm_k224)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from upgpt_b200 import _C, ops
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "conv224"
+if which == "conv224":
+    B, H, W, C = 8, 32, 32, 224
+    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half(); w = (torch.randn(C, 9, C, device=dev) * 0.02).half()
+    out = torch.empty(B * H * W, C, device=dev); bias = torch.randn(C, device=dev)
+    fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias)
+elif which == "gemm_small":
+    M, N, K = 128, 896, 896
+    a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)
+    fn = lambda: ops.gemm(a=a, w=w, mode=0, M=M, N=N, K=K, block_n=64, splits=1, out32=out)
+else:
+    M, N, K = 8192, 224, 224
+    a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)
+    r = torch.randn(M, N, device=dev)
+    fn = lambda: ops.gemm(a=a, w=w, mode=0, M=M, N=N, K=K, out32=out, res32=r)
+for _ in range(6):
+    fn()
+torch.cuda.synchronize()
+print("ok")

@@ -89,13 +89,14 @@ class AttnArgs(C.Structure):
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _PROTOS = {
     "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
+    "upgpt_debug_set_gemm_timestamps": [_vp],
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
     "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
     "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_softmax_rows": [_vp, _i, _ll, _i, _f, _vp, _i, _vp],
     "upgpt_attention": [C.POINTER(AttnArgs), _vp],
     "upgpt_conv_small_cin": [_vp, _i, _vp, _i, _f, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],
-    "upgpt_timestep_embedding": [_vp, _i, _i, _f, _vp, _vp],
+    "upgpt_timestep_embedding": [_vp, _i, _i, _f, _vp, _vp, _vp],
     "upgpt_linear_small_m": [_vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "upgpt_ddim_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
     "upgpt_ddpm_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],

@@ -65,12 +65,14 @@ conv_small_cin_kernel(const float* __restrict__ x1, int C1, const float* __restr
 // Sinusoidal timestep embedding: out[b] = [cos(t*f_k) | sin(t*f_k)], f_k = exp(-ln(max_period) * k / half)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float max_period,
-                                          float* __restrict__ out) {
+                                          const float* __restrict__ freqs, float* __restrict__ out) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
   const int b = i / half, k = i % half;
-  const float freq = expf(-logf(max_period) * (float)k / (float)half);
+  // freqs (optional): the host-computed fp32 table exp(-ln(max_period) * k / half), so that the table is bit-identical
+  // to the reference's torch.exp on the CPU (a 1-ulp difference in a frequency moves cos(t*f) by ~6e-5 at t ~ 1000)
+  const float freq = freqs ? freqs[k] : expf(-logf(max_period) * (float)k / (float)half);
   const float arg = (float)t[b] * freq;
   out[(size_t)b * dim + k] = cosf(arg);
   out[(size_t)b * dim + half + k] = sinf(arg);
@@ -81,27 +83,41 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 // out[b][n] = act_out( sum_k act_in(x[b][k]) * W[n][k] + bias[n] )   for small row counts (B <= 64)
 // one warp per output feature n; the W row is read once (float4, coalesced) and reused for all rows.
 // ------------------------------------------------------------------------------------------------------------------
-template <int RB>
+template <int RB, bool VEC>
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ w, const float* __restrict__ bias,
                       int N, int K, int silu_in, int silu_out, float* __restrict__ out, int ldo) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
-  const float4* wr = (const float4*)(w + (size_t)n * K);
-  const int K4 = K >> 2;
+  const float* wrow = w + (size_t)n * K;
   for (int r0 = 0; r0 < rows; r0 += RB) {
     float acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-    for (int i = lane; i < K4; i += 32) {
-      const float4 wv = __ldg(wr + i);
+    if (VEC) {
+      const float4* wr = (const float4*)wrow;
+      for (int i = lane; i < (K >> 2); i += 32) {
+        const float4 wv = __ldg(wr + i);
 #pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        if (r0 + r < rows) {
-          float4 xv = *(const float4*)(x + (size_t)(r0 + r) * ldx + 4 * i);
-          if (silu_in) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
-          acc[r] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        for (int r = 0; r < RB; ++r) {
+          if (r0 + r < rows) {
+            float4 xv = *(const float4*)(x + (size_t)(r0 + r) * ldx + 4 * i);
+            if (silu_in) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+            acc[r] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+          }
+        }
+      }
+    } else {   // K or the row pitches are not multiples of 4 (e.g. the 85-d SMPL vector): scalar loads
+      for (int i = lane; i < K; i += 32) {
+        const float wv = __ldg(wrow + i);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          if (r0 + r < rows) {
+            float xv = x[(size_t)(r0 + r) * ldx + i];
+            if (silu_in) xv = silu_f(xv);
+            acc[r] = fmaf(xv, wv, acc[r]);
+          }
         }
       }
     }
@@ -220,11 +236,12 @@ extern "C" int upgpt_conv_small_cin(const float* x1, int C1, const float* x2, in
   return 0;
 }
 
-extern "C" int upgpt_timestep_embedding(const long long* t, int B, int dim, float max_period, float* out, void* stream_) {
+extern "C" int upgpt_timestep_embedding(const long long* t, int B, int dim, float max_period, const float* freqs, float* out,
+                                        void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(t && out && dim >= 2, "timestep_embedding: bad args");
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, B, dim, max_period, out);
+  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, B, dim, max_period, freqs, out);
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -233,13 +250,17 @@ extern "C" int upgpt_timestep_embedding(const long long* t, int B, int dim, floa
 extern "C" int upgpt_linear_small_m(const float* x, int ldx, int rows, const float* w, const float* bias, int N, int K,
                                     int silu_in, int silu_out, float* out, int ldo, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  UPGPT_REQUIRE(x && w && out && K % 4 == 0 && rows > 0, "linear_small_m: bad args (K=%d)", K);
+  UPGPT_REQUIRE(x && w && out && K > 0 && rows > 0, "linear_small_m: bad args (K=%d)", K);
   if (ldx <= 0) ldx = K;
   if (ldo <= 0) ldo = N;
-  UPGPT_REQUIRE(ldx % 4 == 0, "linear_small_m: ldx must be a multiple of 4");
+  const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x | (uintptr_t)w) % 16 == 0);
   const int blocks = (N + 7) / 8;
-  if (rows <= 4) linear_small_m_kernel<4><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
-  else linear_small_m_kernel<8><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+  if (vec) {
+    if (rows <= 4) linear_small_m_kernel<4, true><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+    else linear_small_m_kernel<8, true><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+  } else {
+    linear_small_m_kernel<4, false><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+  }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

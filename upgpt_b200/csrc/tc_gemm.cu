@@ -23,6 +23,9 @@ namespace upgpt {
 static constexpr int kGemmThreads = 192;
 static constexpr int kABytes = 128 * 64 * 2;  // smem slot for one A stage
 
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TS(slot) do { if (p.debug_ts) p.debug_ts[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmParams p) {
@@ -37,9 +40,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_base_smem = (uint32_t*)(bar_tempty + 2);
   uint32_t* split_flag = tmem_base_smem + 1;
+  float* stage = (float*)(((uintptr_t)(split_flag + 1) + 127) & ~(uintptr_t)127);   // 2 x [128][32] fp32 epilogue staging
+  long long* row_tab = (long long*)(stage + 2 * 128 * 32);   // [128] global output row of each tile row (-1 = not stored)
+  int* grp_tab = (int*)(row_tab + 128);                      // [128] row group (image / batch entry) of each tile row
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TS(0);
 
   // accumulator ring: 2 stages of block_n columns
   uint32_t tmem_cols = 32;
@@ -63,6 +70,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  if (threadIdx.x == 0) TS(1);
 
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
   const int tiles_per_batch = tiles_mn * p.num_splits;
@@ -86,13 +94,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.flags & GEMM_CONV) {
           if (p.tile_imgs > 1) {
             c1 = 0; c2 = 0; c3 = mt * p.tile_imgs;
-          } else if (p.tiles_per_row > 1) {
-            const int img = mt / p.tiles_per_img;
-            const int t = mt - img * p.tiles_per_img;
-            c1 = (t % p.tiles_per_row) * 128; c2 = t / p.tiles_per_row; c3 = img;
           } else {
             const int img = mt / p.tiles_per_img;
-            c1 = 0; c2 = (mt - img * p.tiles_per_img) * p.tile_rows; c3 = img;
+            const int t = mt - img * p.tiles_per_img;
+            const int ty = t / p.tiles_per_row;
+            c1 = (t - ty * p.tiles_per_row) * p.tile_cols; c2 = ty * p.tile_rows; c3 = img;
           }
         } else {
           c1 = mt * 128; c2 = 0; c3 = bidx;
@@ -107,8 +113,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
                       c2 + p.tap_dy[tap], c3 + p.tap_dn[tap]);
           tma_load_4d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx);
+          if (kit == k_begin) TS(2);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        TS(3);
       }
     }
   } else if (warp == 1) {
@@ -130,6 +138,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
+          if (kit == k_begin) TS(4);
+          if (kit == k_begin + 1) TS(5);
+          if (kit == k_end - 1) TS(6);
           const uint64_t adesc = make_desc_kmajor_sw128(smem_u32(sA + (size_t)stage * kABytes));
           const uint64_t bdesc = make_desc_kmajor_sw128(smem_u32(sB + (size_t)stage * b_bytes));
 #pragma unroll
@@ -142,6 +153,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&bar_tfull[acc]);
+        TS(7);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -151,6 +163,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r = quad * 32 + lane;       // accumulator row handled by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
+    int buf = 0;
     const bool conv = (p.flags & GEMM_CONV) != 0;
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -167,15 +180,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int img = mt * p.tile_imgs + rr / p.HW;
             ok = (rr < p.tile_imgs * p.HW) && (img < p.n_imgs);
             gr = (long long)mt * p.tile_imgs * p.HW + rr;
-          } else if (p.tiles_per_row > 1) {
-            ok = true;                          // W % 128 == 0: every lane is a pixel
-            gr = (long long)mt * 128 + rr;      // tiles enumerate the image in raster order
           } else {
+            // tile = tile_rows x tile_cols pixels of one image (tile_cols divides W; the last row tile may be ragged)
             const int img = mt / p.tiles_per_img;
-            const int y0 = (mt - img * p.tiles_per_img) * p.tile_rows;
-            const int y = y0 + rr / p.W;
-            ok = (rr < p.tile_rows * p.W) && (y < p.H);
-            gr = (long long)img * p.HW + (long long)y0 * p.W + rr;
+            const int t = mt - img * p.tiles_per_img;
+            const int ty = t / p.tiles_per_row;
+            const int x0 = (t - ty * p.tiles_per_row) * p.tile_cols;
+            const int ry = rr / p.tile_cols;
+            const int y = ty * p.tile_rows + ry;
+            ok = (rr < p.tile_rows * p.tile_cols) && (y < p.H);
+            gr = (long long)img * p.HW + (long long)y * p.W + x0 + (rr - ry * p.tile_cols);
           }
         } else {
           const int m = mt * 128 + rr;
@@ -191,181 +205,262 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* rv = p.rowvec ? p.rowvec + (size_t)group * p.ld_rowvec : nullptr;
       const float* rs = p.res32 ? p.res32 + (size_t)grow * p.ldres : nullptr;
       const float* bs = p.bias;
+      // publish this thread's row bookkeeping for the flat (coalesced) passes: first wait until every epilogue thread has
+      // finished reading the previous tile's tables; the staging barrier orders these writes before the first read
+      named_bar_sync(1, 128);
+      row_tab[r] = valid ? grow : -1;
+      grp_tab[r] = group;
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
+      if (r == 0) TS(8);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * p.block_n) + ((uint32_t)(quad * 32) << 16);
 
+      // --------------------------------------------------------------------------------------------------------
+      // Epilogue data path: TMEM -> registers (one accumulator row per thread) -> XOR-swizzled smem staging chunk
+      // [128 rows][32 fp32] -> flat coalesced pass (8 consecutive threads cover one row's 128 bytes) that applies
+      // bias / row vector / residual and stores fp32 / fp16 / split-K partials with full-line transactions and 8
+      // independent residual loads in flight per thread.  Channel-major stores skip the staging: there one row per
+      // thread is already the coalesced direction.
+      // --------------------------------------------------------------------------------------------------------
+      const bool splitk = p.num_splits > 1;
+      const size_t ws_split_stride = (size_t)p.ws_rows * p.ws_ld;
+
+      // writes this thread's row (ncols fp32, ncols in {16, 32}) into staging buffer `st`
+      auto stage_row = [&](float* st, const float* f, int ncols) {
+        float* rowp = st + r * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q * 4 < ncols) *(float4*)(rowp + ((q ^ (r & 7)) << 2)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      };
+      // flat pass over a staged chunk; mode 0: final values (+extras) -> out32/out16, 1: split-K partial -> workspace,
+      // 2: GEGLU result -> out16 only (n_out0 = first output column of the chunk)
+      auto flush_chunk = [&](const float* st, int n_out0, int ncols, int mode) {
+        // thread r owns float4 column q = r % (ncols/4) of rows (r / (ncols/4)) + k * (128 / (ncols/4)), k = 0..ncols/4-1:
+        // the column (hence bias) is loop-invariant and the k iterations are independent (loads first, then stores)
+        const int sh = ncols == 32 ? 3 : 2;
+        const int q = r & ((1 << sh) - 1);
+        const int rr0 = r >> sh;
+        const int rstep = 128 >> sh;
+        const int n = n_out0 + (q << 2);
+        const int iters = 1 << sh;
+        if (mode == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k >= iters) break;
+            const int rr = rr0 + k * rstep;
+            const long long gr = row_tab[rr];
+            if (gr < 0) continue;
+            const float4 v = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
+            __stcg((float4*)(p.ws + (size_t)split * ws_split_stride + (size_t)gr * p.ws_ld + n), v);
+          }
+          return;
+        }
+        if (mode == 2) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k >= iters) break;
+            const int rr = rr0 + k * rstep;
+            const long long gr = row_tab[rr];
+            if (gr < 0) continue;
+            const float4 v = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
+            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+            *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+          }
+          return;
+        }
+        if (n >= p.N_total) return;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b4 = *(const float4*)(p.bias + n);
+        long long gr[8];
+        float4 v[8], e1[8], e2[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gr[k] = -1;
+          if (k >= iters) continue;
+          const int rr = rr0 + k * rstep;
+          gr[k] = row_tab[rr];
+          v[k] = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
+          e1[k] = make_float4(0.f, 0.f, 0.f, 0.f); e2[k] = e1[k];
+          if (gr[k] >= 0) {
+            if (p.rowvec) e1[k] = *(const float4*)(p.rowvec + (size_t)grp_tab[rr] * p.ld_rowvec + n);
+            if (p.res32) e2[k] = *(const float4*)(p.res32 + (size_t)gr[k] * p.ldres + n);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k >= iters || gr[k] < 0) continue;
+          float4 o = v[k];
+          o.x += b4.x + e1[k].x + e2[k].x; o.y += b4.y + e1[k].y + e2[k].y; o.z += b4.z + e1[k].z + e2[k].z; o.w += b4.w + e1[k].w + e2[k].w;
+          if (p.out32) *(float4*)(p.out32 + (size_t)gr[k] * p.ld32 + n) = o;
+          if (p.out16) {
+            __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+            *(uint2*)(p.out16 + (size_t)gr[k] * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+          }
+        }
+      };
+
       if (p.flags & GEMM_GEGLU) {
+        // tile columns are [x (half) | gate (half)]; out16[:, nt*half + j] = (x + bx) * gelu(gate + bg)
         const int half_n = p.block_n >> 1;
-        for (int j0 = 0; j0 < half_n; j0 += 16) {
-          uint32_t xr[16], gr[16];
-          tmem_ld16(t_acc + (uint32_t)j0, xr);
-          tmem_ld16(t_acc + (uint32_t)(half_n + j0), gr);
-          tmem_ld_wait();
-          if (valid) {
-            const int ncol_x = nt * p.block_n + j0;            // packed column of x
-            const int ncol_g = nt * p.block_n + half_n + j0;   // packed column of gate
-            const int ocol = nt * half_n + j0;
-            __align__(16) __half o[16];
+        for (int j0 = 0; j0 < half_n; j0 += 32) {
+          const int ncols = min(32, half_n - j0);
+          float f[32];
+          for (int h0 = 0; h0 < ncols; h0 += 16) {
+            uint32_t xr[16], gr_[16];
+            tmem_ld16(t_acc + (uint32_t)(j0 + h0), xr);
+            tmem_ld16(t_acc + (uint32_t)(half_n + j0 + h0), gr_);
+            tmem_ld_wait();
+            const int ncol_x = nt * p.block_n + j0 + h0;
+            const int ncol_g = ncol_x + half_n;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float xv = __uint_as_float(xr[i]) + (bs ? bs[ncol_x + i] : 0.f);
-              float gv = __uint_as_float(gr[i]) + (bs ? bs[ncol_g + i] : 0.f);
-              o[i] = __float2half_rn(xv * gelu_erf_f(gv));
+              const float xv = __uint_as_float(xr[i]) + (bs ? bs[ncol_x + i] : 0.f);
+              const float gv = __uint_as_float(gr_[i]) + (bs ? bs[ncol_g + i] : 0.f);
+              f[h0 + i] = xv * gelu_erf_f(gv);
             }
-            uint4* dst = (uint4*)(p.out16 + (size_t)grow * p.ld16 + ocol);
-            dst[0] = ((uint4*)o)[0];
-            dst[1] = ((uint4*)o)[1];
+          }
+          float* st = stage + buf * (128 * 32);
+          stage_row(st, f, ncols);
+          named_bar_sync(1, 128);
+          flush_chunk(st, nt * half_n + j0, ncols, 2);
+          buf ^= 1;
+        }
+      } else if (chw) {
+        for (int j0 = 0; j0 < p.block_n; j0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + (uint32_t)j0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = nt * p.block_n + j0 + i;
+              if (n < p.N_total) {
+                float x = __uint_as_float(v[i]) * p.out_scale;
+                if (bs) x += bs[n];
+                if (rv) x += rv[n];
+                if (rs) x += rs[n];
+                const size_t o = ((size_t)group * p.N_total + n) * (size_t)p.ldT + rig;
+                if (p.out32) p.out32[o] = x;
+                if (p.out16) p.out16[o] = __float2half_rn(x);
+              }
+            }
           }
         }
       } else {
-        // applies bias / row vector / residual to 16 consecutive columns of this thread's row and stores them
-        auto store_cols = [&](int n0, float (&f)[16]) {
+        for (int j0 = 0; j0 < p.block_n; j0 += 32) {
+          const int ncols = min(32, p.block_n - j0);
+          float f[32];
+          if (ncols == 32) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + (uint32_t)j0, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + i;
-            if (n < p.N_total) {
-              if (p.bias) f[i] += p.bias[n];
-              if (rv) f[i] += rv[n];
-              if (rs) f[i] += rs[n];
-            }
-          }
-          if (chw) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + i;
-              if (n < p.N_total) {
-                const size_t o = ((size_t)group * p.N_total + n) * (size_t)p.ldT + rig;
-                if (p.out32) p.out32[o] = f[i];
-                if (p.out16) p.out16[o] = __float2half_rn(f[i]);
-              }
-            }
-          } else if (n0 + 16 <= p.N_total) {
-            if (p.out32) {
-              float* dst = p.out32 + (size_t)grow * p.ld32 + n0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) ((float4*)dst)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-            if (p.out16) {
-              __align__(16) __half o[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float2half_rn(f[i]);
-              uint4* dst = (uint4*)(p.out16 + (size_t)grow * p.ld16 + n0);
-              dst[0] = ((uint4*)o)[0];
-              dst[1] = ((uint4*)o)[1];
-            }
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
           } else {
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + i;
-              if (n < p.N_total) {
-                if (p.out32) p.out32[(size_t)grow * p.ld32 + n] = f[i];
-                if (p.out16) p.out16[(size_t)grow * p.ld16 + n] = __float2half_rn(f[i]);
-              }
-            }
-          }
-        };
-        if (p.num_splits == 1) {
-          for (int j0 = 0; j0 < p.block_n; j0 += 16) {
             uint32_t v[16];
             tmem_ld16(t_acc + (uint32_t)j0, v);
             tmem_ld_wait();
-            if (valid) {
-              float f[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
-              store_cols(nt * p.block_n + j0, f);
-            }
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
           }
-        } else {
-          // ---- deterministic split-K: partial tile -> workspace; the last split to arrive reduces in fixed order ----
-          const size_t ws_split_stride = (size_t)p.ws_rows * p.ws_ld;
-          float* wrow = p.ws + (size_t)split * ws_split_stride + (size_t)grow * p.ws_ld + nt * p.block_n;
-          for (int j0 = 0; j0 < p.block_n; j0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_acc + (uint32_t)j0, v);
-            tmem_ld_wait();
-            if (valid) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                __stcg((float4*)(wrow + j0) + i, make_float4(__uint_as_float(v[4 * i]) * p.out_scale, __uint_as_float(v[4 * i + 1]) * p.out_scale,
-                                                          __uint_as_float(v[4 * i + 2]) * p.out_scale, __uint_as_float(v[4 * i + 3]) * p.out_scale));
-            }
-          }
-          // the accumulator stage can be recycled now
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-          __threadfence();
+          float* st = stage + buf * (128 * 32);
+          if (r == 0 && j0 == 0) TS(12);
+          stage_row(st, f, ncols);
+          if (r == 0 && j0 == 0) TS(13);
           named_bar_sync(1, 128);
-          if (r == 0) {
-            int* ctr = p.counters + (bidx * tiles_mn + nt * p.num_m_tiles + mt);
-            const int prev = atomicAdd(ctr, 1);
-            const int last = prev == p.num_splits - 1;
-            if (last) *ctr = 0;   // self-reset: the counters are zero again when the kernel ends
-            *split_flag = (uint32_t)last;
-          }
-          named_bar_sync(1, 128);
-          const bool is_last = *split_flag != 0;
-          named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
-          if (is_last) {
-            // coalesced reduction: the 128 epilogue threads sweep the tile as a flat array of float4
-            __threadfence();
-            const int n4 = p.block_n >> 2;
-            for (int idx = r; idx < 128 * n4; idx += 128) {
-              const int rr = idx / n4;
-              const int c = (idx - rr * n4) << 2;
-              bool ok; long long gr;
-              row_of(rr, ok, gr);
-              const int n = nt * p.block_n + c;
-              if (!ok || n >= p.N_total) continue;
-              const float4* src = (const float4*)(p.ws + (size_t)gr * p.ws_ld + n);
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              int sp = 0;
-              for (; sp + 4 <= p.num_splits; sp += 4) {   // 4 independent loads in flight, summed in split order
-                const float4 t0 = __ldcg(src + (size_t)(sp + 0) * (ws_split_stride >> 2));
-                const float4 t1 = __ldcg(src + (size_t)(sp + 1) * (ws_split_stride >> 2));
-                const float4 t2 = __ldcg(src + (size_t)(sp + 2) * (ws_split_stride >> 2));
-                const float4 t3 = __ldcg(src + (size_t)(sp + 3) * (ws_split_stride >> 2));
-                a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
-                a.x += t1.x; a.y += t1.y; a.z += t1.z; a.w += t1.w;
-                a.x += t2.x; a.y += t2.y; a.z += t2.z; a.w += t2.w;
-                a.x += t3.x; a.y += t3.y; a.z += t3.z; a.w += t3.w;
-              }
-              for (; sp < p.num_splits; ++sp) {
-                const float4 t0 = __ldcg(src + (size_t)sp * (ws_split_stride >> 2));
-                a.x += t0.x; a.y += t0.y; a.z += t0.z; a.w += t0.w;
-              }
-              if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
-              if (p.rowvec) {
-                const float4 b4 = *(const float4*)(p.rowvec + (size_t)(gr / p.rows_per_group) * p.ld_rowvec + n);
-                a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-              }
-              if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr * p.ldres + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
-              if (p.out32) *(float4*)(p.out32 + (size_t)gr * p.ld32 + n) = a;
-              if (p.out16) {
-                __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-                *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
-              }
-            }
-          }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          continue;
+          if (r == 0 && j0 == 0) TS(14);
+          flush_chunk(st, nt * p.block_n + j0, ncols, splitk ? 1 : 0);
+          if (r == 0 && j0 == 0) TS(15);
+          buf ^= 1;
         }
       }
+      // the accumulator stage can be recycled now
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (r == 0) TS(9);
+
+      if (splitk) {
+        // ---- deterministic split-K: the last split to arrive reduces the partial tiles in fixed split order ----
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (r == 0) {
+          int* ctr = p.counters + (bidx * tiles_mn + nt * p.num_m_tiles + mt);
+          const int prev = atomicAdd(ctr, 1);
+          const int last = prev == p.num_splits - 1;
+          if (last) *ctr = 0;   // self-reset: the counters are zero again when the kernel ends
+          *split_flag = (uint32_t)last;
+        }
+        named_bar_sync(1, 128);
+        const bool is_last = *split_flag != 0;
+        named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
+        if (is_last) {
+          __threadfence();
+          const int n4 = p.block_n >> 2;
+          const int total = 128 * n4;
+          const size_t stride4 = ws_split_stride >> 2;
+          for (int idx0 = r; idx0 < total; idx0 += 4 * 128) {
+            // 4 independent float4 columns per thread per trip -> 4 x num_splits loads in flight
+            float4 a[4];
+            const float4* src[4];
+            bool ok[4];
+            long long gr[4];
+            int nn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = idx0 + u * 128;
+              a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              ok[u] = false; gr[u] = 0; nn[u] = 0; src[u] = (const float4*)p.ws;
+              if (idx < total) {
+                const int rr = idx / n4;
+                nn[u] = nt * p.block_n + ((idx - rr * n4) << 2);
+                bool okr;
+                row_of(rr, okr, gr[u]);
+                ok[u] = okr && nn[u] < p.N_total;
+                if (ok[u]) src[u] = (const float4*)(p.ws + (size_t)gr[u] * p.ws_ld + nn[u]);
+              }
+            }
+#pragma unroll 2
+            for (int sp = 0; sp < p.num_splits; ++sp) {   // fixed split order => deterministic sum
+              float4 t[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) t[u] = ok[u] ? __ldcg(src[u] + (size_t)sp * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { a[u].x += t[u].x; a[u].y += t[u].y; a[u].z += t[u].z; a[u].w += t[u].w; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (!ok[u]) continue;
+              const int n = nn[u];
+              float4 v = a[u];
+              if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+              if (p.rowvec) {
+                const float4 b4 = *(const float4*)(p.rowvec + (size_t)(gr[u] / p.rows_per_group) * p.ld_rowvec + n);
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+              }
+              if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr[u] * p.ldres + n); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+              if (p.out32) *(float4*)(p.out32 + (size_t)gr[u] * p.ld32 + n) = v;
+              if (p.out16) {
+                __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                *(uint2*)(p.out16 + (size_t)gr[u] * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              }
+            }
+          }
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TS(10);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+  if (threadIdx.x == 32) TS(11);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -378,6 +473,7 @@ static float* g_ws = nullptr;                 // split-K partial-tile workspace 
 static size_t g_ws_bytes = 0;
 static int* g_counters = nullptr;
 static constexpr int kMaxCounters = 1 << 16;
+static long long* g_debug_ts = nullptr;
 
 static int gemm_device_setup() {
   if (g_attr_set) return 0;
@@ -438,27 +534,31 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   int m_rows_total;
   if (conv) {
     UPGPT_REQUIRE(a->H > 0 && a->W > 0 && a->n_imgs > 0, "upgpt_gemm(conv): bad geometry");
-    UPGPT_REQUIRE(a->W <= 128 || a->W % 128 == 0, "upgpt_gemm(conv): W=%d > 128 must be a multiple of 128", a->W);
-    p.flags |= GEMM_CONV;
+      p.flags |= GEMM_CONV;
     p.H = a->H; p.W = a->W; p.HW = a->H * a->W; p.n_imgs = a->n_imgs;
     uint32_t box[4];
     p.tiles_per_row = 1;
-    if (a->W > 128) {
-      p.tile_imgs = 1; p.tile_rows = 1; p.tiles_per_row = a->W / 128;
-      p.tiles_per_img = p.tiles_per_row * a->H;
-      p.num_m_tiles = p.tiles_per_img * a->n_imgs;
-      box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
-    } else if (p.HW <= 64) {
+    p.tile_cols = a->W;
+    if (p.HW <= 64) {
       p.tile_imgs = 128 / p.HW; p.tile_rows = a->H; p.tiles_per_img = 1;
       if (p.tile_imgs > a->n_imgs) p.tile_imgs = a->n_imgs;
       if (p.tile_imgs < 1) p.tile_imgs = 1;
       p.num_m_tiles = (a->n_imgs + p.tile_imgs - 1) / p.tile_imgs;
       box[0] = 64; box[1] = a->W; box[2] = a->H; box[3] = p.tile_imgs;
     } else {
-      p.tile_imgs = 1; p.tile_rows = 128 / a->W; if (p.tile_rows > a->H) p.tile_rows = a->H;
-      p.tiles_per_img = (a->H + p.tile_rows - 1) / p.tile_rows;
+      // tile_cols = the divisor of W (<= 128) that fills most of the 128 accumulator lanes
+      int best_tc = 1, best_fill = 0;
+      for (int tc = 1; tc <= 128 && tc <= a->W; ++tc) {
+        if (a->W % tc) continue;
+        int tr = 128 / tc; if (tr > a->H) tr = a->H;
+        if (tc * tr >= best_fill) { best_fill = tc * tr; best_tc = tc; }
+      }
+      p.tile_imgs = 1; p.tile_cols = best_tc;
+      p.tile_rows = 128 / best_tc; if (p.tile_rows > a->H) p.tile_rows = a->H;
+      p.tiles_per_row = a->W / best_tc;
+      p.tiles_per_img = p.tiles_per_row * ((a->H + p.tile_rows - 1) / p.tile_rows);
       p.num_m_tiles = p.tiles_per_img * a->n_imgs;
-      box[0] = 64; box[1] = a->W; box[2] = p.tile_rows; box[3] = 1;
+      box[0] = 64; box[1] = p.tile_cols; box[2] = p.tile_rows; box[3] = 1;
     }
     p.a_bytes = box[0] * box[1] * box[2] * box[3] * 2;
     const int a_imgs = (a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) ? 4 * a->n_imgs : a->n_imgs;
@@ -546,24 +646,30 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     if (make_tmap_f16(&tmB, a->w, 4, dims, strides, box, true)) return -3;
   }
 
+  p.debug_ts = g_debug_ts;
   p.out32 = a->out32; p.ld32 = a->ld32 > 0 ? a->ld32 : a->N;
   p.out16 = (__half*)a->out16; p.ld16 = a->ld16 > 0 ? a->ld16 : ((p.flags & GEMM_GEGLU) ? a->N / 2 : a->N);
   p.bias = a->bias; p.rowvec = a->rowvec; p.ld_rowvec = a->ld_rowvec > 0 ? a->ld_rowvec : a->N;
   p.res32 = a->res32; p.ldres = a->ldres > 0 ? a->ldres : a->N;
   p.ldT = a->ldT > 0 ? a->ldT : p.rows_per_group;
   if (!(p.flags & GEMM_CHW)) {
+    UPGPT_REQUIRE(a->N % 4 == 0, "upgpt_gemm: N (=%d) must be a multiple of 4 unless the channel-major epilogue is used", a->N);
+    UPGPT_REQUIRE(!p.bias || ((uintptr_t)p.bias & 15) == 0, "upgpt_gemm: bias must be 16-byte aligned");
+    UPGPT_REQUIRE(!p.rowvec || (((uintptr_t)p.rowvec & 15) == 0 && p.ld_rowvec % 4 == 0), "upgpt_gemm: rowvec must be 16-byte aligned with ld%%4==0");
+    UPGPT_REQUIRE(!p.res32 || (((uintptr_t)p.res32 & 15) == 0 && p.ldres % 4 == 0), "upgpt_gemm: res32 must be 16-byte aligned with ld%%4==0");
     UPGPT_REQUIRE(!p.out32 || (p.ld32 % 4 == 0 && ((uintptr_t)p.out32 & 15) == 0), "upgpt_gemm: out32 must be 16-byte aligned with ld%%4==0");
     UPGPT_REQUIRE(!p.out16 || (p.ld16 % 8 == 0 && ((uintptr_t)p.out16 & 15) == 0), "upgpt_gemm: out16 must be 16-byte aligned with ld%%8==0");
   }
 
   // ---- pipeline depth from the smem budget ----
   const size_t stage_bytes = (size_t)kABytes + (size_t)bn * 128;
-  int stages = (int)(((size_t)g_smem_optin - 1024 - 256) / stage_bytes);
+  constexpr size_t kEpiStageBytes = 2 * 128 * 32 * sizeof(float) + 128 + 128 * 8 + 128 * 4;
+  int stages = (int)(((size_t)g_smem_optin - 1024 - 256 - kEpiStageBytes) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > k_iters / splits + 1) stages = k_iters / splits + 1;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16 + kEpiStageBytes;
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
@@ -571,5 +677,11 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// bring-up instrumentation: when set, every CTA of tc_gemm_kernel stamps %globaltimer at 12 points into buf[cta][16]
+extern "C" int upgpt_debug_set_gemm_timestamps(long long* buf) {
+  g_debug_ts = buf;
   return 0;
 }

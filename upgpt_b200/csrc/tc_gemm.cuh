@@ -28,7 +28,8 @@ struct GemmParams {
   int tile_rows;        // image rows per M tile (tile_imgs == 1)
   int tile_imgs;        // whole images per M tile (HW * tile_imgs <= 128)
   int tiles_per_img;
-  int tiles_per_row;    // > 1 when W > 128: a tile is a 128-pixel segment of one image row
+  int tiles_per_row;    // column tiles per image row (W / tile_cols)
+  int tile_cols;        // pixels per tile row (divides W)
   int n_imgs;           // number of images addressed by the output
   int tap_dy[9], tap_dx[9], tap_dn[9];
   // ---- epilogue ----
@@ -48,6 +49,7 @@ struct GemmParams {
   float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
   int ws_rows, ws_ld;
   int* counters;        // one arrival counter per (batch, n tile, m tile); zero between launches
+  long long* debug_ts;  // optional [gridDim.x][16] globaltimer stamps (bring-up instrumentation), null in production
 };
 
 }  // namespace upgpt

@@ -60,10 +60,24 @@ def attention(**kw):
     _C.check(_C.lib().upgpt_attention(C.byref(a), stream()), "upgpt_attention")
 
 
+def timestep_freqs(dim, max_period=10000, device=None):
+    """The reference's frequency table (util.py:163-165), computed with the same fp32 CPU torch ops."""
+    import math
+    half = dim // 2
+    f = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+    return f.to(device) if device is not None else f
+
+
+_FREQS = {}
+
+
 def timestep_embedding(t, dim, max_period=10000):
     t = _req(t.to(torch.int64), torch.int64, "timesteps")
+    key = (dim, max_period, t.device)
+    if key not in _FREQS:
+        _FREQS[key] = timestep_freqs(dim, max_period, t.device)
     out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
-    _C.check(_C.lib().upgpt_timestep_embedding(_p(t), t.shape[0], dim, float(max_period), _p(out), stream()),
+    _C.check(_C.lib().upgpt_timestep_embedding(_p(t), t.shape[0], dim, float(max_period), _p(_FREQS[key]), _p(out), stream()),
              "upgpt_timestep_embedding")
     return out
 

@@ -278,6 +278,8 @@ class UNetEngine(EngineBase):
                     w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
                     put(q + ".ff1.weight", w1.half()); put(q + ".ff1.bias", b1)
                     put(q + ".ff2.weight", sd[q + ".ff.net.2.weight"].half()); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
+        from .ops import timestep_freqs
+        put("temb.freqs", timestep_freqs(self.mc))
         put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
         self.emb_total = off
         put("out.0.weight", sd["out.0.weight"]); put("out.0.bias", sd["out.0.bias"])
@@ -379,7 +381,7 @@ class UNetEngine(EngineBase):
         eps = self.buf("eps", (B, self.out_ch, H, W))
         if not self._sizing:
             P = self.prog
-            P.add(L_.upgpt_timestep_embedding, t_in.data_ptr(), B, self.mc, 10000.0, temb.data_ptr())
+            P.add(L_.upgpt_timestep_embedding, t_in.data_ptr(), B, self.mc, 10000.0, self.w["temb.freqs"].data_ptr(), temb.data_ptr())
             P.add(L_.upgpt_linear_small_m, temb.data_ptr(), self.mc, B, self.w["time_embed.0.weight"].data_ptr(),
                   self.w["time_embed.0.bias"].data_ptr(), 4 * self.mc, self.mc, 0, 1, emb1.data_ptr(), 4 * self.mc)
             P.add(L_.upgpt_linear_small_m, emb1.data_ptr(), 4 * self.mc, B, self.w["time_embed.2.weight"].data_ptr(),
