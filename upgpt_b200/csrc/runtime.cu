@@ -35,8 +35,8 @@ static void load_encode() {
   if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = (PFN_encodeTiled)fn;
 }
 
-int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool swizzle128) {
+int make_tmap(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, bool swizzle128) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) {
     set_last_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -65,8 +65,8 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
       return -3;
     }
   }
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
-                        es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = g_encode(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                        const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -77,6 +77,11 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     return -3;
   }
   return 0;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool swizzle128) {
+  return make_tmap(out, 2, base, rank, dims, strides_bytes, box, swizzle128);
 }
 
 }  // namespace upgpt

@@ -28,21 +28,31 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // carve-up by integer offsets from the __shared__ array, so that every access below compiles to LDS/STS (casting
+  // through uintptr_t would demote the pointers to the generic address space)
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
   const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * kABytes;
-  uint64_t* bar_full = (uint64_t*)(sB + (size_t)p.stages * b_bytes);
+  const uint32_t off_bar = (uint32_t)p.stages * (kABytes + b_bytes);
+  uint64_t* bar_full = (uint64_t*)(smem + off_bar);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_tfull = bar_empty + p.stages;
   uint64_t* bar_tempty = bar_tfull + 2;
-  uint32_t* tmem_base_smem = (uint32_t*)(bar_tempty + 2);
+  uint64_t* bar_res = bar_tempty + 2;                        // [2] residual chunk landed (TMA epilogue)
+  uint32_t* tmem_base_smem = (uint32_t*)(bar_res + 2);
   uint32_t* split_flag = tmem_base_smem + 1;
-  float* stage = (float*)(((uintptr_t)(split_flag + 1) + 127) & ~(uintptr_t)127);   // 2 x [128][32] fp32 epilogue staging
-  long long* row_tab = (long long*)(stage + 2 * 128 * 32);   // [128] global output row of each tile row (-1 = not stored)
-  int* grp_tab = (int*)(row_tab + 128);                      // [128] row group (image / batch entry) of each tile row
+  const uint32_t off_stage = (off_bar + (2u * p.stages + 6u) * 8u + 8u + 1023u) & ~1023u;
+  float* stage = (float*)(smem + off_stage);                 // 2 x [128 rows][128 B] epilogue staging (swizzle-128B layout)
+  float* resbuf = (float*)(smem + off_stage + 2 * 16384);    // 2 x [128 rows][32 fp32] residual chunks (only if res_tma)
+  const uint32_t off_tab = off_stage + 2 * 16384 + (p.res_tma ? 2 * 16384 : 0);
+  long long* row_tab = (long long*)(smem + off_tab);         // [128] global output row of each tile row (-1 = not stored)
+  int* grp_tab = (int*)(smem + off_tab + 128 * 8);           // [128] row group (image / batch entry) of each tile row
+  float* bias_s = (float*)(smem + off_tab + 128 * 8 + 128 * 4);   // [256] bias of this tile's columns
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -62,7 +72,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
       mbar_init(&bar_tempty[s], 4);
+      mbar_init(&bar_res[s], 1);
     }
+    tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmR);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_smem, tmem_cols);
@@ -78,6 +91,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int k_iters_total = p.taps * p.kblocks_per_tap;
   const int k_per_split = (k_iters_total + p.num_splits - 1) / p.num_splits;
 
+  // origin (coords 1..3) of M tile `mt` in the 4-D A / C / R tensor maps
+  auto tile_origin = [&](int mt, int bidx, int& c1, int& c2, int& c3) {
+    if (p.flags & GEMM_CONV) {
+      if (p.tile_imgs > 1) {
+        c1 = 0; c2 = 0; c3 = mt * p.tile_imgs;
+      } else {
+        const int img = mt / p.tiles_per_img;
+        const int t = mt - img * p.tiles_per_img;
+        const int ty = t / p.tiles_per_row;
+        c1 = (t - ty * p.tiles_per_row) * p.tile_cols; c2 = ty * p.tile_rows; c3 = img;
+      }
+    } else {
+      c1 = mt * 128; c2 = 0; c3 = bidx;
+    }
+  };
+
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
@@ -91,18 +120,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt = rem / p.num_m_tiles;
         const int mt = rem - nt * p.num_m_tiles;
         int c1, c2, c3;  // A box origin (before tap shift)
-        if (p.flags & GEMM_CONV) {
-          if (p.tile_imgs > 1) {
-            c1 = 0; c2 = 0; c3 = mt * p.tile_imgs;
-          } else {
-            const int img = mt / p.tiles_per_img;
-            const int t = mt - img * p.tiles_per_img;
-            const int ty = t / p.tiles_per_row;
-            c1 = (t - ty * p.tiles_per_row) * p.tile_cols; c2 = ty * p.tile_rows; c3 = img;
-          }
-        } else {
-          c1 = mt * 128; c2 = 0; c3 = bidx;
-        }
+        tile_origin(mt, bidx, c1, c2, c3);
         const int k_begin = split * k_per_split;
         const int k_end = min(k_begin + k_per_split, k_iters_total);
         for (int kit = k_begin; kit < k_end; ++kit) {
@@ -164,6 +182,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    uint32_t res_phase0 = 0, res_phase1 = 0;
     const bool conv = (p.flags & GEMM_CONV) != 0;
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -210,6 +229,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar_sync(1, 128);
       row_tab[r] = valid ? grow : -1;
       grp_tab[r] = group;
+      const bool tma_epi = p.epi_mode != 0 && p.num_splits == 1;
+      int oc1 = 0, oc2 = 0, oc3 = 0;
+      if (tma_epi) {
+        tile_origin(mt, bidx, oc1, oc2, oc3);
+        for (int i = r; i < p.block_n; i += 128) {
+          const int n = nt * p.block_n + i;
+          bias_s[i] = (p.bias && n < p.N_total) ? p.bias[n] : 0.f;
+        }
+        if (p.res_tma && r == 0) {
+          // prefetch the residual chunks 0 and 1 of this tile while the main loop is still running
+          const int nch = (p.block_n + 31) >> 5;
+          for (int c = 0; c < 2 && c < nch; ++c) {
+            const int b = buf ^ c;
+            mbar_arrive_expect_tx(&bar_res[b], p.a_bytes);
+            tma_load_4d(resbuf + b * 4096, &tmR, &bar_res[b], nt * p.block_n + c * 32, oc1, oc2, oc3);
+          }
+        }
+      }
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
@@ -300,6 +337,113 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
 
+      if (tma_epi) {
+        // ---- TMA-store epilogue: extras are applied in registers on the thread's own row, the finished chunk is staged in
+        //      the swizzle-128B layout and one elected thread hands it to the TMA unit (clipping = tile raggedness) ----
+        const bool f16out = p.epi_mode == 2;
+        const int cw = f16out ? 64 : 32;
+        const int nch = (p.block_n + cw - 1) / cw;
+        for (int c = 0; c < nch; ++c) {
+          const int j0 = c * cw;
+          const int n0 = nt * p.block_n + j0;
+          float* st = stage + buf * 4096;
+          uint32_t pk[32];   // the 128 staged bytes of this thread's row
+          if (!f16out) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + (uint32_t)j0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_s[j0 + i]);
+            if (rv) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (n0 + 4 * q + 3 < p.N_total) {
+                  const float4 e = *(const float4*)(rv + n0 + 4 * q);
+                  f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
+                }
+              }
+            }
+            if (p.res_tma) {
+              if (buf == 0) { mbar_wait(&bar_res[0], res_phase0); res_phase0 ^= 1; }
+              else { mbar_wait(&bar_res[1], res_phase1); res_phase1 ^= 1; }
+              const float* rb = resbuf + buf * 4096 + r * 32;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 e = *(const float4*)(rb + ((q ^ (r & 7)) << 2));
+                f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
+              }
+            } else if (rs) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (valid && n0 + 4 * q + 3 < p.N_total) {
+                  const float4 e = *(const float4*)(rs + n0 + 4 * q);
+                  f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = __float_as_uint(f[i]);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t v[32];
+              tmem_ld32(t_acc + (uint32_t)(j0 + 32 * h), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_s[j0 + 32 * h + i]);
+                const float a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_s[j0 + 32 * h + i + 1]);
+                __half2 hh = __floats2half2_rn(a0, a1);
+                pk[16 * h + (i >> 1)] = *(uint32_t*)&hh;
+              }
+            }
+          }
+          if (c == nch - 1) {   // all TMEM reads of this tile are done: recycle the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+          }
+          if (r == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has finished reading st
+          named_bar_sync(1, 128);
+          {
+            uint8_t* rowp = (uint8_t*)st + r * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *(uint4*)(rowp + ((q ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (r == 0) {
+            tma_store_4d(&tmC, st, n0, oc1, oc2, oc3);
+            tma_store_commit();
+            if (p.res_tma && c + 2 < nch) {
+              mbar_arrive_expect_tx(&bar_res[buf], p.a_bytes);
+              tma_load_4d(resbuf + buf * 4096, &tmR, &bar_res[buf], n0 + 64, oc1, oc2, oc3);
+            }
+          }
+          if (!f16out && p.out16) {
+            // secondary fp16 copy of the finished fp32 chunk: coalesced flat pass over the staged values
+            const int q = r & 7, rr0 = r >> 3;
+            const int n = n0 + (q << 2);
+            if (n < p.N_total) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int rr = rr0 + k * 16;
+                const long long gr = row_tab[rr];
+                if (gr < 0) continue;
+                const float4 o = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
+                __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+              }
+            }
+          }
+          buf ^= 1;
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (r == 0) TS(9);
+        continue;
+      }
       if (p.flags & GEMM_GEGLU) {
         // tile columns are [x (half) | gate (half)]; out16[:, nt*half + j] = (x + bx) * gelu(gate + bg)
         const int half_n = p.block_n >> 1;
@@ -453,6 +597,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  if (warp >= 2 && ((warp & 3) * 32 + lane) == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TS(10);
@@ -490,24 +635,32 @@ static int gemm_device_setup() {
   return 0;
 }
 
-// Tile-width heuristic: the widest legal UMMA N (multiple of 16, <= 256) that divides N when the M tiles alone fill the
-// machine; otherwise the narrowest divisor (>= 64) whose tile count still fits in one wave, so that small-M layers
-// (weight-bandwidth bound) spread their weight stream over all SMs before split-K has to.
-static int pick_block_n(int N, int base_tiles, int num_sms) {
-  static const int cands[] = {256, 224, 192, 160, 128, 112, 96, 80, 64};
-  int widest = 0;
-  for (int c : cands) if (N % c == 0) { widest = c; break; }
-  if (!widest) {
-    int n = ((N + 15) / 16) * 16;
-    return n <= 256 ? n : 128;   // ragged N: TMA zero-fills the weight tail
+// Tile-width heuristic. `gran` = column granularity the epilogue needs (32: fp32 TMA chunks, 64: fp16 TMA chunks, 16: flat).
+// N need not be a multiple of the tile: TMA zero-fills the weight tail on load and clips the tail on store.
+// If the M tiles alone fill the machine take the widest tile (fewest operand re-reads); otherwise narrow the tile so
+// that m_tiles x n_tiles approaches one wave - small-M layers are weight-stream bound and want every SM pulling weights.
+static int pick_block_n(int N, int base_tiles, int num_sms, int gran, bool must_divide) {
+  const int nmax = 256;
+  auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
+  int widest = round_up(N < nmax ? N : nmax, gran);
+  if (widest > nmax) widest = nmax / gran * gran;
+  if (N > nmax) {
+    // prefer an exact divisor near the top (no wasted MMA columns)
+    for (int c = nmax / gran * gran; c >= 128; c -= gran) if (N % c == 0) { widest = c; break; }
   }
-  if (base_tiles * (N / widest) >= num_sms) return widest;
-  int best = widest;
-  for (int c : cands) {
-    if (N % c) continue;
-    if (base_tiles * (N / c) <= num_sms) best = c; else break;
+  int bn = widest;
+  if (base_tiles * ((N + widest - 1) / widest) < num_sms) {
+    int want_tiles = num_sms / (base_tiles > 0 ? base_tiles : 1);
+    if (want_tiles < 1) want_tiles = 1;
+    bn = round_up((N + want_tiles - 1) / want_tiles, gran);
+    if (bn < 64) bn = 64;
+    if (bn > widest) bn = widest;
   }
-  return best;
+  if (must_divide) {
+    while (bn > gran && N % bn) bn -= gran;
+    if (N % bn) bn = gran;
+  }
+  return bn;
 }
 
 }  // namespace upgpt
@@ -597,8 +750,23 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   }
 
   // ---- tile shape / split-K ----
+  // epilogue flavour: TMA-store of finished chunks when the layout allows it (row-major output, 16-byte aligned rows)
+  const bool chw_out = (p.flags & GEMM_CHW) != 0;
+  const bool geglu = (p.flags & GEMM_GEGLU) != 0;
+  int epi_mode = 0;
+  if (!chw_out && !geglu) {
+    const int ld32 = a->ld32 > 0 ? a->ld32 : a->N;
+    const int ld16 = a->ld16 > 0 ? a->ld16 : a->N;
+    if (a->out32 && ld32 % 4 == 0 && ((uintptr_t)a->out32 & 15) == 0) epi_mode = 1;
+    else if (!a->out32 && a->out16 && ld16 % 8 == 0 && ((uintptr_t)a->out16 & 15) == 0 && !a->res32 && !a->rowvec) epi_mode = 2;
+  }
   int bn = a->block_n;
-  if (bn <= 0) bn = pick_block_n(a->N, p.num_m_tiles * p.batch, g_num_sms);
+  if (bn > 0 && ((epi_mode == 1 && bn % 32) || (epi_mode == 2 && bn % 64))) epi_mode = 0;   // explicit tile width wins
+  if (bn <= 0) {
+    const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
+    bn = pick_block_n(a->N, p.num_m_tiles * p.batch, g_num_sms, gran, /*must_divide=*/epi_mode == 0 && a->N > 16);
+    if (epi_mode == 0 && a->N <= 16) bn = 16;
+  }
   UPGPT_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "upgpt_gemm: block_n=%d illegal", bn);
   if (p.flags & GEMM_GEGLU) UPGPT_REQUIRE(bn % 32 == 0 && a->N % bn == 0 && a->out16, "upgpt_gemm: GEGLU needs block_n%%32==0, N%%block_n==0, out16");
   p.block_n = bn;
@@ -661,20 +829,51 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     UPGPT_REQUIRE(!p.out16 || (p.ld16 % 8 == 0 && ((uintptr_t)p.out16 & 15) == 0), "upgpt_gemm: out16 must be 16-byte aligned with ld%%8==0");
   }
 
+  // ---- epilogue maps (TMA store of C, TMA prefetch of the residual) ----
+  p.epi_mode = (splits > 1) ? 0 : epi_mode;
+  p.res_tma = 0;
+  CUtensorMap tmC = tmA, tmR = tmA;   // placeholders when unused (never dereferenced)
+  if (p.epi_mode) {
+    const int eb = p.epi_mode == 1 ? 4 : 2;
+    const uint32_t cw = p.epi_mode == 1 ? 32 : 64;
+    const void* cbase = p.epi_mode == 1 ? (const void*)p.out32 : (const void*)p.out16;
+    const uint64_t ldc = p.epi_mode == 1 ? (uint64_t)p.ld32 : (uint64_t)p.ld16;
+    uint64_t dims[4], strides[3];
+    uint32_t box[4];
+    if (conv) {
+      dims[0] = a->N; dims[1] = a->W; dims[2] = a->H; dims[3] = a->n_imgs;
+      strides[0] = ldc * eb; strides[1] = ldc * eb * a->W; strides[2] = ldc * eb * a->W * a->H;
+      box[0] = cw; box[1] = p.tile_imgs > 1 ? a->W : p.tile_cols; box[2] = p.tile_imgs > 1 ? a->H : p.tile_rows;
+      box[3] = p.tile_imgs > 1 ? p.tile_imgs : 1;
+    } else {
+      dims[0] = a->N; dims[1] = a->M; dims[2] = 1; dims[3] = p.batch;
+      strides[0] = ldc * eb; strides[1] = ldc * eb * a->M; strides[2] = ldc * eb * a->M;
+      box[0] = cw; box[1] = 128; box[2] = 1; box[3] = 1;
+    }
+    if (make_tmap(&tmC, eb, cbase, 4, dims, strides, box, true)) return -3;
+    if (p.epi_mode == 1 && p.res32 && p.ldres % 4 == 0 && ((uintptr_t)p.res32 & 15) == 0) {
+      const uint64_t ldr = p.ldres;
+      if (conv) { strides[0] = ldr * 4; strides[1] = ldr * 4 * a->W; strides[2] = ldr * 4 * a->W * a->H; }
+      else { strides[0] = ldr * 4; strides[1] = ldr * 4 * a->M; strides[2] = ldr * 4 * a->M; }
+      if (make_tmap(&tmR, 4, p.res32, 4, dims, strides, box, true)) return -3;
+      p.res_tma = 1;
+    }
+  }
+
   // ---- pipeline depth from the smem budget ----
+  const size_t epi_bytes = 2 * 16384 + (p.res_tma ? 2 * 16384 : 0) + 128 * 8 + 128 * 4 + 256 * 4 + 1024 /*alignment slack*/;
   const size_t stage_bytes = (size_t)kABytes + (size_t)bn * 128;
-  constexpr size_t kEpiStageBytes = 2 * 128 * 32 * sizeof(float) + 128 + 128 * 8 + 128 * 4;
-  int stages = (int)(((size_t)g_smem_optin - 1024 - 256 - kEpiStageBytes) / stage_bytes);
+  int stages = (int)(((size_t)g_smem_optin - 1024 - 256 - epi_bytes) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages > k_iters / splits + 1) stages = k_iters / splits + 1;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 4) * 8 + 16 + kEpiStageBytes;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * 8 + 16 + epi_bytes;
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, p);
+  tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

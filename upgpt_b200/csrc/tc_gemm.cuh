@@ -49,6 +49,9 @@ struct GemmParams {
   float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
   int ws_rows, ws_ld;
   int* counters;        // one arrival counter per (batch, n tile, m tile); zero between launches
+  // ---- TMA epilogue ----
+  int epi_mode;         // 0 flat stores; 1 fp32 tile chunks [rows][32] by TMA store; 2 fp16 chunks [rows][64] by TMA store
+  int res_tma;          // residual tile chunks prefetched by TMA load (epi_mode 1)
   long long* debug_ts;  // optional [gridDim.x][16] globaltimer stamps (bring-up instrumentation), null in production
 };
 
