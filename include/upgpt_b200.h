@@ -81,6 +81,9 @@ int upgpt_debug_set_gemm_timestamps(long long* buf);
 /* stats[b][g] = {sum, sum of squares} (double) over group g of image b of the channel-concat [x1 | x2] (x2 may be NULL). */
 int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
                           void* stream);
+/* same, and also scale_shift[b] = {scale[C], shift[C]} with y = x*scale + shift == GroupNorm(x; gamma, beta, eps) */
+int upgpt_groupnorm_affine(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
+                           const float* gamma, const float* beta, float eps, float* scale_shift, void* stream);
 typedef struct upgpt_prep_args {
   const float* x1; int C1;   /* fp32 NHWC [B][H][W][C1] */
   const float* x2; int C2;   /* optional second tensor, concatenated on channels */
@@ -93,6 +96,7 @@ typedef struct upgpt_prep_args {
   int split3;                /* emit error-compensated operand planes [hi | lo | hi] (3C channels) */
   void* out; int ldo;        /* fp16 output, ldo elements per pixel (0 = C or 3C) */
   void* raw; int ldraw;      /* optional un-normalised fp16 copy (layout 0) */
+  const float* scale_shift;  /* optional [B][2][C] affine from upgpt_groupnorm_affine (then stats/gamma/beta/eps are ignored) */
 } upgpt_prep_args;
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
 int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,

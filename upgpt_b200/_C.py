@@ -74,7 +74,7 @@ class PrepArgs(C.Structure):
         ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
         ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("silu", C.c_int), ("layout", C.c_int), ("split3", C.c_int),
-        ("out", C.c_void_p), ("ldo", C.c_int), ("raw", C.c_void_p), ("ldraw", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_int), ("raw", C.c_void_p), ("ldraw", C.c_int), ("scale_shift", C.c_void_p),
     ]
 
 
@@ -91,6 +91,7 @@ _PROTOS = {
     "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
     "upgpt_debug_set_gemm_timestamps": [_vp],
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
+    "upgpt_groupnorm_affine": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp],
     "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
     "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_softmax_rows": [_vp, _i, _ll, _i, _f, _vp, _i, _vp],

@@ -28,14 +28,21 @@ struct AttnParams {
   int ldo;
 };
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;     // warp0 TMA, warp1 MMA, warps2-9 softmax (two threads per query row)
 static constexpr int kTileBytes = 128 * 64 * 2;  // one [128][64] fp16 chunk
 
-__global__ void __launch_bounds__(kAttnThreads)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
   const int dch = p.dpad >> 6;                       // 64-wide d chunks (1 or 2)
   const uint32_t qk_bytes = (uint32_t)dch * kTileBytes;      // Q tile or K tile
   const uint32_t vt_chunk = (uint32_t)p.dpad * 128u;          // V^T chunk: [dpad rows][64 keys]
@@ -43,15 +50,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + qk_bytes;                        // 2 stages
   uint8_t* sV = sK + 2 * qk_bytes;                    // 2 stages
-  uint8_t* sP = sV + 2 * vt_bytes;                    // [2 chunks][128][64]
-  uint64_t* bars = (uint64_t*)(sP + 2 * kTileBytes);
+  uint8_t* sP = sV + 2 * vt_bytes;                    // [2 key chunks][128][64] fp16
+  const uint32_t off_bar = 3 * qk_bytes + 2 * vt_bytes + 2 * kTileBytes;
+  uint64_t* bars = (uint64_t*)(smem + off_bar);
   uint64_t* bar_q = bars;
   uint64_t* bar_kv_full = bars + 1;    // [2]
   uint64_t* bar_kv_empty = bars + 3;   // [2]
-  uint64_t* bar_s = bars + 5;
-  uint64_t* bar_p = bars + 6;
-  uint64_t* bar_o = bars + 7;
-  uint32_t* tmem_base_smem = (uint32_t*)(bars + 8);
+  uint64_t* bar_s = bars + 5;          // [2] S buffer b written by the tensor core
+  uint64_t* bar_sfree = bars + 7;      // [2] S buffer b consumed by all softmax warps
+  uint64_t* bar_p = bars + 9;          // P tile staged (and O rescaled)
+  uint64_t* bar_o = bars + 10;         // O += P V finished
+  uint32_t* tmem_base_smem = (uint32_t*)(bars + 11);
+  float* xch = (float*)(smem + off_bar + 128);   // [2 tiles parity][2 halves][128 rows] row-max exchange, then row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.num_q_tiles;
@@ -63,19 +73,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1);
+      mbar_init(&bar_s[s], 1); mbar_init(&bar_sfree[s], 8);
+    }
+    mbar_init(bar_p, 8);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_smem, 256);
+  if (warp == 1) tmem_alloc(tmem_base_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  const uint32_t tS = tmem_base;          // 128 columns
-  const uint32_t tO = tmem_base + 128;    // dpad columns
+  const uint32_t tO = tmem_base + 256;    // dpad columns; S buffers at columns [0,128) and [128,256)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -95,147 +106,148 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, 128);
       const uint32_t idesc_o = make_idesc_f16(128, (uint32_t)p.dpad);
+      auto issue_pv = [&](int jj) {   // O (+)= P(jj) V(jj)
+        const int sp = jj & 1;
+        for (int c = 0; c < 2; ++c) {
+          const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
+          const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (jj > 0 || c > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(&bar_kv_empty[sp]);
+        tc_commit(bar_o);
+      };
       mbar_wait(bar_q, 0);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         mbar_wait(&bar_kv_full[s], (j >> 1) & 1);
-        if (j > 0) mbar_wait(bar_p, (j - 1) & 1);   // softmax finished reading S(j-1) and wrote P(j-1)
+        mbar_wait(&bar_sfree[s], ((j >> 1) & 1) ^ 1);     // softmax is done with what S buffer s held two tiles ago
         tc_fence_after();
-        if (j > 0) {
-          // O += P(j-1) V(j-1)
-          const int sp = (j - 1) & 1;
-          for (int c = 0; c < 2; ++c) {
-            const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
-            const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (j > 1 || c > 0 || k > 0) ? 1u : 0u);
-          }
-          tc_commit(&bar_kv_empty[sp]);
-          tc_commit(bar_o);
-        }
-        // S(j) = Q K(j)^T
+        // S(j) = Q K(j)^T into S buffer s -- issued before waiting for P(j-1), so it overlaps softmax(j-1)
+        const uint32_t tS = tmem_base + (uint32_t)(s * 128);
         for (int c = 0; c < dch; ++c) {
           const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + c * kTileBytes));
           const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + s * qk_bytes + c * kTileBytes));
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tS, ad + 2 * k, bd + 2 * k, idesc_s, (c > 0 || k > 0) ? 1u : 0u);
         }
-        tc_commit(bar_s);
-      }
-      // tail: O += P(last) V(last)
-      {
-        const int j = n_kv;
-        mbar_wait(bar_p, (j - 1) & 1);
-        tc_fence_after();
-        const int sp = (j - 1) & 1;
-        for (int c = 0; c < 2; ++c) {
-          const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
-          const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (j > 1 || c > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&bar_s[s]);
+        if (j > 0) {
+          mbar_wait(bar_p, (j - 1) & 1);
+          tc_fence_after();
+          issue_pv(j - 1);
         }
-        tc_commit(bar_o);
       }
+      mbar_wait(bar_p, (n_kv - 1) & 1);
+      tc_fence_after();
+      issue_pv(n_kv - 1);
     }
   } else {
-    // ================================ softmax / epilogue ================================
-    const int quad = warp & 3;
+    // ================================ softmax / epilogue: 2 threads per query row ================================
+    const int we = warp - 2;
+    const int hf = we >> 2;                 // which 64-key half of each tile / which half of the O columns
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may touch
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY, l_part = 0.f;
     const float c2 = p.scale_log2e;
+    const int ocols = p.dpad >> 1;          // O columns owned by this thread
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(bar_s, j & 1);
+      const int sb = j & 1;
+      mbar_wait(&bar_s[sb], (j >> 1) & 1);
       tc_fence_after();
-      const int kbase = j * 128;
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + cc * 32, v);
+      uint32_t v[64];
+      {
+        const uint32_t ts = tmem_base + (uint32_t)(sb * 128 + hf * 64) + lane_off;
+        uint32_t a[32], bb[32];
+        tmem_ld32(ts, a);
+        tmem_ld32(ts + 32, bb);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = (kbase + cc * 32 + i < p.Nk) ? __uint_as_float(v[i]) : -INFINITY;
-          m_tile = fmaxf(m_tile, sv);
-        }
+        for (int i = 0; i < 32; ++i) { v[i] = a[i]; v[32 + i] = bb[i]; }
       }
-      const float m_new = fmaxf(m_run, m_tile);
-      const float alpha = exp2f((m_run - m_new) * c2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_sfree[sb]);
+      const int kbase = j * 128 + hf * 64;
+      float m_loc = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const float sv = (kbase + i < p.Nk) ? __uint_as_float(v[i]) : -INFINITY;
+        v[i] = __float_as_uint(sv);
+        m_loc = fmaxf(m_loc, sv);
+      }
+      float* mx = xch + (j & 1) * 256;
+      mx[hf * 128 + r] = m_loc;
+      named_bar_sync(2, 256);
+      const float m_new = fmaxf(m_run, fmaxf(mx[r], mx[128 + r]));
+      const float alpha = ex2_approx((m_run - m_new) * c2);
       const float mc = m_new * c2;
+      float l_tile = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c2, -mc));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c2, -mc));
+        l_tile += p0 + p1;
+        __half2 hh = __floats2half2_rn(p0, p1);
+        pk[i >> 1] = *(uint32_t*)&hh;
+      }
+      l_part = l_part * alpha + l_tile;
+      m_run = m_new;
       // P smem and the O accumulator are busy until PV(j-1) has completed
       if (j > 0) {
         mbar_wait(bar_o, (j - 1) & 1);
         tc_fence_after();
       }
-      // pass 2: p = exp2(s*c - m*c), row sum, fp16 P into swizzled smem
-      float l_tile = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + cc * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      {
+        uint8_t* rowp = sP + hf * kTileBytes + r * 128;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int key = kbase + cc * 32 + i;
-          float p0 = (key < p.Nk) ? exp2f(fmaf(__uint_as_float(v[i]), c2, -mc)) : 0.f;
-          float p1 = (key + 1 < p.Nk) ? exp2f(fmaf(__uint_as_float(v[i + 1]), c2, -mc)) : 0.f;
-          l_tile += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[i >> 1] = *(uint32_t*)&hh;
-        }
-        // 32 keys = 4 x 16-byte units; chunk = cc / 2, unit index within the 128-byte row = (cc & 1) * 4 + u
-        uint8_t* rowp = sP + (cc >> 1) * kTileBytes + r * 128;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int unit = ((cc & 1) * 4 + u) ^ (r & 7);
-          *(uint4*)(rowp + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
+        for (int u = 0; u < 8; ++u)
+          *(uint4*)(rowp + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
-      l_run = l_run * alpha + l_tile;
-      m_run = m_new;
-      // rescale the O accumulator (skip on the first tile: PV(0) overwrites)
-      if (j > 0) {
+      // rescale this thread's half of the O row only when some row of the warp moved its running max
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
-        for (int cc = 0; cc < p.dpad / 32; ++cc) {
-          uint32_t v[32];
-          tmem_ld32(tO + lane_off + cc * 32, v);
+        for (int cc = 0; cc < ocols; cc += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_off + (uint32_t)(hf * ocols + cc), o);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st32(tO + lane_off + cc * 32, v);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + lane_off + (uint32_t)(hf * ocols + cc), o);
         }
         tmem_st_wait();
       }
       fence_proxy_async_smem();   // P (generic-proxy stores) -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(bar_p);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p);
     }
     // ---- epilogue: O / l -> fp16 ----
+    float* lx = xch + (n_kv & 1) * 256;
+    lx[hf * 128 + r] = l_part;
+    named_bar_sync(2, 256);
+    const float inv_l = 1.f / (lx[r] + lx[128 + r]);
     mbar_wait(bar_o, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.f / l_run;
     const int q = q0 + r;
-    __half* orow = p.out + ((size_t)b * p.Nq + q) * p.ldo + h * p.dpad;
+    __half* orow = p.out + ((size_t)b * p.Nq + q) * p.ldo + h * p.dpad + hf * ocols;
 #pragma unroll 1
-    for (int cc = 0; cc < p.dpad / 32; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tO + lane_off + cc * 32, v);
+    for (int cc = 0; cc < ocols; cc += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_off + (uint32_t)(hf * ocols + cc), o);
       tmem_ld_wait();
       if (q < p.Nq) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          __half2 hh = __floats2half2_rn(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+          __half2 hh = __floats2half2_rn(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
           pk[i >> 1] = *(uint32_t*)&hh;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          *(uint4*)(orow + cc * 32 + u * 8) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          *(uint4*)(orow + cc + u * 8) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
       }
     }
   }
@@ -244,7 +256,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -261,7 +273,7 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   UPGPT_REQUIRE(a->Nq > 0 && a->Nk > 0 && a->H > 0 && a->B > 0, "attention: bad sizes");
   UPGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0, "attention: ld must be multiples of 8");
   if (!g_attn_attr) {
-    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     g_attn_attr = true;
   }
   CUtensorMap tmQ, tmK, tmVt;
@@ -291,7 +303,7 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = (__half*)a->out; p.ldo = a->ldo;
   const int dch = a->dpad / 64;
-  const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128;
+  const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);
   attention_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmVt, p);
   count_launch();

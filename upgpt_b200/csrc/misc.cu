@@ -97,14 +97,23 @@ linear_small_m_kernel(const float* __restrict__ x, int ldx, int rows, const floa
     for (int r = 0; r < RB; ++r) acc[r] = 0.f;
     if (VEC) {
       const float4* wr = (const float4*)wrow;
-      for (int i = lane; i < (K >> 2); i += 32) {
-        const float4 wv = __ldg(wr + i);
+      const int K4 = K >> 2;
+      // the weight row is streamed once from HBM: keep 4 x 512 B of it in flight per warp
+      for (int i0 = lane; i0 < K4; i0 += 128) {
+        float4 wv[4];
 #pragma unroll
-        for (int r = 0; r < RB; ++r) {
-          if (r0 + r < rows) {
-            float4 xv = *(const float4*)(x + (size_t)(r0 + r) * ldx + 4 * i);
-            if (silu_in) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
-            acc[r] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        for (int u = 0; u < 4; ++u) wv[u] = (i0 + 32 * u < K4) ? __ldg(wr + i0 + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 32 * u;
+          if (i >= K4) break;
+#pragma unroll
+          for (int r = 0; r < RB; ++r) {
+            if (r0 + r < rows) {
+              float4 xv = *(const float4*)(x + (size_t)(r0 + r) * ldx + 4 * i);
+              if (silu_in) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+              acc[r] += xv.x * wv[u].x + xv.y * wv[u].y + xv.z * wv[u].z + xv.w * wv[u].w;
+            }
           }
         }
       }

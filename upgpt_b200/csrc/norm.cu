@@ -22,9 +22,11 @@ namespace upgpt {
 template <int MAXC_PER_THREAD>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW, int chunk,
-                int groups, double* __restrict__ stats, double* __restrict__ partials, int* __restrict__ counters) {
+                int groups, double* __restrict__ stats, double* __restrict__ partials, int* __restrict__ counters,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
   extern __shared__ float shc[];  // per-channel {sum, sumsq}: [2][C]
   __shared__ int s_last;
+  __shared__ double s_red[4][64];
   const int C = C1 + C2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
@@ -34,7 +36,26 @@ gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ 
   float s[MAXC_PER_THREAD], q[MAXC_PER_THREAD];
 #pragma unroll
   for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  for (int p = p0; p < p1; ++p) {
+  // 4 pixels per trip: 4 x MAXC independent loads in flight per thread
+  int p = p0;
+  for (; p + 4 <= p1; p += 4) {
+    float v[4][MAXC_PER_THREAD];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t row = (size_t)b * HW + p + u;
+#pragma unroll
+      for (int j = 0; j < MAXC_PER_THREAD; ++j) {
+        const int c = threadIdx.x + j * 256;
+        v[u][j] = 0.f;
+        if (c < C) v[u][j] = c < C1 ? __ldg(x1 + row * C1 + c) : __ldg(x2 + row * C2 + (c - C1));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] += v[u][j]; q[j] = fmaf(v[u][j], v[u][j], q[j]); }
+  }
+  for (; p < p1; ++p) {
     const size_t row = (size_t)b * HW + p;
 #pragma unroll
     for (int j = 0; j < MAXC_PER_THREAD; ++j) {
@@ -62,30 +83,58 @@ gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ 
     for (int k = 0; k < cpg; ++k) acc += (double)src[k];
     if (nchunks == 1) stats[(size_t)b * nout + i] = acc; else __stcg(my + i, acc);
   }
-  if (nchunks == 1) return;
-  // deterministic cross-chunk reduction: the last chunk to arrive sums all partials of image b in chunk order
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int prev = atomicAdd(&counters[b], 1);
-    s_last = prev == nchunks - 1;
-    if (s_last) counters[b] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const double* base = partials + (size_t)b * nchunks * nout;
-  for (int i = threadIdx.x; i < nout; i += blockDim.x) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= nchunks; k += 4) {
-      a0 += __ldcg(base + (size_t)(k + 0) * nout + i);
-      a1 += __ldcg(base + (size_t)(k + 1) * nout + i);
-      a2 += __ldcg(base + (size_t)(k + 2) * nout + i);
-      a3 += __ldcg(base + (size_t)(k + 3) * nout + i);
+  if (nchunks > 1) {
+    // deterministic cross-chunk reduction: the last chunk to arrive sums all partials of image b in a fixed order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int prev = atomicAdd(&counters[b], 1);
+      s_last = prev == nchunks - 1;
+      if (s_last) counters[b] = 0;
     }
-    for (; k < nchunks; ++k) a0 += __ldcg(base + (size_t)k * nout + i);
-    stats[(size_t)b * nout + i] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const double* base = partials + (size_t)b * nchunks * nout;
+    // 4 threads per output, each over an interleaved quarter of the chunks (4 loads in flight), combined in fixed order
+    if (nout <= 64) {
+      const int i = threadIdx.x & 63, part = threadIdx.x >> 6;
+      double a0 = 0.0, a1 = 0.0;
+      if (i < nout) {
+        int k = part;
+        for (; k + 4 < nchunks; k += 8) {
+          a0 += __ldcg(base + (size_t)k * nout + i);
+          a1 += __ldcg(base + (size_t)(k + 4) * nout + i);
+        }
+        if (k < nchunks) a0 += __ldcg(base + (size_t)k * nout + i);
+      }
+      s_red[part][i] = a0 + a1;
+      __syncthreads();
+      if (threadIdx.x < nout) stats[(size_t)b * nout + threadIdx.x] = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+    } else {
+      for (int i = threadIdx.x; i < nout; i += blockDim.x) {
+        double a0 = 0.0;
+        for (int k = 0; k < nchunks; ++k) a0 += __ldcg(base + (size_t)k * nout + i);
+        stats[(size_t)b * nout + i] = a0;
+      }
+    }
+  }
+  if (!scale_shift) return;
+  // per-(image, channel) affine of the normalisation, so the apply kernel is a pure fma: y = x * scale + shift
+  __syncthreads();
+  const double inv_n = 1.0 / ((double)cpg * HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double su = stats[(size_t)b * nout + 2 * g];
+    const double sq = stats[(size_t)b * nout + 2 * g + 1];
+    const double mean = su * inv_n;
+    double var = sq * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float be = beta ? beta[c] : 0.f;
+    scale_shift[(size_t)b * 2 * C + c] = rstd * ga;
+    scale_shift[(size_t)b * 2 * C + C + c] = be - (float)mean * rstd * ga;
   }
 }
 
@@ -100,6 +149,7 @@ struct PrepParams {
   int chunk;
   int groups;
   const double* stats;     // null -> no normalisation
+  const float* scale_shift;   // optional [B][2][C] precomputed affine (from gn_stats); replaces stats/gamma/beta
   const float* gamma; const float* beta;
   float eps;
   int silu;
@@ -118,7 +168,11 @@ prep_kernel(const PrepParams p) {
   float* scale = shf;
   float* shift = shf + C;
   const int b = blockIdx.y;
-  if (p.stats) {
+  if (p.scale_shift) {
+    const float* ss = p.scale_shift + (size_t)b * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) shf[c] = ss[c];
+    __syncthreads();
+  } else if (p.stats) {
     const int cpg = C / p.groups;
     const double inv_n = 1.0 / ((double)cpg * HW);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -150,7 +204,7 @@ prep_kernel(const PrepParams p) {
       uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
       *(uint2*)(p.raw + row * p.ldraw + c) = pk;
     }
-    if (p.stats) {
+    if (p.stats || p.scale_shift) {
       v.x = fmaf(v.x, scale[c], shift[c]);
       v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
       v.z = fmaf(v.z, scale[c + 2], shift[c + 2]);
@@ -288,9 +342,8 @@ static int* g_gn_counters = nullptr;
 static constexpr size_t kGnPartialDoubles = (size_t)1 << 21;   // 16 MB
 static constexpr int kGnMaxBatch = 4096;
 
-extern "C" int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups,
-                                     double* stats, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
+                                const float* gamma, const float* beta, float eps, float* scale_shift, cudaStream_t stream) {
   const int C = C1 + C2;
   UPGPT_REQUIRE(x1 && stats && C > 0 && C % groups == 0, "groupnorm_stats: bad args (C=%d groups=%d)", C, groups);
   UPGPT_REQUIRE(C <= 2048 && B <= kGnMaxBatch, "groupnorm_stats: C=%d > 2048 or B=%d too large", C, B);
@@ -299,18 +352,36 @@ extern "C" int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, i
     UPGPT_CHECK_CUDA(cudaMalloc(&g_gn_counters, kGnMaxBatch * sizeof(int)));
     UPGPT_CHECK_CUDA(cudaMemset(g_gn_counters, 0, kGnMaxBatch * sizeof(int)));
   }
-  int chunk = pick_chunk(HW, B);
-  if ((HW + chunk - 1) / chunk > 256) chunk = (HW + 255) / 256;
+  // ~2 CTAs per SM in total, at least 8 pixels per CTA, at most 256 chunks per image (cross-chunk reduction cost)
+  int per_img = (2 * 148 + B - 1) / B;
+  if (per_img > 256) per_img = 256;
+  int chunk = (HW + per_img - 1) / per_img;
+  if (chunk < 8) chunk = 8;
+  if (chunk > HW) chunk = HW;
   while ((size_t)B * ((HW + chunk - 1) / chunk) * 2 * groups > kGnPartialDoubles) chunk *= 2;
   dim3 grid((HW + chunk - 1) / chunk, B);
   const size_t sm = sizeof(float) * 2 * C;
-  if (C <= 256) gn_stats_kernel<1><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
-  else if (C <= 512) gn_stats_kernel<2><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
-  else if (C <= 1024) gn_stats_kernel<4><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
-  else gn_stats_kernel<8><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, g_gn_counters);
+#define UPGPT_GN_LAUNCH(MC) gn_stats_kernel<MC><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, \
+                                                                         g_gn_counters, gamma, beta, eps, scale_shift)
+  if (C <= 256) UPGPT_GN_LAUNCH(1);
+  else if (C <= 512) UPGPT_GN_LAUNCH(2);
+  else if (C <= 1024) UPGPT_GN_LAUNCH(4);
+  else UPGPT_GN_LAUNCH(8);
+#undef UPGPT_GN_LAUNCH
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int upgpt_groupnorm_stats(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups,
+                                     double* stats, void* stream_) {
+  return groupnorm_stats_impl(x1, C1, x2, C2, B, HW, groups, stats, nullptr, nullptr, 0.f, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int upgpt_groupnorm_affine(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
+                                      const float* gamma, const float* beta, float eps, float* scale_shift, void* stream_) {
+  UPGPT_REQUIRE(scale_shift, "groupnorm_affine: scale_shift is null");
+  return groupnorm_stats_impl(x1, C1, x2, C2, B, HW, groups, stats, gamma, beta, eps, scale_shift, (cudaStream_t)stream_);
 }
 
 extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
@@ -318,11 +389,12 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   UPGPT_REQUIRE(a && a->x1 && a->out, "prep_operand: null");
   const int C = a->C1 + a->C2;
   UPGPT_REQUIRE(a->C1 % 4 == 0 && a->C2 % 4 == 0 && C > 0, "prep_operand: channels must be multiples of 4");
-  UPGPT_REQUIRE(!a->stats || (a->groups > 0 && C % a->groups == 0), "prep_operand: bad groups");
+  UPGPT_REQUIRE(!a->stats || a->scale_shift || (a->groups > 0 && C % a->groups == 0), "prep_operand: bad groups");
   UPGPT_REQUIRE(a->layout != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "prep_operand: stride-2 phases need even H, W");
   UPGPT_REQUIRE(!a->raw || a->layout == 0, "prep_operand: raw copy only with layout 0");
   PrepParams p{};
   p.x1 = a->x1; p.C1 = a->C1; p.x2 = a->x2; p.C2 = a->C2; p.H = a->H; p.W = a->W; p.B = a->B;
+  p.scale_shift = a->scale_shift;
   p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
   p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 3 * C : C);

@@ -138,15 +138,17 @@ class EngineBase:
         return 0 if t is None else t.data_ptr()
 
     # ---- emitters ----
-    def e_gn_stats(self, x1, C1, x2, C2, B, HW, stats):
+    def e_gn_affine(self, x1, C1, x2, C2, B, HW, stats, gamma, beta, eps, ss):
         if self._sizing:
             return
-        self.prog.add(self.L.upgpt_groupnorm_stats, self.p(x1), C1, self.p(x2), C2, B, HW, 32, self.p(stats))
+        self.prog.add(self.L.upgpt_groupnorm_affine, self.p(x1), C1, self.p(x2), C2, B, HW, 32, self.p(stats), self.p(gamma), self.p(beta),
+                      eps, self.p(ss))
 
-    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False):
+    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, ss=None):
         if self._sizing:
             return
         a = _C.PrepArgs()
+        a.scale_shift = self.p(ss)
         a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
         a.B, a.H, a.W, a.groups = B, H, W, 32
         a.stats, a.gamma, a.beta, a.eps = self.p(stats), self.p(gamma), self.p(beta), eps
@@ -183,9 +185,9 @@ class EngineBase:
         op = self.scratch("op16", B * H * W * mult * Cc * (3 if split3 else 1), torch.float16)
         raw = self.scratch("raw16", B * H * W * Cc, torch.float16) if want_raw else None
         if gname is not None:
-            self.e_gn_stats(x1, C1, x2, C2, B, H * W, stats)
-            self.e_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu,
-                        layout, op, raw, split3)
+            ss = self.scratch("gn_ss", B * 2 * Cc, torch.float32)
+            self.e_gn_affine(x1, C1, x2, C2, B, H * W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, ss)
+            self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, eps, silu, layout, op, raw, split3, ss=ss)
         else:
             self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3)
         return op, raw
@@ -385,9 +387,11 @@ class UNetEngine(EngineBase):
             P.add(L_.upgpt_linear_small_m, temb.data_ptr(), self.mc, B, self.w["time_embed.0.weight"].data_ptr(),
                   self.w["time_embed.0.bias"].data_ptr(), 4 * self.mc, self.mc, 0, 1, emb1.data_ptr(), 4 * self.mc)
             P.add(L_.upgpt_linear_small_m, emb1.data_ptr(), 4 * self.mc, B, self.w["time_embed.2.weight"].data_ptr(),
-                  self.w["time_embed.2.bias"].data_ptr(), 4 * self.mc, 4 * self.mc, 0, 0, emb.data_ptr(), 4 * self.mc)
+                  self.w["time_embed.2.bias"].data_ptr(), 4 * self.mc, 4 * self.mc, 0, 1, emb.data_ptr(), 4 * self.mc)
+            # `emb` only ever feeds the ResBlocks' emb_layers = Linear(SiLU(emb)) (openaimodel.py:218-224): the SiLU is applied once
+            # at the output of time_embed (silu_out above) instead of once per output feature of the 22 projections
             P.add(L_.upgpt_linear_small_m, emb.data_ptr(), 4 * self.mc, B, self.w["emb_all.weight"].data_ptr(),
-                  self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 1, 0, emb_all.data_ptr(), self.emb_total)
+                  self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 0, 0, emb_all.data_ptr(), self.emb_total)
         # ---- input blocks ----
         hs = []
         h = self.buf("h_in0", (B, H * W, self.mc))
