@@ -41,3 +41,9 @@ M2 = 8192
 a2 = (torch.randn(M2, 224, device=dev) * 0.5).half(); w2 = (torch.randn(224, 224, device=dev) * 0.02).half(); out2 = torch.empty(M2, 224, device=dev); r2 = torch.randn(M2, 224, device=dev)
 for cold in (False, True):
     run("gemm M8192 N224 K224 +res", lambda: ops.gemm(a=a2, w=w2, mode=0, M=M2, N=224, K=224, out32=out2, res32=r2), cold)
+
+for (B_, H_, C_) in ((8, 4, 896), (8, 8, 896), (8, 16, 448)):
+    x4 = (torch.randn(B_, H_, H_, C_, device=dev) * 0.5).half(); w4 = (torch.randn(C_, 9, C_, device=dev) * 0.02).half()
+    o4 = torch.empty(B_ * H_ * H_, C_, device=dev); b4 = torch.randn(C_, device=dev); e4 = torch.randn(B_, C_, device=dev)
+    for cold in (False, True):
+        run(f"conv {C_}->{C_} @{H_}x{H_} B8 auto", lambda: ops.gemm(a=x4, w=w4, mode=_C.GEMM_CONV3X3, N=C_, K=C_, n_imgs=B_, H=H_, W=H_, out32=o4, bias=b4, rowvec=e4), cold)

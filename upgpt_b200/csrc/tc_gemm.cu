@@ -338,6 +338,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
 
       if (tma_epi) {
+        named_bar_sync(1, 128);   // bias_s of this tile is complete before any thread reads it
         // ---- TMA-store epilogue: extras are applied in registers on the thread's own row, the finished chunk is staged in
         //      the swizzle-128B layout and one elected thread hands it to the TMA unit (clipping = tile raggedness) ----
         const bool f16out = p.epi_mode == 2;
@@ -527,69 +528,89 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (r == 0) TS(9);
 
       if (splitk) {
-        // ---- deterministic split-K: the last split to arrive reduces the partial tiles in fixed split order ----
+        // ---- deterministic split-K reduction (fixed split order => bit-reproducible) ----
+        const int tile_id = bidx * tiles_mn + nt * p.num_m_tiles + mt;
+        int* ctr = p.counters + 2 * tile_id;
+        const int n4 = p.block_n >> 2;
+        const size_t stride4 = ws_split_stride >> 2;
+        // sums element (row rr, float4 column q4) over all splits, applies the extras and stores
+        auto reduce_store = [&](int rr, int q4) {
+          const long long gr = row_tab[rr];
+          const int n = nt * p.block_n + (q4 << 2);
+          if (gr < 0 || n >= p.N_total) return;
+          const float4* src = (const float4*)(p.ws + (size_t)gr * p.ws_ld + n);
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          int sp = 0;
+          for (; sp + 8 <= p.num_splits; sp += 8) {      // 8 independent L2 loads in flight, summed in split order
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (size_t)(sp + u) * stride4);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
+          }
+          {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (sp + u < p.num_splits) ? __ldcg(src + (size_t)(sp + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
+          }
+          if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
+          if (p.rowvec) {
+            const float4 b4 = *(const float4*)(p.rowvec + (size_t)grp_tab[rr] * p.ld_rowvec + n);
+            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          }
+          if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr * p.ldres + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
+          if (p.out32) *(float4*)(p.out32 + (size_t)gr * p.ld32 + n) = a;
+          if (p.out16) {
+            __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+            *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+          }
+        };
         __threadfence();
         named_bar_sync(1, 128);
-        if (r == 0) {
-          int* ctr = p.counters + (bidx * tiles_mn + nt * p.num_m_tiles + mt);
-          const int prev = atomicAdd(ctr, 1);
-          const int last = prev == p.num_splits - 1;
-          if (last) *ctr = 0;   // self-reset: the counters are zero again when the kernel ends
-          *split_flag = (uint32_t)last;
-        }
-        named_bar_sync(1, 128);
-        const bool is_last = *split_flag != 0;
-        named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
-        if (is_last) {
+        if (p.coop_reduce) {
+          // every split of this tile is resident (cooperative launch, one tile per CTA): all of them wait for the last
+          // partial and then each reduces its own 1/num_splits slice of the tile -> the reduction is parallel as well
+          if (r == 0) {
+            atomicAdd(ctr, 1);
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+              if (seen < p.num_splits) __nanosleep(40);
+            } while (seen < p.num_splits);
+          }
+          named_bar_sync(1, 128);
           __threadfence();
-          const int n4 = p.block_n >> 2;
           const int total = 128 * n4;
-          const size_t stride4 = ws_split_stride >> 2;
-          for (int idx0 = r; idx0 < total; idx0 += 4 * 128) {
-            // 4 independent float4 columns per thread per trip -> 4 x num_splits loads in flight
-            float4 a[4];
-            const float4* src[4];
-            bool ok[4];
-            long long gr[4];
-            int nn[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = idx0 + u * 128;
-              a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              ok[u] = false; gr[u] = 0; nn[u] = 0; src[u] = (const float4*)p.ws;
-              if (idx < total) {
-                const int rr = idx / n4;
-                nn[u] = nt * p.block_n + ((idx - rr * n4) << 2);
-                bool okr;
-                row_of(rr, okr, gr[u]);
-                ok[u] = okr && nn[u] < p.N_total;
-                if (ok[u]) src[u] = (const float4*)(p.ws + (size_t)gr[u] * p.ws_ld + nn[u]);
-              }
-            }
-#pragma unroll 2
-            for (int sp = 0; sp < p.num_splits; ++sp) {   // fixed split order => deterministic sum
-              float4 t[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) t[u] = ok[u] ? __ldcg(src[u] + (size_t)sp * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) { a[u].x += t[u].x; a[u].y += t[u].y; a[u].z += t[u].z; a[u].w += t[u].w; }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (!ok[u]) continue;
-              const int n = nn[u];
-              float4 v = a[u];
-              if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-              if (p.rowvec) {
-                const float4 b4 = *(const float4*)(p.rowvec + (size_t)(gr[u] / p.rows_per_group) * p.ld_rowvec + n);
-                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-              }
-              if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr[u] * p.ldres + n); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-              if (p.out32) *(float4*)(p.out32 + (size_t)gr[u] * p.ld32 + n) = v;
-              if (p.out16) {
-                __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-                *(uint2*)(p.out16 + (size_t)gr[u] * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
-              }
+          const int per = (total + p.num_splits - 1) / p.num_splits;
+          const int lo = split * per, hi = min(lo + per, total);
+          for (int idx = lo + r; idx < hi; idx += 128) {
+            const int rr = idx / n4;
+            reduce_store(rr, idx - rr * n4);
+          }
+          named_bar_sync(1, 128);
+          if (r == 0) {
+            const int d = atomicAdd(ctr + 1, 1);
+            if (d == p.num_splits - 1) { ctr[0] = 0; ctr[1] = 0; }   // last reader re-arms the counters for the next launch
+          }
+        } else {
+          // fallback (several tiles per CTA): the last split to arrive reduces the whole tile
+          if (r == 0) {
+            const int prev = atomicAdd(ctr, 1);
+            const int last = prev == p.num_splits - 1;
+            if (last) *ctr = 0;
+            *split_flag = (uint32_t)last;
+          }
+          named_bar_sync(1, 128);
+          const bool is_last = *split_flag != 0;
+          named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
+          if (is_last) {
+            __threadfence();
+            const int total = 128 * n4;
+            for (int idx = r; idx < total; idx += 128) {
+              const int rr = idx / n4;
+              reduce_store(rr, idx - rr * n4);
             }
           }
         }
@@ -635,32 +656,36 @@ static int gemm_device_setup() {
   return 0;
 }
 
-// Tile-width heuristic. `gran` = column granularity the epilogue needs (32: fp32 TMA chunks, 64: fp16 TMA chunks, 16: flat).
-// N need not be a multiple of the tile: TMA zero-fills the weight tail on load and clips the tail on store.
-// If the M tiles alone fill the machine take the widest tile (fewest operand re-reads); otherwise narrow the tile so
-// that m_tiles x n_tiles approaches one wave - small-M layers are weight-stream bound and want every SM pulling weights.
-static int pick_block_n(int N, int base_tiles, int num_sms, int gran, bool must_divide) {
-  const int nmax = 256;
+// Tile-width / split-K choice by a small cost model of THIS kernel (measured on B200 with the in-kernel %globaltimer
+// timeline, tools/gpu_gemm_timeline.py): a CTA ingests operands through TMA at ~100 GB/s (one [128][64] fp16 A box plus one
+// [bn][64] B box per k-iteration, ~0.3 us for 44 KB), pays ~2.5 us of prologue/teardown, ~0.6 us per 32-column epilogue chunk,
+// and a split-K tile additionally writes + re-reads its fp32 partial tile and synchronises (~2.5 us + 0.9 us per chunk).
+// Wide tiles minimise A re-reads; split-K supplies the parallelism that small-M layers lack.
+struct TileChoice { int bn; int splits; };
+static TileChoice choose_tiling(int N, int m_tiles_x_batch, int k_iters, int num_sms, int gran, bool must_divide, bool allow_split,
+                                int chunk_cols) {
+  TileChoice best{gran, 1};
+  double best_t = 1e30;
   auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
-  int widest = round_up(N < nmax ? N : nmax, gran);
-  if (widest > nmax) widest = nmax / gran * gran;
-  if (N > nmax) {
-    // prefer an exact divisor near the top (no wasted MMA columns)
-    for (int c = nmax / gran * gran; c >= 128; c -= gran) if (N % c == 0) { widest = c; break; }
+  const int n_cap = round_up(N, gran) < 256 ? round_up(N, gran) : 256 / gran * gran;
+  for (int bn = n_cap; bn >= (n_cap < 64 ? n_cap : 64); bn -= gran) {
+    if (must_divide && N % bn) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const int base = m_tiles_x_batch * n_tiles;
+    const double us_per_iter = (16384.0 + 128.0 * bn) / 100e3;          // bytes / (100 GB/s) in us
+    const double epi = 0.6 * ((bn + chunk_cols - 1) / chunk_cols);
+    const int max_splits = allow_split ? (k_iters / 2 < 32 ? k_iters / 2 : 32) : 1;
+    for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
+      const int ctas = base * sp;
+      if (sp > 1 && ctas > num_sms) break;                              // cooperative reduction needs one wave
+      const int waves = (ctas + num_sms - 1) / num_sms;
+      const int iters = (k_iters + sp - 1) / sp;
+      double t = waves * (2.5 + iters * us_per_iter + (sp == 1 ? epi : 0.9 * ((bn + 31) / 32)));
+      if (sp > 1) t += 2.5;
+      if (t < best_t - 1e-9) { best_t = t; best = {bn, sp}; }
+    }
   }
-  int bn = widest;
-  if (base_tiles * ((N + widest - 1) / widest) < num_sms) {
-    int want_tiles = num_sms / (base_tiles > 0 ? base_tiles : 1);
-    if (want_tiles < 1) want_tiles = 1;
-    bn = round_up((N + want_tiles - 1) / want_tiles, gran);
-    if (bn < 64) bn = 64;
-    if (bn > widest) bn = widest;
-  }
-  if (must_divide) {
-    while (bn > gran && N % bn) bn -= gran;
-    if (N % bn) bn = gran;
-  }
-  return bn;
+  return best;
 }
 
 }  // namespace upgpt
@@ -760,28 +785,34 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     if (a->out32 && ld32 % 4 == 0 && ((uintptr_t)a->out32 & 15) == 0) epi_mode = 1;
     else if (!a->out32 && a->out16 && ld16 % 8 == 0 && ((uintptr_t)a->out16 & 15) == 0 && !a->res32 && !a->rowvec) epi_mode = 2;
   }
+  const int k_iters = p.taps * p.kblocks_per_tap;
   int bn = a->block_n;
+  int splits = a->splits;
   if (bn > 0 && ((epi_mode == 1 && bn % 32) || (epi_mode == 2 && bn % 64))) epi_mode = 0;   // explicit tile width wins
-  if (bn <= 0) {
+  if (bn <= 0 || splits <= 0) {
     const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
-    bn = pick_block_n(a->N, p.num_m_tiles * p.batch, g_num_sms, gran, /*must_divide=*/epi_mode == 0 && a->N > 16);
-    if (epi_mode == 0 && a->N <= 16) bn = 16;
+    const bool can_split = !chw_out && !geglu && a->N % 4 == 0 && splits <= 0;
+    if (bn <= 0 && a->N <= 16) { bn = 16; }
+    if (bn <= 0) {
+      const TileChoice tc = choose_tiling(a->N, p.num_m_tiles * p.batch, k_iters, g_num_sms, gran, /*must_divide=*/epi_mode == 0,
+                                          can_split, epi_mode == 2 ? 64 : 32);
+      bn = tc.bn;
+      if (splits <= 0) splits = tc.splits;
+    } else if (splits <= 0) {
+      splits = 1;
+      const int base = p.num_m_tiles * ((a->N + bn - 1) / bn) * p.batch;
+      if (can_split && base * 2 <= g_num_sms && k_iters >= 8) {
+        splits = g_num_sms / base;
+        if (splits > k_iters / 2) splits = k_iters / 2;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+      }
+    }
   }
   UPGPT_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "upgpt_gemm: block_n=%d illegal", bn);
   if (p.flags & GEMM_GEGLU) UPGPT_REQUIRE(bn % 32 == 0 && a->N % bn == 0 && a->out16, "upgpt_gemm: GEGLU needs block_n%%32==0, N%%block_n==0, out16");
   p.block_n = bn;
   p.num_n_tiles = (a->N + bn - 1) / bn;
-  const int k_iters = p.taps * p.kblocks_per_tap;
-  int splits = a->splits;
-  if (splits <= 0) {
-    splits = 1;
-    const int base_tiles = p.num_m_tiles * p.num_n_tiles * p.batch;
-    if (!(p.flags & (GEMM_GEGLU | GEMM_CHW)) && base_tiles * 2 <= g_num_sms && k_iters >= 8) {
-      splits = g_num_sms / base_tiles;
-      if (splits > k_iters / 4) splits = k_iters / 4;
-      if (splits < 1) splits = 1;
-    }
-  }
   if (splits > k_iters) splits = k_iters;
   // every split must own at least one k iteration
   while (splits > 1 && (splits - 1) * ((k_iters + splits - 1) / splits) >= k_iters) --splits;
@@ -794,7 +825,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     p.ws_ld = p.num_n_tiles * bn;
     p.ws_rows = m_rows_total * p.batch;
     const size_t need = (size_t)splits * p.ws_rows * p.ws_ld * sizeof(float);
-    const int n_ctr = p.num_m_tiles * p.num_n_tiles * p.batch;
+    const int n_ctr = 2 * p.num_m_tiles * p.num_n_tiles * p.batch;
     if (need > g_ws_bytes || n_ctr > kMaxCounters) {
       // shrink the split factor to fit the fixed workspace (its address must stay stable for captured graphs)
       while (splits > 1 && ((size_t)splits * p.ws_rows * p.ws_ld * sizeof(float) > g_ws_bytes || n_ctr > kMaxCounters)) --splits;
@@ -873,7 +904,19 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  p.coop_reduce = (p.num_splits > 1 && num_tiles <= grid) ? 1 : 0;
+  if (p.coop_reduce) {
+    // the distributed split-K reduction spins on the arrival of sibling CTAs: a cooperative launch guarantees (or refuses)
+    // co-residency instead of risking a deadlock
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, p));
+  } else {
+    tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -48,7 +48,8 @@ struct GemmParams {
   // ---- deterministic split-K ----
   float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
   int ws_rows, ws_ld;
-  int* counters;        // one arrival counter per (batch, n tile, m tile); zero between launches
+  int* counters;        // {arrived, done} counters per (batch, n tile, m tile); zero between launches
+  int coop_reduce;      // all splits of a tile are co-resident (cooperative launch): parallel distributed reduction
   // ---- TMA epilogue ----
   int epi_mode;         // 0 flat stores; 1 fp32 tile chunks [rows][32] by TMA store; 2 fp16 chunks [rows][64] by TMA store
   int res_tma;          // residual tile chunks prefetched by TMA load (epi_mode 1)
