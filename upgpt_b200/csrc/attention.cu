@@ -64,6 +64,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   float* xch = (float*)(smem + off_bar + 128);   // [2 tiles parity][2 halves][128 rows] row-max exchange, then row-sum exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int qt = blockIdx.x % p.num_q_tiles;
   const int bh = blockIdx.x / p.num_q_tiles;
   const int h = bh % p.H, b = bh / p.H;
@@ -86,6 +87,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();
   const uint32_t tO = tmem_base + 256;    // dpad columns; S buffers at columns [0,128) and [128,256)
 
   if (warp == 0) {
@@ -305,7 +307,7 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   const int dch = a->dpad / 64;
   const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);
-  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(tmQ, tmK, tmVt, p);
+  UPGPT_CHECK_CUDA(launch_k(attention_kernel, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -37,7 +37,28 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 int make_tmap(CUtensorMap* out, int elem_bytes, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, bool swizzle128);
 
+bool pdl_enabled();   // programmatic dependent launch (UPGPT_PDL=0 disables)
+
 #ifdef __CUDACC__
+// Launches `k` with the programmatic-stream-serialization attribute: the kernel may begin (and run its prologue) while its
+// predecessor drains; every kernel of this library calls pdl_wait() before touching global memory written by predecessors.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    n = 1;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------------------------

@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256)
 conv_small_cin_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, float in_scale, int H,
                       int W, int ksize, const float* __restrict__ wt, const float* __restrict__ bias, int Cout,
                       float* __restrict__ out, int out_nchw) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int TP = 8;
   __shared__ float patch[TP][8 * 9];
   const int Cin = C1 + C2, HW = H * W;
@@ -66,6 +68,8 @@ conv_small_cin_kernel(const float* __restrict__ x1, int C1, const float* __restr
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float max_period,
                                           const float* __restrict__ freqs, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -87,6 +91,8 @@ template <int RB, bool VEC>
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ w, const float* __restrict__ bias,
                       int N, int K, int silu_in, int silu_out, float* __restrict__ out, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -152,6 +158,8 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    const float* __restrict__ coef, const int* __restrict__ step_ptr, int step_imm,
                                    float* __restrict__ x_prev, float* __restrict__ pred_x0, size_t n,
                                    size_t noise_step_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = step_ptr ? *step_ptr : step_imm;
   const float* c = coef + (size_t)step * 5;
   const float a_t = c[0], a_prev = c[1], sigma = c[2], s1m = c[3], temp = c[4];
@@ -177,6 +185,8 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
                                    const float* __restrict__ coef, const int* __restrict__ step_ptr, int step_imm,
                                    float* __restrict__ x_prev, float* __restrict__ pred_x0, size_t n,
                                    size_t noise_step_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = step_ptr ? *step_ptr : step_imm;
   const float* c = coef + (size_t)step * 6;
   const float sr = c[0], srm1 = c[1], c1 = c[2], c2 = c[3], logvar = c[4], nzmask = c[5];
@@ -193,6 +203,8 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
 }
 
 __global__ void step_state_kernel(int* step_ptr, int op, int value, long long* t_buf, int B, const long long* t_table) {
+  pdl_launch_dependents();
+  pdl_wait();
   // op 0: set *step = value ; op 1: *step += value ; then (optionally) broadcast t_table[*step] into t_buf[0..B)
   __shared__ int s;
   if (threadIdx.x == 0) {
@@ -209,12 +221,16 @@ __global__ void step_state_kernel(int* step_ptr, int op, int value, long long* t
 // out = a * sa + b * sb   (mask blend / q_sample style helpers, ddim.py:144-147; ddpm.py:281-284)
 __global__ void axpby_kernel(const float* __restrict__ a, float sa, const float* __restrict__ b, float sb,
                              float* __restrict__ out, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = fmaf(a[i], sa, b ? b[i] * sb : 0.f);
 }
 
 // image post-processing of generate_utils.py:165-168: clamp(-1,1) * 0.5 + 0.5, NCHW fp32 -> NHWC uint8 (x255, rounded)
 __global__ void to_uint8_nhwc_kernel(const float* __restrict__ x, int B, int C, int HW, uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n = (size_t)B * C * HW;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -238,8 +254,8 @@ extern "C" int upgpt_conv_small_cin(const float* x1, int C1, const float* x2, in
   UPGPT_REQUIRE(C1 + C2 <= 8 && (ksize == 1 || ksize == 3), "conv_small_cin: Cin<=8, ksize in {1,3}");
   dim3 grid((H * W + 7) / 8, B);
   const int threads = Cout >= 256 ? 256 : ((Cout + 31) / 32) * 32;
-  conv_small_cin_kernel<<<grid, threads, 0, stream>>>(x1, C1, x2, C2, in_scale == 0.f ? 1.f : in_scale, H, W, ksize,
-                                                      wt_kmajor, bias, Cout, out, out_nchw);
+  UPGPT_CHECK_CUDA(launch_k(conv_small_cin_kernel, grid, dim3(threads), 0, stream, x1, C1, x2, C2, in_scale == 0.f ? 1.f : in_scale, H, W, ksize,
+                            wt_kmajor, bias, Cout, out, out_nchw));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -250,7 +266,7 @@ extern "C" int upgpt_timestep_embedding(const long long* t, int B, int dim, floa
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(t && out && dim >= 2, "timestep_embedding: bad args");
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, stream>>>(t, B, dim, max_period, freqs, out);
+  UPGPT_CHECK_CUDA(launch_k(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), 0, stream, t, B, dim, max_period, freqs, out));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -265,10 +281,10 @@ extern "C" int upgpt_linear_small_m(const float* x, int ldx, int rows, const flo
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && (((uintptr_t)x | (uintptr_t)w) % 16 == 0);
   const int blocks = (N + 7) / 8;
   if (vec) {
-    if (rows <= 4) linear_small_m_kernel<4, true><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
-    else linear_small_m_kernel<8, true><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+    if (rows <= 4) UPGPT_CHECK_CUDA(launch_k(linear_small_m_kernel<4, true>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo));
+    else UPGPT_CHECK_CUDA(launch_k(linear_small_m_kernel<8, true>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo));
   } else {
-    linear_small_m_kernel<4, false><<<blocks, 256, 0, stream>>>(x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo);
+    UPGPT_CHECK_CUDA(launch_k(linear_small_m_kernel<4, false>, dim3(blocks), dim3(256), 0, stream, x, ldx, rows, w, bias, N, K, silu_in, silu_out, out, ldo));
   }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
@@ -285,8 +301,8 @@ extern "C" int upgpt_ddim_step(const float* x, const float* eps, const float* no
                                long long n, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(x && eps && coef && x_prev && n > 0, "ddim_step: bad args");
-  ddim_update_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, eps, noise, coef, step_ptr, step_imm, x_prev, pred_x0,
-                                                            (size_t)n, (size_t)noise_step_stride);
+  UPGPT_CHECK_CUDA(launch_k(ddim_update_kernel, dim3(ew_grid((size_t)n)), dim3(256), 0, stream, x, eps, noise, coef, step_ptr, step_imm, x_prev, pred_x0,
+                            (size_t)n, (size_t)noise_step_stride));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -297,8 +313,8 @@ extern "C" int upgpt_ddpm_step(const float* x, const float* eps, const float* no
                                long long n, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(x && eps && coef && x_prev && n > 0, "ddpm_step: bad args");
-  ddpm_update_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(x, eps, noise, coef, step_ptr, step_imm, x_prev, pred_x0,
-                                                            (size_t)n, (size_t)noise_step_stride);
+  UPGPT_CHECK_CUDA(launch_k(ddpm_update_kernel, dim3(ew_grid((size_t)n)), dim3(256), 0, stream, x, eps, noise, coef, step_ptr, step_imm, x_prev, pred_x0,
+                            (size_t)n, (size_t)noise_step_stride));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -308,7 +324,7 @@ extern "C" int upgpt_step_state(int* step_ptr, int op, int value, long long* t_b
                                 void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(step_ptr, "step_state: null");
-  step_state_kernel<<<1, 64, 0, stream>>>(step_ptr, op, value, t_buf, B, t_table);
+  UPGPT_CHECK_CUDA(launch_k(step_state_kernel, dim3(1), dim3(64), 0, stream, step_ptr, op, value, t_buf, B, t_table));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -317,7 +333,7 @@ extern "C" int upgpt_step_state(int* step_ptr, int op, int value, long long* t_b
 extern "C" int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(a && out && n > 0, "axpby: bad args");
-  axpby_kernel<<<ew_grid((size_t)n), 256, 0, stream>>>(a, sa, b, sb, out, (size_t)n);
+  UPGPT_CHECK_CUDA(launch_k(axpby_kernel, dim3(ew_grid((size_t)n)), dim3(256), 0, stream, a, sa, b, sb, out, (size_t)n));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -326,7 +342,7 @@ extern "C" int upgpt_axpby(const float* a, float sa, const float* b, float sb, f
 extern "C" int upgpt_to_uint8_nhwc(const float* x, int B, int C, int HW, uint8_t* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(x && out, "to_uint8_nhwc: null");
-  to_uint8_nhwc_kernel<<<ew_grid((size_t)B * C * HW), 256, 0, stream>>>(x, B, C, HW, out);
+  UPGPT_CHECK_CUDA(launch_k(to_uint8_nhwc_kernel, dim3(ew_grid((size_t)B * C * HW)), dim3(256), 0, stream, x, B, C, HW, out));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -26,6 +26,8 @@ gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ 
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
   extern __shared__ float shc[];  // per-channel {sum, sumsq}: [2][C]
   __shared__ int s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double s_red[4][64];
   const int C = C1 + C2;
   const int cpg = C / groups;
@@ -163,6 +165,8 @@ struct PrepParams {
 __global__ void __launch_bounds__(256)
 prep_kernel(const PrepParams p) {
   extern __shared__ float shf[];  // scale[C], shift[C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = p.C1 + p.C2;
   const int HW = p.H * p.W;
   float* scale = shf;
@@ -252,6 +256,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -298,6 +304,8 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const fl
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ x, int ldx, int n, float scale, __half* __restrict__ out, int ldo) {
   __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const float* xr = x + (size_t)blockIdx.x * ldx;
   __half* orow = out + (size_t)blockIdx.x * ldo;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,8 +369,8 @@ static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2
   while ((size_t)B * ((HW + chunk - 1) / chunk) * 2 * groups > kGnPartialDoubles) chunk *= 2;
   dim3 grid((HW + chunk - 1) / chunk, B);
   const size_t sm = sizeof(float) * 2 * C;
-#define UPGPT_GN_LAUNCH(MC) gn_stats_kernel<MC><<<grid, 256, sm, stream>>>(x1, C1, x2, C2, HW, chunk, groups, stats, g_gn_partials, \
-                                                                         g_gn_counters, gamma, beta, eps, scale_shift)
+#define UPGPT_GN_LAUNCH(MC) UPGPT_CHECK_CUDA(launch_k(gn_stats_kernel<MC>, grid, dim3(256), sm, stream, x1, C1, x2, C2, HW, chunk, groups, stats, \
+                                                    g_gn_partials, g_gn_counters, gamma, beta, eps, scale_shift))
   if (C <= 256) UPGPT_GN_LAUNCH(1);
   else if (C <= 512) UPGPT_GN_LAUNCH(2);
   else if (C <= 1024) UPGPT_GN_LAUNCH(4);
@@ -403,7 +411,7 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   const int HW = a->H * a->W;
   p.chunk = pick_chunk(HW, a->B);
   dim3 grid((HW + p.chunk - 1) / p.chunk, a->B);
-  prep_kernel<<<grid, 256, sizeof(float) * 2 * C, stream>>>(p);
+  UPGPT_CHECK_CUDA(launch_k(prep_kernel, grid, dim3(256), sizeof(float) * 2 * C, stream, p));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -419,10 +427,10 @@ extern "C" int upgpt_layernorm(const float* x, int ldx, int rows, int C, const f
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);
   __half* o = (__half*)out16;
-  if (C <= 256) layernorm_kernel<2><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
-  else if (C <= 512) layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
-  else if (C <= 1024) layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
-  else layernorm_kernel<16><<<grid, 256, 0, stream>>>(x, ldx, rows, C, gamma, beta, eps, o, ldo);
+  if (C <= 256) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<2>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
+  else if (C <= 512) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<4>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
+  else if (C <= 1024) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<8>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
+  else UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<16>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -432,7 +440,7 @@ extern "C" int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n
                                   void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(x && out16 && n > 0 && rows > 0, "softmax_rows: bad args");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(x, ldx > 0 ? ldx : n, n, scale, (__half*)out16, ldo > 0 ? ldo : n);
+  UPGPT_CHECK_CUDA(launch_k(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, stream, x, ldx > 0 ? ldx : n, n, scale, (__half*)out16, ldo > 0 ? ldo : n));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

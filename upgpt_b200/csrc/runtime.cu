@@ -4,6 +4,7 @@
 #include "../../include/upgpt_b200.h"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -11,6 +12,12 @@ namespace upgpt {
 
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("UPGPT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

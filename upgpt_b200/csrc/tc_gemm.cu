@@ -57,6 +57,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TS(0);
+  pdl_launch_dependents();
 
   // accumulator ring: 2 stages of block_n columns
   uint32_t tmem_cols = 32;
@@ -83,6 +84,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
   if (threadIdx.x == 0) TS(1);
 
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
@@ -915,7 +917,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     cfg.attrs = attr; cfg.numAttrs = 1;
     UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, p));
   } else {
-    tc_gemm_kernel<<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+    UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
   }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
