@@ -39,7 +39,9 @@ enum {
 };
 enum {
   UPGPT_GEMM_F_GEGLU = 1u << 1, /* W rows packed per tile as [x | gate]; out16 = x * gelu(gate)   (attention.py:37-44) */
-  UPGPT_GEMM_F_CHW = 1u << 2    /* store channel-major: out[(group*N + n)*ldT + row_in_group] (NCHW images, V^T for attention) */
+  UPGPT_GEMM_F_CHW = 1u << 2,   /* store channel-major: out[(group*N + n)*ldT + row_in_group] (NCHW images, V^T for attention) */
+  UPGPT_GEMM_F_SPLIT3OUT = 1u << 4 /* out16 rows = [hi | lo | hi] planes (N columns each, ld16 default 3N): the A operand of a following
+                                     GEMM in the error-compensated fp16x3 mode, whose weights are packed [Wh | Wh | Wl] along K */
 };
 typedef struct upgpt_gemm_args {
   const void* a;            /* fp16 activations */
@@ -101,6 +103,9 @@ typedef struct upgpt_prep_args {
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
 int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     void* out16, int ldo, void* stream);
+/* same with out16 rows = [hi | lo | hi] planes of C columns (ldo default 3C) */
+int upgpt_layernorm_split3(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                           void* out16, int ldo, void* stream);
 /* out16[r][i] = softmax_i(scale * x[r][i]) */
 int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n, float scale, void* out16, int ldo, void* stream);
 
@@ -117,6 +122,7 @@ typedef struct upgpt_attn_args {
   int B, H, Nq, Nk;
   int dpad;                  /* head dim padded with zero columns to 64 or 128 */
   float scale;               /* dim_head ** -0.5 (attention.py:157) */
+  int split3_out;            /* out rows = [hi | lo | hi] planes of H*dpad columns each (ldo >= 3*H*dpad) */
 } upgpt_attn_args;
 int upgpt_attention(const upgpt_attn_args* args, void* stream);
 

@@ -4,7 +4,8 @@ at BASELINE's full size (B=8, 32x32, bbox.yaml U-Net).
 
 Tolerances (metric: max|a-b| / max|b| as defined in SURVEY.md 7.2):
   fp16 operand mode  : 2.5e-3 on eps (measured 1.3e-3..1.7e-3; fp16 rounding of conv/GEMM operands, fp32 everywhere else)
-  fp16x3 (3x3 convs error-compensated): same bound; see DESIGN.md for the measured split.
+  fp16x3 (every GEMM/conv operand error-compensated with hi/lo fp16 planes): 5e-4 asserted, 1.3e-4..1.9e-4 measured --
+                       this is the mode that meets BASELINE.json's 1e-3 tolerance.
 """
 import numpy as np
 import pytest
@@ -60,13 +61,23 @@ def test_unet_eps_vs_reference_golden(dev, golden, tag, kw, B, H, W, L, ts, seed
         assert torch.equal(y, y_eager), "graph replay must be bit-identical to the eager program (deterministic reductions)"
 
 
-def test_unet_fp16x3_mode(dev, golden):
-    m, _ = _unet(BBOX_UNET_KW, 0, dev)
-    x, mask, ctx = synth.synth_inputs(1, 32, 32, 87, 768, 0)
-    eng = m.engine(1, 32, 32, 87, precision="fp16x3")
-    eng.set_context(ctx.to(dev)); eng.stage_inputs(torch.cat([x, mask], 1).to(dev), torch.full((1,), 981, dtype=torch.long, device=dev))
-    y = eng.run(use_graph=False).clone()
-    assert relerr(y, torch.from_numpy(golden["bbox_eps_t981"])) < EPS_TOL
+@pytest.mark.parametrize("tag,kw,B,H,W,L,ts,seed", [
+    ("tiny", TINY_UNET_KW, 2, 16, 16, 87, [981], 0),
+    ("bbox", BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0),
+])
+def test_unet_parity_mode_meets_1e3(dev, golden, tag, kw, B, H, W, L, ts, seed):
+    """BASELINE.json's tolerance: eps within 1e-3 rel of the reference U-Net.  The error-compensated operand mode
+    (precision="fp16x3": every GEMM/conv operand split into hi/lo fp16 planes, fp32 accumulate) meets it with margin
+    (measured 1.3e-4 .. 1.9e-4); the default single-plane fp16 mode sits at 1.3e-3 .. 1.7e-3 (EPS_TOL above)."""
+    m, _ = _unet(kw, seed, dev)
+    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed)
+    eng = m.engine(B, H, W, L, precision="fp16x3")
+    eng.set_context(ctx.to(dev))
+    for t in ts:
+        eng.stage_inputs(torch.cat([x, mask], 1).to(dev), torch.full((B,), t, dtype=torch.long, device=dev))
+        y = eng.run(use_graph=True).clone()
+        assert relerr(y, torch.from_numpy(golden[f"{tag}_eps_t{t}"])) < 5e-4      # target 1e-3 (north_star), measured <= 1.9e-4
+        assert torch.equal(y, eng.run(use_graph=False))
 
 
 def test_unet_weight_repack_after_change(dev):

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 
 GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1 = 0, 1, 2, 3
-GEMM_F_GEGLU, GEMM_F_CHW = 1 << 1, 1 << 2
+GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT = 1 << 1, 1 << 2, 1 << 4
 
 
 def lib():
@@ -82,7 +82,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("k_batch_stride", C.c_longlong),
         ("vt", C.c_void_p), ("ldvt", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
-        ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dpad", C.c_int), ("scale", C.c_float),
+        ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dpad", C.c_int), ("scale", C.c_float), ("split3_out", C.c_int),
     ]
 
 
@@ -94,6 +94,7 @@ _PROTOS = {
     "upgpt_groupnorm_affine": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp],
     "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
     "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
+    "upgpt_layernorm_split3": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_softmax_rows": [_vp, _i, _ll, _i, _f, _vp, _i, _vp],
     "upgpt_attention": [C.POINTER(AttnArgs), _vp],
     "upgpt_conv_small_cin": [_vp, _i, _vp, _i, _f, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp],

@@ -26,6 +26,7 @@ struct AttnParams {
   float scale_log2e;   // softmax scale * log2(e)
   __half* out;         // [B][Nq][ldo], head h at columns h*dpad
   int ldo;
+  int plane;           // > 0: also write [lo | hi] planes at column offsets plane, 2*plane (fp16x3 operand layout)
 };
 
 static constexpr int kAttnThreads = 320;     // warp0 TMA, warp1 MMA, warps2-9 softmax (two threads per query row)
@@ -241,15 +242,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld32(tO + lane_off + (uint32_t)(hf * ocols + cc), o);
       tmem_ld_wait();
       if (q < p.Nq) {
-        uint32_t pk[16];
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          __half2 hh = __floats2half2_rn(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          const float a0 = __uint_as_float(o[i]) * inv_l, a1 = __uint_as_float(o[i + 1]) * inv_l;
+          __half2 hh = __floats2half2_rn(a0, a1);
           pk[i >> 1] = *(uint32_t*)&hh;
+          const float2 fh = __half22float2(hh);
+          __half2 ll = __floats2half2_rn(a0 - fh.x, a1 - fh.y);
+          pl[i >> 1] = *(uint32_t*)&ll;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *(uint4*)(orow + cc + u * 8) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        for (int u = 0; u < 4; ++u) {
+          const uint4 hi = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          *(uint4*)(orow + cc + u * 8) = hi;
+          if (p.plane > 0) {
+            *(uint4*)(orow + p.plane + cc + u * 8) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
+            *(uint4*)(orow + 2 * p.plane + cc + u * 8) = hi;
+          }
+        }
       }
     }
   }
@@ -304,6 +315,8 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   p.num_q_tiles = (a->Nq + 127) / 128;
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = (__half*)a->out; p.ldo = a->ldo;
+  p.plane = a->split3_out ? a->H * a->dpad : 0;
+  UPGPT_REQUIRE(!a->split3_out || a->ldo >= 3 * a->H * a->dpad, "attention: split3_out needs ldo >= 3*H*dpad");
   const int dch = a->dpad / 64;
   const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);

@@ -207,6 +207,12 @@ prep_kernel(const PrepParams p) {
       __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
       uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
       *(uint2*)(p.raw + row * p.ldraw + c) = pk;
+      if (p.split3) {   // the un-normalised copy feeds the skip 1x1 GEMM: same [hi | lo | hi] planes
+        const float2 f0 = __half22float2(r0), f1 = __half22float2(r1);
+        __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+        *(uint2*)(p.raw + row * p.ldraw + C + c) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+        *(uint2*)(p.raw + row * p.ldraw + 2 * C + c) = pk;
+      }
     }
     if (p.stats || p.scale_shift) {
       v.x = fmaf(v.x, scale[c], shift[c]);
@@ -255,7 +261,7 @@ prep_kernel(const PrepParams p) {
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo) {
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out, int ldo, int split3) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -291,9 +297,17 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const fl
     const int i = lane + j * 32;
     if (i < C4) {
       const float4 g = ((const float4*)gamma)[i], be = ((const float4*)beta)[i];
-      __half2 h0 = __floats2half2_rn((v[j].x - mean) * rstd * g.x + be.x, (v[j].y - mean) * rstd * g.y + be.y);
-      __half2 h1 = __floats2half2_rn((v[j].z - mean) * rstd * g.z + be.z, (v[j].w - mean) * rstd * g.w + be.w);
-      *(uint2*)(orow + 4 * i) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+      const float y0 = (v[j].x - mean) * rstd * g.x + be.x, y1 = (v[j].y - mean) * rstd * g.y + be.y;
+      const float y2 = (v[j].z - mean) * rstd * g.z + be.z, y3 = (v[j].w - mean) * rstd * g.w + be.w;
+      __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+      const uint2 hi = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+      *(uint2*)(orow + 4 * i) = hi;
+      if (split3) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        __half2 l0 = __floats2half2_rn(y0 - f0.x, y1 - f0.y), l1 = __floats2half2_rn(y2 - f1.x, y3 - f1.y);
+        *(uint2*)(orow + C + 4 * i) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+        *(uint2*)(orow + 2 * C + 4 * i) = hi;
+      }
     }
   }
 }
@@ -406,7 +420,7 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
   p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 3 * C : C);
-  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : C;
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 3 * C : C);
   UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "prep_operand: ld must be a multiple of 4");
   const int HW = a->H * a->W;
   p.chunk = pick_chunk(HW, a->B);
@@ -417,23 +431,32 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   return 0;
 }
 
-extern "C" int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
-                               void* out16, int ldo, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int layernorm_impl(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps, void* out16,
+                          int ldo, int split3, cudaStream_t stream) {
   UPGPT_REQUIRE(x && out16 && gamma && beta && C % 4 == 0 && C <= 2048, "layernorm: bad args (C=%d)", C);
   if (ldx <= 0) ldx = C;
-  if (ldo <= 0) ldo = C;
+  if (ldo <= 0) ldo = split3 ? 3 * C : C;
   UPGPT_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: ld must be multiple of 4");
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);
   __half* o = (__half*)out16;
-  if (C <= 256) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<2>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
-  else if (C <= 512) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<4>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
-  else if (C <= 1024) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<8>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
-  else UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<16>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo));
+  if (C <= 256) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<2>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo, split3));
+  else if (C <= 512) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<4>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo, split3));
+  else if (C <= 1024) UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<8>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo, split3));
+  else UPGPT_CHECK_CUDA(launch_k(layernorm_kernel<16>, grid, dim3(256), 0, stream, x, ldx, rows, C, gamma, beta, eps, o, ldo, split3));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                               void* out16, int ldo, void* stream_) {
+  return layernorm_impl(x, ldx, rows, C, gamma, beta, eps, out16, ldo, 0, (cudaStream_t)stream_);
+}
+
+extern "C" int upgpt_layernorm_split3(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                                      void* out16, int ldo, void* stream_) {
+  return layernorm_impl(x, ldx, rows, C, gamma, beta, eps, out16, ldo, 1, (cudaStream_t)stream_);
 }
 
 extern "C" int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n, float scale, void* out16, int ldo,

@@ -26,6 +26,20 @@ static constexpr int kABytes = 128 * 64 * 2;  // smem slot for one A stage
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define TS(slot) do { if (p.debug_ts) p.debug_ts[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
+// fp16 store of 4 consecutive columns; with `plane` > 0 also the error-compensation planes [hi | lo | hi] at column
+// offsets 0, plane, 2*plane (operand layout of the fp16x3 precision mode)
+__device__ __forceinline__ void store_h4(__half* dst, float4 v, int plane) {
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const uint2 hi = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+  *(uint2*)dst = hi;
+  if (plane > 0) {
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    *(uint2*)(dst + plane) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
+    *(uint2*)(dst + 2 * plane) = hi;
+  }
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -303,8 +317,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const long long gr = row_tab[rr];
             if (gr < 0) continue;
             const float4 v = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
-            __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-            *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+            store_h4(p.out16 + (size_t)gr * p.ld16 + n, v, p.out16_plane);
           }
           return;
         }
@@ -332,10 +345,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float4 o = v[k];
           o.x += b4.x + e1[k].x + e2[k].x; o.y += b4.y + e1[k].y + e2[k].y; o.z += b4.z + e1[k].z + e2[k].z; o.w += b4.w + e1[k].w + e2[k].w;
           if (p.out32) *(float4*)(p.out32 + (size_t)gr[k] * p.ld32 + n) = o;
-          if (p.out16) {
-            __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-            *(uint2*)(p.out16 + (size_t)gr[k] * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
-          }
+          if (p.out16) store_h4(p.out16 + (size_t)gr[k] * p.ld16 + n, o, p.out16_plane);
         }
       };
 
@@ -436,8 +446,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const long long gr = row_tab[rr];
                 if (gr < 0) continue;
                 const float4 o = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
-                __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-                *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
+                store_h4(p.out16 + (size_t)gr * p.ld16 + n, o, p.out16_plane);
               }
             }
           }
@@ -564,10 +573,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr * p.ldres + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
           if (p.out32) *(float4*)(p.out32 + (size_t)gr * p.ld32 + n) = a;
-          if (p.out16) {
-            __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
-            *(uint2*)(p.out16 + (size_t)gr * p.ld16 + n) = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
-          }
+          if (p.out16) store_h4(p.out16 + (size_t)gr * p.ld16 + n, a, p.out16_plane);
         };
         __threadfence();
         named_bar_sync(1, 128);
@@ -699,6 +705,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   if (gemm_device_setup()) return -2;
   UPGPT_REQUIRE(a && a->a && a->w, "upgpt_gemm: null operand");
   UPGPT_REQUIRE(a->out32 || a->out16, "upgpt_gemm: no output");
+  UPGPT_REQUIRE(!((a->flags & UPGPT_GEMM_F_SPLIT3OUT) && (a->flags & UPGPT_GEMM_F_CHW)), "upgpt_gemm: SPLIT3OUT is not available with channel-major stores");
   UPGPT_REQUIRE(a->K > 0 && a->N > 0, "upgpt_gemm: bad K/N");
   UPGPT_REQUIRE(a->K % 8 == 0, "upgpt_gemm: K (=%d) must be a multiple of 8 (16-byte TMA rows)", a->K);
   const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE || a->mode == UPGPT_GEMM_CONV1X1;
@@ -785,7 +792,8 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     const int ld32 = a->ld32 > 0 ? a->ld32 : a->N;
     const int ld16 = a->ld16 > 0 ? a->ld16 : a->N;
     if (a->out32 && ld32 % 4 == 0 && ((uintptr_t)a->out32 & 15) == 0) epi_mode = 1;
-    else if (!a->out32 && a->out16 && ld16 % 8 == 0 && ((uintptr_t)a->out16 & 15) == 0 && !a->res32 && !a->rowvec) epi_mode = 2;
+    else if (!a->out32 && a->out16 && ld16 % 8 == 0 && ((uintptr_t)a->out16 & 15) == 0 && !a->res32 && !a->rowvec &&
+             !(a->flags & UPGPT_GEMM_F_SPLIT3OUT)) epi_mode = 2;
   }
   const int k_iters = p.taps * p.kblocks_per_tap;
   int bn = a->block_n;
@@ -849,7 +857,9 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
 
   p.debug_ts = g_debug_ts;
   p.out32 = a->out32; p.ld32 = a->ld32 > 0 ? a->ld32 : a->N;
-  p.out16 = (__half*)a->out16; p.ld16 = a->ld16 > 0 ? a->ld16 : ((p.flags & GEMM_GEGLU) ? a->N / 2 : a->N);
+  const int n_out16 = (p.flags & GEMM_GEGLU) ? a->N / 2 : a->N;
+  p.out16_plane = (a->flags & UPGPT_GEMM_F_SPLIT3OUT) ? n_out16 : 0;
+  p.out16 = (__half*)a->out16; p.ld16 = a->ld16 > 0 ? a->ld16 : (p.out16_plane ? 3 * n_out16 : n_out16);
   p.bias = a->bias; p.rowvec = a->rowvec; p.ld_rowvec = a->ld_rowvec > 0 ? a->ld_rowvec : a->N;
   p.res32 = a->res32; p.ldres = a->ldres > 0 ? a->ldres : a->N;
   p.ldT = a->ldT > 0 ? a->ldT : p.rows_per_group;

@@ -8,7 +8,8 @@ namespace upgpt {
 enum GemmFlags : uint32_t {
   GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
   GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
-  GEMM_CONV = 1u << 3,     // A rows are image pixels addressed through a 4-D (C, W, H, N) tensor map
+  GEMM_CONV = 1u << 3,
+  GEMM_SPLIT3OUT = 1u << 4,  // (public flag) out16 written as error-compensated planes     // A rows are image pixels addressed through a 4-D (C, W, H, N) tensor map
 };
 
 struct GemmParams {
@@ -37,6 +38,7 @@ struct GemmParams {
   int ld32;
   __half* out16;        // optional fp16 copy of the result (GEGLU: the only output)
   int ld16;
+  int out16_plane;      // > 0: out16 rows are [hi | lo | hi] planes of this many columns each (fp16x3 operand layout)
   const float* bias;    // [N_total] or null
   const float* rowvec;  // [groups, ld_rowvec] added per row-group (timestep-embedding bias), or null
   int ld_rowvec;

@@ -167,7 +167,8 @@ class EngineBase:
     def e_layernorm(self, x, rows, Cc, gamma, beta, out16):
         if self._sizing:
             return
-        self.prog.add(self.L.upgpt_layernorm, self.p(x), Cc, rows, Cc, self.p(gamma), self.p(beta), 1e-5, self.p(out16), Cc)
+        fn = self.L.upgpt_layernorm_split3 if self.split3 else self.L.upgpt_layernorm
+        self.prog.add(fn, self.p(x), Cc, rows, Cc, self.p(gamma), self.p(beta), 1e-5, self.p(out16), 0)
 
     def e_attention(self, **kw):
         if self._sizing:
@@ -183,7 +184,7 @@ class EngineBase:
         stats = self.buf("gn_stats", (B, 32, 2), torch.float64)
         mult = 4 if layout == 1 else 1
         op = self.scratch("op16", B * H * W * mult * Cc * (3 if split3 else 1), torch.float16)
-        raw = self.scratch("raw16", B * H * W * Cc, torch.float16) if want_raw else None
+        raw = self.scratch("raw16", B * H * W * Cc * (3 if split3 else 1), torch.float16) if want_raw else None
         if gname is not None:
             ss = self.scratch("gn_ss", B * 2 * Cc, torch.float32)
             self.e_gn_affine(x1, C1, x2, C2, B, H * W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, ss)
@@ -217,10 +218,13 @@ class UNetEngine(EngineBase):
         self._emit_context(unet)
 
     # ------------------------------------------------------------------------------------------------ weights
+    def _w16(self, w):
+        """fp32 weight [..., K] -> fp16 operand; in fp16x3 mode the K axis carries the planes [Wh | Wh | Wl]."""
+        return split3_w(w) if self.split3 else w.half()
+
     def _conv_w(self, w):
         """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x3 planes in fp16x3 mode)."""
-        w = w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1])
-        return split3_w(w) if self.split3 else w.half()
+        return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]))
 
     def pack_weights(self, unet):
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in unet.state_dict().items()}
@@ -241,14 +245,14 @@ class UNetEngine(EngineBase):
                 put(p + ".conv2.weight", self._conv_w(sd[p + ".out_layers.3.weight"])); put(p + ".conv2.bias", sd[p + ".out_layers.3.bias"])
                 if (p + ".skip_connection.weight") in sd:
                     ws = sd[p + ".skip_connection.weight"]
-                    put(p + ".skip.weight", ws.reshape(ws.shape[0], ws.shape[1]).half()); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
+                    put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]))); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
                 emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
                 self.emb_off[p] = off
                 off += mod.out_channels
             elif isinstance(mod, (om.Downsample, om.Upsample)):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
                 w = sd[name + sub + ".weight"]
-                put(name + ".weight", w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]).half())
+                put(name + ".weight", self._conv_w(w))
                 put(name + ".bias", sd[name + sub + ".bias"])
             elif isinstance(mod, SpatialTransformer):
                 p = name
@@ -257,29 +261,29 @@ class UNetEngine(EngineBase):
                 assert d <= 128, "head dim > 128 not supported by the attention kernel"
                 put(p + ".norm.weight", sd[p + ".norm.weight"]); put(p + ".norm.bias", sd[p + ".norm.bias"])
                 wpi = sd[p + ".proj_in.weight"]
-                put(p + ".proj_in.weight", wpi.reshape(wpi.shape[0], wpi.shape[1]).half()); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
+                put(p + ".proj_in.weight", self._w16(wpi.reshape(wpi.shape[0], wpi.shape[1]))); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
                 wpo = sd[p + ".proj_out.weight"]
-                put(p + ".proj_out.weight", wpo.reshape(wpo.shape[0], wpo.shape[1]).half()); put(p + ".proj_out.bias", sd[p + ".proj_out.bias"])
+                put(p + ".proj_out.weight", self._w16(wpo.reshape(wpo.shape[0], wpo.shape[1]))); put(p + ".proj_out.bias", sd[p + ".proj_out.bias"])
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{p}.transformer_blocks.{bi}"
                     for n in ("norm1", "norm2", "norm3"):
                         put(f"{q}.{n}.weight", sd[f"{q}.{n}.weight"]); put(f"{q}.{n}.bias", sd[f"{q}.{n}.bias"])
                     wq = pad_heads_rows(sd[q + ".attn1.to_q.weight"], Hh, d, dpad)
                     wk = pad_heads_rows(sd[q + ".attn1.to_k.weight"], Hh, d, dpad)
-                    put(q + ".attn1.qk.weight", torch.cat([wq, wk], 0).half())
-                    put(q + ".attn1.v.weight", pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad).half())
-                    put(q + ".attn1.out.weight", pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad).half())
+                    put(q + ".attn1.qk.weight", self._w16(torch.cat([wq, wk], 0)))
+                    put(q + ".attn1.v.weight", self._w16(pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad)))
+                    put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad)))
                     put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
-                    put(q + ".attn2.q.weight", pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad).half())
-                    put(q + ".attn2.k.weight", pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad).half())
-                    put(q + ".attn2.v.weight", pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad).half())
-                    put(q + ".attn2.out.weight", pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad).half())
+                    put(q + ".attn2.q.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.k.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.v.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad)))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
                     half = geglu_half(inner)
                     w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
-                    put(q + ".ff1.weight", w1.half()); put(q + ".ff1.bias", b1)
-                    put(q + ".ff2.weight", sd[q + ".ff.net.2.weight"].half()); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
+                    put(q + ".ff1.weight", self._w16(w1)); put(q + ".ff1.bias", b1)
+                    put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"])); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
         from .ops import timestep_freqs
         put("temb.freqs", timestep_freqs(self.mc))
         put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
@@ -303,7 +307,7 @@ class UNetEngine(EngineBase):
         op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=self.split3)
         if has_skip:
             skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
-            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
+            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin * kmul, out32=skip32,
                         bias=self.w.get(p + ".skip.bias"))
             res = skip32
         else:
@@ -318,51 +322,53 @@ class UNetEngine(EngineBase):
         dpad = 64 if d <= 64 else 128
         HD = Hh * dpad
         L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
-        op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False)
+        kx = 3 if self.split3 else 1           # operand planes [hi | lo | hi] in the error-compensated mode
+        s3 = _C.GEMM_F_SPLIT3OUT if self.split3 else 0
+        op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False, split3=self.split3)
         tokA = self.scratch("tokA", M * Cc, torch.float32)
         tokB = self.scratch("tokB", M * Cc, torch.float32)
-        tok16 = self.scratch("tok16", M * Cc, torch.float16)
+        tok16 = self.scratch("tok16", M * Cc * kx, torch.float16)
         qk16 = self.scratch("qk16", M * 2 * HD, torch.float16)
         vt16 = self.scratch("vt16", B * HD * _round_up(HW, 8), torch.float16)
-        att16 = self.scratch("att16", M * HD, torch.float16)
-        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
+        att16 = self.scratch("att16", M * HD * kx, torch.float16)
+        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc * kx, out32=tokA,
                     bias=self.w.get(p + ".proj_in.bias"))
         cur, nxt = tokA, tokB
         for bi in range(len(mod.transformer_blocks)):
             q = f"{p}.transformer_blocks.{bi}"
             g = lambda n: self.w.get(q + n)
             inner = mod.transformer_blocks[bi].ff.net[2].in_features
-            ff16 = self.scratch("ff16", M * inner, torch.float16)
+            ff16 = self.scratch("ff16", M * inner * kx, torch.float16)
             # --- self attention ---
             self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc, out16=qk16)
-            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=vt16, rows_per_group=HW,
+            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc * kx, out16=qk16)
+            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc * kx, out16=vt16, rows_per_group=HW,
                         ldT=_round_up(HW, 8), flags=_C.GEMM_F_CHW)
             kptr = None if self._sizing else qk16[HD:]
             self.e_attention(q=qk16, ldq=2 * HD, k=kptr, ldk=2 * HD, k_batch_stride=0, vt=vt16, ldvt=_round_up(HW, 8), out=att16,
-                             ldo=HD, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad, scale=float(d) ** -0.5)
-            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                             ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
+            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD * kx, out32=nxt,
                         bias=g(".attn1.out.bias"), res32=cur)
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
             self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qk16)
+            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc * kx, out16=qk16)
             kc = self.buf(q + ".ctx_k", (B * L, HD), torch.float16)
             vc = self.buf(q + ".ctx_vt", (B, HD, Lp), torch.float16)
-            self.e_attention(q=qk16, ldq=HD, k=kc, ldk=HD, k_batch_stride=0, vt=vc, ldvt=Lp, out=att16, ldo=HD, B=B, H=Hh,
-                             Nq=HW, Nk=L, dpad=dpad, scale=float(d) ** -0.5)
-            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+            self.e_attention(q=qk16, ldq=HD, k=kc, ldk=HD, k_batch_stride=0, vt=vc, ldvt=Lp, out=att16, ldo=HD * kx, B=B, H=Hh,
+                             Nq=HW, Nk=L, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
+            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD * kx, out32=nxt,
                         bias=g(".attn2.out.bias"), res32=cur)
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
             self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner),
-                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU)
+            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc * kx, block_n=2 * geglu_half(inner),
+                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3)
             last = bi == len(mod.transformer_blocks) - 1
-            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
-                        res32=cur, out16=tok16 if last else None)
+            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner * kx, out32=nxt, bias=g(".ff2.bias"),
+                        res32=cur, out16=tok16 if last else None, flags=s3 if last else 0)
             cur, nxt = nxt, cur
-        self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
+        self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc * kx, out32=out,
                     bias=self.w.get(p + ".proj_out.bias"), res32=x)
 
     def _emit(self, unet):
@@ -419,17 +425,17 @@ class UNetEngine(EngineBase):
                     self._transformer(p, mod, h, ch, B, hh, ww, out)
                     h = out
                 elif isinstance(mod, om.Downsample):
-                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2)
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2, split3=self.split3)
                     hh, ww = hh // 2, ww // 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
-                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch, n_imgs=B,
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch * (3 if self.split3 else 1), n_imgs=B,
                                 H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"))
                     h, ch = out, mod.out_channels
                 elif isinstance(mod, om.Upsample):
-                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1)
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=self.split3)
                     hh, ww = hh * 2, ww * 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
-                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch * (3 if self.split3 else 1), n_imgs=B, H=hh,
                                 W=ww, out32=out, bias=self.w.get(p + ".bias"))
                     h, ch = out, mod.out_channels
                 else:
@@ -454,18 +460,19 @@ class UNetEngine(EngineBase):
         B, L, Lp = self.B, self.ctx_len, _round_up(self.ctx_len, 8)
         main = self.prog
         self.prog = _Program()
+        kx = 3 if self.split3 else 1
         ctx32 = self.buf("ctx32", (B, L, self.ctx_dim))
-        ctx16 = self.buf("ctx16", (B * L, self.ctx_dim), torch.float16)
-        self.e_prep(ctx32, self.ctx_dim, None, 0, B, 1, L, None, None, None, 0.0, False, 0, ctx16)
+        ctx16 = self.buf("ctx16", (B * L, self.ctx_dim * kx), torch.float16)
+        self.e_prep(ctx32, self.ctx_dim, None, 0, B, 1, L, None, None, None, 0.0, False, 0, ctx16, split3=self.split3)
         for name, mod in unet.named_modules():
             if isinstance(mod, SpatialTransformer):
                 dpad = 64 if mod.d_head <= 64 else 128
                 HD = mod.n_heads * dpad
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{name}.transformer_blocks.{bi}"
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim * kx,
                                 out16=self.bufs[q + ".ctx_k"])
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim * kx,
                                 out16=self.bufs[q + ".ctx_vt"], rows_per_group=L, ldT=Lp, flags=_C.GEMM_F_CHW)
         self.ctx_prog = self.prog
         self.prog = main
