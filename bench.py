@@ -33,7 +33,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--eta", type=float, default=1.0, help="DDIM eta (reference default in log_images is 1.0)")
-    ap.add_argument("--precision", default=os.environ.get("UPGPT_PRECISION", "fp16"))
+    ap.add_argument("--precision", default=os.environ.get("UPGPT_PRECISION", "fp16x3"),
+                    help="fp16x3 = error-compensated operands, meets the 1e-3 eps tolerance (headline); fp16 = fast mode")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the additional fp16 fast-mode measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -173,32 +175,55 @@ def build_model(dev, precision):
     return model.to(dev).eval()
 
 
-def roofline_dominant_kernel(dev, pk):
+def roofline_dominant_kernel(dev, pk, precision):
     """Dominant kernel = tc_gemm_kernel (tcgen05 implicit-GEMM conv); its largest single class is the 224->224 3x3 conv at
-    32x32, B=8 (14 launches per U-Net step).  Timed alone with CUDA events on the launching stream, L2 flushed between launches."""
+    32x32, B=8 (14 launches per U-Net step).  Timed with CUDA events on the launching stream as a graph of 16 launches that
+    rotate over 16 operand sets (200 MB > the 126 MB L2, so operands are cold as in the real step).  `achieved` counts the
+    ALGORITHMIC flops of the reference conv (2*M*N*K*9); in fp16x3 the kernel executes 3x that many MMA flops."""
     import torch
     from upgpt_b200 import _C, ops
     B, H, W, C = B_PER_GPU, LAT, LAT, 224
-    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half()
-    w = (torch.randn(C, 9, C, device=dev) * 0.02).half()
+    kx = 3 if precision == "fp16x3" else 1
+    REP, NC = 16, 16
+    xs = [(torch.randn(B, H, W, C * kx, device=dev) * 0.5).half() for _ in range(NC)]
+    ws = [(torch.randn(C, 9, C * kx, device=dev) * 0.02).half() for _ in range(NC)]
     bias = torch.randn(C, device=dev)
     out = torch.empty(B * H * W, C, device=dev)
-    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
-    kw = dict(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias)
-    for _ in range(3):
-        ops.gemm(**kw)
+    call = lambda i: ops.gemm(a=xs[i % NC], w=ws[i % NC], mode=_C.GEMM_CONV3X3, N=C, K=C * kx, n_imgs=B, H=H, W=W, out32=out, bias=bias)
+    for i in range(3):
+        call(i)
+    torch.cuda.synchronize()
+    g = ops.Graph().capture(lambda: [call(i) for i in range(REP)])
+    g.launch(); torch.cuda.synchronize()
     ts = []
-    for _ in range(20):
-        flush.zero_()
+    for _ in range(5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); ops.gemm(**kw); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sum(ts) / len(ts)
+        e0.record(); g.launch(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / REP)
+    ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * B * H * W * 9 * C * C
     ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8)", "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
+    return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % precision, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
             "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": pk["src"] + " (burst: kernel timed alone)",
-            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops}
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": flops * kx,
+            "limiter": "per-SM TMA ingest (~100 GB/s/SM measured with the in-kernel timeline, profiles/r01_gemm_timeline.txt)"}
+
+
+def parity_spot_check(model, dev):
+    """eps of the bbox.yaml U-Net (B=1, t=501) on the GPU vs the CPU oracle, in the benchmark's precision mode."""
+    import torch
+    from oracle import ldm_oracle as O
+    from oracle.ref_loader import BBOX_UNET_KW
+    from upgpt_b200 import synth
+    unet = model.model.diffusion_model
+    sd = {k: v.detach().float().cpu() for k, v in unet.state_dict().items()}
+    x, mask, ctx = synth.synth_inputs(1, LAT, LAT, CTX_LEN, CTX_DIM, 11)
+    t = torch.full((1,), 501, dtype=torch.long)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx)
+        got = unet(torch.cat([x, mask], 1).to(dev), t.to(dev), ctx.to(dev)).cpu()
+    return {"eps_max_rel_vs_oracle": float((got - ref).abs().max() / ref.abs().max()), "eps_l2_rel": float((got - ref).norm() / ref.norm()),
+            "case": "bbox.yaml U-Net, B=1, 32x32, t=501, synthetic weights", "tolerance": 1e-3}
 
 
 def gpu_arm(args, rank, world):
@@ -277,27 +302,39 @@ def gpu_arm(args, rank, world):
     n_img = world * B * args.steps
     value = n_img / (ms * 1e-3)
     e2e_val = n_img / (ms_e2e * 1e-3)
+    fast = None
+    if args.precision != "fp16" and not args.no_fast_mode:
+        # opt-in fast mode (single fp16 operand plane, eps ~1.5e-3): same workload, reported beside the headline
+        os.environ["UPGPT_PRECISION"] = "fp16"
+        ms_f, _, _ = timed(step_resident, max(1, args.warmup - 1), args.steps)
+        os.environ["UPGPT_PRECISION"] = args.precision
+        fast = {"precision": "fp16", "value": n_img / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / args.steps,
+                "eps_max_rel_vs_reference": "1.3e-3 .. 1.7e-3 (tests/test_gpu_hotpath.py)"}
     if rank == 0:
-        roof = roofline_dominant_kernel(dev, pk)
+        roof = roofline_dominant_kernel(dev, pk, args.precision)
         alg_tf_per_step = world * B * (DDIM_STEPS * GF_UNET_PER_SAMPLE_STEP + GF_VAE_PER_IMAGE) / 1e3
-        eng = next(iter(model.model.diffusion_model._engines.values()))
+        eng = [e for k, e in model.model.diffusion_model._engines.items() if k[-1] == args.precision][0]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 operands / f32 accumulate+residual (%s)" % args.precision, "data": "synthetic",
+                "dtype": "f16" if args.precision == "fp16" else "f16 hi+lo operand planes (3 MMAs per product), f32 accumulate / residual / statistics",
+                "data": "synthetic",
                 "config": {"workload": "configs[1]: bbox.yaml U-Net (425.29M params, random init) 32x32x4 latent, 87x768 context, "
                                        "50-step DDIM eta=%g, bs=%d per GPU, + KL-f8 decode to 256x256 uint8" % (args.eta, B),
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
-                           "l2_policy": "inputs+weights (1.9 GB fp16/fp32 per pass) exceed the 126 MB L2; no explicit flush",
-                           "kernels_per_unet_step": eng.launches_per_step + 3, "precision_mode": args.precision},
+                           "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
+                           "kernels_per_unet_step": eng.launches_per_step + 3, "precision_mode": args.precision,
+                           "eps_tolerance": "1e-3 (north_star); measured 1.3e-4 .. 1.9e-4 in fp16x3" if args.precision == "fp16x3" else "fast mode: 1.3e-3 .. 1.7e-3"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
                         "d2h_bytes_per_step": int(out_pin.numel())},
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": roof,
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
-                               "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]}}
+                               "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},
+                "fast_mode": fast}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_quick()
+            line["parity"] = parity_spot_check(model, dev)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -3,7 +3,7 @@ samplers vs the oracle's restatement of the reference loops, the KL-f8 VAE decod
 at BASELINE's full size (B=8, 32x32, bbox.yaml U-Net).
 
 Tolerances (metric: max|a-b| / max|b| as defined in SURVEY.md 7.2):
-  fp16 operand mode  : 2.5e-3 on eps (measured 1.3e-3..1.7e-3; fp16 rounding of conv/GEMM operands, fp32 everywhere else)
+  fp16 fast mode (opt-in): 2.5e-3 on eps (measured 1.3e-3..1.7e-3; single fp16 operand plane, fp32 everywhere else)
   fp16x3 (every GEMM/conv operand error-compensated with hi/lo fp16 planes): 5e-4 asserted, 1.3e-4..1.9e-4 measured --
                        this is the mode that meets BASELINE.json's 1e-3 tolerance.
 """
@@ -47,18 +47,26 @@ def _unet(kw, seed, dev):
     ("bbox", BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0),
 ])
 def test_unet_eps_vs_reference_golden(dev, golden, tag, kw, B, H, W, L, ts, seed):
+    """Public UNetModel.forward (default precision = error-compensated fp16x3) against the reference's own outputs:
+    tolerance 1e-3 (BASELINE.json north_star), 5e-4 asserted; then the opt-in fp16 fast mode at its own bound."""
     m, _ = _unet(kw, seed, dev)
     x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed)
     xc = torch.cat([x, mask], 1).to(dev)
     for t in ts:
         tt = torch.full((B,), t, dtype=torch.long, device=dev)
+        ref = torch.from_numpy(golden[f"{tag}_eps_t{t}"])
         with torch.no_grad():
             y = m(xc, tt, ctx.to(dev))                     # public UNetModel.forward (graph replay)
             eng = m.engine(B, H, W, L)
+            assert eng.precision == "fp16x3"
             eng.stage_inputs(xc, tt); y_eager = eng.run(use_graph=False).clone()
-        ref = torch.from_numpy(golden[f"{tag}_eps_t{t}"])
-        assert relerr(y, ref) < EPS_TOL
+        assert relerr(y, ref) < 5e-4
         assert torch.equal(y, y_eager), "graph replay must be bit-identical to the eager program (deterministic reductions)"
+        fast = m.engine(B, H, W, L, precision="fp16")
+        fast.set_context(ctx.to(dev)); fast.stage_inputs(xc, tt)
+        yf = fast.run(use_graph=True).clone()
+        assert relerr(yf, ref) < EPS_TOL
+        assert torch.equal(yf, fast.run(use_graph=False))
 
 
 @pytest.mark.parametrize("tag,kw,B,H,W,L,ts,seed", [
