@@ -183,13 +183,15 @@ def roofline_dominant_kernel(dev, pk, precision):
     import torch
     from upgpt_b200 import _C, ops
     B, H, W, C = B_PER_GPU, LAT, LAT, 224
-    kx = 3 if precision == "fp16x3" else 1
+    x3 = precision == "fp16x3"
+    kx = 2 if x3 else 1                  # operand planes [hi | lo]
     REP, NC = 16, 16
     xs = [(torch.randn(B, H, W, C * kx, device=dev) * 0.5).half() for _ in range(NC)]
     ws = [(torch.randn(C, 9, C * kx, device=dev) * 0.02).half() for _ in range(NC)]
     bias = torch.randn(C, device=dev)
     out = torch.empty(B * H * W, C, device=dev)
-    call = lambda i: ops.gemm(a=xs[i % NC], w=ws[i % NC], mode=_C.GEMM_CONV3X3, N=C, K=C * kx, n_imgs=B, H=H, W=W, out32=out, bias=bias)
+    call = lambda i: ops.gemm(a=xs[i % NC], w=ws[i % NC], mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias,
+                              flags=_C.GEMM_F_X3 if x3 else 0)
     for i in range(3):
         call(i)
     torch.cuda.synchronize()
@@ -205,7 +207,7 @@ def roofline_dominant_kernel(dev, pk, precision):
     ach = flops / (ms * 1e-3) / 1e12
     return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % precision, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
             "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": pk["src"] + " (burst: kernel timed alone)",
-            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": flops * kx,
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": flops * (3 if x3 else 1),
             "limiter": "per-SM TMA ingest (~100 GB/s/SM measured with the in-kernel timeline, profiles/r01_gemm_timeline.txt)"}
 
 

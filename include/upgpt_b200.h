@@ -40,8 +40,11 @@ enum {
 enum {
   UPGPT_GEMM_F_GEGLU = 1u << 1, /* W rows packed per tile as [x | gate]; out16 = x * gelu(gate)   (attention.py:37-44) */
   UPGPT_GEMM_F_CHW = 1u << 2,   /* store channel-major: out[(group*N + n)*ldT + row_in_group] (NCHW images, V^T for attention) */
-  UPGPT_GEMM_F_SPLIT3OUT = 1u << 4 /* out16 rows = [hi | lo | hi] planes (N columns each, ld16 default 3N): the A operand of a following
-                                     GEMM in the error-compensated fp16x3 mode, whose weights are packed [Wh | Wh | Wl] along K */
+  UPGPT_GEMM_F_SPLIT3OUT = 1u << 4, /* out16 rows = [hi | lo] fp16 planes (N columns each, ld16 default 2N; x ~= hi + lo to ~22 bits):
+                                      the A operand of a following UPGPT_GEMM_F_X3 GEMM */
+  UPGPT_GEMM_F_X3 = 1u << 5         /* error-compensated fp16x3 product (the precision mode that meets the 1e-3 eps tolerance):
+                                      A rows = [Ah | Al] planes of K columns (lda default 2K), W rows per tap = [Wh | Wl] (ldw
+                                      default 2K); D = Ah*Wh + Al*Wh + Ah*Wl in fp32: 3 MMAs per k-step on 2 loaded plane pairs */
 };
 typedef struct upgpt_gemm_args {
   const void* a;            /* fp16 activations */
@@ -95,15 +98,15 @@ typedef struct upgpt_prep_args {
   const float* gamma; const float* beta; float eps;
   int silu;                  /* apply x*sigmoid(x) after the affine */
   int layout;                /* 0 same; 1 nearest-x2 upsampled [B][2H][2W][C]; 2 stride-2 phases [4][B][H/2][W/2][C] */
-  int split3;                /* emit error-compensated operand planes [hi | lo | hi] (3C channels) */
-  void* out; int ldo;        /* fp16 output, ldo elements per pixel (0 = C or 3C) */
+  int split3;                /* emit error-compensated operand planes [hi | lo] (2C channels) */
+  void* out; int ldo;        /* fp16 output, ldo elements per pixel (0 = C or 2C) */
   void* raw; int ldraw;      /* optional un-normalised fp16 copy (layout 0) */
   const float* scale_shift;  /* optional [B][2][C] affine from upgpt_groupnorm_affine (then stats/gamma/beta/eps are ignored) */
 } upgpt_prep_args;
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
 int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     void* out16, int ldo, void* stream);
-/* same with out16 rows = [hi | lo | hi] planes of C columns (ldo default 3C) */
+/* same with out16 rows = [hi | lo] planes of C columns (ldo default 2C) */
 int upgpt_layernorm_split3(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                            void* out16, int ldo, void* stream);
 /* out16[r][i] = softmax_i(scale * x[r][i]) */
@@ -122,7 +125,7 @@ typedef struct upgpt_attn_args {
   int B, H, Nq, Nk;
   int dpad;                  /* head dim padded with zero columns to 64 or 128 */
   float scale;               /* dim_head ** -0.5 (attention.py:157) */
-  int split3_out;            /* out rows = [hi | lo | hi] planes of H*dpad columns each (ldo >= 3*H*dpad) */
+  int split3_out;            /* out rows = [hi | lo] planes of H*dpad columns each (ldo >= 2*H*dpad) */
 } upgpt_attn_args;
 int upgpt_attention(const upgpt_attn_args* args, void* stream);
 

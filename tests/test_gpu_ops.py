@@ -129,10 +129,53 @@ def test_prep_layouts_and_split3(dev):
     ops.prep(x1=xd, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=0.0, silu=0, layout=1, split3=0, out=up, raw=None)
     ref = F.interpolate(x.reshape(B, H, W, C).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     assert relerr(up.reshape(B, 2 * H, 2 * W, C).permute(0, 3, 1, 2), ref) < 1e-3
-    s3 = torch.zeros(B * H * W * 3 * C, device=dev, dtype=torch.half)
+    s3 = torch.zeros(B * H * W * 2 * C, device=dev, dtype=torch.half)
     ops.prep(x1=xd, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=0.0, silu=0, layout=0, split3=1, out=s3, raw=None)
-    o = s3.reshape(B * H * W, 3, C).float().cpu()
-    assert float((o[:, 0] + o[:, 1] - x.reshape(-1, C)).abs().max()) < 1e-6 and torch.equal(o[:, 0], o[:, 2])
+    o = s3.reshape(B * H * W, 2, C).float().cpu()      # planes [hi | lo]: hi = fp16(x), lo = fp16(x - hi)
+    assert float((o[:, 0] + o[:, 1] - x.reshape(-1, C)).abs().max()) < 1e-6 and torch.equal(o[:, 0], x.reshape(-1, C).half().float())
+
+
+def _planes(t):
+    """fp32 [..., K] -> fp16 [..., 2K] = [hi | lo]."""
+    hi = t.half()
+    return torch.cat([hi, (t - hi.float()).half()], -1)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 64, 64, 0), (8192, 224, 224, 0), (300, 448, 448, 0), (128, 896, 896, 4), (128, 896, 8064, 0),
+                                          (696, 256, 768, 0), (512, 2048, 224, 0)])
+def test_gemm_x3_error_compensated(dev, M, N, K, splits):
+    """UPGPT_GEMM_F_X3: operands are [hi | lo] planes, product Ah*Wh + Al*Wh + Ah*Wl -> fp32-grade result (the parity mode).
+    K = 224 / 448 exercise the zero-filled k-block tail per plane (planes are a tensor-map dimension, not a K offset)."""
+    from upgpt_b200 import ops, _C
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g) * 0.5; W = torch.randn(N, K, generator=g) * 0.1
+    b = torch.randn(N, generator=g); r = torch.randn(M, N, generator=g)
+    ref = (A.double() @ W.double().t() + b + r).float()
+    out = torch.full((M, N), float("nan"), device=dev)
+    o16 = torch.zeros(M, 2 * N, device=dev, dtype=torch.half)
+    ops.gemm(a=_planes(A).to(dev), w=_planes(W).to(dev), mode=0, M=M, N=N, K=K, splits=splits, out32=out, out16=o16, bias=b.to(dev), res32=r.to(dev),
+             flags=_C.GEMM_F_X3 | _C.GEMM_F_SPLIT3OUT)
+    torch.cuda.synchronize()
+    err = relerr(out, ref)
+    assert err < 1e-5, err                  # single-plane fp16 operands give ~3e-4 here
+    o = o16.float().cpu().reshape(M, 2, N)
+    assert relerr(o[:, 0] + o[:, 1], ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 32, 32, 224, 224), (8, 16, 16, 672, 448), (8, 4, 4, 1792, 896), (2, 32, 24, 224, 224)])
+def test_conv3x3_x3_error_compensated(dev, B, H, W, Cin, Cout):
+    from upgpt_b200 import ops, _C
+    g = torch.Generator().manual_seed(B * H + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g) * 0.5
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (Cin * 9) ** -0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), padding=1).float()
+    out = torch.full((B * H * W, Cout), float("nan"), device=dev)
+    ops.gemm(a=_planes(x).to(dev), w=_planes(w.permute(0, 2, 3, 1).contiguous()).to(dev), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W,
+             out32=out, bias=b.to(dev), flags=_C.GEMM_F_X3)
+    torch.cuda.synchronize()
+    err = relerr(out.reshape(B, H, W, Cout).permute(0, 3, 1, 2), ref)
+    assert err < 1e-5, err                  # fp32 accumulation over K = 9*Cin; single-plane fp16 operands give ~3e-4
 
 
 @pytest.mark.parametrize("rows,C", [(300, 224), (64, 448), (17, 896), (5, 64)])

@@ -96,8 +96,8 @@ def test_weight_packing_helpers():
     torch.testing.assert_close(ypk[:, :, 1].reshape(5, inner), y[:, inner:])
     w3 = split3_w(w1)
     k = 224
-    rec = w3[:, :k].float() + w3[:, 2 * k:].float()
-    assert float((rec - w1).abs().max()) < 1e-6 and torch.equal(w3[:, :k], w3[:, k:2 * k])
+    rec = w3[:, :k].float() + w3[:, k:].float()            # planes [Wh | Wl]
+    assert w3.shape[1] == 2 * k and float((rec - w1).abs().max()) < 1e-6 and torch.equal(w3[:, :k], w1.half())
 
 
 def test_conditioning_routing():

@@ -7,7 +7,7 @@ from upgpt_b200 import _C, ops
 dev = torch.device("cuda:0")
 L = _C.lib()
 names = ["start", "setup done", "prod first issue", "prod last issue", "mma first full", "mma second full", "mma last full", "mma tile committed",
-         "epi tfull", "epi stores issued", "all joined", "dealloc done", "c0 tmem loaded", "c0 staged", "c0 barrier", "c0 flushed"]
+         "epi tfull", "epi stores issued", "all joined", "dealloc done", "c0 tmem loaded | splitK partials fenced", "c0 staged | siblings arrived", "c0 barrier | my slice reduced", "c0 flushed | slice barrier"]
 ts = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)
 
@@ -47,3 +47,10 @@ for (B_, H_, C_) in ((8, 4, 896), (8, 8, 896), (8, 16, 448)):
     o4 = torch.empty(B_ * H_ * H_, C_, device=dev); b4 = torch.randn(C_, device=dev); e4 = torch.randn(B_, C_, device=dev)
     for cold in (False, True):
         run(f"conv {C_}->{C_} @{H_}x{H_} B8 auto", lambda: ops.gemm(a=x4, w=w4, mode=_C.GEMM_CONV3X3, N=C_, K=C_, n_imgs=B_, H=H_, W=H_, out32=o4, bias=b4, rowvec=e4), cold)
+
+# error-compensated mode (UPGPT_GEMM_F_X3): [hi | lo] operand planes, 3 MMAs per k-step on 2 loaded plane pairs
+for (B_, H_, C_) in ((8, 32, 224), (8, 16, 448), (8, 8, 896), (8, 4, 896)):
+    x4 = (torch.randn(B_, H_, H_, 2 * C_, device=dev) * 0.5).half(); w4 = (torch.randn(C_, 9, 2 * C_, device=dev) * 0.02).half()
+    o4 = torch.empty(B_ * H_ * H_, C_, device=dev); b4 = torch.randn(C_, device=dev); e4 = torch.randn(B_, C_, device=dev)
+    for cold in (False, True):
+        run(f"X3 conv {C_}->{C_} @{H_}x{H_} B8 auto", lambda: ops.gemm(a=x4, w=w4, mode=_C.GEMM_CONV3X3, N=C_, K=C_, n_imgs=B_, H=H_, W=H_, out32=o4, bias=b4, rowvec=e4, flags=_C.GEMM_F_X3), cold)

@@ -8,9 +8,11 @@ dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "conv224"
 if which == "conv224":
     B, H, W, C = 8, 32, 32, 224
-    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half(); w = (torch.randn(C, 9, C, device=dev) * 0.02).half()
+    x3 = int(os.environ.get("X3", 0))    # 1 = the error-compensated fp16x3 mode the parity gate runs ([hi | lo] operand planes)
+    kx = 2 if x3 else 1
+    x = (torch.randn(B, H, W, C * kx, device=dev) * 0.5).half(); w = (torch.randn(C, 9, C * kx, device=dev) * 0.02).half()
     out = torch.empty(B * H * W, C, device=dev); bias = torch.randn(C, device=dev)
-    fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias)
+    fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, flags=_C.GEMM_F_X3 if x3 else 0)
 elif which == "gemm_small":
     M, N, K = 128, 896, 896
     a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)

@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
 
 
 GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1 = 0, 1, 2, 3
-GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT = 1 << 1, 1 << 2, 1 << 4
+GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT, GEMM_F_X3 = 1 << 1, 1 << 2, 1 << 4, 1 << 5
 
 
 def lib():

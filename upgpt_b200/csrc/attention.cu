@@ -26,7 +26,7 @@ struct AttnParams {
   float scale_log2e;   // softmax scale * log2(e)
   __half* out;         // [B][Nq][ldo], head h at columns h*dpad
   int ldo;
-  int plane;           // > 0: also write [lo | hi] planes at column offsets plane, 2*plane (fp16x3 operand layout)
+  int plane;           // > 0: also write the lo plane at column offset plane (fp16x3 operand layout [hi | lo])
 };
 
 static constexpr int kAttnThreads = 320;     // warp0 TMA, warp1 MMA, warps2-9 softmax (two threads per query row)
@@ -258,7 +258,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           *(uint4*)(orow + cc + u * 8) = hi;
           if (p.plane > 0) {
             *(uint4*)(orow + p.plane + cc + u * 8) = make_uint4(pl[4 * u], pl[4 * u + 1], pl[4 * u + 2], pl[4 * u + 3]);
-            *(uint4*)(orow + 2 * p.plane + cc + u * 8) = hi;
           }
         }
       }
@@ -316,7 +315,7 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = (__half*)a->out; p.ldo = a->ldo;
   p.plane = a->split3_out ? a->H * a->dpad : 0;
-  UPGPT_REQUIRE(!a->split3_out || a->ldo >= 3 * a->H * a->dpad, "attention: split3_out needs ldo >= 3*H*dpad");
+  UPGPT_REQUIRE(!a->split3_out || a->ldo >= 2 * a->H * a->dpad, "attention: split3_out needs ldo >= 2*H*dpad");
   const int dch = a->dpad / 64;
   const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);

@@ -2,7 +2,7 @@
 //
 //   gn_stats   : per-(image, group) sum / sum-of-squares of an NHWC fp32 tensor (optionally the channel concat of two)
 //   prep       : [GroupNorm-apply] [SiLU] fp32 NHWC -> fp16 tensor-core operand, optionally nearest-x2 upsampled,
-//                split into the 4 stride-2 phases, or emitted as error-compensated hi/lo/hi planes
+//                split into the 4 stride-2 phases, or emitted as error-compensated hi/lo planes
 //   layernorm  : per-token LayerNorm fp32 -> fp16 operand
 //   softmax    : row softmax fp32 -> fp16 (VAE single-head attention)
 //
@@ -156,7 +156,7 @@ struct PrepParams {
   float eps;
   int silu;
   int layout;              // 0 same, 1 nearest-up x2, 2 stride-2 phases
-  int split3;              // output channels = 3C: [hi | lo | hi]
+  int split3;              // output channels = 2C: [hi | lo]
   __half* out; int ldo;    // elements per output pixel (>= C or 3C)
   __half* raw; int ldraw;  // optional un-normalised fp16 copy (layout 0)
   int B;
@@ -207,11 +207,10 @@ prep_kernel(const PrepParams p) {
       __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
       uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
       *(uint2*)(p.raw + row * p.ldraw + c) = pk;
-      if (p.split3) {   // the un-normalised copy feeds the skip 1x1 GEMM: same [hi | lo | hi] planes
+      if (p.split3) {   // the un-normalised copy feeds the skip 1x1 GEMM: same [hi | lo] planes
         const float2 f0 = __half22float2(r0), f1 = __half22float2(r1);
         __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
         *(uint2*)(p.raw + row * p.ldraw + C + c) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
-        *(uint2*)(p.raw + row * p.ldraw + 2 * C + c) = pk;
       }
     }
     if (p.stats || p.scale_shift) {
@@ -232,7 +231,7 @@ prep_kernel(const PrepParams p) {
     if (p.layout == 0) {
       __half* o = p.out + row * p.ldo + c;
       *(uint2*)o = hi;
-      if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+      if (p.split3) *(uint2*)(o + C) = lo;
     } else if (p.layout == 1) {
       const int y = pp / p.W, x = pp % p.W;
       const int W2 = 2 * p.W;
@@ -242,7 +241,7 @@ prep_kernel(const PrepParams p) {
         for (int j = 0; j < 2; ++j) {
           __half* o = p.out + ((size_t)b * 4 * HW + (size_t)(2 * y + i) * W2 + (2 * x + j)) * p.ldo + c;
           *(uint2*)o = hi;
-          if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+          if (p.split3) *(uint2*)(o + C) = lo;
         }
     } else {
       const int y = pp / p.W, x = pp % p.W;
@@ -250,7 +249,7 @@ prep_kernel(const PrepParams p) {
       const int Ho = p.H >> 1, Wo = p.W >> 1;
       __half* o = p.out + ((((size_t)ph * p.B + b) * Ho + (y >> 1)) * Wo + (x >> 1)) * p.ldo + c;
       *(uint2*)o = hi;
-      if (p.split3) { *(uint2*)(o + C) = lo; *(uint2*)(o + 2 * C) = hi; }
+      if (p.split3) *(uint2*)(o + C) = lo;
     }
   }
 }
@@ -306,7 +305,6 @@ layernorm_kernel(const float* __restrict__ x, int ldx, int rows, int C, const fl
         const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
         __half2 l0 = __floats2half2_rn(y0 - f0.x, y1 - f0.y), l1 = __floats2half2_rn(y2 - f1.x, y3 - f1.y);
         *(uint2*)(orow + C + 4 * i) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
-        *(uint2*)(orow + 2 * C + 4 * i) = hi;
       }
     }
   }
@@ -419,8 +417,8 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   p.scale_shift = a->scale_shift;
   p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
-  p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 3 * C : C);
-  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 3 * C : C);
+  p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
   UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "prep_operand: ld must be a multiple of 4");
   const int HW = a->H * a->W;
   p.chunk = pick_chunk(HW, a->B);
@@ -435,7 +433,7 @@ static int layernorm_impl(const float* x, int ldx, int rows, int C, const float*
                           int ldo, int split3, cudaStream_t stream) {
   UPGPT_REQUIRE(x && out16 && gamma && beta && C % 4 == 0 && C <= 2048, "layernorm: bad args (C=%d)", C);
   if (ldx <= 0) ldx = C;
-  if (ldo <= 0) ldo = split3 ? 3 * C : C;
+  if (ldo <= 0) ldo = split3 ? 2 * C : C;
   UPGPT_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: ld must be multiple of 4");
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);

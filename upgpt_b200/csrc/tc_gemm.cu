@@ -8,26 +8,32 @@
 //   which *is* the convolution's zero padding, so im2col never exists in memory.
 // * W is (K, taps, N, batch) - one box per (tap, k-block, n-tile); channel tails are zero-filled by TMA.
 // * Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread tcgen05.mma issuer,
-//   warps2-5 = epilogue (tcgen05.ld -> bias / timestep-embedding row vector / residual / GEGLU -> global).
+//   warps2-9 = two epilogue groups (tcgen05.ld -> bias / timestep-embedding row vector / residual / GEGLU -> global).
 // * Persistent over tiles with a 2-deep TMEM accumulator ring so the epilogue of tile i overlaps the MMAs of tile i+1.
+// * Error-compensated mode (GEMM_X3, the precision the parity gate runs in): both operands carry [hi | lo] fp16 planes
+//   (x = hi + lo to ~22 bits). The planes are a 5th tensor-map dimension; per 64-wide k-block the producer loads the hi
+//   pair (Ah, Wh) and the lo pair (Al, Wl) into two consecutive pipeline slots and the issuer forms
+//   Ah*Wh + Al*Wh + Ah*Wl from them: 3x the MMA work on 2x (not 3x) the operand bytes.
 //
 // Replaces (reference call sites): F.conv2d in ResBlock/Downsample/Upsample (openaimodel.py:116-118,151-153,204,230,241),
 // nn.Linear / 1x1 conv in SpatialTransformer/CrossAttention/FeedForward (attention.py:37-64,161-168,233-248),
 // and the VAE decoder convolutions (model.py:82-141,535-568).
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include <type_traits>
+#include <cstdlib>
 #include "../../include/upgpt_b200.h"
 
 namespace upgpt {
 
-static constexpr int kGemmThreads = 192;
+static constexpr int kGemmThreads = 320;   // TMA producer warp + MMA issuer warp + 2 epilogue groups of 4 warps
 static constexpr int kABytes = 128 * 64 * 2;  // smem slot for one A stage
 
-__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
 #define TS(slot) do { if (p.debug_ts) p.debug_ts[(size_t)blockIdx.x * 16 + (slot)] = gtime(); } while (0)
 
-// fp16 store of 4 consecutive columns; with `plane` > 0 also the error-compensation planes [hi | lo | hi] at column
-// offsets 0, plane, 2*plane (operand layout of the fp16x3 precision mode)
+// fp16 store of 4 consecutive columns; with `plane` > 0 also the error-compensation plane: [hi | lo] at column
+// offsets 0, plane (operand layout of the fp16x3 precision mode)
 __device__ __forceinline__ void store_h4(__half* dst, float4 v, int plane) {
   __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
   const uint2 hi = make_uint2(*(uint32_t*)&h0, *(uint32_t*)&h1);
@@ -36,7 +42,6 @@ __device__ __forceinline__ void store_h4(__half* dst, float4 v, int plane) {
     const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
     __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
     *(uint2*)(dst + plane) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
-    *(uint2*)(dst + 2 * plane) = hi;
   }
 }
 
@@ -61,12 +66,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_base_smem = (uint32_t*)(bar_res + 2);
   uint32_t* split_flag = tmem_base_smem + 1;
   const uint32_t off_stage = (off_bar + (2u * p.stages + 6u) * 8u + 8u + 1023u) & ~1023u;
+  // per epilogue group (2 groups): one staging chunk, one residual chunk, the row tables and the tile's bias
   float* stage = (float*)(smem + off_stage);                 // 2 x [128 rows][128 B] epilogue staging (swizzle-128B layout)
   float* resbuf = (float*)(smem + off_stage + 2 * 16384);    // 2 x [128 rows][32 fp32] residual chunks (only if res_tma)
   const uint32_t off_tab = off_stage + 2 * 16384 + (p.res_tma ? 2 * 16384 : 0);
-  long long* row_tab = (long long*)(smem + off_tab);         // [128] global output row of each tile row (-1 = not stored)
-  int* grp_tab = (int*)(smem + off_tab + 128 * 8);           // [128] row group (image / batch entry) of each tile row
-  float* bias_s = (float*)(smem + off_tab + 128 * 8 + 128 * 4);   // [256] bias of this tile's columns
+  long long* row_tab = (long long*)(smem + off_tab);         // 2 x [128] global output row of each tile row (-1 = not stored)
+  int* grp_tab = (int*)(smem + off_tab + 2 * 128 * 8);       // 2 x [128] row group (image / batch entry) of each tile row
+  float* bias_s = (float*)(smem + off_tab + 2 * 128 * 8 + 2 * 128 * 4);   // 2 x [256] bias of this tile's columns
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -86,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_tfull[s], 1);
-      mbar_init(&bar_tempty[s], 4);
+      mbar_init(&bar_tempty[s], 8);
       mbar_init(&bar_res[s], 1);
     }
     tma_prefetch_desc(&tmC);
@@ -106,6 +112,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_tiles = tiles_per_batch * p.batch;
   const int k_iters_total = p.taps * p.kblocks_per_tap;
   const int k_per_split = (k_iters_total + p.num_splits - 1) / p.num_splits;
+
+  // tile index -> (batch entry, k split, n tile, m tile); in cluster mode the splits of one output tile are the CTAs of one cluster
+  auto decode_tile = [&](int tile, int& bidx, int& split, int& nt, int& mt) {
+    if (p.cluster_reduce) {
+      split = tile % p.num_splits;
+      tile /= p.num_splits;
+      bidx = tile / tiles_mn;
+    } else {
+      bidx = tile / tiles_per_batch;
+      tile -= bidx * tiles_per_batch;
+      split = tile / tiles_mn;
+    }
+    const int rem = tile % tiles_mn;
+    nt = rem / p.num_m_tiles;
+    mt = rem - nt * p.num_m_tiles;
+  };
 
   // origin (coords 1..3) of M tile `mt` in the 4-D A / C / R tensor maps
   auto tile_origin = [&](int mt, int bidx, int& c1, int& c2, int& c3) {
@@ -129,12 +151,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int bidx = tile / tiles_per_batch;
-        int rem = tile - bidx * tiles_per_batch;
-        const int split = rem / tiles_mn;
-        rem -= split * tiles_mn;
-        const int nt = rem / p.num_m_tiles;
-        const int mt = rem - nt * p.num_m_tiles;
+        int bidx, split, nt, mt;
+        decode_tile(tile, bidx, split, nt, mt);
         int c1, c2, c3;  // A box origin (before tap shift)
         tile_origin(mt, bidx, c1, c2, c3);
         const int k_begin = split * k_per_split;
@@ -142,13 +160,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kit = k_begin; kit < k_end; ++kit) {
           const int tap = kit / p.kblocks_per_tap;
           const int kb = kit - tap * p.kblocks_per_tap;
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
-          tma_load_4d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
-                      c2 + p.tap_dy[tap], c3 + p.tap_dn[tap]);
-          tma_load_4d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx);
-          if (kit == k_begin) TS(2);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          for (int plane = 0; plane <= p.x3; ++plane) {   // x3: slot pair {(Ah, Wh), (Al, Wl)}
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
+            tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
+                        c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
+            tma_load_5d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx, plane);
+            if (kit == k_begin && plane == 0) TS(2);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
         }
         TS(3);
       }
@@ -162,13 +182,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int rem = tile % tiles_per_batch;
-        const int split = rem / tiles_mn;
+        int bidx, split, nt, mt;
+        decode_tile(tile, bidx, split, nt, mt);
         const int k_begin = split * k_per_split;
         const int k_end = min(k_begin + k_per_split, k_iters_total);
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        if (p.x3) {
+          for (int kit = k_begin; kit < k_end; ++kit) {
+            // slots (stage, stage + 1) hold the hi and lo plane pairs of this k-block (stages is even: same phase)
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            if (kit == k_begin) TS(4);
+            if (kit == k_end - 1) TS(6);
+            const uint64_t ah = make_desc_kmajor_sw128(smem_u32(sA + (size_t)stage * kABytes));
+            const uint64_t wh = make_desc_kmajor_sw128(smem_u32(sB + (size_t)stage * b_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16_ss(d_tmem, ah + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+            mbar_wait(&bar_full[stage + 1], phase);
+            tc_fence_after();
+            const uint64_t al = make_desc_kmajor_sw128(smem_u32(sA + (size_t)(stage + 1) * kABytes));
+            const uint64_t wl = make_desc_kmajor_sw128(smem_u32(sB + (size_t)(stage + 1) * b_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_f16_ss(d_tmem, al + (uint64_t)(2 * k), wh + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_f16_ss(d_tmem, ah + (uint64_t)(2 * k), wl + (uint64_t)(2 * k), idesc, 1u);
+            tc_commit(&bar_empty[stage]);
+            tc_commit(&bar_empty[stage + 1]);
+            stage += 2;
+            if (stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        } else
         for (int kit = k_begin; kit < k_end; ++kit) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
@@ -193,102 +239,112 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================================ epilogue ================================
+    // Two epilogue groups of 4 warps (one warp per TMEM lane quadrant in each): group g drains the accumulator column chunks c with
+    // c % 2 == g.  One warp per SM sub-partition leaves every dependent instruction's latency exposed (measured: ~0.6 us per
+    // 32-column chunk, 3-10 us for a split-K slice reduction); two warps per scheduler overlap them.
+    const int grp = (warp - 2) >> 2;
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
     const int r = quad * 32 + lane;       // accumulator row handled by this thread
+    const int tid2 = grp * 128 + r;       // index among the 256 epilogue threads
+    const uint32_t gbar = 1u + (uint32_t)grp;   // named barrier of this group (128 threads); barrier 3 = both groups (256)
+    float* const st = stage + grp * 4096;        // this group's staging chunk [128 rows][128 B], swizzle-128B layout
+    float* const rbuf = resbuf + grp * 4096;     // this group's residual chunk (res_tma)
+    uint64_t* const rbar = &bar_res[grp];
+    long long* const rtab = row_tab + grp * 128;
+    int* const gtab = grp_tab + grp * 128;
+    float* const bias_g = bias_s + grp * 256;
+    const bool stamp = tid2 == 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    int buf = 0;
-    uint32_t res_phase0 = 0, res_phase1 = 0;
+    uint32_t res_phase = 0;
     const bool conv = (p.flags & GEMM_CONV) != 0;
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int bidx = tile / tiles_per_batch;
-      int rem = tile - bidx * tiles_per_batch;
-      const int split = rem / tiles_mn;
-      rem -= split * tiles_mn;
-      const int nt = rem / p.num_m_tiles;
-      const int mt = rem - nt * p.num_m_tiles;
+      int bidx, split, nt, mt;
+      decode_tile(tile, bidx, split, nt, mt);
       // ---- row bookkeeping: tile row -> (valid, global output row) ----
-      auto row_of = [&](int rr, bool& ok, long long& gr) {
-        if (conv) {
-          if (p.tile_imgs > 1) {
-            const int img = mt * p.tile_imgs + rr / p.HW;
-            ok = (rr < p.tile_imgs * p.HW) && (img < p.n_imgs);
-            gr = (long long)mt * p.tile_imgs * p.HW + rr;
-          } else {
-            // tile = tile_rows x tile_cols pixels of one image (tile_cols divides W; the last row tile may be ragged)
-            const int img = mt / p.tiles_per_img;
-            const int t = mt - img * p.tiles_per_img;
-            const int ty = t / p.tiles_per_row;
-            const int x0 = (t - ty * p.tiles_per_row) * p.tile_cols;
-            const int ry = rr / p.tile_cols;
-            const int y = ty * p.tile_rows + ry;
-            ok = (rr < p.tile_rows * p.tile_cols) && (y < p.H);
-            gr = (long long)img * p.HW + (long long)y * p.W + x0 + (rr - ry * p.tile_cols);
-          }
-        } else {
-          const int m = mt * 128 + rr;
-          ok = m < p.M_total;
-          gr = (long long)bidx * p.M_total + m;
-        }
-      };
       bool valid;
       long long grow;  // global output row of this thread's accumulator lane
-      row_of(r, valid, grow);
+      if (conv) {
+        if (p.tile_imgs > 1) {
+          const int img = mt * p.tile_imgs + r / p.HW;
+          valid = (r < p.tile_imgs * p.HW) && (img < p.n_imgs);
+          grow = (long long)mt * p.tile_imgs * p.HW + r;
+        } else {
+          // tile = tile_rows x tile_cols pixels of one image (tile_cols divides W; the last row tile may be ragged)
+          const int img = mt / p.tiles_per_img;
+          const int t = mt - img * p.tiles_per_img;
+          const int ty = t / p.tiles_per_row;
+          const int x0 = (t - ty * p.tiles_per_row) * p.tile_cols;
+          const int ry = r / p.tile_cols;
+          const int y = ty * p.tile_rows + ry;
+          valid = (r < p.tile_rows * p.tile_cols) && (y < p.H);
+          grow = (long long)img * p.HW + (long long)y * p.W + x0 + (r - ry * p.tile_cols);
+        }
+      } else {
+        const int m = mt * 128 + r;
+        valid = m < p.M_total;
+        grow = (long long)bidx * p.M_total + m;
+      }
       const int group = (int)(grow / p.rows_per_group);
       const int rig = (int)(grow - (long long)group * p.rows_per_group);
       const float* rv = p.rowvec ? p.rowvec + (size_t)group * p.ld_rowvec : nullptr;
       const float* rs = p.res32 ? p.res32 + (size_t)grow * p.ldres : nullptr;
       const float* bs = p.bias;
-      // publish this thread's row bookkeeping for the flat (coalesced) passes: first wait until every epilogue thread has
-      // finished reading the previous tile's tables; the staging barrier orders these writes before the first read
-      named_bar_sync(1, 128);
-      row_tab[r] = valid ? grow : -1;
-      grp_tab[r] = group;
+      // publish this thread's row bookkeeping for the flat (coalesced) passes: first wait until every thread of the group has
+      // finished reading the previous tile's tables / residual chunk; a later group barrier orders the writes before the reads
+      named_bar_sync(gbar, 128);
+      rtab[r] = valid ? grow : -1;
+      gtab[r] = group;
       const bool tma_epi = p.epi_mode != 0 && p.num_splits == 1;
+      const bool f16out = p.epi_mode == 2;
+      const int cw = f16out ? 64 : 32;                 // chunk width of the TMA-store epilogue
+      const int nch = (p.block_n + cw - 1) / cw;
       int oc1 = 0, oc2 = 0, oc3 = 0;
       if (tma_epi) {
         tile_origin(mt, bidx, oc1, oc2, oc3);
         for (int i = r; i < p.block_n; i += 128) {
           const int n = nt * p.block_n + i;
-          bias_s[i] = (p.bias && n < p.N_total) ? p.bias[n] : 0.f;
+          bias_g[i] = (p.bias && n < p.N_total) ? p.bias[n] : 0.f;
         }
-        if (p.res_tma && r == 0) {
-          // prefetch the residual chunks 0 and 1 of this tile while the main loop is still running
-          const int nch = (p.block_n + 31) >> 5;
-          for (int c = 0; c < 2 && c < nch; ++c) {
-            const int b = buf ^ c;
-            mbar_arrive_expect_tx(&bar_res[b], p.a_bytes);
-            tma_load_4d(resbuf + b * 4096, &tmR, &bar_res[b], nt * p.block_n + c * 32, oc1, oc2, oc3);
-          }
+        if (p.res_tma && r == 0 && grp < nch) {
+          // prefetch the residual of this group's first chunk while the main loop is still running
+          mbar_arrive_expect_tx(rbar, p.a_bytes);
+          tma_load_4d(rbuf, &tmR, rbar, nt * p.block_n + grp * 32, oc1, oc2, oc3);
         }
       }
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
-      if (r == 0) TS(8);
+      if (stamp) TS(8);
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * p.block_n) + ((uint32_t)(quad * 32) << 16);
+      // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA issuer
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      };
 
       // --------------------------------------------------------------------------------------------------------
       // Epilogue data path: TMEM -> registers (one accumulator row per thread) -> XOR-swizzled smem staging chunk
-      // [128 rows][32 fp32] -> flat coalesced pass (8 consecutive threads cover one row's 128 bytes) that applies
-      // bias / row vector / residual and stores fp32 / fp16 / split-K partials with full-line transactions and 8
-      // independent residual loads in flight per thread.  Channel-major stores skip the staging: there one row per
-      // thread is already the coalesced direction.
+      // [128 rows][32 fp32] -> either a TMA bulk store of the finished chunk, or a flat coalesced pass (8 consecutive
+      // threads cover one row's 128 bytes) that applies bias / row vector / residual and stores fp32 / fp16 / split-K
+      // partials with full-line transactions.  Channel-major stores skip the staging: there one row per thread is
+      // already the coalesced direction.
       // --------------------------------------------------------------------------------------------------------
       const bool splitk = p.num_splits > 1;
       const size_t ws_split_stride = (size_t)p.ws_rows * p.ws_ld;
 
-      // writes this thread's row (ncols fp32, ncols in {16, 32}) into staging buffer `st`
-      auto stage_row = [&](float* st, const float* f, int ncols) {
+      // writes this thread's row (ncols fp32, ncols in {16, 32}) into the group's staging buffer
+      auto stage_row = [&](const float* f, int ncols) {
         float* rowp = st + r * 32;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (q * 4 < ncols) *(float4*)(rowp + ((q ^ (r & 7)) << 2)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
       };
-      // flat pass over a staged chunk; mode 0: final values (+extras) -> out32/out16, 1: split-K partial -> workspace,
+      // flat pass over the staged chunk; mode 0: final values (+extras) -> out32/out16, 1: split-K partial -> workspace,
       // 2: GEGLU result -> out16 only (n_out0 = first output column of the chunk)
-      auto flush_chunk = [&](const float* st, int n_out0, int ncols, int mode) {
+      auto flush_chunk = [&](int n_out0, int ncols, int mode) {
         // thread r owns float4 column q = r % (ncols/4) of rows (r / (ncols/4)) + k * (128 / (ncols/4)), k = 0..ncols/4-1:
         // the column (hence bias) is loop-invariant and the k iterations are independent (loads first, then stores)
         const int sh = ncols == 32 ? 3 : 2;
@@ -302,7 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 8; ++k) {
             if (k >= iters) break;
             const int rr = rr0 + k * rstep;
-            const long long gr = row_tab[rr];
+            const long long gr = rtab[rr];
             if (gr < 0) continue;
             const float4 v = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
             __stcg((float4*)(p.ws + (size_t)split * ws_split_stride + (size_t)gr * p.ws_ld + n), v);
@@ -314,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < 8; ++k) {
             if (k >= iters) break;
             const int rr = rr0 + k * rstep;
-            const long long gr = row_tab[rr];
+            const long long gr = rtab[rr];
             if (gr < 0) continue;
             const float4 v = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
             store_h4(p.out16 + (size_t)gr * p.ld16 + n, v, p.out16_plane);
@@ -331,11 +387,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           gr[k] = -1;
           if (k >= iters) continue;
           const int rr = rr0 + k * rstep;
-          gr[k] = row_tab[rr];
+          gr[k] = rtab[rr];
           v[k] = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
           e1[k] = make_float4(0.f, 0.f, 0.f, 0.f); e2[k] = e1[k];
           if (gr[k] >= 0) {
-            if (p.rowvec) e1[k] = *(const float4*)(p.rowvec + (size_t)grp_tab[rr] * p.ld_rowvec + n);
+            if (p.rowvec) e1[k] = *(const float4*)(p.rowvec + (size_t)gtab[rr] * p.ld_rowvec + n);
             if (p.res32) e2[k] = *(const float4*)(p.res32 + (size_t)gr[k] * p.ldres + n);
           }
         }
@@ -350,48 +406,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
 
       if (tma_epi) {
-        named_bar_sync(1, 128);   // bias_s of this tile is complete before any thread reads it
+        named_bar_sync(gbar, 128);   // bias_g / tables of this tile are complete before any thread of the group reads them
         // ---- TMA-store epilogue: extras are applied in registers on the thread's own row, the finished chunk is staged in
         //      the swizzle-128B layout and one elected thread hands it to the TMA unit (clipping = tile raggedness) ----
-        const bool f16out = p.epi_mode == 2;
-        const int cw = f16out ? 64 : 32;
-        const int nch = (p.block_n + cw - 1) / cw;
-        for (int c = 0; c < nch; ++c) {
+        if (grp >= nch) release_acc();   // this group has no chunk in such a narrow tile
+        for (int c = grp; c < nch; c += 2) {
           const int j0 = c * cw;
           const int n0 = nt * p.block_n + j0;
-          float* st = stage + buf * 4096;
           uint32_t pk[32];   // the 128 staged bytes of this thread's row
           if (!f16out) {
+            // the per-group row vector (timestep embedding) is fetched before the TMEM load so both latencies overlap
+            float4 e[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              e[q] = (rv && n0 + 4 * q + 3 < p.N_total) ? *(const float4*)(rv + n0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)j0, v);
             tmem_ld_wait();
             float f[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_s[j0 + i]);
-            if (rv) {
+            for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + i]);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                if (n0 + 4 * q + 3 < p.N_total) {
-                  const float4 e = *(const float4*)(rv + n0 + 4 * q);
-                  f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
-                }
-              }
-            }
+            for (int q = 0; q < 8; ++q) { f[4 * q] += e[q].x; f[4 * q + 1] += e[q].y; f[4 * q + 2] += e[q].z; f[4 * q + 3] += e[q].w; }
             if (p.res_tma) {
-              if (buf == 0) { mbar_wait(&bar_res[0], res_phase0); res_phase0 ^= 1; }
-              else { mbar_wait(&bar_res[1], res_phase1); res_phase1 ^= 1; }
-              const float* rb = resbuf + buf * 4096 + r * 32;
+              mbar_wait(rbar, res_phase);
+              res_phase ^= 1;
+              const float* rb = rbuf + r * 32;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float4 e = *(const float4*)(rb + ((q ^ (r & 7)) << 2));
-                f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
+                const float4 x = *(const float4*)(rb + ((q ^ (r & 7)) << 2));
+                f[4 * q] += x.x; f[4 * q + 1] += x.y; f[4 * q + 2] += x.z; f[4 * q + 3] += x.w;
               }
             } else if (rs) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 if (valid && n0 + 4 * q + 3 < p.N_total) {
-                  const float4 e = *(const float4*)(rs + n0 + 4 * q);
-                  f[4 * q] += e.x; f[4 * q + 1] += e.y; f[4 * q + 2] += e.z; f[4 * q + 3] += e.w;
+                  const float4 x = *(const float4*)(rs + n0 + 4 * q);
+                  f[4 * q] += x.x; f[4 * q + 1] += x.y; f[4 * q + 2] += x.z; f[4 * q + 3] += x.w;
                 }
               }
             }
@@ -405,20 +456,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                const float a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_s[j0 + 32 * h + i]);
-                const float a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_s[j0 + 32 * h + i + 1]);
+                const float a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + 32 * h + i]);
+                const float a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_g[j0 + 32 * h + i + 1]);
                 __half2 hh = __floats2half2_rn(a0, a1);
                 pk[16 * h + (i >> 1)] = *(uint32_t*)&hh;
               }
             }
           }
-          if (c == nch - 1) {   // all TMEM reads of this tile are done: recycle the accumulator stage
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+          if (c + 2 >= nch) release_acc();            // last chunk of this group: its TMEM reads are done
+          if (r == 0) tma_store_wait_read<0>();       // the group's previous bulk store has finished reading `st`
+          named_bar_sync(gbar, 128);                  // ... and every thread has finished reading `rbuf`
+          if (p.res_tma && r == 0 && c + 2 < nch) {
+            mbar_arrive_expect_tx(rbar, p.a_bytes);
+            tma_load_4d(rbuf, &tmR, rbar, n0 + 64, oc1, oc2, oc3);
           }
-          if (r == 0) tma_store_wait_read<1>();      // the store issued two chunks ago has finished reading st
-          named_bar_sync(1, 128);
           {
             uint8_t* rowp = (uint8_t*)st + r * 128;
 #pragma unroll
@@ -426,40 +477,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               *(uint4*)(rowp + ((q ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
+          named_bar_sync(gbar, 128);
           if (r == 0) {
             tma_store_4d(&tmC, st, n0, oc1, oc2, oc3);
             tma_store_commit();
-            if (p.res_tma && c + 2 < nch) {
-              mbar_arrive_expect_tx(&bar_res[buf], p.a_bytes);
-              tma_load_4d(resbuf + buf * 4096, &tmR, &bar_res[buf], n0 + 64, oc1, oc2, oc3);
-            }
           }
           if (!f16out && p.out16) {
-            // secondary fp16 copy of the finished fp32 chunk: coalesced flat pass over the staged values
+            // secondary fp16 copy of the finished fp32 chunk: coalesced flat pass over the staged values (the next chunk's
+            // staging writes come after the next group barrier, i.e. after every thread has left this pass)
             const int q = r & 7, rr0 = r >> 3;
             const int n = n0 + (q << 2);
             if (n < p.N_total) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 const int rr = rr0 + k * 16;
-                const long long gr = row_tab[rr];
+                const long long gr = rtab[rr];
                 if (gr < 0) continue;
                 const float4 o = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
                 store_h4(p.out16 + (size_t)gr * p.ld16 + n, o, p.out16_plane);
               }
             }
           }
-          buf ^= 1;
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (r == 0) TS(9);
+        if (stamp) TS(9);
         continue;
       }
       if (p.flags & GEMM_GEGLU) {
         // tile columns are [x (half) | gate (half)]; out16[:, nt*half + j] = (x + bx) * gelu(gate + bg)
         const int half_n = p.block_n >> 1;
-        for (int j0 = 0; j0 < half_n; j0 += 32) {
+        bool first = true;
+        for (int j0 = grp * 32; j0 < half_n; j0 += 64) {
           const int ncols = min(32, half_n - j0);
           float f[32];
           for (int h0 = 0; h0 < ncols; h0 += 16) {
@@ -476,14 +524,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[h0 + i] = xv * gelu_erf_f(gv);
             }
           }
-          float* st = stage + buf * (128 * 32);
-          stage_row(st, f, ncols);
-          named_bar_sync(1, 128);
-          flush_chunk(st, nt * half_n + j0, ncols, 2);
-          buf ^= 1;
+          if (!first) named_bar_sync(gbar, 128);   // the previous chunk's flat pass has left the staging buffer
+          first = false;
+          stage_row(f, ncols);
+          named_bar_sync(gbar, 128);
+          flush_chunk(nt * half_n + j0, ncols, 2);
         }
       } else if (chw) {
-        for (int j0 = 0; j0 < p.block_n; j0 += 16) {
+        for (int j0 = grp * 16; j0 < p.block_n; j0 += 32) {
           uint32_t v[16];
           tmem_ld16(t_acc + (uint32_t)j0, v);
           tmem_ld_wait();
@@ -504,7 +552,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       } else {
-        for (int j0 = 0; j0 < p.block_n; j0 += 32) {
+        bool first = true;
+        for (int j0 = grp * 32; j0 < p.block_n; j0 += 64) {
           const int ncols = min(32, p.block_n - j0);
           float f[32];
           if (ncols == 32) {
@@ -520,67 +569,94 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
           }
-          float* st = stage + buf * (128 * 32);
-          if (r == 0 && j0 == 0) TS(12);
-          stage_row(st, f, ncols);
-          if (r == 0 && j0 == 0) TS(13);
-          named_bar_sync(1, 128);
-          if (r == 0 && j0 == 0) TS(14);
-          flush_chunk(st, nt * p.block_n + j0, ncols, splitk ? 1 : 0);
-          if (r == 0 && j0 == 0) TS(15);
-          buf ^= 1;
+          if (p.cluster_reduce) {
+            // split-K partial of this chunk -> this CTA's smem partial tile P[chunk][128 rows][32 fp32] (swizzled like the staging
+            // chunks), laid over the operand pipeline slots: the main loop of this CTA's only tile has drained them
+            float* rowp = (float*)smem + (j0 >> 5) * 4096 + r * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q * 4 < ncols) *(float4*)(rowp + ((q ^ (r & 7)) << 2)) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            continue;
+          }
+          if (!first) named_bar_sync(gbar, 128);   // the previous chunk's flat pass has left the staging buffer
+          first = false;
+          stage_row(f, ncols);
+          named_bar_sync(gbar, 128);
+          flush_chunk(nt * p.block_n + j0, ncols, splitk ? 1 : 0);
         }
       }
       // the accumulator stage can be recycled now
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+      release_acc();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (r == 0) TS(9);
+      if (stamp) TS(9);
 
-      if (splitk) {
-        // ---- deterministic split-K reduction (fixed split order => bit-reproducible) ----
+      if (splitk && !p.cluster_reduce) {
+        // ---- deterministic split-K reduction through the global workspace (fallback when the splits are not one cluster) ----
         const int tile_id = bidx * tiles_mn + nt * p.num_m_tiles + mt;
         int* ctr = p.counters + 2 * tile_id;
         const int n4 = p.block_n >> 2;
         const size_t stride4 = ws_split_stride >> 2;
-        // sums element (row rr, float4 column q4) over all splits, applies the extras and stores
-        auto reduce_store = [&](int rr, int q4) {
-          const long long gr = row_tab[rr];
-          const int n = nt * p.block_n + (q4 << 2);
-          if (gr < 0 || n >= p.N_total) return;
-          const float4* src = (const float4*)(p.ws + (size_t)gr * p.ws_ld + n);
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          int sp = 0;
-          for (; sp + 8 <= p.num_splits; sp += 8) {      // 8 independent L2 loads in flight, summed in split order
-            float4 t[8];
+        // Sums the elements idx in [lo, hi) of this tile (idx = row * n4 + float4 column) over all splits IN SPLIT ORDER, applies the
+        // extras and stores.  Several elements per thread are in flight at once and the split loop is unrolled, so the L2 round
+        // trips of the partial-tile loads overlap instead of serialising.
+        auto reduce_range = [&](int lo, int hi) {
+          constexpr int U = 2;
+          for (int base = lo + tid2; base < hi; base += 256 * U) {
+            const float4* src[U];
+            long long gr[U];
+            int nn[U], gg[U];
+            float4 a[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldcg(src + (size_t)(sp + u) * stride4);
+            for (int u = 0; u < U; ++u) {
+              const int idx = base + u * 256;
+              gr[u] = -1; nn[u] = 0; gg[u] = 0; src[u] = nullptr;
+              a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (idx < hi) {
+                const int rr = idx / n4;
+                const int n = nt * p.block_n + ((idx - rr * n4) << 2);
+                const long long g = rtab[rr];
+                if (g >= 0 && n < p.N_total) {
+                  gr[u] = g; nn[u] = n; gg[u] = gtab[rr];
+                  src[u] = (const float4*)(p.ws + (size_t)g * p.ws_ld + n);
+                }
+              }
+            }
+            float4 e0[U], e1[U], e2[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
+            for (int u = 0; u < U; ++u) {
+              e0[u] = e1[u] = e2[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (gr[u] < 0) continue;
+              if (p.bias) e0[u] = *(const float4*)(p.bias + nn[u]);
+              if (p.rowvec) e1[u] = *(const float4*)(p.rowvec + (size_t)gg[u] * p.ld_rowvec + nn[u]);
+              if (p.res32) e2[u] = *(const float4*)(p.res32 + (size_t)gr[u] * p.ldres + nn[u]);
+            }
+#pragma unroll 4
+            for (int sp = 0; sp < p.num_splits; ++sp) {
+              float4 t[U];
+#pragma unroll
+              for (int u = 0; u < U; ++u) t[u] = gr[u] >= 0 ? __ldcg(src[u] + (size_t)sp * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int u = 0; u < U; ++u) { a[u].x += t[u].x; a[u].y += t[u].y; a[u].z += t[u].z; a[u].w += t[u].w; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              if (gr[u] < 0) continue;
+              float4 o = a[u];
+              o.x += e0[u].x; o.y += e0[u].y; o.z += e0[u].z; o.w += e0[u].w;
+              o.x += e1[u].x; o.y += e1[u].y; o.z += e1[u].z; o.w += e1[u].w;
+              o.x += e2[u].x; o.y += e2[u].y; o.z += e2[u].z; o.w += e2[u].w;
+              if (p.out32) *(float4*)(p.out32 + (size_t)gr[u] * p.ld32 + nn[u]) = o;
+              if (p.out16) store_h4(p.out16 + (size_t)gr[u] * p.ld16 + nn[u], o, p.out16_plane);
+            }
           }
-          {
-            float4 t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = (sp + u < p.num_splits) ? __ldcg(src + (size_t)(sp + u) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { a.x += t[u].x; a.y += t[u].y; a.z += t[u].z; a.w += t[u].w; }
-          }
-          if (p.bias) { const float4 b4 = *(const float4*)(p.bias + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
-          if (p.rowvec) {
-            const float4 b4 = *(const float4*)(p.rowvec + (size_t)grp_tab[rr] * p.ld_rowvec + n);
-            a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-          }
-          if (p.res32) { const float4 b4 = *(const float4*)(p.res32 + (size_t)gr * p.ldres + n); a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w; }
-          if (p.out32) *(float4*)(p.out32 + (size_t)gr * p.ld32 + n) = a;
-          if (p.out16) store_h4(p.out16 + (size_t)gr * p.ld16 + n, a, p.out16_plane);
         };
         __threadfence();
-        named_bar_sync(1, 128);
+        named_bar_sync(3, 256);
+        if (stamp) TS(12);
         if (p.coop_reduce) {
           // every split of this tile is resident (cooperative launch, one tile per CTA): all of them wait for the last
           // partial and then each reduces its own 1/num_splits slice of the tile -> the reduction is parallel as well
-          if (r == 0) {
+          if (tid2 == 0) {
             atomicAdd(ctr, 1);
             int seen;
             do {
@@ -588,42 +664,129 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (seen < p.num_splits) __nanosleep(40);
             } while (seen < p.num_splits);
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(3, 256);
+          if (stamp) TS(13);
           __threadfence();
           const int total = 128 * n4;
           const int per = (total + p.num_splits - 1) / p.num_splits;
           const int lo = split * per, hi = min(lo + per, total);
-          for (int idx = lo + r; idx < hi; idx += 128) {
-            const int rr = idx / n4;
-            reduce_store(rr, idx - rr * n4);
-          }
-          named_bar_sync(1, 128);
-          if (r == 0) {
+          reduce_range(lo, hi);
+          if (stamp) TS(14);
+          named_bar_sync(3, 256);
+          if (stamp) TS(15);
+          if (tid2 == 0) {
             const int d = atomicAdd(ctr + 1, 1);
             if (d == p.num_splits - 1) { ctr[0] = 0; ctr[1] = 0; }   // last reader re-arms the counters for the next launch
           }
         } else {
           // fallback (several tiles per CTA): the last split to arrive reduces the whole tile
-          if (r == 0) {
+          if (tid2 == 0) {
             const int prev = atomicAdd(ctr, 1);
             const int last = prev == p.num_splits - 1;
             if (last) *ctr = 0;
             *split_flag = (uint32_t)last;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(3, 256);
           const bool is_last = *split_flag != 0;
-          named_bar_sync(1, 128);   // everyone has read the flag before a later tile may overwrite it
+          named_bar_sync(3, 256);   // everyone has read the flag before a later tile may overwrite it
           if (is_last) {
             __threadfence();
-            const int total = 128 * n4;
-            for (int idx = r; idx < total; idx += 128) {
-              const int rr = idx / n4;
-              reduce_store(rr, idx - rr * n4);
-            }
+            reduce_range(0, 128 * n4);
           }
         }
       }
     }
+  }
+
+  if (p.cluster_reduce) {
+    // ---- deterministic split-K reduction over distributed shared memory ----
+    // The num_splits CTAs of this cluster hold the fp32 partials of ONE output tile in their own shared memory.  After a cluster
+    // barrier, CTA `rank` sums slice `rank` of the tile over all CTAs in rank order (bit-reproducible) with ld.shared::cluster,
+    // applies the extras and stores: the partials never travel through L2 (measured: the global-workspace round trip cost 5-10 us
+    // per launch at ~2.5 TB/s aggregate, more than the main loop of the 4x4 / 8x8 levels).
+    cluster_sync_all();
+    if (threadIdx.x == 64) TS(12);
+    if (warp >= 2) {
+      const int grp = (warp - 2) >> 2;
+      const int r = (warp & 3) * 32 + lane;
+      const int tid2 = grp * 128 + r;
+      const long long* rtab = row_tab + grp * 128;
+      const int* gtab = grp_tab + grp * 128;
+      int bidx, split, nt, mt;
+      decode_tile((int)blockIdx.x, bidx, split, nt, mt);
+      const uint32_t p_base = smem_u32(smem);
+      // CTA `split` owns rows [row_lo, row_hi) of the tile.  8 consecutive threads cover one row's 128 bytes of a 32-column chunk
+      // (coalesced 128-byte stores), 32 rows per pass; all index math is shifts and adds (an earlier flat-index version spent
+      // ~0.3 us per element in integer divisions and predicated address arithmetic at two warps per scheduler).
+      auto reduce_slice = [&](auto s_c) {
+        constexpr int SS = decltype(s_c)::value;   // cluster size as a constant: the SS partial loads of an element are all in flight
+        const int rows_per = (128 + SS - 1) / SS;
+        const int row_lo = split * rows_per;
+        const int row_hi = min(row_lo + rows_per, 128);
+        const int q = tid2 & 7;
+        const int nchunks = (p.block_n + 31) >> 5;
+        uint32_t rbase[SS];
+#pragma unroll
+        for (int j = 0; j < SS; ++j) rbase[j] = mapa_shared(p_base, (uint32_t)j);
+        // UC column chunks of a row are processed together: all their partial / row-vector / residual loads are issued before the
+        // first use, so one DSMEM + L2 round trip (~450 cycles under load) is paid per UC elements instead of per element
+        constexpr int UC = SS <= 3 ? 4 : 2;
+        for (int c0 = 0; c0 < nchunks; c0 += UC) {
+          int n[UC];
+          bool ok[UC];
+          float4 b4[UC];
+#pragma unroll
+          for (int u = 0; u < UC; ++u) {
+            const int ncol = (c0 + u) * 32 + q * 4;
+            n[u] = nt * p.block_n + ncol;
+            ok[u] = ncol < p.block_n && n[u] < p.N_total;
+            b4[u] = (ok[u] && p.bias) ? *(const float4*)(p.bias + n[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          for (int rr = row_lo + (tid2 >> 3); rr < row_hi; rr += 32) {
+            const long long g = rtab[rr];
+            if (g < 0) continue;
+            const uint32_t off0 = (uint32_t)(c0 * 16384 + rr * 128 + ((q ^ (rr & 7)) << 4));
+            float4 t[UC][SS], e1[UC], e2[UC];
+            const float* rvp = p.rowvec ? p.rowvec + (size_t)gtab[rr] * p.ld_rowvec : nullptr;
+            const float* rsp = p.res32 ? p.res32 + (size_t)g * p.ldres : nullptr;
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+              const uint32_t off = ok[u] ? off0 + (uint32_t)u * 16384u : off0;   // masked chunks re-read a valid address
+#pragma unroll
+              for (int j = 0; j < SS; ++j) {
+                // own partial through the local port (DSMEM sustains only ~10-20 B/clk per SM)
+                if (j == split) t[u][j] = *(const float4*)(smem + off);
+                else t[u][j] = ld_cluster_f4(rbase[j] + off);
+              }
+              e1[u] = (ok[u] && rvp) ? *(const float4*)(rvp + n[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              e2[u] = (ok[u] && rsp) ? *(const float4*)(rsp + n[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+              if (!ok[u]) continue;
+              float4 o = t[u][0];   // partials are summed in rank order whoever owns the row => bit-reproducible, batch-order independent
+#pragma unroll
+              for (int j = 1; j < SS; ++j) { o.x += t[u][j].x; o.y += t[u][j].y; o.z += t[u][j].z; o.w += t[u][j].w; }
+              o.x += b4[u].x + e1[u].x + e2[u].x; o.y += b4[u].y + e1[u].y + e2[u].y;
+              o.z += b4[u].z + e1[u].z + e2[u].z; o.w += b4[u].w + e1[u].w + e2[u].w;
+              if (p.out32) *(float4*)(p.out32 + (size_t)g * p.ld32 + n[u]) = o;
+              if (p.out16) store_h4(p.out16 + (size_t)g * p.ld16 + n[u], o, p.out16_plane);
+            }
+          }
+        }
+      };
+      switch (p.num_splits) {
+        case 2: reduce_slice(std::integral_constant<int, 2>{}); break;
+        case 3: reduce_slice(std::integral_constant<int, 3>{}); break;
+        case 4: reduce_slice(std::integral_constant<int, 4>{}); break;
+        case 5: reduce_slice(std::integral_constant<int, 5>{}); break;
+        case 6: reduce_slice(std::integral_constant<int, 6>{}); break;
+        case 7: reduce_slice(std::integral_constant<int, 7>{}); break;
+        default: reduce_slice(std::integral_constant<int, 8>{}); break;
+      }
+      if (tid2 == 0) TS(14);
+    }
+    cluster_sync_all();   // no CTA may exit (and release its shared memory) while a sibling still reads its partial tile
   }
 
   if (warp >= 2 && ((warp & 3) * 32 + lane) == 0) tma_store_wait_read<0>();   // smem must outlive the bulk stores' reads
@@ -648,6 +811,7 @@ static size_t g_ws_bytes = 0;
 static int* g_counters = nullptr;
 static constexpr int kMaxCounters = 1 << 16;
 static long long* g_debug_ts = nullptr;
+static int g_max_clusters[9] = {0};           // co-resident clusters of size S (S CTAs must share a GPC), from the occupancy API
 
 static int gemm_device_setup() {
   if (g_attr_set) return 0;
@@ -656,6 +820,17 @@ static int gemm_device_setup() {
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+  for (int S = 1; S <= 8; ++S) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S * g_num_sms); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = g_smem_optin;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = g_num_sms / (2 * S); }
+    g_max_clusters[S] = n;
+  }
   g_ws_bytes = (size_t)96 << 20;
   UPGPT_CHECK_CUDA(cudaMalloc(&g_ws, g_ws_bytes));
   UPGPT_CHECK_CUDA(cudaMalloc(&g_counters, kMaxCounters * sizeof(int)));
@@ -671,7 +846,7 @@ static int gemm_device_setup() {
 // Wide tiles minimise A re-reads; split-K supplies the parallelism that small-M layers lack.
 struct TileChoice { int bn; int splits; };
 static TileChoice choose_tiling(int N, int m_tiles_x_batch, int k_iters, int num_sms, int gran, bool must_divide, bool allow_split,
-                                int chunk_cols) {
+                                int chunk_cols, bool x3) {
   TileChoice best{gran, 1};
   double best_t = 1e30;
   auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
@@ -680,16 +855,22 @@ static TileChoice choose_tiling(int N, int m_tiles_x_batch, int k_iters, int num
     if (must_divide && N % bn) continue;
     const int n_tiles = (N + bn - 1) / bn;
     const int base = m_tiles_x_batch * n_tiles;
-    const double us_per_iter = (16384.0 + 128.0 * bn) / 100e3;          // bytes / (100 GB/s) in us
+    // per k-block: operand ingest at ~100 GB/s/SM vs the MMAs at ~10 TFLOP/s/SM; x3 = 2 plane pairs loaded, 3 products issued
+    const double ingest_us = (x3 ? 2.0 : 1.0) * (16384.0 + 128.0 * bn) / 100e3;
+    const double mma_us = (x3 ? 3.0 : 1.0) * (2.0 * 128.0 * bn * 64.0) / 10e6;
+    const double us_per_iter = ingest_us > mma_us ? ingest_us : mma_us;
     const double epi = 0.6 * ((bn + chunk_cols - 1) / chunk_cols);
-    const int max_splits = allow_split ? (k_iters / 2 < 32 ? k_iters / 2 : 32) : 1;
+    // split-K = the CTAs of one cluster (<= 8): partial tiles stay in shared memory and are reduced over DSMEM
+    const int max_splits = allow_split ? (k_iters / 2 < 8 ? k_iters / 2 : 8) : 1;
     for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
       const int ctas = base * sp;
-      if (sp > 1 && ctas > num_sms) break;                              // cooperative reduction needs one wave
-      const int waves = (ctas + num_sms - 1) / num_sms;
+      const int capacity = sp == 1 ? num_sms : g_max_clusters[sp] * sp;   // CTAs of size-sp clusters that fit at once
+      if (sp > 1 && ctas > capacity) break;                               // keep split tiles to one wave
+      const int waves = (ctas + capacity - 1) / capacity;
       const int iters = (k_iters + sp - 1) / sp;
-      double t = waves * (2.5 + iters * us_per_iter + (sp == 1 ? epi : 0.9 * ((bn + 31) / 32)));
-      if (sp > 1) t += 2.5;
+      double t = waves * (2.5 + iters * us_per_iter + (sp == 1 ? epi : 0.3 * ((bn + 31) / 32)));
+      // DSMEM reduction: every CTA pulls (sp-1)/sp of a [128][bn] fp32 tile from its siblings at ~35 GB/s, + 2 cluster barriers
+      if (sp > 1) t += 1.2 + 512.0 * bn * (sp - 1) / sp / 35e3;
       if (t < best_t - 1e-9) { best_t = t; best = {bn, sp}; }
     }
   }
@@ -711,6 +892,9 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE || a->mode == UPGPT_GEMM_CONV1X1;
   GemmParams p{};
   p.flags = a->flags;
+  p.x3 = (a->flags & UPGPT_GEMM_F_X3) ? 1 : 0;
+  const uint64_t n_planes = p.x3 ? 2 : 1;          // operand planes [hi | lo] = 5th tensor-map dimension, K elements apart
+  const uint64_t ld_default = n_planes * (uint64_t)a->K;
   p.batch = conv ? 1 : (a->batch > 0 ? a->batch : 1);
   p.N_total = a->N;
   p.taps = (a->mode == UPGPT_GEMM_CONV3X3 || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) ? 9 : 1;
@@ -723,7 +907,8 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     UPGPT_REQUIRE(a->H > 0 && a->W > 0 && a->n_imgs > 0, "upgpt_gemm(conv): bad geometry");
       p.flags |= GEMM_CONV;
     p.H = a->H; p.W = a->W; p.HW = a->H * a->W; p.n_imgs = a->n_imgs;
-    uint32_t box[4];
+    uint32_t box[5];
+    box[4] = 1;
     p.tiles_per_row = 1;
     p.tile_cols = a->W;
     if (p.HW <= 64) {
@@ -749,10 +934,10 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     }
     p.a_bytes = box[0] * box[1] * box[2] * box[3] * 2;
     const int a_imgs = (a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) ? 4 * a->n_imgs : a->n_imgs;
-    uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a_imgs};
-    const uint64_t lda = a->lda > 0 ? a->lda : a->K;
-    uint64_t strides[3] = {lda * 2, lda * 2 * a->W, lda * 2 * a->W * a->H};
-    if (make_tmap_f16(&tmA, a->a, 4, dims, strides, box, true)) return -3;
+    uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a_imgs, n_planes};
+    const uint64_t lda = a->lda > 0 ? a->lda : ld_default;
+    uint64_t strides[4] = {lda * 2, lda * 2 * a->W, lda * 2 * a->W * a->H, (uint64_t)a->K * 2};
+    if (make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = p.tap_dx[t] = p.tap_dn[t] = 0; }
     if (a->mode == UPGPT_GEMM_CONV3X3) {
       for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; }
@@ -772,12 +957,12 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     p.M_total = a->M;
     p.num_m_tiles = (a->M + 127) / 128;
     p.a_bytes = kABytes;
-    const uint64_t lda = a->lda > 0 ? a->lda : a->K;
+    const uint64_t lda = a->lda > 0 ? a->lda : ld_default;
     const uint64_t abs_ = a->a_batch_stride > 0 ? (uint64_t)a->a_batch_stride : lda * (uint64_t)a->M;
-    uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)a->M, 1, (uint64_t)p.batch};
-    uint64_t strides[3] = {lda * 2, abs_ * 2, abs_ * 2};
-    uint32_t box[4] = {64, 128, 1, 1};
-    if (make_tmap_f16(&tmA, a->a, 4, dims, strides, box, true)) return -3;
+    uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->M, 1, (uint64_t)p.batch, n_planes};
+    uint64_t strides[4] = {lda * 2, abs_ * 2, abs_ * 2, (uint64_t)a->K * 2};
+    uint32_t box[5] = {64, 128, 1, 1, 1};
+    if (make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = p.tap_dx[t] = p.tap_dn[t] = 0; }
     m_rows_total = a->M;
     p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : a->M;
@@ -805,7 +990,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     if (bn <= 0 && a->N <= 16) { bn = 16; }
     if (bn <= 0) {
       const TileChoice tc = choose_tiling(a->N, p.num_m_tiles * p.batch, k_iters, g_num_sms, gran, /*must_divide=*/epi_mode == 0,
-                                          can_split, epi_mode == 2 ? 64 : 32);
+                                          can_split, epi_mode == 2 ? 64 : 32, p.x3 != 0);
       bn = tc.bn;
       if (splits <= 0) splits = tc.splits;
     } else if (splits <= 0) {
@@ -814,7 +999,8 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
       if (can_split && base * 2 <= g_num_sms && k_iters >= 8) {
         splits = g_num_sms / base;
         if (splits > k_iters / 2) splits = k_iters / 2;
-        if (splits > 32) splits = 32;
+        if (splits > 8) splits = 8;
+        while (splits > 1 && base * splits > g_max_clusters[splits] * splits) --splits;
         if (splits < 1) splits = 1;
       }
     }
@@ -846,20 +1032,20 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     p.counters = g_counters;
   }
   {
-    const uint64_t ldw = a->ldw > 0 ? a->ldw : a->K;  // elements between taps
+    const uint64_t ldw = a->ldw > 0 ? a->ldw : ld_default;  // elements between taps
     const uint64_t n_stride = ldw * p.taps;            // elements between output channels
     const uint64_t wbs = a->w_batch_stride > 0 ? (uint64_t)a->w_batch_stride : n_stride * (uint64_t)a->N;
-    uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)p.taps, (uint64_t)a->N, (uint64_t)p.batch};
-    uint64_t strides[3] = {ldw * 2, n_stride * 2, wbs * 2};
-    uint32_t box[4] = {64, 1, (uint32_t)bn, 1};
-    if (make_tmap_f16(&tmB, a->w, 4, dims, strides, box, true)) return -3;
+    uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)p.taps, (uint64_t)a->N, (uint64_t)p.batch, n_planes};
+    uint64_t strides[4] = {ldw * 2, n_stride * 2, wbs * 2, (uint64_t)a->K * 2};
+    uint32_t box[5] = {64, 1, (uint32_t)bn, 1, 1};
+    if (make_tmap_f16(&tmB, a->w, 5, dims, strides, box, true)) return -3;
   }
 
   p.debug_ts = g_debug_ts;
   p.out32 = a->out32; p.ld32 = a->ld32 > 0 ? a->ld32 : a->N;
   const int n_out16 = (p.flags & GEMM_GEGLU) ? a->N / 2 : a->N;
   p.out16_plane = (a->flags & UPGPT_GEMM_F_SPLIT3OUT) ? n_out16 : 0;
-  p.out16 = (__half*)a->out16; p.ld16 = a->ld16 > 0 ? a->ld16 : (p.out16_plane ? 3 * n_out16 : n_out16);
+  p.out16 = (__half*)a->out16; p.ld16 = a->ld16 > 0 ? a->ld16 : (p.out16_plane ? 2 * n_out16 : n_out16);
   p.bias = a->bias; p.rowvec = a->rowvec; p.ld_rowvec = a->ld_rowvec > 0 ? a->ld_rowvec : a->N;
   p.res32 = a->res32; p.ldres = a->ldres > 0 ? a->ldres : a->N;
   p.ldT = a->ldT > 0 ? a->ldT : p.rows_per_group;
@@ -904,11 +1090,20 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   }
 
   // ---- pipeline depth from the smem budget ----
-  const size_t epi_bytes = 2 * 16384 + (p.res_tma ? 2 * 16384 : 0) + 128 * 8 + 128 * 4 + 256 * 4 + 1024 /*alignment slack*/;
   const size_t stage_bytes = (size_t)kABytes + (size_t)bn * 128;
-  int stages = (int)(((size_t)g_smem_optin - 1024 - 256 - epi_bytes) / stage_bytes);
-  if (stages > 6) stages = 6;
-  if (stages > k_iters / splits + 1) stages = k_iters / splits + 1;
+  size_t epi_bytes = 0;
+  int stages = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    epi_bytes = 2 * 16384 + (p.res_tma ? 2 * 16384 : 0) + 2 * (128 * 8 + 128 * 4 + 256 * 4) + 1024 /*alignment slack*/;
+    stages = (int)(((size_t)g_smem_optin - 1024 - 256 - epi_bytes) / stage_bytes);
+    // x3 needs two slot pairs in flight to overlap loads with MMAs: give up the residual TMA prefetch buffers first
+    if (p.x3 && stages < 4 && p.res_tma) { p.res_tma = 0; continue; }
+    break;
+  }
+  const int loads_per_split = (p.x3 ? 2 : 1) * ((k_iters + splits - 1) / splits);
+  if (stages > (p.x3 ? 8 : 6)) stages = p.x3 ? 8 : 6;
+  if (stages > loads_per_split + 1) stages = loads_per_split + 1;
+  if (p.x3) stages &= ~1;
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * 8 + 16 + epi_bytes;
@@ -916,8 +1111,27 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  p.coop_reduce = (p.num_splits > 1 && num_tiles <= grid) ? 1 : 0;
-  if (p.coop_reduce) {
+  // split-K flavour: the splits of a tile as one thread-block cluster reducing over DSMEM (one tile per CTA; the fp32 partial
+  // tile [128][bn] is laid over the drained operand slots), else the global-workspace reduction
+  p.cluster_reduce = (p.num_splits > 1 && p.num_splits <= 8 && (size_t)stages * stage_bytes >= (size_t)512 * bn &&
+                      getenv("UPGPT_NO_CLUSTER_SPLITK") == nullptr) ? 1 : 0;
+  p.coop_reduce = (!p.cluster_reduce && p.num_splits > 1 && num_tiles <= grid) ? 1 : 0;
+  if (p.cluster_reduce) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_tiles); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = p.num_splits; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, p));
+  } else if (p.coop_reduce) {
     // the distributed split-K reduction spins on the arrival of sibling CTAs: a cooperative launch guarantees (or refuses)
     // co-residency instead of risking a deadlock
     cudaLaunchConfig_t cfg{};

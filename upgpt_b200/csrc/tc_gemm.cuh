@@ -9,7 +9,8 @@ enum GemmFlags : uint32_t {
   GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
   GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
   GEMM_CONV = 1u << 3,
-  GEMM_SPLIT3OUT = 1u << 4,  // (public flag) out16 written as error-compensated planes     // A rows are image pixels addressed through a 4-D (C, W, H, N) tensor map
+  GEMM_SPLIT3OUT = 1u << 4,  // (public flag) out16 written as error-compensated [hi | lo] planes
+  GEMM_X3 = 1u << 5,         // (public flag) operands carry [hi | lo] planes; D = Ah*Wh + Al*Wh + Ah*Wl
 };
 
 struct GemmParams {
@@ -21,7 +22,8 @@ struct GemmParams {
   int num_m_tiles, num_n_tiles, num_splits;
   int taps;             // 1 (GEMM / 1x1) or 9 (3x3)
   int kblocks_per_tap;  // ceil(K_per_tap / 64)
-  int stages;           // smem pipeline depth
+  int stages;           // smem pipeline depth (even in x3 mode: a k-block occupies the slot pair {hi planes, lo planes})
+  int x3;               // error-compensated product of [hi | lo] operand planes: 3 MMAs per k-step on 2 loaded plane pairs
   uint32_t a_bytes;     // bytes one A TMA box delivers (<= 16384)
   uint32_t flags;
   // ---- conv geometry (GEMM_CONV) ----
@@ -38,7 +40,7 @@ struct GemmParams {
   int ld32;
   __half* out16;        // optional fp16 copy of the result (GEGLU: the only output)
   int ld16;
-  int out16_plane;      // > 0: out16 rows are [hi | lo | hi] planes of this many columns each (fp16x3 operand layout)
+  int out16_plane;      // > 0: out16 rows are [hi | lo] planes of this many columns each (fp16x3 operand layout)
   const float* bias;    // [N_total] or null
   const float* rowvec;  // [groups, ld_rowvec] added per row-group (timestep-embedding bias), or null
   int ld_rowvec;
@@ -52,6 +54,7 @@ struct GemmParams {
   int ws_rows, ws_ld;
   int* counters;        // {arrived, done} counters per (batch, n tile, m tile); zero between launches
   int coop_reduce;      // all splits of a tile are co-resident (cooperative launch): parallel distributed reduction
+  int cluster_reduce;   // the splits of a tile form one thread-block cluster: partials stay in shared memory, reduced over DSMEM
   // ---- TMA epilogue ----
   int epi_mode;         // 0 flat stores; 1 fp32 tile chunks [rows][32] by TMA store; 2 fp16 chunks [rows][64] by TMA store
   int res_tma;          // residual tile chunks prefetched by TMA load (epi_mode 1)

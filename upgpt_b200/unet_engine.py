@@ -69,10 +69,11 @@ def pack_geglu(w, b, inner, half):
 
 
 def split3_w(w):
-    """Error-compensated fp16 weights along K: [Wh | Wh | Wl] matching operand planes [Ah | Al | Ah]."""
+    """Error-compensated fp16 weights: planes [Wh | Wl] along K (w ~= Wh + Wl to ~22 bits).  The GEMM (UPGPT_GEMM_F_X3)
+    forms Ah*Wh + Al*Wh + Ah*Wl from these and the activation planes [Ah | Al]."""
     wh = w.half()
     wl = (w - wh.float()).half()
-    return torch.cat([wh, wh, wl], dim=-1)
+    return torch.cat([wh, wl], dim=-1)
 
 
 class _Program:
@@ -103,6 +104,8 @@ class EngineBase:
         self.dev = device
         self.precision = precision
         self.split3 = precision == "fp16x3"
+        self.x3 = _C.GEMM_F_X3 if self.split3 else 0     # GEMM flag: operands carry [hi | lo] planes
+        self.kx = 2 if self.split3 else 1                # storage planes per fp16 operand
         self.L = _C.lib()
         self.w = {}
         self.bufs = {}
@@ -188,8 +191,8 @@ class EngineBase:
         Cc = C1 + C2
         stats = self.buf("gn_stats", (B, 32, 2), torch.float64)
         mult = 4 if layout == 1 else 1
-        op = self.scratch("op16", B * H * W * mult * Cc * (3 if split3 else 1), torch.float16)
-        raw = self.scratch("raw16", B * H * W * Cc * (3 if split3 else 1), torch.float16) if want_raw else None
+        op = self.scratch("op16", B * H * W * mult * Cc * (2 if split3 else 1), torch.float16)
+        raw = self.scratch("raw16", B * H * W * Cc * (2 if split3 else 1), torch.float16) if want_raw else None
         if gname is not None:
             ss = self.scratch("gn_ss", B * 2 * Cc, torch.float32)
             self.e_gn_affine(x1, C1, x2, C2, B, H * W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, ss)
@@ -224,11 +227,11 @@ class UNetEngine(EngineBase):
 
     # ------------------------------------------------------------------------------------------------ weights
     def _w16(self, w):
-        """fp32 weight [..., K] -> fp16 operand; in fp16x3 mode the K axis carries the planes [Wh | Wh | Wl]."""
+        """fp32 weight [..., K] -> fp16 operand; in fp16x3 mode the K axis carries the planes [Wh | Wl]."""
         return split3_w(w) if self.split3 else w.half()
 
     def _conv_w(self, w):
-        """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x3 planes in fp16x3 mode)."""
+        """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x2 planes in fp16x3 mode)."""
         return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]))
 
     def pack_weights(self, unet):
@@ -305,21 +308,20 @@ class UNetEngine(EngineBase):
         has_skip = (p + ".skip.weight") in self.w
         op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=self.split3)
         h32 = self.scratch("res_h", B * HW * Cout, torch.float32)
-        kmul = 3 if self.split3 else 1
         emb = None if self._sizing else self.bufs["emb_all"][:, self.emb_off[p]:]
-        self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin * kmul, n_imgs=B, H=H, W=W,
-                    out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total)
+        self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W,
+                    out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=self.x3)
         op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=self.split3)
         if has_skip:
             skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
-            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin * kmul, out32=skip32,
-                        bias=self.w.get(p + ".skip.bias"))
+            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
+                        bias=self.w.get(p + ".skip.bias"), flags=self.x3)
             res = skip32
         else:
             assert x2 is None or self._sizing or C2 == 0
             res = x1
-        self.e_gemm(a=op2, w=self.w.get(p + ".conv2.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cout * kmul, n_imgs=B, H=H, W=W,
-                    out32=out, bias=self.w.get(p + ".conv2.bias"), res32=res)
+        self.e_gemm(a=op2, w=self.w.get(p + ".conv2.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cout, n_imgs=B, H=H, W=W,
+                    out32=out, bias=self.w.get(p + ".conv2.bias"), res32=res, flags=self.x3)
 
     def _transformer(self, p, mod, x, Cc, B, H, W, out):
         HW, M = H * W, B * H * W
@@ -327,7 +329,8 @@ class UNetEngine(EngineBase):
         dpad = 64 if d <= 64 else 128
         HD = Hh * dpad
         L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
-        kx = 3 if self.split3 else 1           # operand planes [hi | lo | hi] in the error-compensated mode
+        kx = self.kx                           # operand planes [hi | lo] in the error-compensated mode
+        x3 = self.x3
         s3 = _C.GEMM_F_SPLIT3OUT if self.split3 else 0
         op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False, split3=self.split3)
         tokA = self.scratch("tokA", M * Cc, torch.float32)
@@ -336,8 +339,8 @@ class UNetEngine(EngineBase):
         qk16 = self.scratch("qk16", M * 2 * HD, torch.float16)
         vt16 = self.scratch("vt16", B * HD * _round_up(HW, 8), torch.float16)
         att16 = self.scratch("att16", M * HD * kx, torch.float16)
-        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc * kx, out32=tokA,
-                    bias=self.w.get(p + ".proj_in.bias"))
+        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
+                    bias=self.w.get(p + ".proj_in.bias"), flags=x3)
         cur, nxt = tokA, tokB
         for bi in range(len(mod.transformer_blocks)):
             q = f"{p}.transformer_blocks.{bi}"
@@ -346,35 +349,35 @@ class UNetEngine(EngineBase):
             ff16 = self.scratch("ff16", M * inner * kx, torch.float16)
             # --- self attention ---
             self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc * kx, out16=qk16)
-            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc * kx, out16=vt16, rows_per_group=HW,
-                        ldT=_round_up(HW, 8), flags=_C.GEMM_F_CHW)
+            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc, out16=qk16, flags=x3)
+            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=vt16, rows_per_group=HW,
+                        ldT=_round_up(HW, 8), flags=_C.GEMM_F_CHW | x3)
             kptr = None if self._sizing else qk16[HD:]
             self.e_attention(q=qk16, ldq=2 * HD, k=kptr, ldk=2 * HD, k_batch_stride=0, vt=vt16, ldvt=_round_up(HW, 8), out=att16,
                              ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
-            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD * kx, out32=nxt,
-                        bias=g(".attn1.out.bias"), res32=cur)
+            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                        bias=g(".attn1.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
             self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc * kx, out16=qk16)
+            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qk16, flags=x3)
             kc = self.buf(q + ".ctx_k", (B * L, HD), torch.float16)
             vc = self.buf(q + ".ctx_vt", (B, HD, Lp), torch.float16)
             self.e_attention(q=qk16, ldq=HD, k=kc, ldk=HD, k_batch_stride=0, vt=vc, ldvt=Lp, out=att16, ldo=HD * kx, B=B, H=Hh,
                              Nq=HW, Nk=L, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
-            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD * kx, out32=nxt,
-                        bias=g(".attn2.out.bias"), res32=cur)
+            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                        bias=g(".attn2.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
             self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc * kx, block_n=2 * geglu_half(inner),
-                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3)
+            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner),
+                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3 | x3)
             last = bi == len(mod.transformer_blocks) - 1
-            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner * kx, out32=nxt, bias=g(".ff2.bias"),
-                        res32=cur, out16=tok16 if last else None, flags=s3 if last else 0)
+            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
+                        res32=cur, out16=tok16 if last else None, flags=(s3 if last else 0) | x3)
             cur, nxt = nxt, cur
-        self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc * kx, out32=out,
-                    bias=self.w.get(p + ".proj_out.bias"), res32=x)
+        self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
+                    bias=self.w.get(p + ".proj_out.bias"), res32=x, flags=x3)
 
     def _emit(self, unet):
         B, H, W = self.B, self.H, self.W
@@ -433,15 +436,15 @@ class UNetEngine(EngineBase):
                     op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2, split3=self.split3)
                     hh, ww = hh // 2, ww // 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
-                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch * (3 if self.split3 else 1), n_imgs=B,
-                                H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"))
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch, n_imgs=B,
+                                H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=self.x3)
                     h, ch = out, mod.out_channels
                 elif isinstance(mod, om.Upsample):
                     op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=self.split3)
                     hh, ww = hh * 2, ww * 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
-                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch * (3 if self.split3 else 1), n_imgs=B, H=hh,
-                                W=ww, out32=out, bias=self.w.get(p + ".bias"))
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
+                                W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=self.x3)
                     h, ch = out, mod.out_channels
                 else:
                     raise NotImplementedError(type(mod))
@@ -457,15 +460,15 @@ class UNetEngine(EngineBase):
             h, ch, ch_h, ch_w = run_layers(f"output_blocks.{i}", blk, h, ch, ch_h, ch_w, skip=(s, sc))
         # ---- out: GN + SiLU + conv3x3 -> eps (NCHW fp32) ----
         op, _ = self.norm_operand(h, ch, None, 0, B, H, W, "out.0", 1e-5, True, split3=self.split3)
-        self.e_gemm(a=op, w=self.w.get("out.conv.weight"), mode=_C.GEMM_CONV3X3, N=self.out_ch, K=ch * (3 if self.split3 else 1),
-                    n_imgs=B, H=H, W=W, block_n=16, splits=1, out32=eps, bias=self.w.get("out.conv.bias"), flags=_C.GEMM_F_CHW)
+        self.e_gemm(a=op, w=self.w.get("out.conv.weight"), mode=_C.GEMM_CONV3X3, N=self.out_ch, K=ch,
+                    n_imgs=B, H=H, W=W, block_n=16, splits=1, out32=eps, bias=self.w.get("out.conv.bias"), flags=_C.GEMM_F_CHW | self.x3)
 
     def _emit_context(self, unet):
         """Program that fills the per-layer context K / V^T caches (timestep-invariant: attention.py:162-163,175-176)."""
         B, L, Lp = self.B, self.ctx_len, _round_up(self.ctx_len, 8)
         main = self.prog
         self.prog = _Program()
-        kx = 3 if self.split3 else 1
+        kx, x3 = self.kx, self.x3
         ctx32 = self.buf("ctx32", (B, L, self.ctx_dim))
         ctx16 = self.buf("ctx16", (B * L, self.ctx_dim * kx), torch.float16)
         self.e_prep(ctx32, self.ctx_dim, None, 0, B, 1, L, None, None, None, 0.0, False, 0, ctx16, split3=self.split3)
@@ -475,10 +478,10 @@ class UNetEngine(EngineBase):
                 HD = mod.n_heads * dpad
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{name}.transformer_blocks.{bi}"
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim * kx,
-                                out16=self.bufs[q + ".ctx_k"])
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim * kx,
-                                out16=self.bufs[q + ".ctx_vt"], rows_per_group=L, ldT=Lp, flags=_C.GEMM_F_CHW)
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                                out16=self.bufs[q + ".ctx_k"], flags=x3)
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
+                                out16=self.bufs[q + ".ctx_vt"], rows_per_group=L, ldT=Lp, flags=_C.GEMM_F_CHW | x3)
         self.ctx_prog = self.prog
         self.prog = main
 
