@@ -104,6 +104,11 @@ typedef struct upgpt_prep_args {
   const float* scale_shift;  /* optional [B][2][C] affine from upgpt_groupnorm_affine (then stats/gamma/beta/eps are ignored) */
 } upgpt_prep_args;
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
+/* GroupNorm(gamma, beta, eps) [+ SiLU] + cast of `args` in ONE call (args->stats / scale_shift are ignored; `stats` receives the
+ * {sum, sumsq} moments). One launch when an image's [H*W][C] fp32 tile fits the shared memory of a thread-block cluster (one
+ * cluster per image: TMA bulk load, moments exchanged over distributed shared memory, normalised out of shared memory), else
+ * upgpt_groupnorm_affine + upgpt_prep_operand internally.   replaces: GroupNorm32 + SiLU (openaimodel.py:201-203,225-227) */
+int upgpt_groupnorm_prep(const upgpt_prep_args* args, double* stats, void* stream);
 int upgpt_layernorm(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     void* out16, int ldo, void* stream);
 /* same with out16 rows = [hi | lo] planes of C columns (ldo default 2C) */

@@ -119,6 +119,65 @@ def test_groupnorm_silu_prep(dev, B, H, W, C1, C2, silu, eps):
     assert relerr(out.reshape(B, H, W, Cc).permute(0, 3, 1, 2), ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,W,C1,C2,silu,eps,layout,split3", [
+    (8, 32, 32, 224, 0, True, 1e-5, 0, 1),      # U-Net level 0: 8-CTA cluster per image
+    (8, 32, 32, 448, 224, True, 1e-5, 0, 1),    # level-0 skip concat (2.75 MB per image): 16-CTA cluster or the two-launch fallback
+    (2, 16, 16, 896, 448, True, 1e-5, 0, 0),    # concat, group boundaries straddle the two sources
+    (3, 4, 3, 896, 896, True, 1e-5, 0, 1),      # 12 pixels: ragged split over the cluster (empty trailing CTAs)
+    (2, 8, 8, 448, 0, False, 1e-6, 1, 1),       # SpatialTransformer / Upsample flavour: eps 1e-6, no SiLU, nearest-x2 layout
+    (1, 24, 32, 224, 0, True, 1e-5, 2, 0),      # stride-2 phase layout on the real bbox.yaml latent aspect (32x24)
+    (1, 128, 128, 128, 0, True, 1e-6, 0, 0),    # VAE-sized: does not fit a cluster -> internal gn_stats + prep
+])
+def test_groupnorm_prep_fused_cluster(dev, B, H, W, C1, C2, silu, eps, layout, split3):
+    """upgpt_groupnorm_prep (one cluster per image, moments over DSMEM) == the two-launch path bit for bit, and == F.group_norm."""
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(C1 + C2 + H)
+    x1 = torch.randn(B, H * W, C1, generator=g) * 2 + 0.5
+    x2 = torch.randn(B, H * W, C2, generator=g) - 1.0 if C2 else None
+    Cc = C1 + C2
+    gamma = 1 + 0.1 * torch.randn(Cc, generator=g); beta = 0.1 * torch.randn(Cc, generator=g)
+    x1d, x2d, gd, bd = x1.to(dev), (x2.to(dev) if C2 else None), gamma.to(dev), beta.to(dev)
+    kx = 2 if split3 else 1
+    mult = 4 if layout == 1 else 1
+    outs, raws, stats = [], [], []
+    for fused in (True, False):
+        st = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64)
+        out = torch.zeros(B * H * W * mult * Cc * kx, device=dev, dtype=torch.half)
+        raw = torch.zeros(B * H * W * Cc * kx, device=dev, dtype=torch.half) if layout == 0 else None
+        kw = dict(x1=x1d, C1=C1, x2=x2d, C2=C2, B=B, H=H, W=W, groups=32, gamma=gd, beta=bd, eps=eps, silu=int(silu), layout=layout,
+                  split3=split3, out=out, raw=raw)
+        if fused:
+            ops.groupnorm_prep(st, **kw)
+        else:
+            ops.groupnorm_stats(x1d, x2d, B, H * W, st)
+            ops.prep(stats=st, **kw)
+        torch.cuda.synchronize()
+        outs.append(out); raws.append(raw); stats.append(st)
+    assert float((stats[0] - stats[1]).abs().max() / stats[1].abs().max()) < 1e-6
+    # same arithmetic after the moments; the moments differ only in the fp32 partial-sum tree -> a few fp16 ulps at most
+    d = (outs[0].float() - outs[1].float()).abs().max()
+    assert float(d) <= 2e-3 * float(outs[1].float().abs().max()), float(d)
+    if raws[0] is not None:
+        assert torch.equal(raws[0], raws[1])
+    xc = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.group_norm(xc.reshape(B, H, W, Cc).permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    ref = F.silu(ref) if silu else ref
+    if layout == 1:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+        got = outs[0].reshape(B, 2 * H, 2 * W, kx, Cc).float().cpu()
+    elif layout == 2:
+        got = outs[0].reshape(2, 2, B, H // 2, W // 2, kx, Cc).float().cpu()
+        full = torch.zeros(B, H, W, kx, Cc)
+        for i in range(2):
+            for j in range(2):
+                full[:, i::2, j::2] = got[i, j]
+        got = full
+    else:
+        got = outs[0].reshape(B, H, W, kx, Cc).float().cpu()
+    val = got.sum(3)      # hi (+ lo)
+    assert relerr(val.permute(0, 3, 1, 2), ref) < (2e-5 if split3 else 2e-3)
+
+
 def test_prep_layouts_and_split3(dev):
     from upgpt_b200 import ops
     g = torch.Generator().manual_seed(9)

@@ -93,6 +93,7 @@ _PROTOS = {
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
     "upgpt_groupnorm_affine": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp],
     "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
+    "upgpt_groupnorm_prep": [C.POINTER(PrepArgs), _vp, _vp],
     "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_layernorm_split3": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_softmax_rows": [_vp, _i, _ll, _i, _f, _vp, _i, _vp],

@@ -275,6 +275,19 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
   return ra;
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ double ld_cluster_f64(uint32_t cluster_addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(cluster_addr));
+  return v;
+}
+// 1-D bulk copy global -> shared through the TMA engine (size multiple of 16 B, 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 // 16-byte load through the cluster window (distributed shared memory)
 __device__ __forceinline__ float4 ld_cluster_f4(uint32_t cluster_addr) {
   float4 v;

@@ -11,68 +11,91 @@
 // F.interpolate nearest x2 (openaimodel.py:116; model.py:53), th.cat([h, hs.pop()]) (openaimodel.py:736),
 // softmax (model.py:184).
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/upgpt_b200.h"
 
 namespace upgpt {
 
 // ------------------------------------------------------------------------------------------------------------------
 // GroupNorm statistics. stats[b][g] = {sum, sumsq} in double (zeroed by the launcher).
-// grid = (pixel chunks, B); thread t owns channels t, t+blockDim, ... and walks the chunk's pixels (coalesced rows).
+// grid = (pixel chunks, B); thread = (channel quad, row lane): float4 loads, 4 rows in flight, fixed-order reductions.
 // ------------------------------------------------------------------------------------------------------------------
-template <int MAXC_PER_THREAD>
+template <int NQ>   // channel quads (float4) per thread: C/4 <= 256 * NQ
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int HW, int chunk,
                 int groups, double* __restrict__ stats, double* __restrict__ partials, int* __restrict__ counters,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float* __restrict__ scale_shift) {
-  extern __shared__ float shc[];  // per-channel {sum, sumsq}: [2][C]
+  extern __shared__ float shc[];  // per-channel {sum, sumsq}: [2][C], then per-row-lane partials [lanes][2][C]
   __shared__ int s_last;
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double s_red[4][64];
   const int C = C1 + C2;
+  const int C4 = C >> 2;
   const int cpg = C / groups;
   const int b = blockIdx.y;
   const int nchunks = gridDim.x;
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(p0 + chunk, HW);
-  float s[MAXC_PER_THREAD], q[MAXC_PER_THREAD];
+  // Thread layout: (channel quad, row lane). With C/4 < 256 the CTA's threads are spread over `lanes` pixel rows as well, every
+  // thread streams float4 loads (16 B) and keeps 4 rows x NQ quads in flight: a CTA has up to 16 KB outstanding instead of the
+  // 256 x 4 x 4 B of a scalar channel-per-thread walk (which ran the VAE's 256x256 levels at 1/5 of HBM speed).
+  const int lanes = NQ > 1 ? 1 : (256 / C4 < 1 ? 1 : 256 / C4);
+  const int qi = NQ > 1 ? threadIdx.x : threadIdx.x % C4;
+  const int lane = NQ > 1 ? 0 : threadIdx.x / C4;
+  float4 s[NQ], q[NQ];
 #pragma unroll
-  for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  // 4 pixels per trip: 4 x MAXC independent loads in flight per thread
-  int p = p0;
-  for (; p + 4 <= p1; p += 4) {
-    float v[4][MAXC_PER_THREAD];
+  for (int j = 0; j < NQ; ++j) { s[j] = make_float4(0.f, 0.f, 0.f, 0.f); q[j] = s[j]; }
+  auto ld4 = [&](int row_in_img, int c4) -> float4 {
+    const size_t row = (size_t)b * HW + row_in_img;
+    const int c = c4 << 2;
+    return c < C1 ? __ldg((const float4*)(x1 + row * C1 + c)) : __ldg((const float4*)(x2 + row * C2 + (c - C1)));
+  };
+  if (lane < lanes) {
+    int p = p0 + lane;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+      float4 v[4][NQ];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const size_t row = (size_t)b * HW + p + u;
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int j = 0; j < MAXC_PER_THREAD; ++j) {
-        const int c = threadIdx.x + j * 256;
-        v[u][j] = 0.f;
-        if (c < C) v[u][j] = c < C1 ? __ldg(x1 + row * C1 + c) : __ldg(x2 + row * C2 + (c - C1));
+        for (int j = 0; j < NQ; ++j) {
+          const int c4 = qi + j * 256;
+          v[u][j] = c4 < C4 ? ld4(p + u * lanes, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          s[j].x += v[u][j].x; s[j].y += v[u][j].y; s[j].z += v[u][j].z; s[j].w += v[u][j].w;
+          q[j].x = fmaf(v[u][j].x, v[u][j].x, q[j].x); q[j].y = fmaf(v[u][j].y, v[u][j].y, q[j].y);
+          q[j].z = fmaf(v[u][j].z, v[u][j].z, q[j].z); q[j].w = fmaf(v[u][j].w, v[u][j].w, q[j].w);
+        }
+    }
+    for (; p < p1; p += lanes) {
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        const int c4 = qi + j * 256;
+        if (c4 < C4) {
+          const float4 v = ld4(p, c4);
+          s[j].x += v.x; s[j].y += v.y; s[j].z += v.z; s[j].w += v.w;
+          q[j].x = fmaf(v.x, v.x, q[j].x); q[j].y = fmaf(v.y, v.y, q[j].y); q[j].z = fmaf(v.z, v.z, q[j].z); q[j].w = fmaf(v.w, v.w, q[j].w);
+        }
       }
     }
+    // per-lane per-channel partials -> smem [lane][2][C]
+    float* mine = shc + 2 * C + (size_t)lane * 2 * C;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int j = 0; j < MAXC_PER_THREAD; ++j) { s[j] += v[u][j]; q[j] = fmaf(v[u][j], v[u][j], q[j]); }
-  }
-  for (; p < p1; ++p) {
-    const size_t row = (size_t)b * HW + p;
-#pragma unroll
-    for (int j = 0; j < MAXC_PER_THREAD; ++j) {
-      const int c = threadIdx.x + j * 256;
-      if (c < C) {
-        const float v = c < C1 ? __ldg(x1 + row * C1 + c) : __ldg(x2 + row * C2 + (c - C1));
-        s[j] += v;
-        q[j] = fmaf(v, v, q[j]);
-      }
+    for (int j = 0; j < NQ; ++j) {
+      const int c4 = qi + j * 256;
+      if (c4 < C4) { *(float4*)(mine + 4 * c4) = s[j]; *(float4*)(mine + C + 4 * c4) = q[j]; }
     }
   }
-#pragma unroll
-  for (int j = 0; j < MAXC_PER_THREAD; ++j) {
-    const int c = threadIdx.x + j * 256;
-    if (c < C) { shc[c] = s[j]; shc[C + c] = q[j]; }
+  __syncthreads();
+  // fixed-order sum over the row lanes -> per-channel {sum, sumsq} of this chunk
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += shc[2 * C + (size_t)l * 2 * C + i];
+    shc[i] = acc;
   }
   __syncthreads();
   // one thread per (group, moment): fixed-order double sum over the group's channels -> this chunk's partial
@@ -162,47 +185,13 @@ struct PrepParams {
   int B;
 };
 
-__global__ void __launch_bounds__(256)
-prep_kernel(const PrepParams p) {
-  extern __shared__ float shf[];  // scale[C], shift[C]
-  pdl_launch_dependents();
-  pdl_wait();
+// One item = 4 consecutive channels of one pixel: optional raw fp16 copy, affine (GroupNorm apply), SiLU, fp16 [hi | lo] planes,
+// stored in the requested layout. Shared by prep_kernel and the fused GroupNorm kernel.
+__device__ __forceinline__ void prep_emit(const PrepParams& p, int b, int pp, int c, float4 v, const float* scale, const float* shift,
+                                          bool affine) {
   const int C = p.C1 + p.C2;
   const int HW = p.H * p.W;
-  float* scale = shf;
-  float* shift = shf + C;
-  const int b = blockIdx.y;
-  if (p.scale_shift) {
-    const float* ss = p.scale_shift + (size_t)b * 2 * C;
-    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) shf[c] = ss[c];
-    __syncthreads();
-  } else if (p.stats) {
-    const int cpg = C / p.groups;
-    const double inv_n = 1.0 / ((double)cpg * HW);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cpg;
-      const double su = p.stats[((size_t)b * p.groups + g) * 2];
-      const double sq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
-      const double mean = su * inv_n;
-      double var = sq * inv_n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
-      const float ga = p.gamma ? p.gamma[c] : 1.f;
-      const float be = p.beta ? p.beta[c] : 0.f;
-      scale[c] = rstd * ga;
-      shift[c] = be - (float)mean * rstd * ga;
-    }
-    __syncthreads();
-  }
-  const int C4 = C >> 2;
-  const int p0 = blockIdx.x * p.chunk;
-  const int p1 = min(p0 + p.chunk, HW);
-  const int total = (p1 - p0) * C4;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pp = p0 + idx / C4;
-    const int c = (idx % C4) << 2;
-    const size_t row = (size_t)b * HW + pp;
-    float4 v = c < p.C1 ? *(const float4*)(p.x1 + row * p.C1 + c) : *(const float4*)(p.x2 + row * p.C2 + (c - p.C1));
+  const size_t row = (size_t)b * HW + pp;
     if (p.raw) {
       __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
       uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
@@ -213,7 +202,7 @@ prep_kernel(const PrepParams p) {
         *(uint2*)(p.raw + row * p.ldraw + C + c) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
       }
     }
-    if (p.stats || p.scale_shift) {
+    if (affine) {
       v.x = fmaf(v.x, scale[c], shift[c]);
       v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
       v.z = fmaf(v.z, scale[c + 2], shift[c + 2]);
@@ -251,7 +240,186 @@ prep_kernel(const PrepParams p) {
       *(uint2*)o = hi;
       if (p.split3) *(uint2*)(o + C) = lo;
     }
+}
+
+__global__ void __launch_bounds__(256)
+prep_kernel(const PrepParams p) {
+  extern __shared__ float shf[];  // scale[C], shift[C]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = p.C1 + p.C2;
+  const int HW = p.H * p.W;
+  float* scale = shf;
+  float* shift = shf + C;
+  const int b = blockIdx.y;
+  if (p.scale_shift) {
+    const float* ss = p.scale_shift + (size_t)b * 2 * C;
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) shf[c] = ss[c];
+    __syncthreads();
+  } else if (p.stats) {
+    const int cpg = C / p.groups;
+    const double inv_n = 1.0 / ((double)cpg * HW);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double su = p.stats[((size_t)b * p.groups + g) * 2];
+      const double sq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+      const double mean = su * inv_n;
+      double var = sq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      const float ga = p.gamma ? p.gamma[c] : 1.f;
+      const float be = p.beta ? p.beta[c] : 0.f;
+      scale[c] = rstd * ga;
+      shift[c] = be - (float)mean * rstd * ga;
+    }
+    __syncthreads();
   }
+  const int C4 = C >> 2;
+  const int p0 = blockIdx.x * p.chunk;
+  const int p1 = min(p0 + p.chunk, HW);
+  const int total = (p1 - p0) * C4;
+  // four items per thread per trip, all loads issued before the first use (the stores of one item would otherwise fence the
+  // loads of the next: the compiler cannot prove that out / raw do not alias x1 / x2)
+  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * blockDim.x) {
+    float4 vin[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = idx0 + u * blockDim.x;
+      vin[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total) {
+        const size_t row = (size_t)b * HW + p0 + idx / C4;
+        const int c = (idx % C4) << 2;
+        vin[u] = c < p.C1 ? __ldg((const float4*)(p.x1 + row * p.C1 + c)) : __ldg((const float4*)(p.x2 + row * p.C2 + (c - p.C1)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const int idx = idx0 + u * blockDim.x;
+    if (idx >= total) break;
+    const int pp = p0 + idx / C4;
+    const int c = (idx % C4) << 2;
+    prep_emit(p, b, pp, c, vin[u], scale, shift, p.stats || p.scale_shift);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused GroupNorm (+SiLU) -> fp16 operand in ONE launch: one thread-block cluster per image.
+//   Every CTA of the cluster bulk-copies its pixel chunk (contiguous in NHWC) into shared memory with the TMA engine, computes
+//   the chunk's per-group moments from there, the cluster exchanges the 2*groups partial moments over distributed shared memory
+//   (summed in rank order: bit-reproducible), and every CTA then normalises its chunk straight out of shared memory.
+//   The tensor is read from HBM/L2 exactly once and the statistics never leave the chip; the two-kernel form (gn_stats with a
+//   last-CTA cross-chunk reduction, then prep) cost ~9 us + ~9 us per GroupNorm at the U-Net's sizes, almost all of it latency.
+// grid = (CL, B), cluster = (CL, 1, 1), 512 threads; dynamic smem = chunk + reduction scratch.
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kFusedThreads = 512;
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+gn_prep_fused_kernel(const PrepParams p, int cl, int px_per_cta, double* __restrict__ stats_out) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int C = p.C1 + p.C2;
+  const int C4 = C >> 2;
+  const int HW = p.H * p.W;
+  const int b = blockIdx.y;
+  const int rank = blockIdx.x;                   // == %cluster_ctarank for cluster dims (cl, 1, 1)
+  const int p0 = rank * px_per_cta;
+  const int npx = max(0, min(px_per_cta, HW - p0));
+  const int groups = p.groups;
+  const int cpg = C / groups;
+  // smem carve-up
+  const size_t bytes1 = (size_t)px_per_cta * p.C1 * 4, bytes2 = (size_t)px_per_cta * p.C2 * 4;
+  float* sx1 = (float*)fsm;                       // [px][C1]
+  float* sx2 = (float*)(fsm + bytes1);            // [px][C2]
+  const int lanes = kFusedThreads / C4 < 1 ? 1 : kFusedThreads / C4;
+  float* lane_part = (float*)(fsm + bytes1 + bytes2);          // [lanes][2][C]
+  float* chan = lane_part + (size_t)lanes * 2 * C;              // [2][C]
+  float* scale = chan + 2 * C;                                  // [C]
+  float* shift = scale + C;                                     // [C]
+  double* gs = (double*)(((uintptr_t)(shift + C) + 15) & ~(uintptr_t)15);   // [2*groups] this CTA's partial moments
+  double* gtot = gs + 2 * groups;                               // [2*groups] cluster totals
+  uint64_t* bar = (uint64_t*)(gtot + 2 * groups);
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncthreads();
+  pdl_wait();
+  // ---- phase 0: bulk copy of the chunk (TMA, no registers involved) ----
+  if (threadIdx.x == 0) {
+    const size_t n1 = (size_t)npx * p.C1 * 4, n2 = (size_t)npx * p.C2 * 4;
+    mbar_arrive_expect_tx(bar, (uint32_t)(n1 + n2));
+    const uint8_t* g1 = (const uint8_t*)(p.x1 + ((size_t)b * HW + p0) * p.C1);
+    for (size_t o = 0; o < n1; o += 65536) bulk_g2s((uint8_t*)sx1 + o, g1 + o, (uint32_t)min((size_t)65536, n1 - o), bar);
+    if (p.C2 > 0) {
+      const uint8_t* g2 = (const uint8_t*)(p.x2 + ((size_t)b * HW + p0) * p.C2);
+      for (size_t o = 0; o < n2; o += 65536) bulk_g2s((uint8_t*)sx2 + o, g2 + o, (uint32_t)min((size_t)65536, n2 - o), bar);
+    }
+  }
+  mbar_wait(bar, 0);
+  auto lds4 = [&](int px, int c) -> float4 {
+    return c < p.C1 ? *(const float4*)(sx1 + (size_t)px * p.C1 + c) : *(const float4*)(sx2 + (size_t)px * p.C2 + (c - p.C1));
+  };
+  // ---- phase 1: per-channel moments of the chunk; thread = (channel quad, row lane) ----
+  {
+    const int qi = threadIdx.x % C4, lane = threadIdx.x / C4;
+    if (lane < lanes && C4 <= kFusedThreads) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+      for (int px = lane; px < npx; px += lanes) {
+        const float4 v = lds4(px, qi << 2);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
+      float* mine = lane_part + (size_t)lane * 2 * C;
+      *(float4*)(mine + 4 * qi) = s;
+      *(float4*)(mine + C + 4 * qi) = q;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kFusedThreads) {   // fixed-order sum over the row lanes
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += lane_part[(size_t)l * 2 * C + i];
+    chan[i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += kFusedThreads) {   // (group, moment): double sum over the group's channels
+    const int g = i >> 1, which = i & 1;
+    const float* src = chan + which * C + g * cpg;
+    double acc = 0.0;
+    for (int k = 0; k < cpg; ++k) acc += (double)src[k];
+    gs[i] = acc;
+  }
+  // ---- phase 2: cluster-wide moments over DSMEM, then the per-channel affine ----
+  cluster_sync_all();
+  for (int i = threadIdx.x; i < 2 * groups; i += kFusedThreads) {
+    double acc = 0.0;
+    for (int r = 0; r < cl; ++r) acc += ld_cluster_f64(mapa_shared(smem_u32(gs + i), (uint32_t)r));
+    gtot[i] = acc;
+    if (stats_out && rank == 0) stats_out[(size_t)b * 2 * groups + i] = acc;
+  }
+  cluster_arrive();   // my DSMEM reads are done (the matching wait is at the end: nobody exits while a sibling may still read)
+  __syncthreads();
+  {
+    const double inv_n = 1.0 / ((double)cpg * HW);
+    for (int c = threadIdx.x; c < C; c += kFusedThreads) {
+      const int g = c / cpg;
+      const double mean = gtot[2 * g] * inv_n;
+      double var = gtot[2 * g + 1] * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      const float ga = p.gamma ? p.gamma[c] : 1.f;
+      const float be = p.beta ? p.beta[c] : 0.f;
+      scale[c] = rstd * ga;
+      shift[c] = be - (float)mean * rstd * ga;
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: normalise (+SiLU) out of shared memory, emit the fp16 operand ----
+  const int total = npx * C4;
+  for (int idx = threadIdx.x; idx < total; idx += kFusedThreads) {
+    const int px = idx / C4;
+    const int c = (idx - px * C4) << 2;
+    prep_emit(p, b, p0 + px, c, lds4(px, c), scale, shift, true);
+  }
+  cluster_wait();
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -380,13 +548,13 @@ static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2
   if (chunk > HW) chunk = HW;
   while ((size_t)B * ((HW + chunk - 1) / chunk) * 2 * groups > kGnPartialDoubles) chunk *= 2;
   dim3 grid((HW + chunk - 1) / chunk, B);
-  const size_t sm = sizeof(float) * 2 * C;
+  const int gn_lanes = C / 4 > 256 ? 1 : (256 / (C / 4) < 1 ? 1 : 256 / (C / 4));
+  const size_t sm = sizeof(float) * 2 * C * (1 + gn_lanes);
 #define UPGPT_GN_LAUNCH(MC) UPGPT_CHECK_CUDA(launch_k(gn_stats_kernel<MC>, grid, dim3(256), sm, stream, x1, C1, x2, C2, HW, chunk, groups, stats, \
                                                     g_gn_partials, g_gn_counters, gamma, beta, eps, scale_shift))
-  if (C <= 256) UPGPT_GN_LAUNCH(1);
-  else if (C <= 512) UPGPT_GN_LAUNCH(2);
-  else if (C <= 1024) UPGPT_GN_LAUNCH(4);
-  else UPGPT_GN_LAUNCH(8);
+  UPGPT_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0, "groupnorm_stats: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
+  if (C <= 1024) UPGPT_GN_LAUNCH(1);
+  else UPGPT_GN_LAUNCH(2);
 #undef UPGPT_GN_LAUNCH
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
@@ -424,6 +592,91 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   p.chunk = pick_chunk(HW, a->B);
   dim3 grid((HW + p.chunk - 1) / p.chunk, a->B);
   UPGPT_CHECK_CUDA(launch_k(prep_kernel, grid, dim3(256), sizeof(float) * 2 * C, stream, p));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// GroupNorm(+SiLU) + cast in one call. Fused single-launch cluster kernel when one image's [HW][C] fp32 tile fits the shared
+// memory of a cluster (<= 16 CTAs); otherwise statistics (gn_stats) and apply (prep) as two launches.
+static float* g_fused_ss = nullptr;            // scale/shift scratch of the two-launch fallback
+static constexpr size_t kFusedSsFloats = (size_t)1 << 20;
+static int g_fused_max_cl = -1;
+static int g_fused_smem_optin = 0;
+
+extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(a && a->x1 && a->out && stats, "groupnorm_prep: null");
+  const int C = a->C1 + a->C2;
+  const int HW = a->H * a->W;
+  UPGPT_REQUIRE(a->groups > 0 && C > 0 && C % a->groups == 0 && a->C1 % 4 == 0 && a->C2 % 4 == 0, "groupnorm_prep: bad channels (C1=%d C2=%d groups=%d)", a->C1, a->C2, a->groups);
+  if (g_fused_max_cl < 0) {
+    int dev = 0;
+    UPGPT_CHECK_CUDA(cudaGetDevice(&dev));
+    UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_fused_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(gn_prep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_fused_smem_optin));
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(gn_prep_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    UPGPT_CHECK_CUDA(cudaMalloc(&g_fused_ss, kFusedSsFloats * sizeof(float)));
+    // can a 16-CTA cluster with the full shared-memory carve-out be scheduled on this part at all?
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(16, 8); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = g_fused_smem_optin;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    const bool ok16 = cudaOccupancyMaxActiveClusters(&n, gn_prep_fused_kernel, &cfg) == cudaSuccess && n >= 1;
+    (void)cudaGetLastError();
+    g_fused_max_cl = (ok16 && getenv("UPGPT_NO_CLUSTER16") == nullptr) ? 16 : 8;
+    if (getenv("UPGPT_NO_FUSED_GN")) g_fused_max_cl = 0;
+  }
+  // cluster size: the smallest power of two whose chunk fits, but at least 8 px per CTA and preferably >= 8 CTAs per image
+  int cl = 0, px_per_cta = 0;
+  size_t smem = 0;
+  const int lanes = kFusedThreads / (C / 4) < 1 ? 1 : kFusedThreads / (C / 4);
+  const size_t scratch = (size_t)lanes * 2 * C * 4 + (size_t)4 * C * 4 + 16 + (size_t)4 * a->groups * 8 + 64;
+  if (C / 4 <= kFusedThreads) {
+    for (int c = 1; c <= g_fused_max_cl; c *= 2) {
+      const int px = (HW + c - 1) / c;
+      const size_t need = (size_t)px * C * 4 + scratch;
+      if (need + 256 > (size_t)g_fused_smem_optin) continue;
+      cl = c; px_per_cta = px; smem = need + 128;
+      if (c >= 8 || px <= 8) break;     // enough CTAs pulling, or chunks already tiny
+    }
+  }
+  if (cl == 0) {
+    // two-launch fallback (VAE-sized images)
+    UPGPT_REQUIRE((size_t)a->B * 2 * C <= kFusedSsFloats, "groupnorm_prep: scale/shift scratch too small");
+    int rc = groupnorm_stats_impl(a->x1, a->C1, a->x2, a->C2, a->B, HW, a->groups, stats, a->gamma, a->beta, a->eps, g_fused_ss, stream);
+    if (rc) return rc;
+    upgpt_prep_args b = *a;
+    b.stats = nullptr; b.scale_shift = g_fused_ss;
+    return upgpt_prep_operand(&b, stream_);
+  }
+  UPGPT_REQUIRE(a->layout != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "groupnorm_prep: stride-2 phases need even H, W");
+  UPGPT_REQUIRE(!a->raw || a->layout == 0, "groupnorm_prep: raw copy only with layout 0");
+  PrepParams p{};
+  p.x1 = a->x1; p.C1 = a->C1; p.x2 = a->x2; p.C2 = a->C2; p.H = a->H; p.W = a->W; p.B = a->B;
+  p.groups = a->groups; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+  p.layout = a->layout; p.split3 = a->split3;
+  p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
+  UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "groupnorm_prep: ld must be a multiple of 4");
+  UPGPT_REQUIRE((((uintptr_t)a->x1) & 15) == 0 && (!a->x2 || (((uintptr_t)a->x2) & 15) == 0), "groupnorm_prep: inputs must be 16-byte aligned");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(cl, a->B); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gn_prep_fused_kernel, p, cl, px_per_cta, stats));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;

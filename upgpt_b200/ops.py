@@ -47,6 +47,14 @@ def prep(**kw):
     _C.check(_C.lib().upgpt_prep_operand(C.byref(a), stream()), "upgpt_prep_operand")
 
 
+def groupnorm_prep(stats, **kw):
+    """Fused GroupNorm(+SiLU)+cast (upgpt_groupnorm_prep): keyword = field of upgpt_prep_args."""
+    a = _C.PrepArgs()
+    for k, v in kw.items():
+        setattr(a, k, _p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
+    _C.check(_C.lib().upgpt_groupnorm_prep(C.byref(a), C.c_void_p(stats.data_ptr()), stream()), "upgpt_groupnorm_prep")
+
+
 def layernorm(x, gamma, beta, out16, eps=1e-5):
     rows, Cc = x.shape[0], x.shape[1]
     _C.check(_C.lib().upgpt_layernorm(_p(x), Cc, rows, Cc, _p(gamma), _p(beta), eps, _p(out16), out16.shape[1], stream()),

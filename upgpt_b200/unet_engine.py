@@ -164,6 +164,19 @@ class EngineBase:
         a.out, a.ldo, a.raw, a.ldraw = self.p(out), 0, self.p(raw), 0
         self.prog.add_struct(self.L.upgpt_prep_operand, a)
 
+    def e_gn_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False):
+        if self._sizing:
+            return
+        a = _C.PrepArgs()
+        a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
+        a.B, a.H, a.W, a.groups = B, H, W, 32
+        a.stats, a.scale_shift = 0, 0
+        a.gamma, a.beta, a.eps = self.p(gamma), self.p(beta), eps
+        a.silu, a.layout, a.split3 = int(silu), layout, int(split3)
+        a.out, a.ldo, a.raw, a.ldraw = self.p(out), 0, self.p(raw), 0
+        self.prog.keep.append(a)
+        self.prog.calls.append((self.L.upgpt_groupnorm_prep, (C.byref(a), C.c_void_p(self.p(stats)))))
+
     def e_gemm(self, **kw):
         if self._sizing:
             return
@@ -194,9 +207,9 @@ class EngineBase:
         op = self.scratch("op16", B * H * W * mult * Cc * (2 if split3 else 1), torch.float16)
         raw = self.scratch("raw16", B * H * W * Cc * (2 if split3 else 1), torch.float16) if want_raw else None
         if gname is not None:
-            ss = self.scratch("gn_ss", B * 2 * Cc, torch.float32)
-            self.e_gn_affine(x1, C1, x2, C2, B, H * W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, ss)
-            self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, eps, silu, layout, op, raw, split3, ss=ss)
+            # GroupNorm(+SiLU) + cast: one fused cluster launch per GroupNorm (two launches internally for VAE-sized images)
+            self.e_gn_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
+                           raw, split3)
         else:
             self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3)
         return op, raw
