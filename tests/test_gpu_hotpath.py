@@ -218,3 +218,70 @@ def test_full_size_properties_b8(dev):
     assert relerr(yp, y[perm]) < 1e-6, "samples are independent chains: permuting the batch permutes the output"
     y1 = m.engine(1, 32, 32, 87).forward(xc[:1].contiguous(), tt[:1], c[:1].contiguous())
     assert relerr(y1, y[:1]) < 5e-3, "batch-of-1 engine (different tiling / split-K) agrees with row 0 of the batch-of-8 engine"
+
+
+def test_config4_smpl_interpolation_sequence_cond_cache(dev):
+    """BASELINE configs[3] in miniature: keyframes alpha in linspace(1, 0, K) lerp the SMPL vector and the person mask between two
+    poses (app.py:298-301) with text / style tokens fixed, one DDIM sample per keyframe through ONE sampler / engine. Each keyframe's
+    context differs from the previous one only in its SMPL token: the K/V cond-cache must be rebuilt per keyframe (a stale cache
+    would reproduce keyframe 0) and every keyframe must match the CPU oracle run on that keyframe's conditioning."""
+    from ldm.models.diffusion.ddim import DDIMSampler
+    model, sd = _tiny_ldm(dev)
+    usd = {k[len("model.diffusion_model."):]: v for k, v in sd.items() if k.startswith("model.diffusion_model.")}
+    B, K, S = 2, 4, 4          # S must divide 1000 as in the reference (util.py:46-60 indexes alphas_cumprod[t+1])
+    x, mask_a, ctx = synth.synth_inputs(B, 16, 16, 87, 128, 0)
+    _, mask_b, _ = synth.synth_inputs(B, 16, 16, 87, 128, 5)
+    g = torch.Generator().manual_seed(17)
+    smpl_a, smpl_b = torch.randn(B, 1, 85, generator=g) * 0.5, torch.randn(B, 1, 85, generator=g) * 0.5
+    Wp, bp = sd["extra_cond_models.1.model.weight"], sd["extra_cond_models.1.model.bias"]
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    sampler = DDIMSampler(model)
+    outs = []
+    for alpha in torch.linspace(1, 0, K).tolist():
+        smpl = alpha * smpl_a + (1 - alpha) * smpl_b
+        mask = alpha * mask_a + (1 - alpha) * mask_b
+        tok_dev = model.extra_cond_models[1](smpl.to(dev))                    # LinearProject on the device (poses.py:3-9)
+        tok_ref = torch.nn.functional.linear(smpl, Wp, bp)
+        assert relerr(tok_dev, tok_ref) < 1e-5
+        c_ref = torch.cat([ctx[:, :86], tok_ref], 1)
+        cond = {"c_crossattn": torch.cat([ctx[:, :86].to(dev), tok_dev], 1), "c_concat": [mask.to(dev)]}
+        z, _ = sampler.sample(S, B, (4, 16, 16), conditioning=cond, eta=0.0, x_T=x.to(dev), verbose=False)
+        with torch.no_grad():
+            z_ref = O.ddim_sample(lambda xx, tt: O.unet_forward(usd, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, c_ref), x, S, 0.0, sched)
+        assert relerr(z, z_ref) < 5e-3, "keyframe alpha=%g" % alpha
+        outs.append(z)
+        # the cond-cache itself: staged context == this keyframe's, and the cached K of the first cross-attention (context @ Wk^T,
+        # head-padded) follows the SMPL token (row 86) -- a stale cache (e.g. keyed on a recycled device address) fails here
+        eng = next(iter(model.model.diffusion_model._engines.values()))
+        assert torch.equal(eng.bufs["ctx32"].cpu(), c_ref.to(eng.bufs["ctx32"].dtype)) or relerr(eng.bufs["ctx32"], c_ref) < 1e-6
+        qn = next(k for k in eng.bufs if k.endswith(".ctx_k"))
+        wk = usd[qn[:-len(".ctx_k")] + ".attn2.to_k.weight"]
+        k_ref = (c_ref.reshape(-1, c_ref.shape[-1]) @ wk.t())                  # [B*87, heads*d]
+        kc = eng.bufs[qn].float().cpu()
+        heads = TINY_UNET_KW["num_heads"] if "num_heads" in TINY_UNET_KW else kc.shape[1] // 64
+        dpad = kc.shape[1] // heads
+        d = k_ref.shape[1] // heads
+        kc = kc.reshape(-1, heads, dpad)[:, :, :d].reshape(-1, heads * d)
+        assert relerr(kc[86::87], k_ref[86::87]) < 2e-3, "cached K row of the SMPL token, keyframe alpha=%g" % alpha
+    assert not torch.equal(outs[1], outs[0]) and not torch.equal(outs[-1], outs[0])
+    assert len(model.model.diffusion_model._engines) == 1, "all keyframes ran through one engine (one packed weight set, one step graph)"
+
+
+def test_config5_64x64_latent_b4(dev, golden):
+    """BASELINE configs[4] shape: 64x64x4 latent (512x512 image), B=4, bbox.yaml U-Net. eps of sample 0 against the CPU oracle at
+    B=1 (the oracle needs ~20 s for one 64x64 forward), plus size-independent properties at B=4 (N = 4096 self-attention keys,
+    16-CTA GroupNorm clusters / two-launch fallback, column-tiled convs)."""
+    m, sd = _unet(BBOX_UNET_KW, 0, dev)
+    B = 4
+    x, mask, ctx = synth.synth_inputs(B, 64, 64, 87, 768, 21)
+    xc, c = torch.cat([x, mask], 1), ctx
+    tt = torch.full((B,), 481, dtype=torch.long)
+    y = m(xc.to(dev), tt.to(dev), c.to(dev))
+    assert tuple(y.shape) == (B, 4, 64, 64) and torch.isfinite(y).all()
+    assert torch.equal(y, m(xc.to(dev), tt.to(dev), c.to(dev))), "determinism"
+    with torch.no_grad():
+        ref0 = O.unet_forward(sd, BBOX_UNET_KW, xc[:1], tt[:1], c[:1])
+    assert relerr(y[:1], ref0) < 1e-3, "eps tolerance of BASELINE.json at the 64x64 shape (fp16x3 parity mode)"
+    perm = torch.tensor([2, 0, 3, 1])
+    yp = m(xc[perm].contiguous().to(dev), tt.to(dev), c[perm].contiguous().to(dev))
+    assert relerr(yp, y[perm.to(dev)]) < 1e-6

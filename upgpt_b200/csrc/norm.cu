@@ -602,6 +602,7 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
 static float* g_fused_ss = nullptr;            // scale/shift scratch of the two-launch fallback
 static constexpr size_t kFusedSsFloats = (size_t)1 << 20;
 static int g_fused_max_cl = -1;
+static int g_fused_n16 = 0;                   // co-resident 16-CTA clusters (occupancy API, full shared-memory carve-out)
 static int g_fused_smem_optin = 0;
 
 extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, void* stream_) {
@@ -627,6 +628,7 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
     int n = 0;
     const bool ok16 = cudaOccupancyMaxActiveClusters(&n, gn_prep_fused_kernel, &cfg) == cudaSuccess && n >= 1;
     (void)cudaGetLastError();
+    g_fused_n16 = ok16 ? n : 0;
     g_fused_max_cl = (ok16 && getenv("UPGPT_NO_CLUSTER16") == nullptr) ? 16 : 8;
     if (getenv("UPGPT_NO_FUSED_GN")) g_fused_max_cl = 0;
   }
@@ -636,12 +638,15 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
   const int lanes = kFusedThreads / (C / 4) < 1 ? 1 : kFusedThreads / (C / 4);
   const size_t scratch = (size_t)lanes * 2 * C * 4 + (size_t)4 * C * 4 + 16 + (size_t)4 * a->groups * 8 + 64;
   if (C / 4 <= kFusedThreads) {
+    // the largest cluster that keeps >= 8 pixels per CTA (more SMs pulling and normalising); 16-CTA clusters (non-portable size)
+    // only while all images' clusters are co-resident
     for (int c = 1; c <= g_fused_max_cl; c *= 2) {
       const int px = (HW + c - 1) / c;
       const size_t need = (size_t)px * C * 4 + scratch;
+      if (c > 1 && px < 8) break;
+      if (c == 16 && a->B > g_fused_n16 && cl != 0) break;
       if (need + 256 > (size_t)g_fused_smem_optin) continue;
       cl = c; px_per_cta = px; smem = need + 128;
-      if (c >= 8 || px <= 8) break;     // enough CTAs pulling, or chunks already tiny
     }
   }
   if (cl == 0) {

@@ -511,6 +511,9 @@ class UNetEngine(EngineBase):
         self.bufs["ctx32"].copy_(context)
         self.ctx_prog.run(self._stream())
         self._ctx_key = key
+        # the key is only sound while the keyed tensor is alive: a freed context's address is handed to the next one by the caching
+        # allocator (same ptr, version 0, same shape -> a stale cond-cache for the next keyframe of an interpolation sequence)
+        self._ctx_ref = context
 
     def stage_inputs(self, x, timesteps, c_concat=None):
         """x: (B, in_ch, H, W) already concatenated, or the (B, lat_ch, H, W) latent with c_concat given separately."""
