@@ -205,10 +205,47 @@ def roofline_dominant_kernel(dev, pk, precision):
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * B * H * W * 9 * C * C
     ach = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch,
+    if os.path.exists(tp):                                                 # from the committed `ncu --set full` capture of this kernel
+        traffic = json.load(open(tp)).get("conv224_" + ("fp16x3" if x3 else "fp16"), {}).get("dram_bytes")
+    exe = flops * (3 if x3 else 1)
     return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % precision, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
-            "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": None, "peak_source": pk["src"] + " (burst: kernel timed alone)",
-            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": flops * (3 if x3 else 1),
-            "limiter": "per-SM TMA ingest (~100 GB/s/SM measured with the in-kernel timeline, profiles/r01_gemm_timeline.txt)"}
+            "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic, "peak_source": pk["src"] + " (burst: kernel timed alone)",
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": exe,
+            "executed_mma_frac_of_peak": exe / (ms * 1e-3) / 1e12 / pk["tf_burst"],
+            "algorithmic_bytes_per_launch": (B * H * W * C * kx + C * 9 * C * kx) * 2 + B * H * W * C * 4,
+            "limiter": "fp16x3 issues 3 MMAs per algorithmic product (Ah*Wh + Al*Wh + Ah*Wl on 2 loaded plane pairs): the main loop runs at the "
+                       "tensor pipe's rate (~0.6 us per 64-wide k-block of a 128x128 tile, in-kernel timeline profiles/r01_gemm_timeline.txt); "
+                       "the rest is prologue (~1.9 us), accumulator drain + DSMEM split-K reduction (~5 us) at 128 of 148 SMs"}
+
+
+def roofline_hbm_kernel(dev, pk):
+    """The HBM-bound side of the path: GroupNorm apply + swish + fp16 cast (prep_kernel) at the VAE decoder's 256x256x128 level,
+    B=8: reads the fp32 tensor once, writes the fp16 operand once. Algorithmic bytes = B*H*W*C*(4 + 2); timed alone with CUDA
+    events, operands (402 MB) exceed the 126 MB L2."""
+    import torch
+    from upgpt_b200 import ops
+    B, H, W, C = B_PER_GPU, 256, 256, 128
+    x = torch.randn(B, H * W, C, device=dev)
+    ss = torch.randn(B, 2, C, device=dev)
+    out = torch.empty(B * H * W * C, device=dev, dtype=torch.half)
+    call = lambda: ops.prep(x1=x, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=1e-6, silu=1,
+                            layout=0, split3=0, out=out, raw=None, scale_shift=ss)
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(7):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); call(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    nbytes = B * H * W * C * 6.0
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "prep_kernel (GroupNorm apply + swish + fp16 cast, VAE level 256x256x128, B=8)", "bound": "hbm", "achieved": ach,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "us_per_launch": ms * 1e3,
+            "algorithmic_bytes_per_launch": nbytes, "peak_source": pk["src"] + " (copy bandwidth)"}
 
 
 def parity_spot_check(model, dev):
@@ -314,6 +351,7 @@ def gpu_arm(args, rank, world):
                 "eps_max_rel_vs_reference": "1.3e-3 .. 1.7e-3 (tests/test_gpu_hotpath.py)"}
     if rank == 0:
         roof = roofline_dominant_kernel(dev, pk, args.precision)
+        roof_hbm = roofline_hbm_kernel(dev, pk)
         alg_tf_per_step = world * B * (DDIM_STEPS * GF_UNET_PER_SAMPLE_STEP + GF_VAE_PER_IMAGE) / 1e3
         eng = [e for k, e in model.model.diffusion_model._engines.items() if k[-1] == args.precision][0]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -325,12 +363,13 @@ def gpu_arm(args, rank, world):
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
                            "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
                            "kernels_per_unet_step": eng.launches_per_step + 3, "precision_mode": args.precision,
-                           "eps_tolerance": "1e-3 (north_star); measured 1.3e-4 .. 1.9e-4 in fp16x3" if args.precision == "fp16x3" else "fast mode: 1.3e-3 .. 1.7e-3"},
+                           "eps_tolerance": "1e-3 (north_star); measured 0.8e-4 .. 1.9e-4 in fp16x3" if args.precision == "fp16x3" else "fast mode: 1.3e-3 .. 1.7e-3"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
                         "d2h_bytes_per_step": int(out_pin.numel())},
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": roof,
+                "roofline_hbm": roof_hbm,
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
                                "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},
                 "fast_mode": fast}
