@@ -53,17 +53,18 @@ gn_stats_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ 
   };
   if (lane < lanes) {
     int p = p0 + lane;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {
-      float4 v[4][NQ];
+    constexpr int R = NQ > 1 ? 4 : 8;   // rows in flight per thread
+    for (; p + (R - 1) * lanes < p1; p += R * lanes) {
+      float4 v[R][NQ];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < R; ++u)
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
           const int c4 = qi + j * 256;
           v[u][j] = c4 < C4 ? ld4(p + u * lanes, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < R; ++u)
 #pragma unroll
         for (int j = 0; j < NQ; ++j) {
           s[j].x += v[u][j].x; s[j].y += v[u][j].y; s[j].z += v[u][j].z; s[j].w += v[u][j].w;
@@ -277,29 +278,29 @@ prep_kernel(const PrepParams p) {
   const int C4 = C >> 2;
   const int p0 = blockIdx.x * p.chunk;
   const int p1 = min(p0 + p.chunk, HW);
-  const int total = (p1 - p0) * C4;
   // four items per thread per trip, all loads issued before the first use (the stores of one item would otherwise fence the
-  // loads of the next: the compiler cannot prove that out / raw do not alias x1 / x2)
-  for (int idx0 = threadIdx.x; idx0 < total; idx0 += 4 * blockDim.x) {
+  // loads of the next: the compiler cannot prove that out / raw do not alias x1 / x2). (pixel, channel-quad) of an item advance
+  // incrementally: an integer division per item made this kernel instruction-bound (3.5 TB/s at the VAE's 256x256 level).
+  const int dpx = (int)blockDim.x / C4, dc = (int)blockDim.x % C4;
+  int px = (int)threadIdx.x / C4, c4 = (int)threadIdx.x % C4;     // item idx = px * C4 + c4, idx = threadIdx.x + k * blockDim.x
+  const int npx = p1 - p0;
+  while (px < npx) {
     float4 vin[4];
+    int ipx[4], ic[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int idx = idx0 + u * blockDim.x;
+      ipx[u] = px; ic[u] = c4 << 2;
       vin[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx < total) {
-        const size_t row = (size_t)b * HW + p0 + idx / C4;
-        const int c = (idx % C4) << 2;
-        vin[u] = c < p.C1 ? __ldg((const float4*)(p.x1 + row * p.C1 + c)) : __ldg((const float4*)(p.x2 + row * p.C2 + (c - p.C1)));
+      if (px < npx) {
+        const size_t row = (size_t)b * HW + p0 + px;
+        vin[u] = ic[u] < p.C1 ? __ldg((const float4*)(p.x1 + row * p.C1 + ic[u])) : __ldg((const float4*)(p.x2 + row * p.C2 + (ic[u] - p.C1)));
       }
+      px += dpx; c4 += dc;
+      if (c4 >= C4) { c4 -= C4; ++px; }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-    const int idx = idx0 + u * blockDim.x;
-    if (idx >= total) break;
-    const int pp = p0 + idx / C4;
-    const int c = (idx % C4) << 2;
-    prep_emit(p, b, pp, c, vin[u], scale, shift, p.stats || p.scale_shift);
-    }
+    for (int u = 0; u < 4; ++u)
+      if (ipx[u] < npx) prep_emit(p, b, p0 + ipx[u], ic[u], vin[u], scale, shift, p.stats || p.scale_shift);
   }
 }
 
@@ -390,8 +391,14 @@ gn_prep_fused_kernel(const PrepParams p, int cl, int px_per_cta, double* __restr
   // ---- phase 2: cluster-wide moments over DSMEM, then the per-channel affine ----
   cluster_sync_all();
   for (int i = threadIdx.x; i < 2 * groups; i += kFusedThreads) {
+    // all (<= 16) sibling loads are issued before the first add: one DSMEM round trip instead of `cl` serialised ones
+    double t[16];
+    const uint32_t my = smem_u32(gs + i);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t[r] = ld_cluster_f64(mapa_shared(my, (uint32_t)min(r, cl - 1)));
     double acc = 0.0;
-    for (int r = 0; r < cl; ++r) acc += ld_cluster_f64(mapa_shared(smem_u32(gs + i), (uint32_t)r));
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc += r < cl ? t[r] : 0.0;    // rank order: bit-reproducible
     gtot[i] = acc;
     if (stats_out && rank == 0) stats_out[(size_t)b * 2 * groups + i] = acc;
   }
@@ -413,11 +420,14 @@ gn_prep_fused_kernel(const PrepParams p, int cl, int px_per_cta, double* __restr
   }
   __syncthreads();
   // ---- phase 3: normalise (+SiLU) out of shared memory, emit the fp16 operand ----
-  const int total = npx * C4;
-  for (int idx = threadIdx.x; idx < total; idx += kFusedThreads) {
-    const int px = idx / C4;
-    const int c = (idx - px * C4) << 2;
-    prep_emit(p, b, p0 + px, c, lds4(px, c), scale, shift, true);
+  {
+    const int dpx = kFusedThreads / C4, dc = kFusedThreads % C4;
+    int px = (int)threadIdx.x / C4, c4 = (int)threadIdx.x % C4;
+    while (px < npx) {
+      prep_emit(p, b, p0 + px, c4 << 2, lds4(px, c4 << 2), scale, shift, true);
+      px += dpx; c4 += dc;
+      if (c4 >= C4) { c4 -= C4; ++px; }
+    }
   }
   cluster_wait();
 }
@@ -515,8 +525,10 @@ softmax_rows_kernel(const float* __restrict__ x, int ldx, int n, float scale, __
 static int pick_chunk(int HW, int B) {
   // aim for >= ~4 CTAs per SM without making chunks tiny
   int chunk = (int)(((long long)HW * B + 591) / 592);
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("UPGPT_PREP_CHUNK_MAX"); cap = e ? atoi(e) : 64; }
   if (chunk < 4) chunk = 4;
-  if (chunk > 64) chunk = 64;
+  if (chunk > cap) chunk = cap;
   if (chunk > HW) chunk = HW;
   return chunk;
 }
@@ -541,7 +553,7 @@ static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2
     UPGPT_CHECK_CUDA(cudaMemset(g_gn_counters, 0, kGnMaxBatch * sizeof(int)));
   }
   // ~2 CTAs per SM in total, at least 8 pixels per CTA, at most 256 chunks per image (cross-chunk reduction cost)
-  int per_img = (2 * 148 + B - 1) / B;
+  int per_img = (4 * 148 + B - 1) / B;
   if (per_img > 256) per_img = 256;
   int chunk = (HW + per_img - 1) / per_img;
   if (chunk < 8) chunk = 8;
