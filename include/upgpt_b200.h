@@ -35,7 +35,9 @@ enum {
   UPGPT_GEMM_PLAIN = 0,           /* A [batch][M][K] tokens, W [batch?][N][K] */
   UPGPT_GEMM_CONV3X3 = 1,         /* A NHWC [n_imgs][H][W][K], W [N][9][K], stride 1, zero pad 1 */
   UPGPT_GEMM_CONV3X3_S2PHASE = 2, /* stride-2 conv; A holds the 4 stride-2 phases [4][n_imgs][H][W][K] (H,W = OUTPUT size) */
-  UPGPT_GEMM_CONV1X1 = 3          /* A NHWC, W [N][K] (image addressing, used when the epilogue needs per-image rows) */
+  UPGPT_GEMM_CONV1X1 = 3,         /* A NHWC, W [N][K] (image addressing, used when the epilogue needs per-image rows) */
+  UPGPT_GEMM_CONV3X3_S2PHASE_ASYM = 4 /* stride-2 conv with zero pad (0,1,0,1) = right/bottom only (VAE Encoder Downsample, model.py:59-79):
+                                      out(y,x) tap (r,s) reads in(2y+r, 2x+s); A = the 4 stride-2 phases as in S2PHASE */
 };
 enum {
   UPGPT_GEMM_F_GEGLU = 1u << 1, /* W rows packed per tile as [x | gate]; out16 = x * gelu(gate)   (attention.py:37-44) */
@@ -162,6 +164,10 @@ int upgpt_ddpm_step(const float* x, const float* eps, const float* noise, long l
 int upgpt_step_state(int* step_ptr, int op, int value, long long* t_buf, int B, const long long* t_table, void* stream);
 /* out = a*sa + b*sb (b may be NULL): q_sample / mask blend helpers (ddpm.py:281-284, ddim.py:144-147) */
 int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream);
+/* VAE posterior: moments NCHW [B][2C][HW] = {mean | logvar} -> out [B][C][HW] = (mean + exp(0.5*clamp(logvar,-30,20))*noise)*out_scale;
+ * noise == NULL gives the mode (mean*out_scale).  replaces DiagonalGaussianDistribution.sample/.mode (distributions.py:24-37) and
+ * the scale_factor multiply of get_first_stage_encoding (ddpm.py:569-576) */
+int upgpt_gaussian_sample(const float* moments, const float* noise, float out_scale, float* out, int B, int C, int HW, void* stream);
 /* clamp(-1,1)*0.5+0.5 -> uint8 NHWC (generate_utils.py:165-168) */
 int upgpt_to_uint8_nhwc(const float* x, int B, int C, int HW, uint8_t* out, void* stream);
 

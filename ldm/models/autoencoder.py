@@ -1,13 +1,14 @@
-"""AutoencoderKL first stage (reference ldm/models/autoencoder.py:285-423) -- decode path on the B200 engine.
+"""AutoencoderKL first stage (reference ldm/models/autoencoder.py:285-423) on the B200 engines.
 
-Only `decode` (post_quant_conv -> Decoder, autoencoder.py:330-333) is on the denoising hot path.  The encoder
-(autoencoder.py:324-328) is a 'next' row of SURVEY.md section 8(f): its parameters are not instantiated here, so
-checkpoints load with strict=False exactly as the reference's inference facade does (generate_utils.py:40).
+`decode` (post_quant_conv -> Decoder, autoencoder.py:330-333) is on the denoising hot path.  `encode` (Encoder -> quant_conv ->
+DiagonalGaussianDistribution, autoencoder.py:324-328) is the first 'next' row of SURVEY.md section 8(f): log_images'
+reconstruction, img2img / mask-inpaint starts (`stochastic_encode`) and `get_input` need it.
 """
 import torch
 from torch import nn
 
-from ldm.modules.diffusionmodules.model import Decoder
+from ldm.modules.diffusionmodules.model import Decoder, Encoder
+from ldm.modules.distributions.distributions import DiagonalGaussianDistribution
 
 
 class AutoencoderKL(nn.Module):
@@ -17,7 +18,9 @@ class AutoencoderKL(nn.Module):
         ddconfig = dict(ddconfig)
         assert ddconfig["double_z"]
         self.image_key, self.embed_dim, self.ddconfig = image_key, embed_dim, ddconfig
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.monitor = monitor
         self._engines = {}
@@ -66,8 +69,23 @@ class AutoencoderKL(nn.Module):
         B, _, H, W = z.shape
         return self.engine(B, H, W).decode(z, in_scale)
 
+    def encoder_engine(self, B, H, W):
+        from upgpt_b200.vae_engine import VAEEncoderEngine
+        key = ("enc", B, H, W)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = VAEEncoderEngine(self, B, H, W)
+            self._engines[key] = eng
+        if eng.weights_version != self._weights_version:
+            eng.pack_weights(self)
+        return eng
+
     def encode(self, x):
-        raise NotImplementedError("AutoencoderKL.encode (VAE encoder) is outside the B200 hot path -- SURVEY.md 8(f) rank 2")
+        """x (B, 3, H, W) fp32 NCHW image in [-1, 1] -> DiagonalGaussianDistribution over (B, embed_dim, H/8, W/8) (autoencoder.py:324-328)."""
+        if not x.is_cuda:
+            raise RuntimeError("upgpt_b200: AutoencoderKL.encode requires CUDA tensors (sm_100a engine; no CPU fallback)")
+        B, _, H, W = x.shape
+        return DiagonalGaussianDistribution(self.encoder_engine(B, H, W).encode(x))
 
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("autoencoder training/reconstruction is outside the B200 hot path")

@@ -304,11 +304,19 @@ class LatentDiffusion(DDPM):
     @torch.no_grad()
     def get_input(self, batch, k, return_first_stage_outputs=False, force_c_encode=False, cond_key=None,
                   return_original_cond=False, bs=None, return_loss_w=False):
-        """Builds [z, {'c_crossattn': c, 'c_concat': [person_mask]}] (ddpm.py:684-769). The VAE *encoder* is outside the
-        hot path: z is None unless the batch carries a pre-computed latent under 'z'."""
+        """Builds [z, {'c_crossattn': c, 'c_concat': [person_mask]}] (ddpm.py:684-769). z = scale_factor * sample of the VAE
+        posterior of batch[k] (ddpm.py:689-692) when the batch carries the image (B,H,W,3 as the reference's data loaders emit, or
+        B,3,H,W), a pre-computed latent under 'z', or None (UPGPT's inference facade passes a dummy image it never uses)."""
         cut = (lambda t: t[:bs]) if bs is not None else (lambda t: t)
         z = batch.get("z")
         z = None if z is None else cut(z).to(self.device)
+        x_img = None
+        if z is None and isinstance(batch.get(k), torch.Tensor) and batch[k].dim() == 4:
+            x_img = cut(batch[k]).to(self.device).float()
+            if x_img.shape[-1] == 3 and x_img.shape[1] != 3:      # DDPM.get_input: 'b h w c -> b c h w' (ddpm.py:334-341)
+                x_img = x_img.permute(0, 3, 1, 2)
+            x_img = x_img.contiguous()
+            z = self.get_first_stage_encoding(self.encode_first_stage(x_img))
         concat_c = None
         if self.concat_key:
             concat_c = cut(batch[self.concat_key]).to(self.device)
@@ -318,7 +326,7 @@ class LatentDiffusion(DDPM):
         c = cut(self.assemble_context(batch, c))
         out = [z, {"c_crossattn": c, "c_concat": [concat_c]}]
         if return_first_stage_outputs:
-            out.extend([None, None if z is None else self.decode_first_stage(z)])
+            out.extend([x_img, None if z is None else self.decode_first_stage(z)])
         if return_original_cond:
             out.append(xc)
         if return_loss_w:
@@ -334,7 +342,17 @@ class LatentDiffusion(DDPM):
 
     @torch.no_grad()
     def encode_first_stage(self, x):
+        """-> DiagonalGaussianDistribution (ddpm.py:892-931, non-split path)."""
         return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """scale_factor * posterior sample (ddpm.py:569-576); the multiply is folded into the sampling kernel."""
+        from ldm.modules.distributions.distributions import DiagonalGaussianDistribution
+        if isinstance(encoder_posterior, DiagonalGaussianDistribution):
+            return encoder_posterior.sample(scale=float(self.scale_factor))
+        if isinstance(encoder_posterior, torch.Tensor):
+            return float(self.scale_factor) * encoder_posterior
+        raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
 
     # ---- eps prediction ----
     def apply_model(self, x_noisy, t, cond, return_ids=False):

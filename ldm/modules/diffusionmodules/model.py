@@ -1,7 +1,7 @@
-"""KL-f8 VAE Decoder parameter tree (reference ldm/modules/diffusionmodules/model.py:38-57,82-202,462-568).
+"""KL-f8 VAE Decoder / Encoder parameter trees (reference ldm/modules/diffusionmodules/model.py:38-79,82-202,368-568).
 
-Owns the parameters under the reference's names (`decoder.up.3.block.0.conv1.weight`, ...); AutoencoderKL.decode runs the
-network on the B200 engine (upgpt_b200.vae_engine)."""
+Own the parameters under the reference's names (`decoder.up.3.block.0.conv1.weight`, `encoder.down.0.block.0.conv1.weight`, ...);
+AutoencoderKL.decode / .encode run the networks on the B200 engines (upgpt_b200.vae_engine)."""
 from torch import nn
 
 
@@ -15,6 +15,16 @@ class Upsample(nn.Module):
         self.with_conv = with_conv
         if with_conv:
             self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+
+
+class Downsample(nn.Module):
+    """3x3 stride-2 conv over the input zero-padded (0,1,0,1) -- right / bottom only (model.py:59-79)."""
+
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        assert with_conv, "UPGPT's KL-f8 encoder downsamples with convolutions"
+        self.with_conv = with_conv
+        self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
 
 class ResnetBlock(nn.Module):
@@ -79,3 +89,40 @@ class Decoder(nn.Module):
 
     def forward(self, z):
         raise RuntimeError("upgpt_b200: Decoder executes through AutoencoderKL.decode on the CUDA engine (no eager fallback)")
+
+
+class Encoder(nn.Module):
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0, resamp_with_conv=True,
+                 in_channels, resolution, z_channels, double_z=True, use_linear_attn=False, attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        assert attn_type == "vanilla" and not use_linear_attn
+        assert len(attn_resolutions) == 0, "UPGPT's KL-f8 encoder has attention only in the middle block"
+        self.ch, self.temb_ch = ch, 0
+        self.ch_mult = list(ch_mult)
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels, self.z_channels, self.double_z = resolution, in_channels, z_channels, double_z
+        self.conv_in = nn.Conv2d(in_channels, ch, kernel_size=3, stride=1, padding=1)
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block = nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+            down = nn.Module()
+            down.block, down.attn = block, nn.ModuleList()
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x):
+        raise RuntimeError("upgpt_b200: Encoder executes through AutoencoderKL.encode on the CUDA engine (no eager fallback)")

@@ -212,6 +212,36 @@ def vae_decoder_forward(sd, ddconfig, z, prefix="decoder"):
     return conv(h, sd, prefix + ".conv_out")
 
 
+def vae_encoder_forward(sd, ddconfig, x, prefix="encoder"):
+    """Encoder.forward (model.py:427-459); Downsample = zero pad (0,1,0,1) then 3x3 stride-2 conv without padding (model.py:59-79)."""
+    nres, nrb = len(ddconfig["ch_mult"]), ddconfig["num_res_blocks"]
+    h = conv(x, sd, prefix + ".conv_in")
+    for i_level in range(nres):
+        for i_block in range(nrb):
+            h = vae_resnet_block(h, sd, f"{prefix}.down.{i_level}.block.{i_block}")
+        if i_level != nres - 1:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = conv(h, sd, f"{prefix}.down.{i_level}.downsample.conv", stride=2, padding=0)
+    h = vae_resnet_block(h, sd, prefix + ".mid.block_1")
+    h = vae_attn_block(h, sd, prefix + ".mid.attn_1")
+    h = vae_resnet_block(h, sd, prefix + ".mid.block_2")
+    h = silu(group_norm(h, sd, prefix + ".norm_out", 1e-6))
+    return conv(h, sd, prefix + ".conv_out")
+
+
+def encode_first_stage_moments(sd, ddconfig, x):
+    """AutoencoderKL.encode up to the posterior's parameters: quant_conv(encoder(x)) (autoencoder.py:324-328)."""
+    return conv(vae_encoder_forward(sd, ddconfig, x), sd, "quant_conv", padding=0)
+
+
+def gaussian_sample(moments, noise, scale_factor):
+    """scale_factor * DiagonalGaussianDistribution(moments).sample() with the draw given (distributions.py:24-37; ddpm.py:569-576)."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    z = mean if noise is None else mean + torch.exp(0.5 * logvar) * noise
+    return scale_factor * z
+
+
 def decode_first_stage(sd, ddconfig, z, scale_factor):
     """LatentDiffusion.decode_first_stage -> AutoencoderKL.decode (ddpm.py:779,829; autoencoder.py:330-333)."""
     z = 1. / scale_factor * z

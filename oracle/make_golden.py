@@ -124,6 +124,25 @@ def main():
         out[f"{tag}_img_sub"] = y_ref[:, :, ::8, ::8].numpy() if hw == 32 else y_ref.numpy()
         out[f"{tag}_stats"] = np.array([y_ref.mean().item(), y_ref.std().item(), y_ref.abs().max().item()])
 
+    # ---- VAE encoder ('next' row 8(f)-2): Encoder + quant_conv, tiny and the real KL-f8 encoder, B=1 ----
+    for tag, kw, hw in (("vaetiny", TINY_VAE_KW, 32), ("vaebbox", ref_loader.BBOX_VAE_KW, 64)):
+        torch.manual_seed(0)
+        enc = ref.Encoder(**kw).eval()
+        qc = torch.nn.Conv2d(2 * kw["z_channels"], 2 * 4, 1)
+        full_sd = {("encoder." + k): v for k, v in enc.state_dict().items()}
+        full_sd.update({("quant_conv." + k): v for k, v in qc.state_dict().items()})
+        sd = synth.synth_state_dict(full_sd, 0)
+        enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")})
+        qc.load_state_dict({k[len("quant_conv."):]: v for k, v in sd.items() if k.startswith("quant_conv.")})
+        x = torch.tanh(torch.randn(1, 3, hw, hw + 16, generator=torch.Generator().manual_seed(11)))     # rectangular, like 256x192
+        with torch.no_grad():
+            t0 = time.time(); m_ref = qc(enc(x)); dt = time.time() - t0        # autoencoder.py:324-327
+            m_or = O.encode_first_stage_moments(sd, kw, x)
+        e = relerr(m_or, m_ref)
+        print(f"[{tag}-enc] reference encode {dt:.2f}s moments {tuple(m_ref.shape)} oracle-vs-reference max-rel={e:.2e}")
+        assert e < 2e-5
+        out[f"{tag}_enc_moments"] = m_ref.numpy()
+
     np.savez_compressed(os.path.join(OUT, "hotpath_golden.npz"), **out)
     print("wrote", os.path.join(OUT, "hotpath_golden.npz"), os.path.getsize(os.path.join(OUT, "hotpath_golden.npz")), "bytes")
 

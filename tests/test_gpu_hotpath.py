@@ -285,3 +285,59 @@ def test_config5_64x64_latent_b4(dev, golden):
     perm = torch.tensor([2, 0, 3, 1])
     yp = m(xc[perm].contiguous().to(dev), tt.to(dev), c[perm].contiguous().to(dev))
     assert relerr(yp, y[perm.to(dev)]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,kw,hw", [("vaetiny", TINY_VAE_KW, 32), ("vaebbox", BBOX_VAE_KW, 64)])
+def test_vae_encode_vs_reference_golden(dev, golden, tag, kw, hw):
+    """AutoencoderKL.encode (Encoder with (0,1,0,1)-padded stride-2 convs as TMA phase planes, quant_conv,
+    posterior sampling kernel) against the reference's own moments (golden) on a rectangular image."""
+    from ldm.models.autoencoder import AutoencoderKL
+    ae = AutoencoderKL(kw, embed_dim=4)
+    sd = synth.synth_state_dict(ae.state_dict(), 0)
+    ae.load_state_dict(sd); ae = ae.to(dev).eval()
+    x = torch.tanh(torch.randn(1, 3, hw, hw + 16, generator=torch.Generator().manual_seed(11)))
+    post = ae.encode(x.to(dev))
+    ref = torch.from_numpy(golden[f"{tag}_enc_moments"])
+    assert tuple(post.parameters.shape) == tuple(ref.shape)
+    assert relerr(post.parameters, ref) < 5e-3
+    noise = torch.randn(1, 4, *ref.shape[2:], generator=torch.Generator().manual_seed(3))
+    z = post.sample(noise=noise.to(dev), scale=0.18215)
+    assert relerr(z, O.gaussian_sample(post.parameters.cpu(), noise, 0.18215)) < 1e-5
+    assert relerr(post.mode(), post.parameters[:, :4]) < 1e-7
+    x2 = torch.cat([x, x.flip(0).flip(3) * 0.5], 0)                      # batch > 1 through a second engine
+    assert relerr(ae.encode(x2.to(dev)).parameters[:1], post.parameters) < 5e-3
+
+
+def test_vae_encode_full_size_and_reconstruction_path(dev):
+    """Real KL-f8 encoder at the bbox.yaml image size (256x192, B=2) vs the CPU oracle, then LatentDiffusion.get_input /
+    log_images' reconstruction branch (encode -> scale_factor * sample -> decode, ddpm.py:689-692,761)."""
+    import os
+    from conftest import ROOT
+    from ldm.util import load_config, instantiate_from_config
+    cfg = load_config(os.path.join(ROOT, "configs", "deepfashion", "bbox.yaml"))
+    cfg.model.params["use_ema"] = False
+    model = instantiate_from_config(cfg.model)
+    sd = {k: v for k, v in model.state_dict().items() if k.startswith(("model.", "first_stage_model.", "extra_cond_models."))}
+    sdn = synth.synth_state_dict(sd, 0)
+    model.load_state_dict(sdn, strict=False)
+    model = model.to(dev).eval()
+    B = 2
+    g = torch.Generator().manual_seed(5)
+    img = torch.tanh(torch.randn(B, 256, 192, 3, generator=g))            # b h w c, as the data loaders emit
+    vsd = {k[len("first_stage_model."):]: v for k, v in sdn.items() if k.startswith("first_stage_model.")}
+    post = model.encode_first_stage(img.permute(0, 3, 1, 2).contiguous().to(dev))
+    with torch.no_grad():
+        m_ref = O.encode_first_stage_moments(vsd, BBOX_VAE_KW, img.permute(0, 3, 1, 2))
+    assert tuple(post.parameters.shape) == (B, 8, 32, 24)
+    assert relerr(post.parameters, m_ref) < 5e-3
+    from ldm.modules.poses.poses import DummyModel
+    model.extra_cond_models[0] = DummyModel()
+    batch = {"image": img.to(dev), "txt": torch.randn(B, 77, 768, generator=g).to(dev), "styles": torch.randn(B, 9, 768, generator=g).to(dev),
+             "smpl": torch.randn(B, 1, 85, generator=g).to(dev) * 0.5, "person_mask": torch.full((B, 1, 32, 24), -1.0).to(dev)}
+    z, c, x, xrec = model.get_input(batch, "image", return_first_stage_outputs=True, bs=B)
+    assert tuple(z.shape) == (B, 4, 32, 24) and tuple(xrec.shape) == (B, 3, 256, 192) and torch.isfinite(xrec).all()
+    mean_z = 0.18215 * m_ref[:, :4]
+    std_z = 0.18215 * torch.exp(0.5 * m_ref[:, 4:].clamp(-30, 20))
+    assert float(((z.cpu() - mean_z).abs() / std_z).max()) < 6.0, "z is a draw from N(mean, std) * scale_factor"
+    out = model.log_images(batch, N=B, ddim_steps=2, ddim_eta=0.0, seed=1, use_ema_scope=False)
+    assert "reconstruction" in out and tuple(out["reconstruction"].shape) == (B, 3, 256, 192)

@@ -69,6 +69,22 @@ def test_vae_decode_matches_reference_golden(golden, tag, kw, hw):
     assert abs(float(y.mean()) - mean) < 1e-4 * max(1.0, abs(amax)) and abs(float(y.abs().max()) - amax) < 1e-4 * amax
 
 
+@pytest.mark.parametrize("tag,kw,hw", [("vaetiny", TINY_VAE_KW, 32), ("vaebbox", BBOX_VAE_KW, 64)])
+def test_vae_encode_matches_reference_golden(golden, tag, kw, hw):
+    """Encoder + quant_conv restatement (asymmetric (0,1,0,1) pad before the stride-2 convs) vs the reference's own moments."""
+    from ldm.models.autoencoder import AutoencoderKL
+    sd = synth.synth_state_dict(AutoencoderKL(kw, embed_dim=4).state_dict(), 0)
+    x = torch.tanh(torch.randn(1, 3, hw, hw + 16, generator=torch.Generator().manual_seed(11)))
+    with torch.no_grad():
+        m = O.encode_first_stage_moments(sd, kw, x)
+    assert relerr(m, torch.from_numpy(golden[f"{tag}_enc_moments"])) < TOL
+    # posterior sampling identities (distributions.py:24-37)
+    noise = torch.randn(1, 4, *m.shape[2:], generator=torch.Generator().manual_seed(3))
+    z = O.gaussian_sample(m, noise, 0.18215)
+    assert relerr(O.gaussian_sample(m, None, 0.18215), 0.18215 * m[:, :4]) < 1e-7
+    assert float((z / 0.18215 - m[:, :4] - torch.exp(0.5 * m[:, 4:].clamp(-30, 20)) * noise).abs().max()) < 1e-5
+
+
 def test_ddpm_step_closed_form():
     """q_posterior / predict_start_from_noise identities (ddpm.py:224-237): with eps = true noise, x0 is recovered."""
     sched = O.register_schedule(1000, 0.00085, 0.012)

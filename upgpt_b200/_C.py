@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
     ]
 
 
-GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1 = 0, 1, 2, 3
+GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1, GEMM_CONV3X3_S2PHASE_ASYM = 0, 1, 2, 3, 4
 GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT, GEMM_F_X3 = 1 << 1, 1 << 2, 1 << 4, 1 << 5
 
 
@@ -106,6 +106,7 @@ _PROTOS = {
     "upgpt_step_state": [_vp, _i, _i, _vp, _i, _vp, _vp],
     "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
     "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
+    "upgpt_gaussian_sample": [_vp, _vp, _f, _vp, _i, _i, _i, _vp],
     "upgpt_capture_begin": [_vp],
     "upgpt_capture_end": [_vp, C.POINTER(C.c_void_p)],
     "upgpt_graph_launch": [_vp, _vp],

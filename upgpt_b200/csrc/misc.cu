@@ -339,6 +339,40 @@ extern "C" int upgpt_axpby(const float* a, float sa, const float* b, float sb, f
   return 0;
 }
 
+// z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * out_scale from NCHW moments [B][2C][HW] = {mean | logvar}
+// (DiagonalGaussianDistribution.sample / .mode, distributions.py:24-37; x scale_factor of get_first_stage_encoding, ddpm.py:569-576)
+namespace upgpt {
+__global__ void __launch_bounds__(256)
+gaussian_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float out_scale, float* __restrict__ out,
+                       int C, int HW, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t chw = (size_t)C * HW;
+    const size_t b = i / chw, r = i - b * chw;
+    const float mean = moments[b * 2 * chw + r];
+    float v = mean;
+    if (noise) {
+      float lv = moments[b * 2 * chw + chw + r];
+      lv = fminf(fmaxf(lv, -30.f), 20.f);
+      v = fmaf(expf(0.5f * lv), noise[i], mean);
+    }
+    out[i] = v * out_scale;
+  }
+}
+}  // namespace upgpt
+
+extern "C" int upgpt_gaussian_sample(const float* moments, const float* noise, float out_scale, float* out, int B, int C, int HW,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(moments && out && B > 0 && C > 0 && HW > 0, "gaussian_sample: bad args");
+  const size_t n = (size_t)B * C * HW;
+  UPGPT_CHECK_CUDA(launch_k(gaussian_sample_kernel, dim3(ew_grid(n)), dim3(256), 0, stream, moments, noise, out_scale, out, C, HW, n));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int upgpt_to_uint8_nhwc(const float* x, int B, int C, int HW, uint8_t* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(x && out, "to_uint8_nhwc: null");

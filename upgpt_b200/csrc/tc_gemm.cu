@@ -889,7 +889,8 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   UPGPT_REQUIRE(!((a->flags & UPGPT_GEMM_F_SPLIT3OUT) && (a->flags & UPGPT_GEMM_F_CHW)), "upgpt_gemm: SPLIT3OUT is not available with channel-major stores");
   UPGPT_REQUIRE(a->K > 0 && a->N > 0, "upgpt_gemm: bad K/N");
   UPGPT_REQUIRE(a->K % 8 == 0, "upgpt_gemm: K (=%d) must be a multiple of 8 (16-byte TMA rows)", a->K);
-  const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE || a->mode == UPGPT_GEMM_CONV1X1;
+  const bool s2 = a->mode == UPGPT_GEMM_CONV3X3_S2PHASE || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE_ASYM;
+  const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || s2 || a->mode == UPGPT_GEMM_CONV1X1;
   GemmParams p{};
   p.flags = a->flags;
   p.x3 = (a->flags & UPGPT_GEMM_F_X3) ? 1 : 0;
@@ -897,7 +898,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   const uint64_t ld_default = n_planes * (uint64_t)a->K;
   p.batch = conv ? 1 : (a->batch > 0 ? a->batch : 1);
   p.N_total = a->N;
-  p.taps = (a->mode == UPGPT_GEMM_CONV3X3 || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) ? 9 : 1;
+  p.taps = (a->mode == UPGPT_GEMM_CONV3X3 || s2) ? 9 : 1;
   p.kblocks_per_tap = (a->K + 63) / 64;
   p.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
 
@@ -933,7 +934,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
       box[0] = 64; box[1] = p.tile_cols; box[2] = p.tile_rows; box[3] = 1;
     }
     p.a_bytes = box[0] * box[1] * box[2] * box[3] * 2;
-    const int a_imgs = (a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) ? 4 * a->n_imgs : a->n_imgs;
+    const int a_imgs = s2 ? 4 * a->n_imgs : a->n_imgs;
     uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a_imgs, n_planes};
     const uint64_t lda = a->lda > 0 ? a->lda : ld_default;
     uint64_t strides[4] = {lda * 2, lda * 2 * a->W, lda * 2 * a->W * a->H, (uint64_t)a->K * 2};
@@ -947,6 +948,13 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
         const int rr = t / 3, ss = t % 3;
         const int ph = ((rr + 1) & 1) * 2 + ((ss + 1) & 1);
         p.tap_dy[t] = rr == 0 ? -1 : 0; p.tap_dx[t] = ss == 0 ? -1 : 0; p.tap_dn[t] = ph * a->n_imgs;
+      }
+    } else if (a->mode == UPGPT_GEMM_CONV3X3_S2PHASE_ASYM) {
+      // out(y,x) tap (r,s) reads in(2y+r, 2x+s) = phase[r&1][s&1] at (y + (r==2), x + (s==2)); the row/column past the end is TMA zero fill
+      for (int t = 0; t < 9; ++t) {
+        const int rr = t / 3, ss = t % 3;
+        const int ph = (rr & 1) * 2 + (ss & 1);
+        p.tap_dy[t] = rr == 2 ? 1 : 0; p.tap_dx[t] = ss == 2 ? 1 : 0; p.tap_dn[t] = ph * a->n_imgs;
       }
     }
     m_rows_total = a->n_imgs * p.HW;

@@ -169,3 +169,107 @@ class VAEDecoderEngine(EngineBase):
     @property
     def launches_per_decode(self):
         return len(self.prog.calls)
+
+
+class VAEEncoderEngine(VAEDecoderEngine):
+    """AutoencoderKL.encode -> Encoder.forward -> quant_conv (autoencoder.py:324-328; model.py:368-459) on the same kernels as the
+    decoder: 3->ch input conv as a direct small-Cin convolution from the NCHW image, ResnetBlocks (fused GroupNorm+swish -> tcgen05
+    implicit-GEMM convs), Downsample = stride-2 conv over the (0,1,0,1)-padded input as 4 stride-2 phase planes + TMA zero fill
+    (UPGPT_GEMM_CONV3X3_S2PHASE_ASYM), middle single-head attention, conv_out stored channel-major (NCHW moments), 1x1 quant_conv.
+    SURVEY.md 8(f) rank 2 ('next' row): precision is the decoder's (single fp16 operand plane, fp32 everything else)."""
+
+    def __init__(self, ae, B, H, W, precision=None):
+        dev = next(ae.parameters()).device
+        if dev.type != "cuda":
+            raise _C.UpgptError("VAEEncoderEngine needs the module on a CUDA device (no CPU fallback)")
+        EngineBase.__init__(self, dev, "fp16")
+        self.B, self.H, self.W = B, H, W
+        self.enc = ae.encoder
+        nres = self.enc.num_resolutions
+        assert H % (2 ** (nres - 1)) == 0 and W % (2 ** (nres - 1)) == 0, "image size must divide by the encoder stride"
+        self.weights_version = -1
+        self.graph = None
+        self.pack_weights(ae)
+        self._emit()
+        self.finish_sizing()
+        self._emit()
+
+    def pack_weights(self, ae):
+        sd = {k: v.detach().to(self.dev, torch.float32) for k, v in ae.state_dict().items()}
+        put = self.put
+        w = sd["encoder.conv_in.weight"]
+        put("conv_in.weight", w.permute(1, 2, 3, 0).reshape(-1, w.shape[0])); put("conv_in.bias", sd["encoder.conv_in.bias"])
+        w = sd["quant_conv.weight"]
+        put("quant.weight", w.permute(1, 2, 3, 0).reshape(-1, w.shape[0])); put("quant.bias", sd["quant_conv.bias"])
+        for k, v in sd.items():
+            if not k.startswith("encoder.") or k.startswith("encoder.conv_in."):
+                continue
+            n = k[len("encoder."):]
+            if v.dim() == 4 and v.shape[-1] == 3:
+                put(n, self._conv_w(v))
+            elif v.dim() == 4:
+                put(n, v.reshape(v.shape[0], v.shape[1]).half())
+            else:
+                put(n, v)
+        self.weights_version = ae._weights_version
+
+    def _emit(self):
+        B, H, W = self.B, self.H, self.W
+        enc = self.enc
+        if not self._sizing:
+            self.prog = _Program()
+        x_in = self.buf("x_in", (B, enc.in_channels, H, W))
+        ch = enc.ch
+        h = self.buf("h_conv_in", (B, H * W, ch))
+        if not self._sizing:
+            self.prog.add(self.L.upgpt_conv_small_cin, x_in.data_ptr(), enc.in_channels, 0, 0, 1.0, B, H, W, 3, self.w["conv_in.weight"].data_ptr(),
+                          self.w["conv_in.bias"].data_ptr(), ch, h.data_ptr(), 0)
+        hh, ww = H, W
+        for i_level in range(enc.num_resolutions):
+            cout = enc.ch * enc.ch_mult[i_level]
+            for i_block in range(enc.num_res_blocks):
+                p = f"down.{i_level}.block.{i_block}"
+                out = self.buf(f"lvl{i_level}.pp{i_block & 1}.c{cout}", (B, hh * ww, cout))
+                self._resnet(p, ch, cout, h, B, hh, ww, out)
+                h, ch = out, cout
+            if i_level != enc.num_resolutions - 1:
+                p = f"down.{i_level}.downsample.conv"
+                op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2)
+                hh, ww = hh // 2, ww // 2
+                out = self.buf(f"lvl{i_level}.down", (B, hh * ww, ch))
+                self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE_ASYM, N=ch, K=ch, n_imgs=B, H=hh, W=ww, out32=out,
+                            bias=self.w.get(p + ".bias"))
+                h = out
+
+        def newbuf(name, c):
+            return self.buf(name, (B, hh * ww, c))
+
+        out = newbuf("mid.block_1.out", ch); self._resnet("mid.block_1", ch, ch, h, B, hh, ww, out); h = out
+        out = newbuf("mid.attn_1.out", ch); self._attn("mid.attn_1", ch, h, B, hh, ww, out); h = out
+        out = newbuf("mid.block_2.out", ch); self._resnet("mid.block_2", ch, ch, h, B, hh, ww, out); h = out
+        zc2 = enc.conv_out.out_channels
+        h_out = self.buf("h_out", (B, zc2, hh, ww))           # NCHW
+        op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, "norm_out", 1e-6, True)
+        self.e_gemm(a=op, w=self.w.get("conv_out.weight"), mode=_C.GEMM_CONV3X3, N=zc2, K=ch, n_imgs=B, H=hh, W=ww, block_n=16,
+                    splits=1, out32=h_out, bias=self.w.get("conv_out.bias"), flags=_C.GEMM_F_CHW)
+        nq = self.w["quant.bias"].shape[0] if "quant.bias" in self.w else zc2
+        moments = self.buf("moments", (B, nq, hh, ww))         # NCHW {mean | logvar}
+        if not self._sizing:
+            self.prog.add(self.L.upgpt_conv_small_cin, h_out.data_ptr(), zc2, 0, 0, 1.0, B, hh, ww, 1, self.w["quant.weight"].data_ptr(),
+                          self.w["quant.bias"].data_ptr(), nq, moments.data_ptr(), 1)
+
+    def run(self, use_graph=True):
+        if use_graph:
+            if self.graph is None:
+                from .ops import Graph
+                self.prog.run(self._stream())
+                self.graph = Graph().capture(lambda: self.prog.run(self._stream()))
+            self.graph.launch()
+        else:
+            self.prog.run(self._stream())
+        return self.bufs["moments"]
+
+    def encode(self, x, use_graph=True):
+        """x (B, 3, H, W) fp32 NCHW -> moments (B, 2*embed_dim, H/8, W/8) fp32 NCHW."""
+        self.bufs["x_in"].copy_(x)
+        return self.run(use_graph).clone()
