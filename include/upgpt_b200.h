@@ -164,6 +164,10 @@ int upgpt_ddpm_step(const float* x, const float* eps, const float* noise, long l
 int upgpt_step_state(int* step_ptr, int op, int value, long long* t_buf, int B, const long long* t_table, void* stream);
 /* out = a*sa + b*sb (b may be NULL): q_sample / mask blend helpers (ddpm.py:281-284, ddim.py:144-147) */
 int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream);
+/* out = (wa*a + wb*b + wc*c + wd*d) / den, terms with a NULL pointer skipped: the pseudo linear multistep eps combinations of
+ * PLMSSampler.p_sample_plms (plms.py:211-229), e.g. (55 e_t - 59 e_1 + 37 e_2 - 9 e_3) / 24 */
+int upgpt_lincomb4(const float* a, float wa, const float* b, float wb, const float* c, float wc, const float* d, float wd, float den,
+                   float* out, long long n, void* stream);
 /* VAE posterior: moments NCHW [B][2C][HW] = {mean | logvar} -> out [B][C][HW] = (mean + exp(0.5*clamp(logvar,-30,20))*noise)*out_scale;
  * noise == NULL gives the mode (mean*out_scale).  replaces DiagonalGaussianDistribution.sample/.mode (distributions.py:24-37) and
  * the scale_factor multiply of get_first_stage_encoding (ddpm.py:569-576) */

@@ -314,3 +314,40 @@ def ddpm_step(x, e_t, t, sched, noise):
     logvar = ex(sched["posterior_log_variance_clipped"])
     nonzero = (1 - (t == 0).float()).reshape(-1, 1, 1, 1)
     return mean + nonzero * (0.5 * logvar).exp() * noise, x0
+
+
+def plms_sample(apply_model, x_T, S, sched, return_all=False):
+    """PLMSSampler.plms_sampling / p_sample_plms (plms.py:114-236) with eta = 0: pseudo improved Euler on the first step, then
+    Adams-Bashforth combinations of the eps history (orders 2, 3, 4)."""
+    ts, alphas, alphas_prev, sigmas, sqrt_one_minus = ddim_schedule(sched["alphas_cumprod"], S, 0.0)
+    time_range = np.flip(ts)
+    total = len(ts)
+    img = x_T
+    traj = []
+    old_eps = []
+    b = x_T.shape[0]
+
+    def step(x, e, index):
+        return ddim_step(x, e, alphas[index], alphas_prev[index], sigmas[index], sqrt_one_minus[index])
+
+    for i, t in enumerate(time_range):
+        index = total - i - 1
+        tt = torch.full((b,), int(t), dtype=torch.long)
+        tt_next = torch.full((b,), int(time_range[min(i + 1, total - 1)]), dtype=torch.long)
+        e_t = apply_model(img, tt)
+        if len(old_eps) == 0:
+            x_prev, _ = step(img, e_t, index)
+            e_t_next = apply_model(x_prev, tt_next)
+            e_prime = (e_t + e_t_next) / 2
+        elif len(old_eps) == 1:
+            e_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img, _ = step(img, e_prime, index)
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
+        traj.append(img)
+    return (img, traj) if return_all else img

@@ -104,6 +104,17 @@ def main():
         out[f"ddim_S{S}_eta{int(eta)}_alphas_prev"] = np.asarray(sampler.ddim_alphas_prev, dtype=np.float64)
         out[f"ddim_S{S}_eta{int(eta)}_sigmas"] = np.asarray(sampler.ddim_sigmas, dtype=np.float64)
 
+    # ---- PLMS ('next' row 8(f)-3): reference PLMSSampler over the tiny U-Net, S = 10 (exercises all four multistep orders) ----
+    sampler = ref.PLMSSampler(shim)
+    with torch.no_grad():
+        samples, _ = sampler.sample(10, 2, (4, 16, 16), conditioning=None, eta=0.0, x_T=x, verbose=False, log_every_t=1)
+        apply = lambda xx, tt: O.unet_forward(sd_tiny, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, ctx)
+        mine = O.plms_sample(apply, x, 10, sched)
+    e = relerr(mine, samples)
+    print(f"[plms S=10] oracle-vs-reference sampler max-rel={e:.2e}")
+    assert e < 1e-4
+    out["plms_S10_x0"] = samples.numpy()
+
     # ---- VAE decoder: tiny and the real KL-f8 decoder (bbox.yaml ddconfig), B=1 ----
     for tag, kw, hw in (("vaetiny", TINY_VAE_KW, 16), ("vaebbox", ref_loader.BBOX_VAE_KW, 32)):
         torch.manual_seed(0)

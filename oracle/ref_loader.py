@@ -60,10 +60,12 @@ def load_reference():
         from ldm.modules.diffusionmodules.openaimodel import UNetModel
         from ldm.modules.diffusionmodules.model import Decoder, Encoder
         from ldm.models.diffusion.ddim import DDIMSampler
+        from ldm.models.diffusion.plms import PLMSSampler
         from ldm.modules.diffusionmodules import util as dutil
         from ldm.modules import attention as attn
     DDIMSampler.register_buffer = lambda self, n, a: setattr(self, n, a)
-    ns = types.SimpleNamespace(UNetModel=UNetModel, Decoder=Decoder, Encoder=Encoder, DDIMSampler=DDIMSampler,
+    PLMSSampler.register_buffer = lambda self, n, a: setattr(self, n, a)     # same hard-coded "cuda" (plms.py:18-22)
+    ns = types.SimpleNamespace(UNetModel=UNetModel, Decoder=Decoder, Encoder=Encoder, DDIMSampler=DDIMSampler, PLMSSampler=PLMSSampler,
                                util=dutil, attention=attn)
     return ns
 

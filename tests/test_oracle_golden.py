@@ -85,6 +85,17 @@ def test_vae_encode_matches_reference_golden(golden, tag, kw, hw):
     assert float((z / 0.18215 - m[:, :4] - torch.exp(0.5 * m[:, 4:].clamp(-30, 20)) * noise).abs().max()) < 1e-5
 
 
+def test_plms_sampler_matches_reference_golden(golden):
+    """plms.py restatement (pseudo improved Euler + Adams-Bashforth orders 2..4) vs the reference PLMSSampler's own output."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    sd = synth.synth_state_dict(UNetModel(**TINY_UNET_KW).state_dict(), 0)
+    x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, 0)
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    with torch.no_grad():
+        got = O.plms_sample(lambda xx, tt: O.unet_forward(sd, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, ctx), x, 10, sched)
+    assert relerr(got, torch.from_numpy(golden["plms_S10_x0"])) < 1e-4
+
+
 def test_ddpm_step_closed_form():
     """q_posterior / predict_start_from_noise identities (ddpm.py:224-237): with eps = true noise, x0 is recovered."""
     sched = O.register_schedule(1000, 0.00085, 0.012)

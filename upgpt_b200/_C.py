@@ -107,6 +107,7 @@ _PROTOS = {
     "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
     "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "upgpt_gaussian_sample": [_vp, _vp, _f, _vp, _i, _i, _i, _vp],
+    "upgpt_lincomb4": [_vp, _f, _vp, _f, _vp, _f, _vp, _f, _f, _vp, _ll, _vp],
     "upgpt_capture_begin": [_vp],
     "upgpt_capture_end": [_vp, C.POINTER(C.c_void_p)],
     "upgpt_graph_launch": [_vp, _vp],

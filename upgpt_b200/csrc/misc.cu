@@ -339,6 +339,35 @@ extern "C" int upgpt_axpby(const float* a, float sa, const float* b, float sb, f
   return 0;
 }
 
+// out = (wa*a + wb*b + wc*c + wd*d) * inv_den with the products accumulated left to right (null pointers are skipped):
+// the Adams-Bashforth eps combinations of PLMS (plms.py:217-229), e.g. (55 e_t - 59 e_1 + 37 e_2 - 9 e_3) / 24
+namespace upgpt {
+__global__ void __launch_bounds__(256)
+lincomb4_kernel(const float* __restrict__ a, float wa, const float* __restrict__ b, float wb, const float* __restrict__ c, float wc,
+                const float* __restrict__ d, float wd, float den, float* __restrict__ out, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // same association as the reference expression: ((wa*a + wb*b) + wc*c) + wd*d, each product rounded, then one division
+    float v = wa * a[i];
+    if (b) v = v + wb * b[i];
+    if (c) v = v + wc * c[i];
+    if (d) v = v + wd * d[i];
+    out[i] = __fdiv_rn(v, den);
+  }
+}
+}  // namespace upgpt
+
+extern "C" int upgpt_lincomb4(const float* a, float wa, const float* b, float wb, const float* c, float wc, const float* d, float wd,
+                              float den, float* out, long long n, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(a && out && n > 0 && den != 0.f, "lincomb4: bad args");
+  UPGPT_CHECK_CUDA(launch_k(lincomb4_kernel, dim3(ew_grid((size_t)n)), dim3(256), 0, stream, a, wa, b, wb, c, wc, d, wd, den, out, (size_t)n));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * out_scale from NCHW moments [B][2C][HW] = {mean | logvar}
 // (DiagonalGaussianDistribution.sample / .mode, distributions.py:24-37; x scale_factor of get_first_stage_encoding, ddpm.py:569-576)
 namespace upgpt {
