@@ -39,8 +39,8 @@ def unet_case(ref, kw, B, H, W, ctx_len, t_values, seed, tag, out):
     m = ref.UNetModel(**kw).eval()
     sd = synth.synth_state_dict(m.state_dict(), seed)
     m.load_state_dict(sd)
-    x, mask, ctx = synth.synth_inputs(B, H, W, ctx_len, kw["context_dim"], seed)
-    xc = torch.cat([x, mask], 1)
+    x, mask, ctx = synth.synth_inputs(B, H, W, ctx_len, kw["context_dim"], seed, concat_channels=kw["in_channels"] - kw["out_channels"])
+    xc = torch.cat([x[:, :kw["out_channels"]], mask], 1)
     for t in t_values:
         tt = torch.full((B,), t, dtype=torch.long)
         with torch.no_grad():
@@ -62,6 +62,8 @@ def main():
     m_tiny, sd_tiny = unet_case(ref, TINY_UNET_KW, 2, 16, 16, 87, [981, 1], 0, "tiny", out)
     unet_case(ref, TINY_UNET_KW, 3, 16, 24, 20, [500], 1, "tinyrect", out)
     unet_case(ref, ref_loader.BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0, "bbox", out)
+    # the second U-Net family (models/upgpt/upscale/config.yaml): 6 -> 3 channels, 256 model channels, attention at ds 2/4/8, 86 tokens
+    unet_case(ref, ref_loader.UPSCALE_UNET_KW, 1, 32, 24, 86, [481], 2, "upscale", out)
 
     # ---- DDIM: reference DDIMSampler over the tiny U-Net (eta = 0 and eta = 1 with injected noise) ----
     sched = O.register_schedule(1000, 0.00085, 0.012)

@@ -76,3 +76,11 @@ BBOX_UNET_KW = dict(image_size=32, in_channels=5, out_channels=4, model_channels
                     use_checkpoint=False, legacy=False)
 BBOX_VAE_KW = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
                    ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+
+# models/upgpt/upscale/config.yaml:37-55 (the second U-Net family UPGPT ships: 4x super-resolution in a KL-f4 latent; 6 = latent 3 +
+# low-resolution concat 3 input channels, 86-token context = 77 text + 9 style, no SMPL token)
+UPSCALE_UNET_KW = dict(image_size=32, in_channels=6, out_channels=3, model_channels=256, attention_resolutions=[2, 4, 8],
+                       num_res_blocks=2, channel_mult=[1, 2, 2, 4], num_heads=8, use_spatial_transformer=True, transformer_depth=1,
+                       context_dim=768, use_checkpoint=True, legacy=False)
+UPSCALE_VAE_KW = dict(double_z=True, z_channels=3, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=[1, 2, 4],
+                      num_res_blocks=2, attn_resolutions=[], dropout=0.0)

@@ -14,7 +14,7 @@ import torch
 from conftest import tiny_ldm_config
 from oracle import ldm_oracle as O
 from oracle.make_golden import TINY_UNET_KW, TINY_VAE_KW
-from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW, UPSCALE_UNET_KW, UPSCALE_VAE_KW
 from upgpt_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -45,13 +45,14 @@ def _unet(kw, seed, dev):
     ("tiny", TINY_UNET_KW, 2, 16, 16, 87, [981, 1], 0),
     ("tinyrect", TINY_UNET_KW, 3, 16, 24, 20, [500], 1),
     ("bbox", BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0),
+    ("upscale", UPSCALE_UNET_KW, 1, 32, 24, 86, [481], 2),      # the 4x super-resolution U-Net family
 ])
 def test_unet_eps_vs_reference_golden(dev, golden, tag, kw, B, H, W, L, ts, seed):
     """Public UNetModel.forward (default precision = error-compensated fp16x3) against the reference's own outputs:
     tolerance 1e-3 (BASELINE.json north_star), 5e-4 asserted; then the opt-in fp16 fast mode at its own bound."""
     m, _ = _unet(kw, seed, dev)
-    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed)
-    xc = torch.cat([x, mask], 1).to(dev)
+    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed, concat_channels=kw["in_channels"] - kw["out_channels"])
+    xc = torch.cat([x[:, :kw["out_channels"]], mask], 1).to(dev)
     for t in ts:
         tt = torch.full((B,), t, dtype=torch.long, device=dev)
         ref = torch.from_numpy(golden[f"{tag}_eps_t{t}"])
@@ -395,3 +396,32 @@ def test_classifier_free_guidance_vs_oracle(dev):
     assert relerr(unguided, ref_ddim) > relerr(out, ref_ddim), "guidance changes the sample"
     outp, _ = PLMSSampler(model).sample(S, 2, (4, 16, 16), **kw)
     assert relerr(outp, ref_plms) < 1e-2
+
+
+def test_upscale_model_full_size_and_kl_f4(dev):
+    """the upscale configuration at its real shapes -- U-Net on a 128x96x3 latent + 3 low-res concat channels
+    (12288 pixels at level 0, 3072-token self-attention at ds 2, GroupNorm on 12.6 MB images = the two-launch path), B=1 vs the
+    CPU oracle; KL-f4 autoencoder (embed_dim 3, ch_mult [1,2,4]) encode + decode vs the oracle."""
+    from ldm.models.autoencoder import AutoencoderKL
+    m, sd = _unet(UPSCALE_UNET_KW, 2, dev)
+    g = torch.Generator().manual_seed(9)
+    xc = torch.randn(1, 6, 128, 96, generator=g); ctx = torch.randn(1, 86, 768, generator=g)
+    tt = torch.full((1,), 481, dtype=torch.long)
+    y = m(xc.to(dev), tt.to(dev), ctx.to(dev))
+    with torch.no_grad():
+        ref = O.unet_forward(sd, UPSCALE_UNET_KW, xc, tt, ctx)
+    assert tuple(y.shape) == (1, 3, 128, 96)
+    assert relerr(y, ref) < 1e-3
+    ae = AutoencoderKL(UPSCALE_VAE_KW, embed_dim=3)
+    vsd = synth.synth_state_dict(ae.state_dict(), 0)
+    ae.load_state_dict(vsd); ae = ae.to(dev).eval()
+    img = torch.tanh(torch.randn(1, 3, 128, 96, generator=g))
+    post = ae.encode(img.to(dev))
+    with torch.no_grad():
+        m_ref = O.encode_first_stage_moments(vsd, UPSCALE_VAE_KW, img)
+    assert tuple(post.parameters.shape) == (1, 6, 32, 24) and relerr(post.parameters, m_ref) < 5e-3
+    z = post.mode()
+    rec = ae.decode(z)
+    with torch.no_grad():
+        rec_ref = O.decode_first_stage(vsd, UPSCALE_VAE_KW, m_ref[:, :3], 1.0)
+    assert tuple(rec.shape) == (1, 3, 128, 96) and relerr(rec, rec_ref) < 1e-2

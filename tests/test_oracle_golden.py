@@ -6,7 +6,7 @@ import torch
 
 from oracle import ldm_oracle as O
 from oracle.make_golden import TINY_UNET_KW, TINY_VAE_KW
-from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW, UPSCALE_UNET_KW, UPSCALE_VAE_KW
 from upgpt_b200 import synth
 
 TOL = 2e-5   # fp32 reassociation between the reference's nn.Modules and the functional restatement
@@ -25,10 +25,12 @@ def _unet_sd(kw, seed):
     ("tiny", TINY_UNET_KW, 2, 16, 16, 87, [981, 1], 0),
     ("tinyrect", TINY_UNET_KW, 3, 16, 24, 20, [500], 1),
     ("bbox", BBOX_UNET_KW, 1, 32, 32, 87, [981, 481], 0),
+    ("upscale", UPSCALE_UNET_KW, 1, 32, 24, 86, [481], 2),      # models/upgpt/upscale/config.yaml: 6 -> 3 channels, 86 tokens
 ])
 def test_unet_eps_matches_reference_golden(golden, tag, kw, B, H, W, L, ts, seed):
     sd = _unet_sd(kw, seed)
-    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed)
+    x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed, concat_channels=kw["in_channels"] - kw["out_channels"])
+    x = x[:, :kw["out_channels"]]
     for t in ts:
         with torch.no_grad():
             y = O.diffusion_wrapper_hybrid(sd, kw, x, torch.full((B,), t, dtype=torch.long), [mask], [ctx])
