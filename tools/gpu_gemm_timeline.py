@@ -6,7 +6,7 @@ import torch
 from upgpt_b200 import _C, ops
 dev = torch.device("cuda:0")
 L = _C.lib()
-names = ["start", "setup done", "prod first issue", "prod last issue", "mma first full", "mma second full", "mma last full", "mma tile committed",
+names = ["start", "setup done", "prod before first TMA", "prod last issue", "mma first full", "mma second full", "mma last full", "mma tile committed",
          "epi tfull", "epi stores issued", "all joined", "dealloc done", "c0 tmem loaded | splitK partials fenced", "c0 staged | siblings arrived", "c0 barrier | my slice reduced", "c0 flushed | slice barrier"]
 ts = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 flush = torch.empty(512 << 20, device=dev, dtype=torch.uint8)

@@ -100,12 +100,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_smem, tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_smem;
-  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
-  if (threadIdx.x == 0) TS(1);
 
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
   const int tiles_per_batch = tiles_mn * p.num_splits;
@@ -116,16 +110,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // tile index -> (batch entry, k split, n tile, m tile); in cluster mode the splits of one output tile are the CTAs of one cluster
   auto decode_tile = [&](int tile, int& bidx, int& split, int& nt, int& mt) {
     if (p.cluster_reduce) {
-      split = tile % p.num_splits;
-      tile /= p.num_splits;
-      bidx = tile / tiles_mn;
+      const int q = p.fd_splits.div(tile);
+      split = tile - q * p.num_splits;
+      tile = q;
+      bidx = p.fd_tiles_mn.div(tile);
     } else {
-      bidx = tile / tiles_per_batch;
+      bidx = p.fd_tiles_per_batch.div(tile);
       tile -= bidx * tiles_per_batch;
-      split = tile / tiles_mn;
+      split = p.fd_tiles_mn.div(tile);
     }
-    const int rem = tile % tiles_mn;
-    nt = rem / p.num_m_tiles;
+    const int rem = tile - p.fd_tiles_mn.div(tile) * tiles_mn;
+    nt = p.fd_m_tiles.div(rem);
     mt = rem - nt * p.num_m_tiles;
   };
 
@@ -135,15 +130,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.tile_imgs > 1) {
         c1 = 0; c2 = 0; c3 = mt * p.tile_imgs;
       } else {
-        const int img = mt / p.tiles_per_img;
+        const int img = p.fd_tiles_per_img.div(mt);
         const int t = mt - img * p.tiles_per_img;
-        const int ty = t / p.tiles_per_row;
+        const int ty = p.fd_tiles_per_row.div(t);
         c1 = (t - ty * p.tiles_per_row) * p.tile_cols; c2 = ty * p.tile_rows; c3 = img;
       }
     } else {
       c1 = mt * 128; c2 = 0; c3 = bidx;
     }
   };
+
+  // the first tile of this CTA is decoded by every thread here, while the TMEM allocation and the predecessor's tail are still
+  // in flight (it only depends on blockIdx): the producer lane's first TMA is then issued right after the PDL wait
+  int f_bidx, f_split, f_nt, f_mt, f_c1, f_c2, f_c3;
+  decode_tile((int)blockIdx.x, f_bidx, f_split, f_nt, f_mt);
+  tile_origin(f_mt, f_bidx, f_c1, f_c2, f_c3);
+  auto decode_cached = [&](int tile, int& bidx, int& split, int& nt, int& mt) {
+    if (tile == (int)blockIdx.x) { bidx = f_bidx; split = f_split; nt = f_nt; mt = f_mt; }
+    else decode_tile(tile, bidx, split, nt, mt);
+  };
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
+  if (threadIdx.x == 0) TS(1);
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -152,21 +164,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int bidx, split, nt, mt;
-        decode_tile(tile, bidx, split, nt, mt);
+        decode_cached(tile, bidx, split, nt, mt);
         int c1, c2, c3;  // A box origin (before tap shift)
-        tile_origin(mt, bidx, c1, c2, c3);
+        if (tile == (int)blockIdx.x) { c1 = f_c1; c2 = f_c2; c3 = f_c3; }
+        else tile_origin(mt, bidx, c1, c2, c3);
         const int k_begin = split * k_per_split;
         const int k_end = min(k_begin + k_per_split, k_iters_total);
-        for (int kit = k_begin; kit < k_end; ++kit) {
-          const int tap = kit / p.kblocks_per_tap;
-          const int kb = kit - tap * p.kblocks_per_tap;
+        int tap = k_begin / p.kblocks_per_tap;
+        int kb = k_begin - tap * p.kblocks_per_tap;
+        for (int kit = k_begin; kit < k_end; ++kit, ++kb) {
+          if (kb == p.kblocks_per_tap) { kb = 0; ++tap; }
           for (int plane = 0; plane <= p.x3; ++plane) {   // x3: slot pair {(Ah, Wh), (Al, Wl)}
+            if (kit == k_begin && plane == 0) TS(2);       // coordinates decoded, about to issue the first TMA
             mbar_wait(&bar_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
             tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
                         c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
             tma_load_5d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx, plane);
-            if (kit == k_begin && plane == 0) TS(2);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -183,7 +197,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int bidx, split, nt, mt;
-        decode_tile(tile, bidx, split, nt, mt);
+        decode_cached(tile, bidx, split, nt, mt);
         const int k_begin = split * k_per_split;
         const int k_end = min(k_begin + k_per_split, k_iters_total);
         mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
@@ -261,7 +275,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int bidx, split, nt, mt;
-      decode_tile(tile, bidx, split, nt, mt);
+      decode_cached(tile, bidx, split, nt, mt);
       // ---- row bookkeeping: tile row -> (valid, global output row) ----
       bool valid;
       long long grow;  // global output row of this thread's accumulator lane
@@ -712,8 +726,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tid2 = grp * 128 + r;
       const long long* rtab = row_tab + grp * 128;
       const int* gtab = grp_tab + grp * 128;
-      int bidx, split, nt, mt;
-      decode_tile((int)blockIdx.x, bidx, split, nt, mt);
+      const int split = f_split, nt = f_nt;   // cluster mode: this CTA's only tile
       const uint32_t p_base = smem_u32(smem);
       // CTA `split` owns rows [row_lo, row_hi) of the tile.  8 consecutive threads cover one row's 128 bytes of a 32-column chunk
       // (coalesced 128-byte stores), 32 rows per pass; all index math is shifts and adds (an earlier flat-index version spent
@@ -853,6 +866,7 @@ static TileChoice choose_tiling(int N, int m_tiles_x_batch, int k_iters, int num
   const int n_cap = round_up(N, gran) < 256 ? round_up(N, gran) : 256 / gran * gran;
   for (int bn = n_cap; bn >= (n_cap < 64 ? n_cap : 64); bn -= gran) {
     if (must_divide && N % bn) continue;
+    if (x3 && bn > 224 && n_cap > 224) continue;   // a 256-wide x3 tile leaves smem for one {hi, lo} slot pair only: no load / MMA overlap
     const int n_tiles = (N + bn - 1) / bn;
     const int base = m_tiles_x_batch * n_tiles;
     // per k-block: operand ingest at ~100 GB/s/SM vs the MMAs at ~10 TFLOP/s/SM; x3 = 2 plane pairs loaded, 3 products issued
@@ -1118,6 +1132,12 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
+  p.fd_splits = make_fastdiv(p.num_splits);
+  p.fd_tiles_mn = make_fastdiv(p.num_m_tiles * p.num_n_tiles);
+  p.fd_tiles_per_batch = make_fastdiv(p.num_m_tiles * p.num_n_tiles * p.num_splits);
+  p.fd_m_tiles = make_fastdiv(p.num_m_tiles);
+  p.fd_tiles_per_img = make_fastdiv(p.tiles_per_img);
+  p.fd_tiles_per_row = make_fastdiv(p.tiles_per_row);
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   // split-K flavour: the splits of a tile as one thread-block cluster reducing over DSMEM (one tile per CTA; the fp32 partial
   // tile [128][bn] is laid over the drained operand slots), else the global-workspace reduction

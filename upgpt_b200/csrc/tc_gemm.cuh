@@ -13,6 +13,27 @@ enum GemmFlags : uint32_t {
   GEMM_X3 = 1u << 5,         // (public flag) operands carry [hi | lo] planes; D = Ah*Wh + Al*Wh + Ah*Wl
 };
 
+// Division by a launch-invariant divisor as multiply-high + shift (valid for dividends < 2^31). The tile decode of the single TMA
+// producer lane is a chain of ~8 dependent integer divisions: with hardware-emulated division it cost ~1 us before the first load
+// of every launch (in-kernel timeline), i.e. ~0.2 ms per U-Net step.
+struct FastDiv {
+  uint32_t mul, shift, d;
+#ifdef __CUDACC__
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shift); }
+#endif
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f{0, 0, (uint32_t)(d < 1 ? 1 : d)};
+  if (f.d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < f.d) ++l;                    // ceil(log2(d))
+    const uint32_t p = 31 + l;
+    f.mul = (uint32_t)((((uint64_t)1 << p) + f.d - 1) / f.d);
+    f.shift = p - 32;
+  }
+  return f;
+}
+
 struct GemmParams {
   // ---- problem ----
   int M_total;          // rows per batch entry
@@ -59,6 +80,8 @@ struct GemmParams {
   int epi_mode;         // 0 flat stores; 1 fp32 tile chunks [rows][32] by TMA store; 2 fp16 chunks [rows][64] by TMA store
   int res_tma;          // residual tile chunks prefetched by TMA load (epi_mode 1)
   long long* debug_ts;  // optional [gridDim.x][16] globaltimer stamps (bring-up instrumentation), null in production
+  // ---- fast division for the tile decode ----
+  FastDiv fd_splits, fd_tiles_mn, fd_tiles_per_batch, fd_m_tiles, fd_tiles_per_img, fd_tiles_per_row;
 };
 
 }  // namespace upgpt

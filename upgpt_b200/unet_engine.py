@@ -52,8 +52,11 @@ def pad_heads_cols(w, heads, d, dpad):
     return out.reshape(N, heads * dpad)
 
 
-def geglu_half(inner):
-    for h in (128, 112, 96, 80, 64, 48, 32, 16):
+def geglu_half(inner, x3=False):
+    """Half-width of a GEGLU accumulator tile ([x | gate] = 2*half columns). In the fp16x3 mode a 256-column tile leaves shared
+    memory for a single {hi, lo} slot pair (no load / MMA overlap: measured 47 us for M=8192, N=1792, K=224), so 224 is preferred."""
+    order = (112, 96, 64, 128, 80, 48, 32, 16) if x3 else (128, 112, 96, 80, 64, 48, 32, 16)
+    for h in order:
         if inner % h == 0:
             return h
     raise ValueError("GEGLU inner dim %d not a multiple of 16" % inner)
@@ -301,7 +304,7 @@ class UNetEngine(EngineBase):
                     put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad)))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
-                    half = geglu_half(inner)
+                    half = geglu_half(inner, self.split3)
                     w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
                     put(q + ".ff1.weight", self._w16(w1)); put(q + ".ff1.bias", b1)
                     put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"])); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
@@ -383,7 +386,7 @@ class UNetEngine(EngineBase):
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
             self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner),
+            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner, self.split3),
                         out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3 | x3)
             last = bi == len(mod.transformer_blocks) - 1
             self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
