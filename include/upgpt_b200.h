@@ -133,6 +133,9 @@ typedef struct upgpt_attn_args {
   int dpad;                  /* head dim padded with zero columns to 64 or 128 */
   float scale;               /* dim_head ** -0.5 (attention.py:157) */
   int split3_out;            /* out rows = [hi | lo] planes of H*dpad columns each (ldo >= 2*H*dpad) */
+  int v_rowmajor;            /* 1: `vt` holds V row-major [B][Nk][ldvt] with the head layout of K (e.g. a slice of one fused q|k|v
+                                projection); the P V product then reads it as an MN-major tensor-core operand, no transpose anywhere */
+  long long v_batch_stride;  /* v_rowmajor: elements between batches of V (0 = Nk*ldvt) */
 } upgpt_attn_args;
 int upgpt_attention(const upgpt_attn_args* args, void* stream);
 

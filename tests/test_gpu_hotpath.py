@@ -255,10 +255,11 @@ def test_config4_smpl_interpolation_sequence_cond_cache(dev):
         # head-padded) follows the SMPL token (row 86) -- a stale cache (e.g. keyed on a recycled device address) fails here
         eng = next(iter(model.model.diffusion_model._engines.values()))
         assert torch.equal(eng.bufs["ctx32"].cpu(), c_ref.to(eng.bufs["ctx32"].dtype)) or relerr(eng.bufs["ctx32"], c_ref) < 1e-6
-        qn = next(k for k in eng.bufs if k.endswith(".ctx_k"))
-        wk = usd[qn[:-len(".ctx_k")] + ".attn2.to_k.weight"]
+        qn = next(k for k in eng.bufs if k.endswith(".ctx_kv"))
+        wk = usd[qn[:-len(".ctx_kv")] + ".attn2.to_k.weight"]
         k_ref = (c_ref.reshape(-1, c_ref.shape[-1]) @ wk.t())                  # [B*87, heads*d]
         kc = eng.bufs[qn].float().cpu()
+        kc = kc[:, :kc.shape[1] // 2]                                          # cond-cache rows are [K | V]
         heads = TINY_UNET_KW["num_heads"] if "num_heads" in TINY_UNET_KW else kc.shape[1] // 64
         dpad = kc.shape[1] // heads
         d = k_ref.shape[1] // heads

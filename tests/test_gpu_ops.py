@@ -269,6 +269,19 @@ def test_flash_attention(dev, B, Hh, Nq, Nk, d):
     assert relerr(out[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
     if d < dpad:
         assert float(out[..., d:].float().abs().max()) == 0.0      # padded head columns stay exactly zero
+    # row-major V (a slice of a fused q|k|v projection output): the P V product reads it as an MN-major operand, no V^T anywhere
+    QKV = torch.zeros(B, max(Nq, Nk), 3, Hh, dpad, dtype=torch.half)
+    QKV[:, :Nq, 0, :, :d] = q.permute(0, 2, 1, 3); QKV[:, :Nk, 1, :, :d] = k.permute(0, 2, 1, 3); QKV[:, :Nk, 2, :, :d] = v.permute(0, 2, 1, 3)
+    qkv = QKV.to(dev)
+    flat = qkv.reshape(-1)
+    n_rows = max(Nq, Nk)
+    out2 = torch.full((B, Nq, Hh, dpad), float("nan"), device=dev, dtype=torch.half)
+    ops.attention(q=flat, ldq=3 * HD, k=flat[HD:], ldk=3 * HD, k_batch_stride=n_rows * 3 * HD, vt=flat[2 * HD:], ldvt=3 * HD,
+                  v_rowmajor=1, v_batch_stride=n_rows * 3 * HD, out=out2, ldo=HD, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=dpad, scale=d ** -0.5) if Nq == n_rows else None
+    if Nq == n_rows:
+        torch.cuda.synchronize()
+        assert relerr(out2[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
+        assert torch.equal(out2, out), "same arithmetic whichever way V is laid out"
 
 
 def test_small_kernels(dev):

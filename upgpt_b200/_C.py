@@ -83,6 +83,7 @@ class AttnArgs(C.Structure):
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("k_batch_stride", C.c_longlong),
         ("vt", C.c_void_p), ("ldvt", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int),
         ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("dpad", C.c_int), ("scale", C.c_float), ("split3_out", C.c_int),
+        ("v_rowmajor", C.c_int), ("v_batch_stride", C.c_longlong),
     ]
 
 

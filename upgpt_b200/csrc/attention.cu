@@ -27,6 +27,7 @@ struct AttnParams {
   __half* out;         // [B][Nq][ldo], head h at columns h*dpad
   int ldo;
   int plane;           // > 0: also write the lo plane at column offset plane (fp16x3 operand layout [hi | lo])
+  int v_mn;            // V is row-major [Nk][d] (same layout as K): the P V MMA reads it as an MN-major B operand
 };
 
 static constexpr int kAttnThreads = 320;     // warp0 TMA, warp1 MMA, warps2-9 softmax (two threads per query row)
@@ -101,21 +102,38 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_arrive_expect_tx(&bar_kv_full[s], qk_bytes + vt_bytes);
         for (int c = 0; c < dch; ++c)
           tma_load_4d(sK + s * qk_bytes + c * kTileBytes, &tmK, &bar_kv_full[s], c * 64, h, j * 128, b);
-        for (int c = 0; c < 2; ++c)
-          tma_load_3d(sV + s * vt_bytes + c * vt_chunk, &tmVt, &bar_kv_full[s], j * 128 + c * 64, h * p.dpad, b);
+        if (p.v_mn) {
+          // row-major V: the same [128 keys][64 d] swizzled boxes as K
+          for (int c = 0; c < dch; ++c)
+            tma_load_4d(sV + s * vt_bytes + c * kTileBytes, &tmVt, &bar_kv_full[s], c * 64, h, j * 128, b);
+        } else {
+          for (int c = 0; c < 2; ++c)
+            tma_load_3d(sV + s * vt_bytes + c * vt_chunk, &tmVt, &bar_kv_full[s], j * 128 + c * 64, h * p.dpad, b);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_f16(128, 128);
-      const uint32_t idesc_o = make_idesc_f16(128, (uint32_t)p.dpad);
+      const uint32_t idesc_o = make_idesc_f16(128, (uint32_t)p.dpad, false, p.v_mn != 0);
       auto issue_pv = [&](int jj) {   // O (+)= P(jj) V(jj)
         const int sp = jj & 1;
         for (int c = 0; c < 2; ++c) {
           const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
-          const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
+          if (p.v_mn) {
+            // B = V tile [128 keys][dpad] as stored by TMA: MN-major (d contiguous in 128-byte swizzled rows, one row per key).
+            // A 16-key k-step is two 8-row atoms (SBO = 1024 B); dpad = 128 adds a second 64-wide MN chunk kTileBytes further (LBO).
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (jj > 0 || c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t row_off = (uint32_t)(c * 64 + k * 16) * 128u;
+              const uint64_t bd = make_desc_mnmajor_sw128(smem_u32(sV + sp * vt_bytes) + row_off, (uint32_t)kTileBytes, 1024u);
+              tc_mma_f16_ss(tO, ad + 2 * k, bd, idesc_o, (jj > 0 || c > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+            const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sV + sp * vt_bytes + c * vt_chunk));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (jj > 0 || c > 0 || k > 0) ? 1u : 0u);
+          }
         }
         tc_commit(&bar_kv_empty[sp]);
         tc_commit(bar_o);
@@ -302,7 +320,14 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
     uint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap_f16(&tmK, a->k, 4, dims, str, box, true)) return -3;
   }
-  {
+  if (a->v_rowmajor) {
+    // V row-major [B][Nk][ldvt], head h at columns [h*dpad, (h+1)*dpad): same addressing as K
+    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nk, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldvt * 2,
+                       (uint64_t)(a->v_batch_stride > 0 ? a->v_batch_stride : (long long)a->ldvt * a->Nk) * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap_f16(&tmVt, a->vt, 4, dims, str, box, true)) return -3;
+  } else {
     // V^T: [B][H*dpad][ldvt], valid keys = Nk
     uint64_t dims[3] = {(uint64_t)a->Nk, (uint64_t)a->H * a->dpad, (uint64_t)a->B};
     uint64_t str[2] = {(uint64_t)a->ldvt * 2, (uint64_t)a->ldvt * 2 * a->H * a->dpad};
@@ -315,6 +340,7 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = (__half*)a->out; p.ldo = a->ldo;
   p.plane = a->split3_out ? a->H * a->dpad : 0;
+  p.v_mn = a->v_rowmajor ? 1 : 0;
   UPGPT_REQUIRE(!a->split3_out || a->ldo >= 2 * a->H * a->dpad, "attention: split3_out needs ldo >= 2*H*dpad");
   const int dch = a->dpad / 64;
   const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;

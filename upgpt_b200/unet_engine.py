@@ -8,7 +8,7 @@ Program per ResBlock (openaimodel.py:255-275):
     gn_stats -> prep(GN+SiLU -> fp16) -> conv3x3[tcgen05](+bias +timestep-emb row vector) -> gn_stats -> prep
     -> [skip 1x1 GEMM] -> conv3x3(+bias +residual)
 per SpatialTransformer (attention.py:250-261,211-215):
-    gn_stats -> prep(GN) -> proj_in GEMM -> LN -> QK GEMM + V^T GEMM -> flash attention -> to_out GEMM(+res)
+    fused GN -> proj_in GEMM -> LN -> q|k|v GEMM -> flash attention (V row-major, MN-major operand) -> to_out GEMM(+res)
     -> LN -> Q GEMM -> flash attention over the cached context K/V -> to_out GEMM(+res)
     -> LN -> GEGLU GEMM -> ff2 GEMM(+res, +fp16 copy) -> proj_out GEMM(+block input)
 The skip concat th.cat([h, hs.pop()]) (openaimodel.py:736) never exists in fp32: gn_stats / prep read both tensors.
@@ -294,13 +294,13 @@ class UNetEngine(EngineBase):
                         put(f"{q}.{n}.weight", sd[f"{q}.{n}.weight"]); put(f"{q}.{n}.bias", sd[f"{q}.{n}.bias"])
                     wq = pad_heads_rows(sd[q + ".attn1.to_q.weight"], Hh, d, dpad)
                     wk = pad_heads_rows(sd[q + ".attn1.to_k.weight"], Hh, d, dpad)
-                    put(q + ".attn1.qk.weight", self._w16(torch.cat([wq, wk], 0)))
-                    put(q + ".attn1.v.weight", self._w16(pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad)))
+                    wv = pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad)
+                    put(q + ".attn1.qkv.weight", self._w16(torch.cat([wq, wk, wv], 0)))    # one fused q | k | v projection
                     put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad)))
                     put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
                     put(q + ".attn2.q.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad)))
-                    put(q + ".attn2.k.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad)))
-                    put(q + ".attn2.v.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.kv.weight", self._w16(torch.cat([pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad),
+                                                                     pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)], 0)))
                     put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad)))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
@@ -352,8 +352,7 @@ class UNetEngine(EngineBase):
         tokA = self.scratch("tokA", M * Cc, torch.float32)
         tokB = self.scratch("tokB", M * Cc, torch.float32)
         tok16 = self.scratch("tok16", M * Cc * kx, torch.float16)
-        qk16 = self.scratch("qk16", M * 2 * HD, torch.float16)
-        vt16 = self.scratch("vt16", B * HD * _round_up(HW, 8), torch.float16)
+        qkv16 = self.scratch("qkv16", M * 3 * HD, torch.float16)
         att16 = self.scratch("att16", M * HD * kx, torch.float16)
         self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
                     bias=self.w.get(p + ".proj_in.bias"), flags=x3)
@@ -365,22 +364,24 @@ class UNetEngine(EngineBase):
             ff16 = self.scratch("ff16", M * inner * kx, torch.float16)
             # --- self attention ---
             self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn1.qk.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * HD, K=Cc, out16=qk16, flags=x3)
-            self.e_gemm(a=tok16, w=g(".attn1.v.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=vt16, rows_per_group=HW,
-                        ldT=_round_up(HW, 8), flags=_C.GEMM_F_CHW | x3)
-            kptr = None if self._sizing else qk16[HD:]
-            self.e_attention(q=qk16, ldq=2 * HD, k=kptr, ldk=2 * HD, k_batch_stride=0, vt=vt16, ldvt=_round_up(HW, 8), out=att16,
-                             ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
+            # one q | k | v projection (row-major fp16); the attention kernel reads V row-major as an MN-major operand (no V^T)
+            self.e_gemm(a=tok16, w=g(".attn1.qkv.weight"), mode=_C.GEMM_PLAIN, M=M, N=3 * HD, K=Cc, out16=qkv16, flags=x3)
+            kptr = None if self._sizing else qkv16[HD:]
+            vptr = None if self._sizing else qkv16[2 * HD:]
+            self.e_attention(q=qkv16, ldq=3 * HD, k=kptr, ldk=3 * HD, k_batch_stride=HW * 3 * HD, vt=vptr, ldvt=3 * HD, v_rowmajor=1,
+                             v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(self.split3))
             self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
                         bias=g(".attn1.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
             self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qk16, flags=x3)
-            kc = self.buf(q + ".ctx_k", (B * L, HD), torch.float16)
-            vc = self.buf(q + ".ctx_vt", (B, HD, Lp), torch.float16)
-            self.e_attention(q=qk16, ldq=HD, k=kc, ldk=HD, k_batch_stride=0, vt=vc, ldvt=Lp, out=att16, ldo=HD * kx, B=B, H=Hh,
-                             Nq=HW, Nk=L, dpad=dpad, scale=float(d) ** -0.5, split3_out=int(self.split3))
+            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qkv16, flags=x3)
+            kvc = self.buf(q + ".ctx_kv", (B * L, 2 * HD), torch.float16)       # cond-cache: K | V of the context, row-major
+            vcp = None if self._sizing else kvc.reshape(-1)[HD:]
+            self.e_attention(q=qkv16, ldq=HD, k=kvc, ldk=2 * HD, k_batch_stride=L * 2 * HD, vt=vcp, ldvt=2 * HD, v_rowmajor=1,
+                             v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(self.split3))
             self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
                         bias=g(".attn2.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
@@ -494,10 +495,8 @@ class UNetEngine(EngineBase):
                 HD = mod.n_heads * dpad
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{name}.transformer_blocks.{bi}"
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.k.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
-                                out16=self.bufs[q + ".ctx_k"], flags=x3)
-                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.v.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=HD, K=self.ctx_dim,
-                                out16=self.bufs[q + ".ctx_vt"], rows_per_group=L, ldT=Lp, flags=_C.GEMM_F_CHW | x3)
+                    self.e_gemm(a=ctx16, w=self.w[q + ".attn2.kv.weight"], mode=_C.GEMM_PLAIN, M=B * L, N=2 * HD, K=self.ctx_dim,
+                                out16=self.bufs[q + ".ctx_kv"], flags=x3)
         self.ctx_prog = self.prog
         self.prog = main
 
