@@ -204,10 +204,11 @@ __device__ __forceinline__ void prep_emit(const PrepParams& p, int b, int pp, in
       }
     }
     if (affine) {
-      v.x = fmaf(v.x, scale[c], shift[c]);
-      v.y = fmaf(v.y, scale[c + 1], shift[c + 1]);
-      v.z = fmaf(v.z, scale[c + 2], shift[c + 2]);
-      v.w = fmaf(v.w, scale[c + 3], shift[c + 3]);
+      const float4 sc = *(const float4*)(scale + c), sh = *(const float4*)(shift + c);   // 16-byte aligned: C % 4 == 0
+      v.x = fmaf(v.x, sc.x, sh.x);
+      v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z);
+      v.w = fmaf(v.w, sc.w, sh.w);
     }
     if (p.silu) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
     __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
@@ -313,7 +314,7 @@ prep_kernel(const PrepParams p) {
 //   last-CTA cross-chunk reduction, then prep) cost ~9 us + ~9 us per GroupNorm at the U-Net's sizes, almost all of it latency.
 // grid = (CL, B), cluster = (CL, 1, 1), 512 threads; dynamic smem = chunk + reduction scratch.
 // ------------------------------------------------------------------------------------------------------------------
-static constexpr int kFusedThreads = 512;
+static constexpr int kFusedThreads = 1024;   // 32 warps per SM: the emit phase is instruction-latency bound
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 gn_prep_fused_kernel(const PrepParams p, int cl, int px_per_cta, double* __restrict__ stats_out) {
@@ -392,13 +393,17 @@ gn_prep_fused_kernel(const PrepParams p, int cl, int px_per_cta, double* __restr
   cluster_sync_all();
   for (int i = threadIdx.x; i < 2 * groups; i += kFusedThreads) {
     // all (<= 16) sibling loads are issued before the first add: one DSMEM round trip instead of `cl` serialised ones
-    double t[16];
     const uint32_t my = smem_u32(gs + i);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) t[r] = ld_cluster_f64(mapa_shared(my, (uint32_t)min(r, cl - 1)));
     double acc = 0.0;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc += r < cl ? t[r] : 0.0;    // rank order: bit-reproducible
+    for (int r0 = 0; r0 < 16; r0 += 8) {     // 8 sibling loads in flight at a time; summed in rank order: bit-reproducible
+      if (r0 >= cl) break;
+      double t[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t[r] = ld_cluster_f64(mapa_shared(my, (uint32_t)min(r0 + r, cl - 1)));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc += (r0 + r) < cl ? t[r] : 0.0;
+    }
     gtot[i] = acc;
     if (stats_out && rank == 0) stats_out[(size_t)b * 2 * groups + i] = acc;
   }
