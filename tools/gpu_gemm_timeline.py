@@ -54,3 +54,17 @@ for (B_, H_, C_) in ((8, 32, 224), (8, 16, 448), (8, 8, 896), (8, 4, 896)):
     o4 = torch.empty(B_ * H_ * H_, C_, device=dev); b4 = torch.randn(C_, device=dev); e4 = torch.randn(B_, C_, device=dev)
     for cold in (False, True):
         run(f"X3 conv {C_}->{C_} @{H_}x{H_} B8 auto", lambda: ops.gemm(a=x4, w=w4, mode=_C.GEMM_CONV3X3, N=C_, K=C_, n_imgs=B_, H=H_, W=H_, out32=o4, bias=b4, rowvec=e4, flags=_C.GEMM_F_X3), cold)
+
+# GEGLU feed-forward projection at level 0 (M = 8192, N = 2*896 packed [x | gate] per 224-wide tile, K = 224), fp16x3
+M3, K3, inner = 8192, 224, 896
+a3 = (torch.randn(M3, 2 * K3, device=dev) * 0.5).half(); w3 = (torch.randn(2 * inner, 2 * K3, device=dev) * 0.05).half()
+b3 = torch.randn(2 * inner, device=dev); o3 = torch.empty(M3, 2 * inner, device=dev, dtype=torch.half)
+for bn in (128, 256):
+    for cold in (False, True):
+        run(f"X3 GEGLU gemm M8192 N1792 K224 bn{bn}", lambda: ops.gemm(a=a3, w=w3, mode=0, M=M3, N=2 * inner, K=K3, block_n=bn, out16=o3, bias=b3,
+                                                                 flags=_C.GEMM_F_GEGLU | _C.GEMM_F_X3 | _C.GEMM_F_SPLIT3OUT), cold)
+# the same product without the GEGLU epilogue (plain fp16 hi/lo store of all 1792 columns)
+o4 = torch.empty(M3, 4 * inner, device=dev, dtype=torch.half)
+for cold in (False, True):
+    run("X3 gemm M8192 N1792 K224 (no GEGLU, fp16 [hi|lo] out)", lambda: ops.gemm(a=a3, w=w3, mode=0, M=M3, N=2 * inner, K=K3, out16=o4, bias=b3,
+                                                                             flags=_C.GEMM_F_X3 | _C.GEMM_F_SPLIT3OUT), cold)

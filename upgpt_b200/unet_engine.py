@@ -54,7 +54,8 @@ def pad_heads_cols(w, heads, d, dpad):
 
 def geglu_half(inner, x3=False):
     """Half-width of a GEGLU accumulator tile ([x | gate] = 2*half columns). In the fp16x3 mode a 256-column tile leaves shared
-    memory for a single {hi, lo} slot pair (no load / MMA overlap: measured 47 us for M=8192, N=1792, K=224), so 224 is preferred."""
+    memory for a single {hi, lo} slot pair (no load / MMA overlap: measured 47 us for M=8192, N=1792, K=224), so 224 is preferred;
+    a half of 128 gets the TMA-store epilogue (two 64-column fp16 chunks, one per epilogue group)."""
     order = (112, 96, 64, 128, 80, 48, 32, 16) if x3 else (128, 112, 96, 80, 64, 48, 32, 16)
     for h in order:
         if inner % h == 0:
