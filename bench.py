@@ -362,7 +362,7 @@ def gpu_arm(args, rank, world):
                                        "50-step DDIM eta=%g, bs=%d per GPU, + KL-f8 decode to 256x256 uint8" % (args.eta, B),
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
                            "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
-                           "kernels_per_unet_step": eng.launches_per_step + 3, "precision_mode": args.precision,
+                           "kernels_per_unet_step": eng.launches_per_step - eng.n_emb_calls + 3, "precision_mode": args.precision,
                            "eps_tolerance": "1e-3 (north_star); measured 0.8e-4 .. 1.9e-4 in fp16x3" if args.precision == "fp16x3" else "fast mode: 1.3e-3 .. 1.7e-3"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
                         "d2h_bytes_per_step": int(out_pin.numel())},

@@ -165,6 +165,10 @@ int upgpt_ddpm_step(const float* x, const float* eps, const float* noise, long l
                     const int* step_ptr, int step_imm, float* x_prev, float* pred_x0, long long n, void* stream);
 /* op 0: *step = value; op 1: *step += value. Then, if t_buf: t_buf[0..B) = t_table[*step] (ddim.py:142). */
 int upgpt_step_state(int* step_ptr, int op, int value, long long* t_buf, int B, const long long* t_table, void* stream);
+/* dst[b][0..n) = table[*step_ptr * row_stride + 0..n) for b < B (n, row_stride multiples of 4): the per-step row of a table computed
+ * once per schedule, e.g. emb_layers(SiLU(time_embed(timestep_embedding(t_step)))) of all 22 ResBlocks (openaimodel.py:218-224,723-724) --
+ * t is the same for every sample of a batch in ddim.py:142 / ddpm.py:1271, so the 4 embedding launches leave the step graph */
+int upgpt_gather_step_row(const float* table, long long row_stride, const int* step_ptr, float* dst, int B, int n, void* stream);
 /* out = a*sa + b*sb (b may be NULL): q_sample / mask blend helpers (ddpm.py:281-284, ddim.py:144-147) */
 int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream);
 /* out = (wa*a + wb*b + wc*c + wd*d) / den, terms with a NULL pointer skipped: the pseudo linear multistep eps combinations of

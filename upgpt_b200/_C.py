@@ -106,6 +106,7 @@ _PROTOS = {
     "upgpt_ddpm_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
     "upgpt_step_state": [_vp, _i, _i, _vp, _i, _vp, _vp],
     "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
+    "upgpt_gather_step_row": [_vp, _ll, _vp, _vp, _i, _i, _vp],
     "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "upgpt_gaussian_sample": [_vp, _vp, _f, _vp, _i, _i, _i, _vp],
     "upgpt_lincomb4": [_vp, _f, _vp, _f, _vp, _f, _vp, _f, _f, _vp, _ll, _vp],

@@ -339,6 +339,32 @@ extern "C" int upgpt_axpby(const float* a, float sa, const float* b, float sb, f
   return 0;
 }
 
+// dst[b][i] = table[*step * row_stride + i] for b < B: one row of a per-step table broadcast over the batch (the timestep-embedding
+// projections of all denoising steps are computed once per schedule; the step graph only gathers its row)
+namespace upgpt {
+__global__ void __launch_bounds__(256)
+gather_step_row_kernel(const float* __restrict__ table, long long row_stride, const int* __restrict__ step_ptr, float* __restrict__ dst,
+                       int B, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const float* src = table + (size_t)(*step_ptr) * row_stride;
+  const int n4 = n >> 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = __ldg((const float4*)src + i);
+    for (int b = 0; b < B; ++b) *((float4*)(dst + (size_t)b * n) + i) = v;
+  }
+}
+}  // namespace upgpt
+
+extern "C" int upgpt_gather_step_row(const float* table, long long row_stride, const int* step_ptr, float* dst, int B, int n, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(table && step_ptr && dst && B > 0 && n > 0 && n % 4 == 0 && row_stride % 4 == 0, "gather_step_row: bad args (n=%d)", n);
+  UPGPT_CHECK_CUDA(launch_k(gather_step_row_kernel, dim3((n / 4 + 255) / 256), dim3(256), 0, stream, table, row_stride, step_ptr, dst, B, n));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // out = (wa*a + wb*b + wc*c + wd*d) * inv_den with the products accumulated left to right (null pointers are skipped):
 // the Adams-Bashforth eps combinations of PLMS (plms.py:217-229), e.g. (55 e_t - 59 e_1 + 37 e_2 - 9 e_3) / 24
 namespace upgpt {

@@ -1,7 +1,7 @@
 """Fused sampling loops: one captured CUDA graph per denoising step, replayed S times.
 
-Step graph = [broadcast t from a device table] -> [U-Net program (~420 kernels)] -> [DDIM / DDPM update in place on
-the staged latent] -> [advance the device-side step counter].  Schedule coefficients are a device table indexed by the
+Step graph = [gather this step's timestep-embedding row from a per-schedule table] -> [U-Net program] -> [DDIM / DDPM update in
+place on the staged latent] -> [advance the device-side step counter].  Schedule coefficients are a device table indexed by the
 counter, so replays need no host data (reference per-step host work: ddim.py:142,189-192; ddpm.py:1157-1185).
 """
 import ctypes as C
@@ -19,6 +19,7 @@ class FusedSampler:
         self.model = ldm_model
         self.unet = ldm_model.model.diffusion_model
         self._graphs = {}
+        self._emb_tables = {}
 
     # ---- conditioning normalisation (DiffusionWrapper.forward routing, ddpm.py:1557-1577) ----
     @staticmethod
@@ -59,9 +60,27 @@ class FusedSampler:
         eng.buf("s_pred_x0", tuple(x_T.shape), torch.float32)
         return eng
 
-    def _step_graph(self, eng, kind, noise_mode, noise_buf):
+    def _emb_table(self, eng, t_loop):
+        """[S][emb_total] table of the ResBlocks' timestep-embedding projections, one row per loop step (all samples of a batch
+        share t: ddim.py:142, ddpm.py:1271). Computed with the U-Net program's own embedding launches, once per (schedule, weights)."""
+        t_key = np.ascontiguousarray(t_loop, dtype=np.int64).tobytes()
+        key = (id(eng), eng.weights_version, t_key)
+        tab = self._emb_tables.get(key)
+        if tab is None:
+            if len(self._emb_tables) > 8:
+                self._emb_tables.clear()
+            S = len(t_loop)
+            tab = torch.empty(S, eng.emb_total, device=eng.dev, dtype=torch.float32)
+            for i, t in enumerate(np.asarray(t_loop).tolist()):
+                eng.bufs["t_in"].fill_(int(t))
+                eng.run_calls(0, eng.n_emb_calls)
+                tab[i].copy_(eng.bufs["emb_all"][0])
+            self._emb_tables[key] = tab
+        return tab
+
+    def _step_graph(self, eng, kind, noise_mode, noise_buf, emb_tab):
         """kind: 'ddim' | 'ddpm'; noise_mode: 0 none, 1 per-step buffer refreshed by the host loop, 2 strided table."""
-        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), eng.weights_version)
+        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), eng.weights_version, emb_tab.data_ptr())
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -78,8 +97,10 @@ class FusedSampler:
 
         def body():
             s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _C.check(L.upgpt_step_state(b["s_step"].data_ptr(), 1, 0, b["t_in"].data_ptr(), x.shape[0], b["s_ttable"].data_ptr(), s), "step_state")
-            eng.prog.run(s)
+            # this step's timestep-embedding rows from the per-schedule table (replaces 4 launches + 43 MB of fp32 weights per step)
+            _C.check(L.upgpt_gather_step_row(emb_tab.data_ptr(), emb_tab.shape[1], b["s_step"].data_ptr(), b["emb_all"].data_ptr(),
+                                             x.shape[0], emb_tab.shape[1], s), "gather_step_row")
+            eng.run_calls(eng.n_emb_calls, None, s)
             _C.check(step_fn(x.data_ptr(), b["eps"].data_ptr(), noise_ptr, stride, coef.data_ptr(), b["s_step"].data_ptr(), 0,
                              x.data_ptr(), b["s_pred_x0"].data_ptr(), n, s), "sampler_step")
             _C.check(L.upgpt_step_state(b["s_step"].data_ptr(), 1, 1, 0, 0, 0, s), "step_state")
@@ -106,7 +127,9 @@ class FusedSampler:
             else:   # True -> draw on the fly into a single-step buffer
                 noise_mode, noise_buf = 1, b["s_noise1"]
         x_saved = b["x_lat"].clone()
-        g = self._step_graph(eng, kind, noise_mode, noise_buf)   # warm-up run inside mutates x_lat / step: restore
+        emb_tab = self._emb_table(eng, t_loop)
+        ops.step_state(b["s_step"], 0, 0)
+        g = self._step_graph(eng, kind, noise_mode, noise_buf, emb_tab)   # warm-up run inside mutates x_lat / step: restore
         b["x_lat"].copy_(x_saved)
         ops.step_state(b["s_step"], 0, 0)
         for i in range(S):
@@ -142,4 +165,4 @@ class FusedSampler:
     @property
     def launches_per_step(self):
         eng = next(iter(self.unet._engines.values()))
-        return eng.launches_per_step + 3
+        return eng.launches_per_step - eng.n_emb_calls + 3     # gather + U-Net body + update + step++

@@ -424,6 +424,8 @@ class UNetEngine(EngineBase):
             # at the output of time_embed (silu_out above) instead of once per output feature of the 22 projections
             P.add(L_.upgpt_linear_small_m, emb.data_ptr(), 4 * self.mc, B, self.w["emb_all.weight"].data_ptr(),
                   self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 0, 0, emb_all.data_ptr(), self.emb_total)
+        # the launches above depend on the timestep only: samplers may run them once per schedule (sampler_engine.py)
+        self.n_emb_calls = 0 if self._sizing else len(self.prog.calls)
         # ---- input blocks ----
         hs = []
         h = self.buf("h_in0", (B, H * W, self.mc))
@@ -541,6 +543,14 @@ class UNetEngine(EngineBase):
         else:
             self.prog.run(self._stream())
         return self.bufs["eps"]
+
+    def run_calls(self, lo, hi, stream=None):
+        """Runs launches [lo, hi) of the recorded program (hi None = to the end)."""
+        stream = stream or self._stream()
+        for fn, args in self.prog.calls[lo:hi]:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise _C.UpgptError("%s failed (%d): %s" % (fn.__name__, rc, _C.lib().upgpt_last_error().decode()))
 
     def forward(self, x, timesteps, context, use_graph=None):
         """x (B, in_channels, H, W) fp32 NCHW (latent already concatenated with c_concat), timesteps (B,), context (B,L,D)."""
