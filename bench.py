@@ -248,6 +248,50 @@ def roofline_hbm_kernel(dev, pk):
             "algorithmic_bytes_per_launch": nbytes, "peak_source": pk["src"] + " (copy bandwidth)"}
 
 
+def roofline_attention(dev, pk):
+    """The attention cores of the level-0 SpatialTransformer (B=8, 8 heads, d=28 padded to 64, 1024 queries), timed alone with CUDA
+    events as a graph of 8 launches rotating over 8 operand sets: self-attention (1024 keys, q|k|v slices of one fused projection,
+    V row-major) and cross-attention over the 87-token context cache. Algorithmic flops = 4*B*Nq*Nk*(H*d) (attention.py:178-192;
+    the zero-padded head columns are not counted); the standalone cross-attention is HBM-bound, so its GB/s is given too."""
+    import torch
+    from upgpt_b200 import ops
+    B, Hh, Nq, d, dpad = B_PER_GPU, 8, LAT * LAT, 28, 64
+    HD, NC, REP = Hh * dpad, 8, 8
+    res = {}
+    for name, Nk in (("self", Nq), ("cross", CTX_LEN)):
+        if name == "self":
+            qkv = [(torch.randn(B * Nq, 3 * HD, device=dev) * 0.5).half() for _ in range(NC)]
+            args = [dict(q=t, ldq=3 * HD, k=t.reshape(-1)[HD:], ldk=3 * HD, k_batch_stride=Nq * 3 * HD, vt=t.reshape(-1)[2 * HD:], ldvt=3 * HD,
+                         v_rowmajor=1, v_batch_stride=Nq * 3 * HD) for t in qkv]
+        else:
+            qs = [(torch.randn(B * Nq, HD, device=dev) * 0.5).half() for _ in range(NC)]
+            kv = [(torch.randn(B * Nk, 2 * HD, device=dev) * 0.5).half() for _ in range(NC)]
+            args = [dict(q=a, ldq=HD, k=c, ldk=2 * HD, k_batch_stride=Nk * 2 * HD, vt=c.reshape(-1)[HD:], ldvt=2 * HD, v_rowmajor=1,
+                         v_batch_stride=Nk * 2 * HD) for a, c in zip(qs, kv)]
+        out = torch.zeros(B * Nq, 2 * HD, device=dev, dtype=torch.half)
+        call = lambda i: ops.attention(out=out, ldo=2 * HD, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=dpad, scale=float(d) ** -0.5, split3_out=1, **args[i % NC])
+        for i in range(3):
+            call(i)
+        torch.cuda.synchronize()
+        g = ops.Graph().capture(lambda: [call(i) for i in range(REP)])
+        g.launch(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.launch(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / REP)
+        ms = sorted(ts)[len(ts) // 2]
+        flops = 4.0 * B * Nq * Nk * Hh * d
+        nbytes = 2.0 * (B * Nq * HD + 2 * B * Nk * HD) + 2.0 * B * Nq * 2 * HD     # fp16 q, k, v in; [hi | lo] fp16 planes out
+        ach = flops / (ms * 1e-3) / 1e12
+        res[name] = {"kernel": "attention_kernel (%s, B=8, 8 heads, d=28->64, Nq=1024, Nk=%d)" % (name, Nk), "bound": "tensor", "achieved": ach,
+                     "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "us_per_launch": ms * 1e3,
+                     "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
+                     "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "peak_source": pk["src"] + " (burst: kernel timed alone)"}
+    return res
+
+
 def parity_spot_check(model, dev):
     """eps of the bbox.yaml U-Net (B=1, t=501) on the GPU vs the CPU oracle, in the benchmark's precision mode."""
     import torch
@@ -352,6 +396,10 @@ def gpu_arm(args, rank, world):
     if rank == 0:
         roof = roofline_dominant_kernel(dev, pk, args.precision)
         roof_hbm = roofline_hbm_kernel(dev, pk)
+        try:
+            roof_attn = roofline_attention(dev, pk)
+        except Exception as e:      # an auxiliary measurement must never take the headline line down
+            roof_attn = {"error": repr(e)[:300]}
         alg_tf_per_step = world * B * (DDIM_STEPS * GF_UNET_PER_SAMPLE_STEP + GF_VAE_PER_IMAGE) / 1e3
         eng = [e for k, e in model.model.diffusion_model._engines.items() if k[-1] == args.precision][0]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -370,6 +418,7 @@ def gpu_arm(args, rank, world):
                 "clocks": clk,
                 "roofline": roof,
                 "roofline_hbm": roof_hbm,
+                "roofline_attention": roof_attn,
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
                                "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},
                 "fast_mode": fast}

@@ -7,8 +7,10 @@
     DDIM update, step counter -- is ONE captured CUDA graph replayed S times; schedule coefficients live in a device
     table indexed by a device-side step counter, so no host scalar ever crosses per step (the reference does 4
     torch.full + a numpy read per step, ddim.py:189-192).
-  * general path (mask/x0 blending, score correctors, classifier-free guidance, arbitrary `apply_model`): Python loop
-    over `model.apply_model` + the fused update kernel.
+    Classifier-free guidance (ddim.py:171-178) stays on this path: the engine runs the [unconditional | conditional] 2B
+    batch in one pass per step and the graph combines the two eps halves before the update.
+  * general path (mask/x0 blending, score correctors, non-fusable conditioning, `fused=False`): Python loop over
+    `model.apply_model` + the fused update kernel.
 """
 import numpy as np
 import torch
@@ -110,9 +112,11 @@ class DDIMSampler(object):
         total_steps = timesteps if ddim_use_original_steps else timesteps.shape[0]
         intermediates = {"x_inter": [img], "pred_x0": [img]}
 
-        plain = (mask is None and score_corrector is None and not quantize_denoised and noise_dropout == 0.
-                 and (unconditional_conditioning is None or unconditional_guidance_scale == 1.))
+        cfg = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+        plain = mask is None and score_corrector is None and not quantize_denoised and noise_dropout == 0.
         can_fuse = plain and hasattr(self.model, "fused_sampler") and self.model.fused_sampler(cond) is not None
+        if can_fuse and cfg:   # guidance runs as one [unconditional | conditional] 2B-batch step graph
+            can_fuse = self.model.fused_sampler(cond).cfg_fusable(cond, unconditional_conditioning)
         if fused is None:
             fused = can_fuse
         if fused and not can_fuse:
@@ -127,7 +131,9 @@ class DDIMSampler(object):
         if fused:
             eng = self.model.fused_sampler(cond)
             img, intermediates = eng.run_ddim(img, cond, np.asarray(time_range), coef, x_noise if eta_on else None,
-                                              log_every_t, callback, img_callback, intermediates)
+                                              log_every_t, callback, img_callback, intermediates,
+                                              ucond=unconditional_conditioning if cfg else None,
+                                              cfg_scale=float(unconditional_guidance_scale) if cfg else None)
             return img, intermediates
 
         from upgpt_b200 import ops

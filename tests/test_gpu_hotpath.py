@@ -391,8 +391,16 @@ def test_classifier_free_guidance_vs_oracle(dev):
     with torch.no_grad():
         ref_ddim = O.ddim_sample(guided, x, S, 0.0, sched)
         ref_plms = O.plms_sample(guided, x, S, sched)
-    out, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), **kw)
+    out, inter = DDIMSampler(model).sample(S, 2, (4, 16, 16), log_every_t=1, **kw)     # fused: one 2B-batch graph per step
     assert relerr(out, ref_ddim) < 1e-2
+    assert tuple(out.shape) == (2, 4, 16, 16) and all(tuple(t.shape) == (2, 4, 16, 16) for t in inter["x_inter"] + inter["pred_x0"])
+    out_g, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), fused=False, **kw)          # general loop: two passes per step
+    assert relerr(out_g, ref_ddim) < 1e-2
+    assert relerr(out, out_g) < 2e-3, "the 2B-batch graph and the two-pass loop agree"
+    kw1 = dict(kw, eta=1.0, x_noise=torch.randn(S, 2, 4, 16, 16, generator=torch.Generator().manual_seed(3)).to(dev))
+    o1, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), **kw1)
+    o2, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), fused=False, **kw1)
+    assert relerr(o1, o2) < 2e-3
     unguided, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), conditioning=cond, eta=0.0, x_T=x.to(dev), verbose=False)
     assert relerr(unguided, ref_ddim) > relerr(out, ref_ddim), "guidance changes the sample"
     outp, _ = PLMSSampler(model).sample(S, 2, (4, 16, 16), **kw)

@@ -46,18 +46,36 @@ class FusedSampler:
             return None   # concat-only U-Nets have no context: not a UPGPT configuration
         return cc, ct
 
-    def _prepare(self, x_T, cond):
+    def cfg_fusable(self, cond, ucond):
+        """Classifier-free guidance runs as ONE 2B-batch step graph when both conditionings have the same fusable form."""
+        key = self.model.model.conditioning_key
+        a, b = self.split_cond(cond, key), self.split_cond(ucond, key)
+        if a is None or b is None or a[0] is None or b[0] is None or a[0].shape != b[0].shape:
+            return False
+        return (a[1] is None) == (b[1] is None) and (a[1] is None or a[1].shape == b[1].shape)
+
+    def _prepare(self, x_T, cond, ucond=None):
+        """Stages latent / context / concat channels into the engine for this batch. With `ucond` (classifier-free guidance,
+        ddim.py:171-178) the engine runs 2B samples per pass: rows [0, B) = unconditional, rows [B, 2B) = conditional."""
         cc, ct = self.split_cond(cond, self.model.model.conditioning_key)
         B, _, H, W = x_T.shape
-        eng = self.unet.engine(B, H, W, cc.shape[1])
+        x_T = x_T.contiguous().float()
+        if ucond is not None:
+            uc, ut = self.split_cond(ucond, self.model.model.conditioning_key)
+            cc = torch.cat([uc.float(), cc.float()], 0)
+            ct = None if ct is None else torch.cat([ut.float(), ct.float()], 0)
+            x_T = torch.cat([x_T, x_T], 0)
+        eng = self.unet.engine(x_T.shape[0], H, W, cc.shape[1])
         eng.set_context(cc.contiguous().float())
-        eng.stage_inputs(x_T.contiguous().float(), None, None if ct is None else ct.contiguous().float())
-        dev = x_T.device
+        eng.stage_inputs(x_T, None, None if ct is None else ct.contiguous().float())
+        sfx = "" if ucond is None else "_cfg"       # per-sample buffers of the guided half-batch have their own names
         eng.buf("s_step", (1,), torch.int32)
         eng.buf("s_ttable", (self.MAX_STEPS,), torch.int64)
         eng.buf("s_coef", (self.MAX_STEPS, 6), torch.float32)
-        eng.buf("s_noise1", tuple(x_T.shape), torch.float32)
-        eng.buf("s_pred_x0", tuple(x_T.shape), torch.float32)
+        eng.buf("s_noise1" + sfx, (B,) + tuple(x_T.shape[1:]), torch.float32)
+        eng.buf("s_pred_x0" + sfx, (B,) + tuple(x_T.shape[1:]), torch.float32)
+        if ucond is not None:
+            eng.buf("s_eps_cfg", (B,) + tuple(eng.bufs["eps"].shape[1:]), torch.float32)
         return eng
 
     def _emb_table(self, eng, t_loop):
@@ -78,16 +96,23 @@ class FusedSampler:
             self._emb_tables[key] = tab
         return tab
 
-    def _step_graph(self, eng, kind, noise_mode, noise_buf, emb_tab):
-        """kind: 'ddim' | 'ddpm'; noise_mode: 0 none, 1 per-step buffer refreshed by the host loop, 2 strided table."""
-        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), eng.weights_version, emb_tab.data_ptr())
+    def _step_graph(self, eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale=None):
+        """kind: 'ddim' | 'ddpm'; noise_mode: 0 none, 1 per-step buffer refreshed by the host loop, 2 strided table.
+        cfg_scale: classifier-free guidance -- the engine batch is [unconditional | conditional]; after the U-Net pass
+        eps[:B] <- s*eps_c + (1-s)*eps_u, the update runs on the first half of the latent and is mirrored into the second."""
+        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), eng.weights_version, emb_tab.data_ptr(),
+               cfg_scale)
         g = self._graphs.get(key)
         if g is not None:
             return g
         L = _C.lib()
         b = eng.bufs
         x = b["x_lat"]
-        n = x.numel()
+        cfg = cfg_scale is not None
+        n = x.numel() // 2 if cfg else x.numel()     # elements of the B samples the update kernel advances
+        pred_x0 = b["s_pred_x0_cfg" if cfg else "s_pred_x0"]
+        eps = b["eps"]
+        assert x.is_contiguous() and eps.is_contiguous() and eps.numel() == x.numel()
         step_fn = L.upgpt_ddim_step if kind == "ddim" else L.upgpt_ddpm_step
         ncols = 5 if kind == "ddim" else 6
         coef = b["s_coef"]
@@ -101,8 +126,15 @@ class FusedSampler:
             _C.check(L.upgpt_gather_step_row(emb_tab.data_ptr(), emb_tab.shape[1], b["s_step"].data_ptr(), b["emb_all"].data_ptr(),
                                              x.shape[0], emb_tab.shape[1], s), "gather_step_row")
             eng.run_calls(eng.n_emb_calls, None, s)
-            _C.check(step_fn(x.data_ptr(), b["eps"].data_ptr(), noise_ptr, stride, coef.data_ptr(), b["s_step"].data_ptr(), 0,
-                             x.data_ptr(), b["s_pred_x0"].data_ptr(), n, s), "sampler_step")
+            e_ptr = eps.data_ptr()
+            if cfg:   # e = s e_c + (1 - s) e_u  (= e_u + s (e_c - e_u), the same expression as the general loop)
+                e_ptr = b["s_eps_cfg"].data_ptr()
+                _C.check(L.upgpt_axpby(eps.data_ptr() + 4 * n, float(cfg_scale), eps.data_ptr(), 1.0 - float(cfg_scale), e_ptr, n, s),
+                         "cfg_combine")
+            _C.check(step_fn(x.data_ptr(), e_ptr, noise_ptr, stride, coef.data_ptr(), b["s_step"].data_ptr(), 0,
+                             x.data_ptr(), pred_x0.data_ptr(), n, s), "sampler_step")
+            if cfg:   # both halves of the batch carry the same latent
+                _C.check(L.upgpt_axpby(x.data_ptr(), 1.0, 0, 0.0, x.data_ptr() + 4 * n, n, s), "cfg_mirror")
             _C.check(L.upgpt_step_state(b["s_step"].data_ptr(), 1, 1, 0, 0, 0, s), "step_state")
 
         self._coef_cols = ncols
@@ -111,8 +143,11 @@ class FusedSampler:
         self._graphs[key] = g
         return g
 
-    def _loop(self, eng, kind, S, t_loop, coef_loop, x_noise, log_idx, callback, img_callback, intermediates):
+    def _loop(self, eng, kind, S, t_loop, coef_loop, x_noise, log_idx, callback, img_callback, intermediates, cfg_scale=None):
         b = eng.bufs
+        cfg = cfg_scale is not None
+        nB = b["x_lat"].shape[0] // 2 if cfg else b["x_lat"].shape[0]
+        noise1, pred_x0 = b["s_noise1_cfg" if cfg else "s_noise1"], b["s_pred_x0_cfg" if cfg else "s_pred_x0"]
         assert S <= self.MAX_STEPS
         dev = b["x_lat"].device
         b["s_ttable"][:S].copy_(torch.as_tensor(np.ascontiguousarray(t_loop), dtype=torch.int64))
@@ -125,33 +160,35 @@ class FusedSampler:
             if isinstance(x_noise, torch.Tensor):
                 noise_mode, noise_buf = 2, x_noise.contiguous().float()
             else:   # True -> draw on the fly into a single-step buffer
-                noise_mode, noise_buf = 1, b["s_noise1"]
+                noise_mode, noise_buf = 1, noise1
         x_saved = b["x_lat"].clone()
         emb_tab = self._emb_table(eng, t_loop)
         ops.step_state(b["s_step"], 0, 0)
-        g = self._step_graph(eng, kind, noise_mode, noise_buf, emb_tab)   # warm-up run inside mutates x_lat / step: restore
+        g = self._step_graph(eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale)   # warm-up run inside mutates x_lat / step: restore
         b["x_lat"].copy_(x_saved)
         ops.step_state(b["s_step"], 0, 0)
         for i in range(S):
             if noise_mode == 1:
-                b["s_noise1"].normal_()
+                noise1.normal_()
             g.launch()
             if callback:
                 callback(i)
             if img_callback:
-                img_callback(b["s_pred_x0"].clone(), i)
+                img_callback(pred_x0.clone(), i)
             if i in log_idx:
-                intermediates["x_inter"].append(b["x_lat"].clone())
-                intermediates["pred_x0"].append(b["s_pred_x0"].clone())
-        return b["x_lat"].clone(), intermediates
+                intermediates["x_inter"].append(b["x_lat"][:nB].clone())
+                intermediates["pred_x0"].append(pred_x0.clone())
+        return b["x_lat"][:nB].clone(), intermediates
 
     # ---- DDIM (ddim.py:114-163) ----
-    def run_ddim(self, x_T, cond, time_range, coef_by_index, x_noise, log_every_t, callback, img_callback, intermediates):
-        eng = self._prepare(x_T, cond)
+    def run_ddim(self, x_T, cond, time_range, coef_by_index, x_noise, log_every_t, callback, img_callback, intermediates,
+                 ucond=None, cfg_scale=None):
+        eng = self._prepare(x_T, cond, ucond)
         S = len(time_range)
         coef_loop = coef_by_index[:S].flip(0).contiguous()     # loop i uses index S-1-i
         log_idx = {i for i in range(S) if (S - i - 1) % log_every_t == 0 or (S - i - 1) == S - 1}
-        return self._loop(eng, "ddim", S, np.asarray(time_range), coef_loop, x_noise, log_idx, callback, img_callback, intermediates)
+        return self._loop(eng, "ddim", S, np.asarray(time_range), coef_loop, x_noise, log_idx, callback, img_callback, intermediates,
+                          cfg_scale if ucond is not None else None)
 
     # ---- DDPM ancestral (ddpm.py:1244-1292) ----
     def run_ddpm(self, x_T, cond, timesteps, coef_by_t, x_noise, log_every_t, callback, img_callback, intermediates):
