@@ -33,8 +33,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--eta", type=float, default=1.0, help="DDIM eta (reference default in log_images is 1.0)")
-    ap.add_argument("--precision", default=os.environ.get("UPGPT_PRECISION", "fp16x3"),
-                    help="fp16x3 = error-compensated operands, meets the 1e-3 eps tolerance (headline); fp16 = fast mode")
+    ap.add_argument("--precision", default=None,
+                    help="default: upgpt_b200.unet_engine.default_precision(). fp16x3 = error-compensated operands everywhere; mixed = fp16x3 "
+                         "except the deep low-resolution levels (both meet the 1e-3 eps tolerance); fp16 = fast mode")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the additional fp16 fast-mode measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -183,7 +184,7 @@ def roofline_dominant_kernel(dev, pk, precision):
     import torch
     from upgpt_b200 import _C, ops
     B, H, W, C = B_PER_GPU, LAT, LAT, 224
-    x3 = precision == "fp16x3"
+    x3 = precision in ("fp16x3", "mixed")        # the 32x32 level runs fp16x3 in both parity modes
     kx = 2 if x3 else 1                  # operand planes [hi | lo]
     REP, NC = 16, 16
     xs = [(torch.randn(B, H, W, C * kx, device=dev) * 0.5).half() for _ in range(NC)]
@@ -210,7 +211,7 @@ def roofline_dominant_kernel(dev, pk, precision):
     if os.path.exists(tp):                                                 # from the committed `ncu --set full` capture of this kernel
         traffic = json.load(open(tp)).get("conv224_" + ("fp16x3" if x3 else "fp16"), {}).get("dram_bytes")
     exe = flops * (3 if x3 else 1)
-    return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % precision, "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
+    return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % ("fp16x3" if x3 else "fp16"), "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
             "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic, "peak_source": pk["src"] + " (burst: kernel timed alone)",
             "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": flops, "executed_mma_flops_per_launch": exe,
             "executed_mma_frac_of_peak": exe / (ms * 1e-3) / 1e12 / pk["tf_burst"],
@@ -404,14 +405,14 @@ def gpu_arm(args, rank, world):
         eng = [e for k, e in model.model.diffusion_model._engines.items() if k[-1] == args.precision][0]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16" if args.precision == "fp16" else "f16 hi+lo operand planes (3 MMAs per product), f32 accumulate / residual / statistics",
+                "dtype": PRECISION_NOTES[args.precision][0],
                 "data": "synthetic",
                 "config": {"workload": "configs[1]: bbox.yaml U-Net (425.29M params, random init) 32x32x4 latent, 87x768 context, "
                                        "50-step DDIM eta=%g, bs=%d per GPU, + KL-f8 decode to 256x256 uint8" % (args.eta, B),
                            "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
                            "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
                            "kernels_per_unet_step": eng.launches_per_step - eng.n_emb_calls + 3, "precision_mode": args.precision,
-                           "eps_tolerance": "1e-3 (north_star); measured 0.8e-4 .. 1.9e-4 in fp16x3" if args.precision == "fp16x3" else "fast mode: 1.3e-3 .. 1.7e-3"},
+                           "eps_tolerance": PRECISION_NOTES[args.precision][1]},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
                         "d2h_bytes_per_step": int(out_pin.numel())},
                 "gpu_launches": int(launches),
@@ -432,6 +433,16 @@ def gpu_arm(args, rank, world):
         dist.destroy_process_group()
 
 
+PRECISION_NOTES = {
+    "fp16x3": ("f16 hi+lo operand planes (3 MMAs per product), f32 accumulate / residual / statistics",
+               "1e-3 (north_star); measured 0.8e-4 .. 1.9e-4 in fp16x3"),
+    "mixed": ("f16 hi+lo operand planes (3 MMAs per product) at the 32x32 / 16x16 levels and on the residual-path 1x1s, single f16 plane in the "
+              "weight-bound 8x8 / 4x4 levels; f32 accumulate / residual / statistics",
+              "1e-3 (north_star); measured <= 3.5e-4 in mixed (tests assert 5e-4)"),
+    "fp16": ("f16", "fast mode: 1.3e-3 .. 1.7e-3"),
+}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -439,6 +450,9 @@ def main():
     if args.impl == "reference":
         cpu_reference_arm(args, rank)
         return
+    if args.precision is None:
+        from upgpt_b200.unet_engine import default_precision
+        args.precision = default_precision()
     gpu_arm(args, rank, world)
 
 

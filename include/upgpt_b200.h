@@ -182,6 +182,29 @@ int upgpt_gaussian_sample(const float* moments, const float* noise, float out_sc
 /* clamp(-1,1)*0.5+0.5 -> uint8 NHWC (generate_utils.py:165-168) */
 int upgpt_to_uint8_nhwc(const float* x, int B, int C, int HW, uint8_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * CLIP ViT-L/14 conditioning towers: the CUDA-core pieces around upgpt_gemm / upgpt_attention.
+ *   replaces: FrozenCLIPEmbedder.forward -> transformers.CLIPTextModel (ldm/modules/encoders/modules.py:137-162) and
+ *   FrozenClipImageEmbedder2.forward -> clip.model.VisionTransformer (modules.py:234-256; `clip` = openai/CLIP, not vendored)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* out[r] = tok_emb[ids[r]] + pos_emb[r % seq], r < rows = B*seq (CLIPTextEmbeddings); ids int64 on the device, clamped to [0, vocab) */
+int upgpt_embed_tokens(const long long* ids, int rows, int seq, int vocab, const float* tok_emb, const float* pos_emb, int C,
+                       float* out, void* stream);
+/* im2col of the P x P stride-P patch conv: img NCHW fp32 [n][Cin][S][S] -> fp16 rows [n*(S/P)^2][Kpad], one patch per row in
+ * (c, py, px) order (= conv1.weight.reshape(width, -1)), zero columns from Cin*P*P to Kpad (multiple of 8); split3: [hi | lo] planes */
+int upgpt_patchify(const float* img, int n, int Cin, int S, int P, int Kpad, int split3, void* out16, int ldo, void* stream);
+/* out[b][0] = cls + pos[0]; out[b][1+i] = patch[b][i] + pos[1+i] for T tokens of C channels (VisionTransformer.forward before ln_pre) */
+int upgpt_vit_assemble(const float* patch, const float* cls, const float* pos, int n, int T, int C, float* out, void* stream);
+/* LayerNorm with fp32 output (ln_pre / final_layer_norm) */
+int upgpt_layernorm_f32(const float* x, int ldx, int rows, int C, const float* gamma, const float* beta, float eps, float* out, int ldo,
+                        void* stream);
+/* out16 = x * sigmoid(1.702 x) (QuickGELU) as a GEMM operand; split3: [hi | lo] planes of C columns */
+int upgpt_quick_gelu_cast(const float* x, long long rows, int C, int split3, void* out16, int ldo, void* stream);
+/* fp32 softmax attention for short sequences (N <= 128, d <= 64): qkv fp32 [B][N][ld], q at column h*d, k at koff + h*d, v at
+ * voff + h*d; causal: key j <= query i (CLIP text tower). out16 fp16 [B][N][ldo], head h at columns h*d; split3_out: [hi | lo] planes */
+int upgpt_attention_small(const float* qkv, int ld, int koff, int voff, int B, int H, int N, int d, float scale, int causal,
+                          int split3_out, void* out16, int ldo, void* stream);
+
 /* Stream capture of a sequence of upgpt_* calls into an executable CUDA graph. */
 int upgpt_capture_begin(void* stream);
 int upgpt_capture_end(void* stream, void** graph_exec_out);

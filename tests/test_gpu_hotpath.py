@@ -48,8 +48,10 @@ def _unet(kw, seed, dev):
     ("upscale", UPSCALE_UNET_KW, 1, 32, 24, 86, [481], 2),      # the 4x super-resolution U-Net family
 ])
 def test_unet_eps_vs_reference_golden(dev, golden, tag, kw, B, H, W, L, ts, seed):
-    """Public UNetModel.forward (default precision = error-compensated fp16x3) against the reference's own outputs:
-    tolerance 1e-3 (BASELINE.json north_star), 5e-4 asserted; then the opt-in fp16 fast mode at its own bound."""
+    """Public UNetModel.forward (default precision: error-compensated fp16x3 operands, in "mixed" relaxed to single-plane fp16 in the
+    deep levels of a >= 4-level U-Net) against the reference's own outputs: tolerance 1e-3 (BASELINE.json north_star), 5e-4 asserted;
+    then the opt-in fp16 fast mode at its own bound."""
+    from upgpt_b200.unet_engine import default_precision
     m, _ = _unet(kw, seed, dev)
     x, mask, ctx = synth.synth_inputs(B, H, W, L, kw["context_dim"], seed, concat_channels=kw["in_channels"] - kw["out_channels"])
     xc = torch.cat([x[:, :kw["out_channels"]], mask], 1).to(dev)
@@ -59,7 +61,7 @@ def test_unet_eps_vs_reference_golden(dev, golden, tag, kw, B, H, W, L, ts, seed
         with torch.no_grad():
             y = m(xc, tt, ctx.to(dev))                     # public UNetModel.forward (graph replay)
             eng = m.engine(B, H, W, L)
-            assert eng.precision == "fp16x3"
+            assert eng.precision == default_precision() and eng.precision in ("fp16x3", "mixed")
             eng.stage_inputs(xc, tt); y_eager = eng.run(use_graph=False).clone()
         assert relerr(y, ref) < 5e-4
         assert torch.equal(y, y_eager), "graph replay must be bit-identical to the eager program (deterministic reductions)"

@@ -155,3 +155,57 @@ def test_lr_scheduler_stub_matches_reference_formula():
     from ldm.lr_scheduler import LambdaLinearScheduler
     s = LambdaLinearScheduler(warm_up_steps=[100], f_min=[1.0], f_max=[1.0], f_start=[1e-6], cycle_lengths=[10 ** 13])
     assert abs(s(0) - 1e-6) < 1e-12 and abs(s(50) - (1e-6 + (1 - 1e-6) * 0.5)) < 1e-9 and s(1000) == 1.0
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "mixed", "fp16"])
+def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
+    """Host logic of the per-layer precision plan (recorded without a device): every tensor-core GEMM must find its A operand in the
+    plane format ([hi | lo] vs single fp16) its producer wrote -- GroupNorm/prep, LayerNorm, attention output, or a GEMM's fp16 copy."""
+    import torch
+    from upgpt_b200 import _C
+    from upgpt_b200 import unet_engine
+    from upgpt_b200.unet_engine import UNetEngine
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from oracle.ref_loader import BBOX_UNET_KW
+    bbox_arch = (BBOX_UNET_KW["model_channels"], tuple(BBOX_UNET_KW["channel_mult"]), BBOX_UNET_KW["num_res_blocks"],
+                 tuple(BBOX_UNET_KW["attention_resolutions"]))
+    assert unet_engine.MIXED_PROFILES[bbox_arch] == (64, 16)
+    kw = dict(BBOX_UNET_KW, model_channels=64, num_heads=4, context_dim=64)     # same 4-level structure, narrow channels
+    monkeypatch.setitem(unet_engine.MIXED_PROFILES, (64,) + bbox_arch[1:], (64, 16))
+    unet = UNetModel(**kw).eval()
+    eng = UNetEngine(unet, 1, 32, 32, 87, precision=precision, dry=True)
+    L = _C.lib()
+    fmt, n_x3, n_plain = {}, 0, 0
+    for fn, args in eng.prog.calls:
+        if fn in (L.upgpt_prep_operand, L.upgpt_groupnorm_prep):
+            a = args[0]._obj
+            fmt[a.out] = bool(a.split3)
+            if a.raw:
+                fmt[a.raw] = bool(a.split3)
+        elif fn in (L.upgpt_layernorm, L.upgpt_layernorm_split3):
+            fmt[args[7]] = fn is L.upgpt_layernorm_split3
+        elif fn is L.upgpt_attention:
+            a = args[0]._obj
+            fmt[a.out] = bool(a.split3_out)
+        elif fn is L.upgpt_gemm:
+            a = args[0]._obj
+            x3 = bool(a.flags & _C.GEMM_F_X3)
+            n_x3 += x3; n_plain += not x3
+            assert a.a in fmt, "GEMM operand without a recorded producer"
+            assert fmt[a.a] == x3, "operand planes do not match the GEMM's precision flag"
+            if a.out16:
+                fmt[a.out16] = bool(a.flags & _C.GEMM_F_SPLIT3OUT)
+    assert n_x3 + n_plain == 193
+    if precision == "fp16x3":
+        assert n_plain == 0
+    elif precision == "fp16":
+        assert n_x3 == 0
+    else:   # mixed: the 4x4 level entirely, the 8x8 level except skip / proj_in / proj_out and the convs sharing operands with a skip
+        assert n_plain == 64 and eng.mixed
+        assert eng.use_x3("conv", 1024) and not eng.use_x3("resid1x1", 16) and eng.use_x3("resid1x1", 64) and not eng.use_x3("tf", 64)
+    with pytest.raises(_C.UpgptError):
+        eng.run()
+    # an architecture without a probed profile keeps fp16x3 everywhere in "mixed" (the probe shows its deep levels are not cheap in error)
+    from oracle.make_golden import TINY_UNET_KW
+    tiny = UNetEngine(UNetModel(**TINY_UNET_KW).eval(), 2, 16, 16, 87, precision="mixed", dry=True)
+    assert not tiny.mixed and all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.calls if f is L.upgpt_gemm)

@@ -108,6 +108,12 @@ _PROTOS = {
     "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
     "upgpt_gather_step_row": [_vp, _ll, _vp, _vp, _i, _i, _vp],
     "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
+    "upgpt_embed_tokens": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
+    "upgpt_patchify": [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "upgpt_vit_assemble": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
+    "upgpt_layernorm_f32": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
+    "upgpt_quick_gelu_cast": [_vp, _ll, _i, _i, _vp, _i, _vp],
+    "upgpt_attention_small": [_vp, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _vp, _i, _vp],
     "upgpt_gaussian_sample": [_vp, _vp, _f, _vp, _i, _i, _i, _vp],
     "upgpt_lincomb4": [_vp, _f, _vp, _f, _vp, _f, _vp, _f, _f, _vp, _ll, _vp],
     "upgpt_capture_begin": [_vp],

@@ -23,7 +23,7 @@ def synth_tensor(name, shape, seed=0):
     g = _gen(name, seed)
     shape = tuple(shape)
     is_norm = (".norm" in name or "in_layers.0." in name or "out_layers.0." in name or name.startswith("out.0.")
-               or "norm_out" in name)
+               or "norm_out" in name or "layer_norm" in name or ".ln_" in name or name.startswith("ln_"))
     if len(shape) >= 2:
         fan_in = 1
         for s in shape[1:]:

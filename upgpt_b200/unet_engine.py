@@ -25,11 +25,27 @@ from ldm.modules.diffusionmodules import openaimodel as om
 
 def default_precision():
     """Operand precision of the tensor-core GEMMs / convs.
-      "fp16x3" (default): every operand is split into hi + lo fp16 planes and each product is formed as
+      "fp16x3"          : every operand is split into hi + lo fp16 planes and each product is formed as
                           Ah*Wh + Al*Wh + Ah*Wl with fp32 accumulation -> eps within ~1.5e-4 of the fp32 reference
                           (BASELINE.json's tolerance is 1e-3);
+      "mixed" (default) : fp16x3 everywhere except the deep low-resolution levels of a U-Net with a probed profile (MIXED_PROFILES:
+                          the bbox.yaml architecture; any other U-Net runs fp16x3 throughout), whose GEMMs / convs are
+                          weight-bandwidth bound and contribute least to the eps error (CPU probe tests/probe_mixed_precision.py
+                          predicted +2.9e-4 in quadrature at bbox.yaml; measured on B200: eps 3.2e-4 .. 3.4e-4, U-Net step 5.03 ->
+                          4.64 ms): levels with H*W <= 16 run single-plane fp16 throughout, levels with H*W <= 64 all but the
+                          residual-path 1x1s (skip_connection, proj_in, proj_out) and a conv that shares its operand with a skip GEMM;
       "fp16"            : single fp16 plane, ~1.5x faster end to end, eps within ~1.3e-3 .. 1.7e-3 (opt-in fast mode)."""
-    return os.environ.get("UPGPT_PRECISION", "fp16x3")
+    return os.environ.get("UPGPT_PRECISION", "mixed")
+
+
+# "mixed" precision profiles: U-Net architecture (model_channels, channel_mult, num_res_blocks, attention_resolutions) ->
+# (deep_hw, full_hw) thresholds on the tokens per image of a level. How much of eps flows through the deep levels depends on the
+# architecture (the same thresholds cost +2.9e-4 at bbox.yaml but +4.6e-4 on the upscale U-Net fed a 32x24 latent), so a profile is
+# only applied to an architecture it was probed on (tests/probe_mixed_precision.py) and verified against the reference's golden
+# eps on the GPU; every other U-Net keeps fp16x3 throughout.
+MIXED_PROFILES = {
+    (224, (1, 2, 4, 4), 2, (4, 2, 1)): (64, 16),      # configs/deepfashion/bbox.yaml: eps 3.2e-4 .. 3.4e-4, step 5.03 -> 4.64 ms at B=8
+}
 
 
 def _round_up(x, m):
@@ -107,7 +123,8 @@ class EngineBase:
     def __init__(self, device, precision):
         self.dev = device
         self.precision = precision
-        self.split3 = precision == "fp16x3"
+        assert precision in ("fp16x3", "mixed", "fp16"), precision
+        self.split3 = precision in ("fp16x3", "mixed")   # engine-wide default operand format ("mixed" overrides it per layer)
         self.x3 = _C.GEMM_F_X3 if self.split3 else 0     # GEMM flag: operands carry [hi | lo] planes
         self.kx = 2 if self.split3 else 1                # storage planes per fp16 operand
         self.L = _C.lib()
@@ -189,11 +206,11 @@ class EngineBase:
             setattr(a, k, self.p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
         self.prog.add_struct(self.L.upgpt_gemm, a)
 
-    def e_layernorm(self, x, rows, Cc, gamma, beta, out16):
+    def e_layernorm(self, x, rows, Cc, gamma, beta, out16, split3=None, ldx=None):
         if self._sizing:
             return
-        fn = self.L.upgpt_layernorm_split3 if self.split3 else self.L.upgpt_layernorm
-        self.prog.add(fn, self.p(x), Cc, rows, Cc, self.p(gamma), self.p(beta), 1e-5, self.p(out16), 0)
+        fn = self.L.upgpt_layernorm_split3 if (self.split3 if split3 is None else split3) else self.L.upgpt_layernorm
+        self.prog.add(fn, self.p(x), ldx or Cc, rows, Cc, self.p(gamma), self.p(beta), 1e-5, self.p(out16), 0)
 
     def e_attention(self, **kw):
         if self._sizing:
@@ -220,11 +237,13 @@ class EngineBase:
 
 
 class UNetEngine(EngineBase):
-    def __init__(self, unet, B, H, W, ctx_len, precision=None):
+    def __init__(self, unet, B, H, W, ctx_len, precision=None, dry=False):
+        """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run."""
         dev = next(unet.parameters()).device
-        if dev.type != "cuda":
+        if dev.type != "cuda" and not dry:
             raise _C.UpgptError("UNetEngine needs the module on a CUDA device (no CPU fallback)")
         super().__init__(dev, precision or default_precision())
+        self.dry = dry
         self.B, self.H, self.W, self.ctx_len = B, H, W, ctx_len
         self.mc = unet.model_channels
         self.in_ch, self.out_ch = unet.in_channels, unet.out_channels
@@ -235,6 +254,10 @@ class UNetEngine(EngineBase):
         self.weights_version = -1
         self.graph = None
         self._ctx_key = None
+        arch = (unet.model_channels, tuple(unet.channel_mult), unet.num_res_blocks, tuple(unet.attention_resolutions))
+        self.mixed_hw = MIXED_PROFILES.get(arch) if self.precision == "mixed" else None
+        self.mixed = self.mixed_hw is not None
+        self.layer_hw = self._layer_resolutions(unet)
         self.pack_weights(unet)
         # two passes over the same emitter: sizing, then recording
         self._emit(unet)
@@ -242,14 +265,47 @@ class UNetEngine(EngineBase):
         self._emit(unet)
         self._emit_context(unet)
 
-    # ------------------------------------------------------------------------------------------------ weights
-    def _w16(self, w):
-        """fp32 weight [..., K] -> fp16 operand; in fp16x3 mode the K axis carries the planes [Wh | Wl]."""
-        return split3_w(w) if self.split3 else w.half()
+    # ------------------------------------------------------------------------------------------------ precision plan
+    def _layer_resolutions(self, unet):
+        """module path -> tokens per image (H*W) the layer's GEMMs produce (Downsample / Upsample: their output size)."""
+        hw, res = self.H * self.W, {}
 
-    def _conv_w(self, w):
-        """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x2 planes in fp16x3 mode)."""
-        return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]))
+        def walk(prefix, layers, hw):
+            for j, mod in enumerate(layers):
+                if isinstance(mod, om.Downsample):
+                    hw //= 4
+                elif isinstance(mod, om.Upsample):
+                    hw *= 4
+                res[f"{prefix}.{j}"] = hw
+            return hw
+        for i in range(1, len(unet.input_blocks)):
+            hw = walk(f"input_blocks.{i}", unet.input_blocks[i], hw)
+        hw = walk("middle_block", unet.middle_block, hw)
+        for i, blk in enumerate(unet.output_blocks):
+            hw = walk(f"output_blocks.{i}", blk, hw)
+        return res
+
+    def use_x3(self, kind, hw):
+        """Operand format of one GEMM: True = error-compensated [hi | lo] planes (fp16x3), False = single fp16 plane.
+        kind: "conv" (3x3), "conv_skipshared" (3x3 whose operand planes also feed a skip_connection GEMM), "resid1x1" (skip_connection,
+        proj_in, proj_out: they write the residual stream directly), "tf" (attention projections and the feed-forward)."""
+        if not self.mixed:
+            return self.split3
+        deep_hw, full_hw = self.mixed_hw
+        if hw <= full_hw:
+            return False
+        if hw <= deep_hw:
+            return kind in ("resid1x1", "conv_skipshared")
+        return True
+
+    # ------------------------------------------------------------------------------------------------ weights
+    def _w16(self, w, x3=None):
+        """fp32 weight [..., K] -> fp16 operand; as an fp16x3 operand the K axis carries the planes [Wh | Wl]."""
+        return split3_w(w) if (self.split3 if x3 is None else x3) else w.half()
+
+    def _conv_w(self, w, x3=None):
+        """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x2 planes as an fp16x3 operand)."""
+        return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]), x3)
 
     def pack_weights(self, unet):
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in unet.state_dict().items()}
@@ -264,31 +320,36 @@ class UNetEngine(EngineBase):
         for name, mod in unet.named_modules():
             if isinstance(mod, om.ResBlock):
                 p = name
+                hw = self.layer_hw[p]
+                has_skip = (p + ".skip_connection.weight") in sd
+                x3a = self.use_x3("conv_skipshared" if has_skip else "conv", hw)     # conv1 and the skip GEMM read the same operand planes
                 for g in (".in_layers.0", ".out_layers.0"):
                     put(p + g + ".weight", sd[p + g + ".weight"]); put(p + g + ".bias", sd[p + g + ".bias"])
-                put(p + ".conv1.weight", self._conv_w(sd[p + ".in_layers.2.weight"])); put(p + ".conv1.bias", sd[p + ".in_layers.2.bias"])
-                put(p + ".conv2.weight", self._conv_w(sd[p + ".out_layers.3.weight"])); put(p + ".conv2.bias", sd[p + ".out_layers.3.bias"])
-                if (p + ".skip_connection.weight") in sd:
+                put(p + ".conv1.weight", self._conv_w(sd[p + ".in_layers.2.weight"], x3a)); put(p + ".conv1.bias", sd[p + ".in_layers.2.bias"])
+                put(p + ".conv2.weight", self._conv_w(sd[p + ".out_layers.3.weight"], self.use_x3("conv", hw)))
+                put(p + ".conv2.bias", sd[p + ".out_layers.3.bias"])
+                if has_skip:
                     ws = sd[p + ".skip_connection.weight"]
-                    put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]))); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
+                    put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]), x3a)); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
                 emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
                 self.emb_off[p] = off
                 off += mod.out_channels
             elif isinstance(mod, (om.Downsample, om.Upsample)):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
                 w = sd[name + sub + ".weight"]
-                put(name + ".weight", self._conv_w(w))
+                put(name + ".weight", self._conv_w(w, self.use_x3("conv", self.layer_hw[name])))
                 put(name + ".bias", sd[name + sub + ".bias"])
             elif isinstance(mod, SpatialTransformer):
                 p = name
                 Cc, Hh, d = mod.in_channels, mod.n_heads, mod.d_head
                 dpad = 64 if d <= 64 else 128
                 assert d <= 128, "head dim > 128 not supported by the attention kernel"
+                x3p, x3t = self.use_x3("resid1x1", self.layer_hw[p]), self.use_x3("tf", self.layer_hw[p])
                 put(p + ".norm.weight", sd[p + ".norm.weight"]); put(p + ".norm.bias", sd[p + ".norm.bias"])
                 wpi = sd[p + ".proj_in.weight"]
-                put(p + ".proj_in.weight", self._w16(wpi.reshape(wpi.shape[0], wpi.shape[1]))); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
+                put(p + ".proj_in.weight", self._w16(wpi.reshape(wpi.shape[0], wpi.shape[1]), x3p)); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
                 wpo = sd[p + ".proj_out.weight"]
-                put(p + ".proj_out.weight", self._w16(wpo.reshape(wpo.shape[0], wpo.shape[1]))); put(p + ".proj_out.bias", sd[p + ".proj_out.bias"])
+                put(p + ".proj_out.weight", self._w16(wpo.reshape(wpo.shape[0], wpo.shape[1]), x3p)); put(p + ".proj_out.bias", sd[p + ".proj_out.bias"])
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{p}.transformer_blocks.{bi}"
                     for n in ("norm1", "norm2", "norm3"):
@@ -296,19 +357,19 @@ class UNetEngine(EngineBase):
                     wq = pad_heads_rows(sd[q + ".attn1.to_q.weight"], Hh, d, dpad)
                     wk = pad_heads_rows(sd[q + ".attn1.to_k.weight"], Hh, d, dpad)
                     wv = pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad)
-                    put(q + ".attn1.qkv.weight", self._w16(torch.cat([wq, wk, wv], 0)))    # one fused q | k | v projection
-                    put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad)))
+                    put(q + ".attn1.qkv.weight", self._w16(torch.cat([wq, wk, wv], 0), x3t))    # one fused q | k | v projection
+                    put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad), x3t))
                     put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
-                    put(q + ".attn2.q.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.q.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad), x3t))
                     put(q + ".attn2.kv.weight", self._w16(torch.cat([pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad),
                                                                      pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)], 0)))
-                    put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad)))
+                    put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad), x3t))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
-                    half = geglu_half(inner, self.split3)
+                    half = geglu_half(inner, x3t)
                     w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
-                    put(q + ".ff1.weight", self._w16(w1)); put(q + ".ff1.bias", b1)
-                    put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"])); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
+                    put(q + ".ff1.weight", self._w16(w1, x3t)); put(q + ".ff1.bias", b1)
+                    put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"], x3t)); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
         from .ops import timestep_freqs
         put("temb.freqs", timestep_freqs(self.mc))
         put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
@@ -323,22 +384,25 @@ class UNetEngine(EngineBase):
         Cin, Cout = C1 + C2, mod.out_channels
         HW = H * W
         has_skip = (p + ".skip.weight") in self.w
-        op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=self.split3)
+        x3a = self.use_x3("conv_skipshared" if has_skip else "conv", HW)     # conv1 (+ the skip GEMM on the same operand planes)
+        x3b = self.use_x3("conv", HW)                                        # conv2
+        fa, fb = (_C.GEMM_F_X3 if x3a else 0), (_C.GEMM_F_X3 if x3b else 0)
+        op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=x3a)
         h32 = self.scratch("res_h", B * HW * Cout, torch.float32)
         emb = None if self._sizing else self.bufs["emb_all"][:, self.emb_off[p]:]
         self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W,
-                    out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=self.x3)
-        op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=self.split3)
+                    out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=fa)
+        op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=x3b)
         if has_skip:
             skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
-                        bias=self.w.get(p + ".skip.bias"), flags=self.x3)
+                        bias=self.w.get(p + ".skip.bias"), flags=fa)
             res = skip32
         else:
             assert x2 is None or self._sizing or C2 == 0
             res = x1
         self.e_gemm(a=op2, w=self.w.get(p + ".conv2.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cout, n_imgs=B, H=H, W=W,
-                    out32=out, bias=self.w.get(p + ".conv2.bias"), res32=res, flags=self.x3)
+                    out32=out, bias=self.w.get(p + ".conv2.bias"), res32=res, flags=fb)
 
     def _transformer(self, p, mod, x, Cc, B, H, W, out):
         HW, M = H * W, B * H * W
@@ -346,56 +410,60 @@ class UNetEngine(EngineBase):
         dpad = 64 if d <= 64 else 128
         HD = Hh * dpad
         L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
-        kx = self.kx                           # operand planes [hi | lo] in the error-compensated mode
-        x3 = self.x3
-        s3 = _C.GEMM_F_SPLIT3OUT if self.split3 else 0
-        op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False, split3=self.split3)
+        x3p, x3t = self.use_x3("resid1x1", HW), self.use_x3("tf", HW)    # proj_in / proj_out ; attention projections + feed-forward
+        kx = 2 if (x3p or x3t) else 1          # operand planes [hi | lo] of an error-compensated operand (scratch sizing)
+        kxt = 2 if x3t else 1
+        x3 = _C.GEMM_F_X3 if x3t else 0
+        fp = _C.GEMM_F_X3 if x3p else 0
+        s3 = _C.GEMM_F_SPLIT3OUT if x3t else 0
+        op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False, split3=x3p)
         tokA = self.scratch("tokA", M * Cc, torch.float32)
         tokB = self.scratch("tokB", M * Cc, torch.float32)
         tok16 = self.scratch("tok16", M * Cc * kx, torch.float16)
         qkv16 = self.scratch("qkv16", M * 3 * HD, torch.float16)
         att16 = self.scratch("att16", M * HD * kx, torch.float16)
         self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
-                    bias=self.w.get(p + ".proj_in.bias"), flags=x3)
+                    bias=self.w.get(p + ".proj_in.bias"), flags=fp)
         cur, nxt = tokA, tokB
         for bi in range(len(mod.transformer_blocks)):
             q = f"{p}.transformer_blocks.{bi}"
             g = lambda n: self.w.get(q + n)
             inner = mod.transformer_blocks[bi].ff.net[2].in_features
-            ff16 = self.scratch("ff16", M * inner * kx, torch.float16)
+            ff16 = self.scratch("ff16", M * inner * kxt, torch.float16)
             # --- self attention ---
-            self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16)
+            self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16, x3t)
             # one q | k | v projection (row-major fp16); the attention kernel reads V row-major as an MN-major operand (no V^T)
             self.e_gemm(a=tok16, w=g(".attn1.qkv.weight"), mode=_C.GEMM_PLAIN, M=M, N=3 * HD, K=Cc, out16=qkv16, flags=x3)
             kptr = None if self._sizing else qkv16[HD:]
             vptr = None if self._sizing else qkv16[2 * HD:]
             self.e_attention(q=qkv16, ldq=3 * HD, k=kptr, ldk=3 * HD, k_batch_stride=HW * 3 * HD, vt=vptr, ldvt=3 * HD, v_rowmajor=1,
-                             v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
-                             scale=float(d) ** -0.5, split3_out=int(self.split3))
+                             v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(x3t))
             self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
                         bias=g(".attn1.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
-            self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16)
+            self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16, x3t)
             self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qkv16, flags=x3)
             kvc = self.buf(q + ".ctx_kv", (B * L, 2 * HD), torch.float16)       # cond-cache: K | V of the context, row-major
             vcp = None if self._sizing else kvc.reshape(-1)[HD:]
             self.e_attention(q=qkv16, ldq=HD, k=kvc, ldk=2 * HD, k_batch_stride=L * 2 * HD, vt=vcp, ldvt=2 * HD, v_rowmajor=1,
-                             v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kx, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
-                             scale=float(d) ** -0.5, split3_out=int(self.split3))
+                             v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(x3t))
             self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
                         bias=g(".attn2.out.bias"), res32=cur, flags=x3)
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
-            self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16)
-            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner, self.split3),
+            self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16, x3t)
+            self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner, x3t),
                         out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3 | x3)
             last = bi == len(mod.transformer_blocks) - 1
+            # the last block's feed-forward also emits the fp16 operand of proj_out, in proj_out's operand format
             self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
-                        res32=cur, out16=tok16 if last else None, flags=(s3 if last else 0) | x3)
+                        res32=cur, out16=tok16 if last else None, flags=(_C.GEMM_F_SPLIT3OUT if (last and x3p) else 0) | x3)
             cur, nxt = nxt, cur
         self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
-                    bias=self.w.get(p + ".proj_out.bias"), res32=x, flags=x3)
+                    bias=self.w.get(p + ".proj_out.bias"), res32=x, flags=fp)
 
     def _emit(self, unet):
         B, H, W = self.B, self.H, self.W
@@ -453,18 +521,20 @@ class UNetEngine(EngineBase):
                     self._transformer(p, mod, h, ch, B, hh, ww, out)
                     h = out
                 elif isinstance(mod, om.Downsample):
-                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2, split3=self.split3)
+                    x3c = self.use_x3("conv", (hh // 2) * (ww // 2))
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2, split3=x3c)
                     hh, ww = hh // 2, ww // 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
                     self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_S2PHASE, N=mod.out_channels, K=ch, n_imgs=B,
-                                H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=self.x3)
+                                H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
                     h, ch = out, mod.out_channels
                 elif isinstance(mod, om.Upsample):
-                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=self.split3)
+                    x3c = self.use_x3("conv", hh * ww * 4)
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=x3c)
                     hh, ww = hh * 2, ww * 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
                     self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
-                                W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=self.x3)
+                                W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
                     h, ch = out, mod.out_channels
                 else:
                     raise NotImplementedError(type(mod))
@@ -505,6 +575,8 @@ class UNetEngine(EngineBase):
 
     # ------------------------------------------------------------------------------------------------ execution
     def _stream(self):
+        if self.dry or self.dev.type != "cuda":
+            raise _C.UpgptError("UNetEngine recorded without a CUDA device: nothing to run (no CPU fallback)")
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def set_context(self, context, force=False):
