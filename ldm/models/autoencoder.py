@@ -38,9 +38,13 @@ class AutoencoderKL(nn.Module):
         self.load_state_dict(sd, strict=False)
         print(f"Restored from {path}")
 
+    def mark_weights_changed(self):
+        """The engines keep packed fp16 copies of the weights; they re-pack when this version moves."""
+        self._weights_version += 1
+
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
-        self._weights_version += 1
+        self.mark_weights_changed()
         return out
 
     def _apply(self, fn, *args, **kwargs):

@@ -179,9 +179,10 @@ class DDPM(nn.Module):
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
-        dm = getattr(self.model, "diffusion_model", None)
-        if dm is not None and hasattr(dm, "mark_weights_changed"):
-            dm.mark_weights_changed()
+        # every sub-module that keeps a packed shadow copy of its weights in an engine (U-Net, VAE, CLIP towers) re-packs on next use
+        for m in self.modules():
+            if m is not self and hasattr(m, "mark_weights_changed"):
+                m.mark_weights_changed()
         return out
 
     # ---- closed-form pieces (ddpm.py:212-284) ----

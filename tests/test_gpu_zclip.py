@@ -148,3 +148,41 @@ def test_clip_vit_l14_full_size_vs_oracle(dev):
         ref = CO.style_embed(sd, 16, crops)
     y = v.to(dev).encode(crops.to(dev))
     assert tuple(y.shape) == (2, 3, 768) and relerr(y, ref) < 1e-3
+
+
+def test_request_conditioning_through_latent_diffusion(dev):
+    """The whole per-request conditioning step of the reference on the device (ddpm.py:553-565 get_learned_conditioning,
+    ddpm.py:733-739 extra-cond loop): token ids -> text tower, style crops -> image tower, SMPL vector -> LinearProject,
+    concatenated to the (B, 77 + 3 + 1, C) context the U-Net's cond-cache is built from; then one eps through that context."""
+    import copy
+    from conftest import tiny_ldm_config
+    from ldm.util import instantiate_from_config
+    cfg = copy.deepcopy(tiny_ldm_config())
+    vis = dict(TINY_VIS, output_dim=128)
+    cfg["params"]["cond_stage_config"]["params"] = {"arch": dict(TINY_TEXT)}
+    cfg["params"]["extra_cond_stages"]["style_cond"] = {"target": "ldm.modules.encoders.modules.FrozenClipImageEmbedder2",
+                                                        "cond_stage_key": "styles", "params": {"arch": vis}}
+    model = instantiate_from_config(cfg)
+    model.cond_stage_model.materialize(); model.extra_cond_models[0].materialize()
+    sd = synth.synth_state_dict({k: v for k, v in model.state_dict().items()
+                                 if k.startswith(("model.", "cond_stage_model.", "extra_cond_models."))}, 4)
+    model.load_state_dict(sd, strict=False)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4)
+    B = 2
+    ids = torch.randint(0, TINY_TEXT["vocab"], (B, 77), generator=g)
+    crops = torch.randn(B, 3, 3, 56, 56, generator=g)
+    smpl = torch.randn(B, 1, 85, generator=g) * 0.5
+    batch = {"txt": ids.to(dev), "styles": crops.to(dev), "smpl": smpl.to(dev)}
+    c = model.get_learned_conditioning(batch["txt"])
+    ctx = model.assemble_context(batch, c)
+    assert tuple(ctx.shape) == (B, 77 + 3 + 1, 128)
+    pre = lambda p: {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    with torch.no_grad():
+        ref = torch.cat([CO.clip_text_forward(pre("cond_stage_model.transformer."), TINY_TEXT["heads"], ids),
+                         CO.style_embed(pre("extra_cond_models.0.model."), vis["heads"], crops),
+                         F.linear(smpl, sd["extra_cond_models.1.model.weight"], sd["extra_cond_models.1.model.bias"])], 1)
+    assert relerr(ctx, ref) < 1e-3
+    x, mask, _ = synth.synth_inputs(B, 16, 16, 81, 128, 4)
+    eps = model.apply_model(x.to(dev), torch.full((B,), 500, dtype=torch.long, device=dev), {"c_crossattn": ctx, "c_concat": [mask.to(dev)]})
+    assert tuple(eps.shape) == (B, 4, 16, 16) and torch.isfinite(eps).all()

@@ -26,7 +26,8 @@ def main():
     import bench
     from upgpt_b200 import synth
     dev = torch.device("cuda:0")
-    model = bench.build_model(dev, os.environ.get("UPGPT_PRECISION", "fp16x3"))
+    from upgpt_b200.unet_engine import default_precision
+    model = bench.build_model(dev, default_precision())
     eng = model.model.diffusion_model.engine(8, 32, 32, 87)
     rows = [describe(fn, args) for fn, args in eng.prog.calls]
     durs = None

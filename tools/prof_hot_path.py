@@ -9,7 +9,8 @@ from upgpt_b200 import synth, _C
 
 dev = torch.device("cuda:0")
 B, HW, steps = int(os.environ.get("B", 8)), int(os.environ.get("HW", 32)), int(os.environ.get("STEPS", 2))
-prec = os.environ.get("UPGPT_PRECISION", "fp16x3")
+from upgpt_b200.unet_engine import default_precision
+prec = default_precision()
 model = bench.build_model(dev, prec)
 unet = model.model.diffusion_model
 x, mask, ctx = synth.synth_inputs(B, HW, HW, 87, 768, 3)
