@@ -284,6 +284,29 @@ def test_flash_attention(dev, B, Hh, Nq, Nk, d):
         assert torch.equal(out2, out), "same arithmetic whichever way V is laid out"
 
 
+@pytest.mark.parametrize("Nk,ramp", [(1024, 12.0), (1024, 1.0), (300, 30.0)])
+def test_flash_attention_growing_row_max(dev, Nk, ramp):
+    """The online softmax keeps its reference max until a row's max has grown by more than 2^8 and only then rescales O in TMEM:
+    keys whose magnitude ramps up along the sequence push every row through several such rescales (ramp = 1: through none after the
+    first tile); both must agree with the fp32 softmax."""
+    from upgpt_b200 import ops
+    B, Hh, Nq, d, dpad = 1, 2, 256, 28, 64
+    g = torch.Generator().manual_seed(int(Nk + ramp))
+    q = torch.randn(B, Hh, Nq, d, generator=g).half()
+    k = (torch.randn(B, Hh, Nk, d, generator=g) * torch.linspace(1.0, ramp, Nk)[None, None, :, None]).half()
+    v = torch.randn(B, Hh, Nk, d, generator=g).half()
+    ref = torch.softmax(torch.einsum("bhid,bhjd->bhij", q.float(), k.float()) * d ** -0.5, -1) @ v.float()
+    HD = Hh * dpad
+    Q = torch.zeros(B, Nq, Hh, dpad, dtype=torch.half); Q[..., :d] = q.permute(0, 2, 1, 3)
+    KV = torch.zeros(B, Nk, 2, Hh, dpad, dtype=torch.half); KV[:, :, 0, :, :d] = k.permute(0, 2, 1, 3); KV[:, :, 1, :, :d] = v.permute(0, 2, 1, 3)
+    Qd, KVd = Q.to(dev), KV.to(dev)
+    out = torch.full((B, Nq, Hh, dpad), float("nan"), device=dev, dtype=torch.half)
+    ops.attention(q=Qd, ldq=HD, k=KVd, ldk=2 * HD, k_batch_stride=Nk * 2 * HD, vt=KVd.reshape(-1)[HD:], ldvt=2 * HD, v_rowmajor=1,
+                  v_batch_stride=Nk * 2 * HD, out=out, ldo=HD, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=dpad, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    assert relerr(out[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
+
+
 def test_small_kernels(dev):
     from upgpt_b200 import ops
     from oracle import ldm_oracle as O

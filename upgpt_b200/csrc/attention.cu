@@ -28,6 +28,9 @@ struct AttnParams {
   int ldo;
   int plane;           // > 0: also write the lo plane at column offset plane (fp16x3 operand layout [hi | lo])
   int v_mn;            // V is row-major [Nk][d] (same layout as K): the P V MMA reads it as an MN-major B operand
+  int kv_stages;       // K / V ring depth: 2, or 1 when all keys fit one tile (cross-attention over the 87-token context, 8x8 / 4x4 self)
+  uint32_t tmem_cols;  // TMEM columns to allocate: 512 (two S buffers + O), or 256 for the single-tile form (S + O) so that two CTAs
+  uint32_t o_col;      // share an SM; first column of the O accumulator
 };
 
 static constexpr int kAttnThreads = 320;     // warp0 TMA, warp1 MMA, warps2-9 softmax (two threads per query row)
@@ -39,7 +42,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+// MINB = 2: the single-key-tile form (80 KB of shared memory, 256 TMEM columns, <= 96 registers): two CTAs per SM overlap each other's
+// load -> S -> softmax -> PV -> store latency chain, which is all such a CTA consists of.
+template <int MINB>
+__global__ void __launch_bounds__(kAttnThreads, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -49,11 +55,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t qk_bytes = (uint32_t)dch * kTileBytes;      // Q tile or K tile
   const uint32_t vt_chunk = (uint32_t)p.dpad * 128u;          // V^T chunk: [dpad rows][64 keys]
   const uint32_t vt_bytes = 2u * vt_chunk;
+  const uint32_t nst = (uint32_t)p.kv_stages;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + qk_bytes;                        // 2 stages
-  uint8_t* sV = sK + 2 * qk_bytes;                    // 2 stages
-  uint8_t* sP = sV + 2 * vt_bytes;                    // [2 key chunks][128][64] fp16
-  const uint32_t off_bar = 3 * qk_bytes + 2 * vt_bytes + 2 * kTileBytes;
+  uint8_t* sK = sQ + qk_bytes;                        // nst stages
+  uint8_t* sV = sK + nst * qk_bytes;                  // nst stages
+  uint8_t* sP = sV + nst * vt_bytes;                  // [2 key chunks][128][64] fp16
+  const uint32_t off_bar = (1 + nst) * qk_bytes + nst * vt_bytes + 2 * kTileBytes;
   uint64_t* bars = (uint64_t*)(smem + off_bar);
   uint64_t* bar_q = bars;
   uint64_t* bar_kv_full = bars + 1;    // [2]
@@ -84,13 +91,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_smem, 512);
+  if (warp == 1) tmem_alloc(tmem_base_smem, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   pdl_wait();
-  const uint32_t tO = tmem_base + 256;    // dpad columns; S buffers at columns [0,128) and [128,256)
+  const uint32_t tO = tmem_base + p.o_col;    // dpad columns; S buffers at columns [0,128) and (two-stage form) [128,256)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -201,7 +208,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float* mx = xch + (j & 1) * 256;
       mx[hf * 128 + r] = m_loc;
       named_bar_sync(2, 256);
-      const float m_new = fmaxf(m_run, fmaxf(mx[r], mx[128 + r]));
+      // The running reference max only moves when the row max grew by more than 2^8: until then P <= 256 (well inside fp16, same
+      // relative precision) and l / O keep their scale, so the TMEM round trip that rescales O is skipped for most tiles.
+      const float m_cand = fmaxf(m_run, fmaxf(mx[r], mx[128 + r]));
+      const float m_new = ((m_cand - m_run) * c2 > 8.f) ? m_cand : m_run;
       const float alpha = ex2_approx((m_run - m_new) * c2);
       const float mc = m_new * c2;
       float l_tile = 0.f;
@@ -286,7 +296,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -303,7 +313,8 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   UPGPT_REQUIRE(a->Nq > 0 && a->Nk > 0 && a->H > 0 && a->B > 0, "attention: bad sizes");
   UPGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0, "attention: ld must be multiples of 8");
   if (!g_attn_attr) {
-    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
+    UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     g_attn_attr = true;
   }
   CUtensorMap tmQ, tmK, tmVt;
@@ -343,9 +354,15 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   p.v_mn = a->v_rowmajor ? 1 : 0;
   UPGPT_REQUIRE(!a->split3_out || a->ldo >= 2 * a->H * a->dpad, "attention: split3_out needs ldo >= 2*H*dpad");
   const int dch = a->dpad / 64;
-  const size_t smem = 1024 + (size_t)dch * kTileBytes * 3 + 2 * 2 * (size_t)a->dpad * 128 + 2 * kTileBytes + 128 + 2 * 256 * 4 + 64;
+  const bool one_tile = a->Nk <= 128;      // all keys in one tile: no K/V ring, one S buffer
+  p.kv_stages = one_tile ? 1 : 2;
+  p.tmem_cols = one_tile ? 256u : 512u;
+  p.o_col = one_tile ? 128u : 256u;
+  const size_t smem = 1024 + (size_t)dch * kTileBytes * (1 + p.kv_stages) + (size_t)p.kv_stages * 2 * a->dpad * 128 + 2 * kTileBytes + 128 +
+                      2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);
-  UPGPT_CHECK_CUDA(launch_k(attention_kernel, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
+  if (one_tile) UPGPT_CHECK_CUDA(launch_k(attention_kernel<2>, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
+  else UPGPT_CHECK_CUDA(launch_k(attention_kernel<1>, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
