@@ -78,10 +78,21 @@ class _EngineHost(nn.Module):
         self.mark_weights_changed()
         return out
 
+    _PARAM_ROOT = None   # name of the lazily created parameter tree ("transformer" / "model")
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """A checkpoint that carries the tower's weights materialises the parameter tree before the keys are matched, so
+        `LatentDiffusion.load_state_dict(ckpt, strict=False)` works as in the reference (generate_utils.py:33-48)."""
+        root = prefix + self._PARAM_ROOT + "."
+        if getattr(self, self._PARAM_ROOT) is None and any(k.startswith(root) for k in state_dict):
+            self.materialize()
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
 
 class FrozenCLIPEmbedder(AbstractEncoder, _EngineHost):
     """CLIP text tower -> (B, 77, 768) last hidden state (modules.py:137-162)."""
     ARCH = dict(vocab=49408, width=768, layers=12, heads=12, mlp=3072, positions=77)
+    _PARAM_ROOT = "transformer"
 
     def __init__(self, version="openai/clip-vit-large-patch14", device="cuda", max_length=77, arch=None):
         _EngineHost.__init__(self)
@@ -144,6 +155,7 @@ class FrozenCLIPEmbedder(AbstractEncoder, _EngineHost):
 class FrozenClipImageEmbedder2(_EngineHost):
     """CLIP image tower over the style crops: (B, n, 3, 224, 224) -> (B, n, 768) (modules.py:234-256)."""
     ARCH = dict(width=1024, layers=24, heads=16, patch=14, resolution=224, output_dim=768)
+    _PARAM_ROOT = "model"
 
     def __init__(self, model="ViT-L/14", jit=False, device="cuda", antialias=False, arch=None):
         super().__init__()

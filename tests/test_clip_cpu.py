@@ -111,3 +111,27 @@ def test_engine_programs_record_without_a_device():
     assert float(ev.w["patch.weight"][:, 588:592].abs().max()) == 0.0
     with pytest.raises(_C.UpgptError):
         ClipVisionEngine(v, 3)        # not on a CUDA device and not a dry recording
+
+
+def test_checkpoint_with_tower_weights_materialises_the_parameter_trees():
+    """load_state_dict of a parent module whose checkpoint carries `cond_stage_model.transformer...` / `...model.visual...` keys
+    creates the lazily built trees first (the reference builds them in __init__ from the network); without such keys nothing is built."""
+    class Parent(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.cond_stage_model = FrozenCLIPEmbedder(arch=TINY_TEXT)
+            self.style = FrozenClipImageEmbedder2(arch=TINY_VIS)
+    sd_t = synth.synth_state_dict(FrozenCLIPEmbedder(arch=TINY_TEXT).materialize().state_dict(), 7)
+    sd_v = synth.synth_state_dict(FrozenClipImageEmbedder2(arch=TINY_VIS).materialize().state_dict(), 8)
+    full = {**{"cond_stage_model." + k: v for k, v in sd_t.items()}, **{"style." + k: v for k, v in sd_v.items()}}
+    p = Parent()
+    assert len(p.state_dict()) == 0
+    v0 = p.cond_stage_model._weights_version
+    res = p.load_state_dict(full, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    got = p.state_dict()
+    assert set(got) == set(full) and all(torch.equal(got[k], full[k]) for k in full)
+    assert p.cond_stage_model._weights_version > v0
+    q = Parent()
+    q.load_state_dict({}, strict=False)
+    assert q.cond_stage_model.transformer is None and q.style.model is None
