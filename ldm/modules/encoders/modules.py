@@ -125,11 +125,12 @@ class FrozenCLIPEmbedder(AbstractEncoder, _EngineHost):
                              return_overflowing_tokens=False, padding="max_length", return_tensors="pt")
         return enc["input_ids"]
 
-    def engine(self, B, L):
-        from upgpt_b200.clip_engine import ClipTextEngine
-        eng = self._engines.get((B, L))
+    def engine(self, B, L, precision=None):
+        from upgpt_b200.clip_engine import ClipTextEngine, clip_precision
+        precision = precision or clip_precision()
+        eng = self._engines.get((B, L, precision))
         if eng is None:
-            eng = self._engines[(B, L)] = ClipTextEngine(self, B, L)
+            eng = self._engines[(B, L, precision)] = ClipTextEngine(self, B, L, precision=precision)
         if eng.weights_version != self._weights_version:
             eng.pack_weights(self)
         return eng
@@ -173,11 +174,12 @@ class FrozenClipImageEmbedder2(_EngineHost):
             self.mark_weights_changed()
         return self
 
-    def engine(self, n):
-        from upgpt_b200.clip_engine import ClipVisionEngine
-        eng = self._engines.get(n)
+    def engine(self, n, precision=None):
+        from upgpt_b200.clip_engine import ClipVisionEngine, clip_precision
+        precision = precision or clip_precision()
+        eng = self._engines.get((n, precision))
         if eng is None:
-            eng = self._engines[n] = ClipVisionEngine(self, n)
+            eng = self._engines[(n, precision)] = ClipVisionEngine(self, n, precision=precision)
         if eng.weights_version != self._weights_version:
             eng.pack_weights(self)
         return eng

@@ -111,6 +111,14 @@ def test_engine_programs_record_without_a_device():
     assert float(ev.w["patch.weight"][:, 588:592].abs().max()) == 0.0
     with pytest.raises(_C.UpgptError):
         ClipVisionEngine(v, 3)        # not on a CUDA device and not a dry recording
+    # single-plane fp16 mode (the reference's own arithmetic class for the image tower): same program, K-wide operands
+    e16, ev16 = ClipTextEngine(t, 2, 77, dry=True, precision="fp16"), ClipVisionEngine(v, 3, dry=True, precision="fp16")
+    assert e16.launches == e.launches and ev16.launches == ev.launches
+    assert tuple(ev16.w["patch.weight"].shape) == (128, 592) and tuple(e16.w["l0.qkv.weight"].shape) == (3 * 128, 128)
+    L = _C.lib()
+    for eng, x3 in ((e, True), (ev, True), (e16, False), (ev16, False)):
+        gemms = [a[0]._obj for f, a in eng.prog.calls if f is L.upgpt_gemm]
+        assert gemms and all(bool(g.flags & _C.GEMM_F_X3) == x3 for g in gemms)
 
 
 def test_checkpoint_with_tower_weights_materialises_the_parameter_trees():

@@ -124,6 +124,10 @@ def test_clip_image_tower_tiny_vs_transformers_golden(dev):
     y = host.encode(img[None].to(dev))                      # (b=1, n=3, c, h, w) like the style crops
     assert tuple(y.shape) == (1, 3, 96)
     assert relerr(y[0], torch.from_numpy(GOLD["vis_tiny_out"])) < 1e-3
+    # opt-in single-plane fp16 operands (UPGPT_CLIP_PRECISION=fp16): the reference's own arithmetic class for this tower
+    y16 = host.engine(3, precision="fp16").forward(img.to(dev))
+    e16 = relerr(y16, torch.from_numpy(GOLD["vis_tiny_out"]))
+    assert relerr(y[0], torch.from_numpy(GOLD["vis_tiny_out"])) < e16 < 5e-3
 
 
 def test_clip_vit_l14_full_size_vs_oracle(dev):
@@ -146,8 +150,11 @@ def test_clip_vit_l14_full_size_vs_oracle(dev):
     crops = torch.randn(2, 3, 3, 224, 224, generator=torch.Generator().manual_seed(3))
     with torch.no_grad():
         ref = CO.style_embed(sd, 16, crops)
-    y = v.to(dev).encode(crops.to(dev))
+    v = v.to(dev)
+    y = v.encode(crops.to(dev))
     assert tuple(y.shape) == (2, 3, 768) and relerr(y, ref) < 1e-3
+    y16 = v.engine(6, precision="fp16").forward(crops.reshape(6, 3, 224, 224).to(dev)).reshape(2, 3, 768)
+    assert relerr(y16, ref) < 5e-3
 
 
 def test_request_conditioning_through_latent_diffusion(dev):

@@ -37,6 +37,10 @@ M, C, L, T = n * 257, 1024, 24, 257
 gf = (L * (2 * M * C * (3 * C + C + 8 * C) + 4 * n * T * T * C) + 2 * n * 256 * 588 * C + 2 * n * C * 768) / 1e9
 res["image_tower"] = {"shape": "72 crops (8 x 9) of 224x224 -> 257 tokens, 24 layers x 1024", "ms": ms, "launches": eng.launches,
                       "algorithmic_gflop": gf, "tflops": gf / ms}
+eng16 = v.engine(n, precision="fp16"); eng16.bufs["img"].copy_(eng.bufs["img"])
+ms16 = timed(lambda: eng16.run(True), 5)
+res["image_tower_fp16"] = {"shape": res["image_tower"]["shape"], "ms": ms16, "tflops": gf / ms16,
+                           "max_rel_vs_fp16x3": float((eng16.bufs["out"] - eng.bufs["out"]).abs().max() / eng.bufs["out"].abs().max())}
 print(json.dumps(res, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "clip_timing.json"), "w"), indent=1)

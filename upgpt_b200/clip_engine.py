@@ -17,6 +17,7 @@ Operands are error-compensated fp16x3 planes throughout (the towers run once per
 on CUDA via clip.load, the text tower fp32).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -24,18 +25,27 @@ from . import _C
 from .unet_engine import EngineBase, _Program, split3_w, _round_up
 
 
+def clip_precision():
+    """"fp16x3" (default: error-compensated operand planes, within 1e-3 of the fp32 oracle) or "fp16" (single operand plane = the
+    arithmetic class of the reference itself, whose clip.load model holds fp16 weights on CUDA; ~2.5x faster image tower)."""
+    return os.environ.get("UPGPT_CLIP_PRECISION", "fp16x3")
+
+
 class _ClipEngineBase(EngineBase):
-    def __init__(self, device, dry=False):
+    def __init__(self, device, dry=False, precision=None):
         """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run."""
         if device.type != "cuda" and not dry:
             raise _C.UpgptError("CLIP engines need the module on a CUDA device (no CPU fallback)")
-        super().__init__(device, "fp16x3")
+        precision = precision or clip_precision()
+        assert precision in ("fp16x3", "fp16"), precision
+        super().__init__(device, precision)
+        self.s3 = int(self.split3)             # producers emit [hi | lo] planes
         self.dry = dry
         self.weights_version = -1
         self.graph = None
 
     def _w16(self, w):
-        return split3_w(w)
+        return split3_w(w) if self.split3 else w.half()
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -63,15 +73,15 @@ class _ClipEngineBase(EngineBase):
         self.e_layernorm(cur, M, Cc, g(ln2 + ".weight"), g(ln2 + ".bias"), tok16)
         self.e_gemm(a=tok16, w=g(".fc1.weight"), mode=_C.GEMM_PLAIN, M=M, N=inner, K=Cc, out32=h32, bias=g(".fc1.bias"), flags=self.x3)
         if not self._sizing:
-            self.prog.add(self.L.upgpt_quick_gelu_cast, h32.data_ptr(), M, inner, 1, h16.data_ptr(), 2 * inner)
+            self.prog.add(self.L.upgpt_quick_gelu_cast, h32.data_ptr(), M, inner, self.s3, h16.data_ptr(), self.kx * inner)
         self.e_gemm(a=h16, w=g(".fc2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".fc2.bias"), res32=cur, flags=self.x3)
         return nxt, cur
 
 
 class ClipTextEngine(_ClipEngineBase):
-    def __init__(self, host, B, L, dry=False):
+    def __init__(self, host, B, L, dry=False, precision=None):
         tm = host.transformer.text_model
-        super().__init__(tm.final_layer_norm.weight.device, dry)
+        super().__init__(tm.final_layer_norm.weight.device, dry, precision)
         a = host.arch
         self.B, self.seq = B, L
         self.Cc, self.heads, self.inner, self.vocab = a["width"], a["heads"], a["mlp"], a["vocab"]
@@ -122,8 +132,8 @@ class ClipTextEngine(_ClipEngineBase):
             self.e_layernorm(cur, M, Cc, g(".layer_norm1.weight"), g(".layer_norm1.bias"), tok16)
             self.e_gemm(a=tok16, w=g(".qkv.weight"), mode=_C.GEMM_PLAIN, M=M, N=3 * Cc, K=Cc, out32=qkv32, bias=g(".qkv.bias"), flags=self.x3)
             if not self._sizing:   # causal mask: CLIPTextTransformer builds it for every input (attention_mask=None in the reference call)
-                self.prog.add(self.L.upgpt_attention_small, qkv32.data_ptr(), 3 * Cc, Cc, 2 * Cc, B, Hh, L, d, float(d) ** -0.5, 1, 1,
-                              att16.data_ptr(), 2 * Cc)
+                self.prog.add(self.L.upgpt_attention_small, qkv32.data_ptr(), 3 * Cc, Cc, 2 * Cc, B, Hh, L, d, float(d) ** -0.5, 1, self.s3,
+                              att16.data_ptr(), self.kx * Cc)
             self.e_gemm(a=att16, w=g(".out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=nxt, bias=g(".out.bias"), res32=cur, flags=self.x3)
             cur, nxt = nxt, cur
             cur, nxt = self._mlp(q, cur, nxt, M, Cc, inner, tok16, h32, h16, ".layer_norm2")
@@ -140,9 +150,9 @@ class ClipTextEngine(_ClipEngineBase):
 
 
 class ClipVisionEngine(_ClipEngineBase):
-    def __init__(self, host, n, dry=False):
+    def __init__(self, host, n, dry=False, precision=None):
         v = host.model.visual
-        super().__init__(v.proj.device, dry)
+        super().__init__(v.proj.device, dry, precision)
         a = host.arch
         self.n, self.Cc, self.heads, self.patch, self.S, self.odim = n, a["width"], a["heads"], a["patch"], a["resolution"], a["output_dim"]
         self.n_layers = len(v.transformer.resblocks)
@@ -183,7 +193,7 @@ class ClipVisionEngine(_ClipEngineBase):
             self.prog = _Program()
         img = self.buf("img", (n, 3, self.S, self.S))
         xa, xb = self.buf("xa", (M, Cc)), self.buf("xb", (M, Cc))
-        cls16 = self.buf("cls16", (n, 2 * Cc), torch.float16)
+        cls16 = self.buf("cls16", (n, self.kx * Cc), torch.float16)
         out = self.buf("out", (n, self.odim))
         pat16 = self.scratch("pat16", Mp * Kp * 2, torch.float16)
         pat32 = self.scratch("h32", max(Mp * Cc, M * inner), torch.float32)       # patch embeddings share the MLP's fp32 scratch
@@ -194,7 +204,7 @@ class ClipVisionEngine(_ClipEngineBase):
         h16 = self.scratch("h16", M * inner * 2, torch.float16)
         if not self._sizing:
             P = self.prog
-            P.add(self.L.upgpt_patchify, img.data_ptr(), n, 3, self.S, self.patch, Kp, 1, pat16.data_ptr(), 2 * Kp)
+            P.add(self.L.upgpt_patchify, img.data_ptr(), n, 3, self.S, self.patch, Kp, self.s3, pat16.data_ptr(), self.kx * Kp)
         self.e_gemm(a=pat16, w=self.w.get("patch.weight"), mode=_C.GEMM_PLAIN, M=Mp, N=Cc, K=Kp, out32=pat32, flags=self.x3)
         if not self._sizing:
             P.add(self.L.upgpt_vit_assemble, pat32.data_ptr(), self.w["cls"].data_ptr(), self.w["pos"].data_ptr(), n, T, Cc, xb.data_ptr())
@@ -210,7 +220,8 @@ class ClipVisionEngine(_ClipEngineBase):
             kptr = None if self._sizing else qkv16[HD:]
             vptr = None if self._sizing else qkv16[2 * HD:]
             self.e_attention(q=qkv16, ldq=3 * HD, k=kptr, ldk=3 * HD, k_batch_stride=T * 3 * HD, vt=vptr, ldvt=3 * HD, v_rowmajor=1,
-                             v_batch_stride=T * 3 * HD, out=att16, ldo=2 * HD, B=n, H=Hh, Nq=T, Nk=T, dpad=d, scale=float(d) ** -0.5, split3_out=1)
+                             v_batch_stride=T * 3 * HD, out=att16, ldo=self.kx * HD, B=n, H=Hh, Nq=T, Nk=T, dpad=d, scale=float(d) ** -0.5,
+                             split3_out=self.s3)
             self.e_gemm(a=att16, w=g(".out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt, bias=g(".out.bias"), res32=cur, flags=self.x3)
             cur, nxt = nxt, cur
             cur, nxt = self._mlp(q, cur, nxt, M, Cc, inner, tok16, h32, h16, ".ln_2")
