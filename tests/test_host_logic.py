@@ -209,3 +209,6 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     from oracle.make_golden import TINY_UNET_KW
     tiny = UNetEngine(UNetModel(**TINY_UNET_KW).eval(), 2, 16, 16, 87, precision="mixed", dry=True)
     assert not tiny.mixed and all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.calls if f is L.upgpt_gemm)
+    monkeypatch.setenv("UPGPT_MIXED_HW", "64,16")          # tuning override: thresholds for an architecture without a profile
+    tiny = UNetEngine(UNetModel(**TINY_UNET_KW).eval(), 2, 16, 16, 87, precision="mixed", dry=True)
+    assert tiny.mixed and not all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.calls if f is L.upgpt_gemm)

@@ -256,6 +256,9 @@ class UNetEngine(EngineBase):
         self._ctx_key = None
         arch = (unet.model_channels, tuple(unet.channel_mult), unet.num_res_blocks, tuple(unet.attention_resolutions))
         self.mixed_hw = MIXED_PROFILES.get(arch) if self.precision == "mixed" else None
+        if self.precision == "mixed" and os.environ.get("UPGPT_MIXED_HW"):    # tuning override "deep_hw,full_hw" for any architecture
+            self.mixed_hw = tuple(int(v) for v in os.environ["UPGPT_MIXED_HW"].split(","))
+            assert len(self.mixed_hw) == 2, "UPGPT_MIXED_HW=deep_hw,full_hw"
         self.mixed = self.mixed_hw is not None
         self.layer_hw = self._layer_resolutions(unet)
         self.pack_weights(unet)
