@@ -14,6 +14,7 @@ from . import _C, ops
 
 class FusedSampler:
     MAX_STEPS = 1024
+    MAX_GRAPHS = 32
 
     def __init__(self, ldm_model):
         self.model = ldm_model
@@ -140,6 +141,8 @@ class FusedSampler:
         self._coef_cols = ncols
         body()   # warm-up outside capture (also validates arguments)
         g = ops.Graph().capture(body)
+        if len(self._graphs) >= self.MAX_GRAPHS:      # a graph bakes the noise / table addresses: bound the cache for long-running callers
+            self._graphs.pop(next(iter(self._graphs)))
         self._graphs[key] = g
         return g
 
