@@ -183,12 +183,16 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
             if a.raw:
                 fmt[a.raw] = bool(a.split3)
         elif fn in (L.upgpt_layernorm, L.upgpt_layernorm_split3):
+            assert args[0] and args[4] and args[5] and args[7]
             fmt[args[7]] = fn is L.upgpt_layernorm_split3
         elif fn is L.upgpt_attention:
             a = args[0]._obj
+            assert a.q and a.k and a.vt and a.out
             fmt[a.out] = bool(a.split3_out)
         elif fn is L.upgpt_gemm:
             a = args[0]._obj
+            assert a.a and a.w and (a.out32 or a.out16), "every GEMM has its operands and an output"
+            assert a.bias or (a.out16 and not a.out32), "only the attention q / k / v projections (fp16-only outputs) have no bias"
             x3 = bool(a.flags & _C.GEMM_F_X3)
             n_x3 += x3; n_plain += not x3
             assert a.a in fmt, "GEMM operand without a recorded producer"
