@@ -22,34 +22,38 @@ SEEN = collections.OrderedDict()
 
 def group_of(kind, prefix, size):
     if kind == "conv":
-        name = "conv3x3" if prefix.endswith(("in_layers.2", "out_layers.3", ".op", ".conv", "out.2")) else ("skip1x1" if "skip" in prefix else ("st_proj" if "proj_" in prefix else "convother"))
+        name = ("conv3x3" if prefix.endswith(("in_layers.2", "out_layers.3", ".op", ".conv", "out.2")) else
+                ("skip1x1" if "skip" in prefix else ("proj_in/out" if "proj_" in prefix else "conv_in")))
     else:
         tail = prefix.split(".transformer_blocks.")[-1] if ".transformer_blocks." in prefix else prefix
         if "attn1.to_q" in tail or "attn1.to_k" in tail or "attn1.to_v" in tail: name = "attn1_qkv"
         elif "attn2.to_q" in tail: name = "attn2_q"
-        elif "attn2.to_k" in tail or "attn2.to_v" in tail: name = "attn2_kv"
+        elif "attn2.to_k" in tail or "attn2.to_v" in tail: name = "attn2_kv(ctx)"
         elif "to_out" in tail: name = "attn_out"
-        elif "ff.net.0" in tail: name = "ff1"
+        elif "ff.net.0" in tail: name = "ff1(geglu)"
         elif "ff.net.2" in tail: name = "ff2"
         else: name = "emb"
     return name, size
 
+
 def conv(x, sd_, prefix, stride=1, padding=1):
-    g = group_of("conv", prefix, x.shape[-1] * (2 if prefix.endswith(".conv") else 1))
+    g = group_of("conv", prefix, x.shape[-1] * x.shape[-2] // (stride * stride))
     SEEN[g] = SEEN.get(g, 0) + 1
     if SEL["fn"](*g):
         w = sd_[prefix + ".weight"].half().float()
         return torch.nn.functional.conv2d(x.half().float(), w, sd_.get(prefix + ".bias"), stride=stride, padding=padding)
     return _conv(x, sd_, prefix, stride, padding)
 
+
 def lin(x, sd_, prefix):
-    size = {1024: 32, 256: 16, 64: 8, 16: 4}.get(x.shape[1], 0) if x.dim() == 3 else 0
+    size = x.shape[1] if x.dim() == 3 else 0
     if "attn2.to_k" in prefix or "attn2.to_v" in prefix: size = -1
     g = group_of("lin", prefix, size)
     SEEN[g] = SEEN.get(g, 0) + 1
     if SEL["fn"](*g):
         return torch.nn.functional.linear(x.half().float(), sd_[prefix + ".weight"].half().float(), sd_.get(prefix + ".bias"))
     return _lin(x, sd_, prefix)
+
 
 O.conv, O.lin = conv, lin
 
@@ -118,17 +122,18 @@ ts = [int(a) for a in sys.argv[1:]] or [981, 481]
 with torch.no_grad():
     for t in ts:
         tt = torch.full((1,), t, dtype=torch.long)
+        SEEN.clear()
         SEL["fn"] = lambda *a: False
         ref = O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx)
         err = lambda y: float((y - ref).abs().max() / ref.abs().max())
         SEL["fn"] = lambda name, size: name != "emb"
         print(f"t={t}: everything fp16: {err(O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx)):.2e}")
-        groups = [g for g in SEEN if g[0] != "emb"]
-        res = {}
+        groups = sorted((g for g in SEEN if g[0] not in ("emb", "conv_in")), key=lambda g: (-g[1], g[0]))
+        counts = dict(SEEN)
         for g in groups:
             SEL["fn"] = lambda name, size, g=g: (name, size) == g
-            res[g] = err(O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx))
-            print(f"   only {g[0]:10s} @{g[1]:3d} (n={SEEN[g]:3d}) fp16: {res[g]:.2e}", flush=True)
-        for size in (32, 16, 8, 4):
+            e = err(O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx))
+            print(f"   only {g[0]:14s} at {g[1]:5d} tokens/image ({counts[g] // 2:3d} GEMMs) in fp16: {e:.2e}", flush=True)
+        for size in (1024, 256, 64, 16):
             SEL["fn"] = lambda name, s, size=size: s == size and name != "emb"
-            print(f"   all groups @{size}: {err(O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx)):.2e}", flush=True)
+            print(f"   every GEMM at {size:5d} tokens/image in fp16: {err(O.unet_forward(sd, BBOX_UNET_KW, xin, tt, ctx)):.2e}", flush=True)
