@@ -213,6 +213,14 @@ int upgpt_graph_destroy(void* graph_exec);
 /* kernel nodes inside a captured graph (each launch of the graph adds this to upgpt_launch_count) */
 long long upgpt_graph_kernel_count(void* graph_exec);
 
+/* Parallel branches of a recorded program (e.g. a ResBlock's skip 1x1 GEMM beside conv1 + GroupNorm, openaimodel.py:241,275):
+ * the library owns two auxiliary non-blocking streams per device. fork: the auxiliary stream waits for everything enqueued on
+ * `main_stream` so far; join: `main_stream` waits for the auxiliary stream. Both are event edges, so they are captured into CUDA
+ * graphs as dependencies. upgpt_gemm launches on an auxiliary stream use their own split-K workspace. */
+void* upgpt_aux_stream(int aux_idx);
+int upgpt_stream_fork(void* main_stream, int aux_idx);
+int upgpt_stream_join(void* main_stream, int aux_idx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,9 +9,10 @@ from torch import nn
 
 from ldm.modules.diffusionmodules.model import Decoder, Encoder
 from ldm.modules.distributions.distributions import DiagonalGaussianDistribution
+from upgpt_b200.host import EngineHostMixin
 
 
-class AutoencoderKL(nn.Module):
+class AutoencoderKL(nn.Module, EngineHostMixin):
     def __init__(self, ddconfig, lossconfig=None, embed_dim=4, ckpt_path=None, ignore_keys=(), image_key="image",
                  colorize_nlabels=None, monitor=None):
         super().__init__()
@@ -23,8 +24,7 @@ class AutoencoderKL(nn.Module):
         self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.monitor = monitor
-        self._engines = {}
-        self._weights_version = 0
+        self._host_init()
         if ckpt_path is not None:
             import os
             if os.path.exists(ckpt_path):
@@ -38,10 +38,6 @@ class AutoencoderKL(nn.Module):
         self.load_state_dict(sd, strict=False)
         print(f"Restored from {path}")
 
-    def mark_weights_changed(self):
-        """The engines keep packed fp16 copies of the weights; they re-pack when this version moves."""
-        self._weights_version += 1
-
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
         self.mark_weights_changed()
@@ -49,22 +45,14 @@ class AutoencoderKL(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        self._engines = {}
-        self._weights_version += 1
+        self._host_reset()
         return out
 
     def engine(self, B, H, W, precision=None):
         from upgpt_b200.vae_engine import VAEDecoderEngine
         from upgpt_b200.unet_engine import default_precision
         precision = precision or default_precision()
-        key = (B, H, W, precision)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = VAEDecoderEngine(self, B, H, W, precision=precision)
-            self._engines[key] = eng
-        if eng.weights_version != self._weights_version:
-            eng.pack_weights(self)
-        return eng
+        return self._engine_get((B, H, W, precision), lambda: VAEDecoderEngine(self, B, H, W, precision=precision))
 
     def decode(self, z, in_scale=1.0):
         """z (B, embed_dim, h, w) fp32 -> image (B, out_ch, 8h, 8w) fp32.  in_scale multiplies z first (1/scale_factor)."""
@@ -75,14 +63,7 @@ class AutoencoderKL(nn.Module):
 
     def encoder_engine(self, B, H, W):
         from upgpt_b200.vae_engine import VAEEncoderEngine
-        key = ("enc", B, H, W)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = VAEEncoderEngine(self, B, H, W)
-            self._engines[key] = eng
-        if eng.weights_version != self._weights_version:
-            eng.pack_weights(self)
-        return eng
+        return self._engine_get(("enc", B, H, W), lambda: VAEEncoderEngine(self, B, H, W))
 
     def encode(self, x):
         """x (B, 3, H, W) fp32 NCHW image in [-1, 1] -> DiagonalGaussianDistribution over (B, embed_dim, H/8, W/8) (autoencoder.py:324-328)."""

@@ -153,7 +153,9 @@ class DDPM(nn.Module):
         if self.use_ema:
             self.model_ema.store(self.model.parameters())
             self.model_ema.copy_to(self.model)
-            self.model.diffusion_model.mark_weights_changed()
+            # the packed copy of the EMA weights is resident beside the training weights' (weights tag, upgpt_b200/host.py): a request
+            # through log_images does not re-pack 425 M parameters or re-capture the step graph on entry and on exit
+            self.model.diffusion_model.use_weights_tag("ema")
             if context is not None:
                 print(f"{context}: Switched to EMA weights")
         try:
@@ -161,7 +163,7 @@ class DDPM(nn.Module):
         finally:
             if self.use_ema:
                 self.model_ema.restore(self.model.parameters())
-                self.model.diffusion_model.mark_weights_changed()
+                self.model.diffusion_model.use_weights_tag("raw")
                 if context is not None:
                     print(f"{context}: Restored training weights")
 
@@ -462,14 +464,21 @@ class LatentDiffusion(DDPM):
         z, c = self.get_input(batch, self.first_stage_key, bs=N)
         N = c["c_crossattn"].shape[0]
         hw = self.image_size if isinstance(self.image_size, (list, tuple)) else (self.image_size, self.image_size)
-        x_T = None
+        x_T, x_noise = None, None
         if seed is not None:   # one seeded latent repeated over the batch (ddpm.py:1433-1437)
             g = torch.Generator(device=self.device).manual_seed(int(seed))
             x_T = torch.randn((1, self.channels, int(hw[0]), int(hw[1])), generator=g, device=self.device).repeat(N, 1, 1, 1)
+            # the reference seeds the GLOBAL generator (torch.manual_seed(seed), ddpm.py:1434), which also fixes the per-step noise
+            # of eta > 0 DDIM / ancestral sampling: draw that noise from the same seeded generator so a seeded request reproduces
+            n_steps = ddim_steps if use_ddim else self.num_timesteps
+            if sample and (not use_ddim or ddim_eta != 0.):
+                x_noise = torch.randn((int(n_steps), N, self.channels, int(hw[0]), int(hw[1])), generator=g, device=self.device)
         if sample:
             ctx = self.ema_scope("Plotting") if use_ema_scope else _null()
             with ctx:
                 extra = dict(eta=ddim_eta, x_T=x_T) if use_ddim else dict(x_T=x_T)
+                if x_noise is not None:
+                    extra["x_noise"] = x_noise
                 samples, inter = self.sample_log(cond=c, batch_size=N, ddim=use_ddim, ddim_steps=ddim_steps, **extra)
             log["samples"] = self.decode_first_stage(samples)
         if z is not None:

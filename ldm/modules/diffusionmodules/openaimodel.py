@@ -9,6 +9,7 @@ from torch import nn
 
 from ldm.modules.attention import SpatialTransformer
 from ldm.modules.diffusionmodules.util import conv_nd, linear, normalization, zero_module
+from upgpt_b200.host import EngineHostMixin
 
 
 class TimestepBlock(nn.Module):
@@ -56,7 +57,7 @@ class ResBlock(TimestepBlock):
                                 else conv_nd(dims, channels, self.out_channels, 1))
 
 
-class UNetModel(nn.Module):
+class UNetModel(nn.Module, EngineHostMixin):
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
                  use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
@@ -129,13 +130,10 @@ class UNetModel(nn.Module):
                 self.output_blocks.append(TimestepEmbedSequential(*layers))
         self.out = nn.Sequential(normalization(ch), nn.SiLU(),
                                  zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
-        self._engines = {}
-        self._weights_version = 0
+        self._host_init()
 
-    # -- weight-change tracking: the engine keeps a packed fp16 shadow copy --
-    def mark_weights_changed(self):
-        self._weights_version += 1
-
+    # -- weight-change tracking: ONE packed fp16 shadow copy per module (and weights tag), shared by its engines (SURVEY.md 8b;
+    #    upgpt_b200/host.py): mark_weights_changed / use_weights_tag / the LRU-bounded engine cache come from EngineHostMixin --
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
         self.mark_weights_changed()
@@ -143,21 +141,13 @@ class UNetModel(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        self._engines = {}
-        self.mark_weights_changed()
+        self._host_reset()
         return out
 
     def engine(self, B, H, W, ctx_len, precision=None):
         from upgpt_b200.unet_engine import UNetEngine, default_precision
         precision = precision or default_precision()
-        key = (B, H, W, ctx_len, precision)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = UNetEngine(self, B, H, W, ctx_len, precision=precision)
-            self._engines[key] = eng
-        if eng.weights_version != self._weights_version:
-            eng.pack_weights(self)
-        return eng
+        return self._engine_get((B, H, W, ctx_len, precision), lambda: UNetEngine(self, B, H, W, ctx_len, precision=precision))
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """x (B, in_channels, H, W) fp32 NCHW, timesteps (B,) int64, context (B, L, context_dim) -> eps (B, out, H, W)."""

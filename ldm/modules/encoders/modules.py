@@ -15,6 +15,8 @@ from collections import OrderedDict
 import torch
 from torch import nn
 
+from upgpt_b200.host import EngineHostMixin
+
 
 class AbstractEncoder(nn.Module):
     def encode(self, *args, **kwargs):
@@ -56,16 +58,12 @@ def clip_visual_params(width=1024, layers=24, heads=16, patch=14, resolution=224
     return v
 
 
-class _EngineHost(nn.Module):
+class _EngineHost(nn.Module, EngineHostMixin):
     """Weight-change tracking shared by the two towers (the engines keep packed fp16 shadow copies)."""
 
     def __init__(self):
         super().__init__()
-        self._engines = {}
-        self._weights_version = 0
-
-    def mark_weights_changed(self):
-        self._weights_version += 1
+        self._host_init()      # LRU-bounded engine cache + one shared packed weight store (upgpt_b200/host.py)
 
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
@@ -74,8 +72,7 @@ class _EngineHost(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
-        self._engines = {}
-        self.mark_weights_changed()
+        self._host_reset()
         return out
 
     _PARAM_ROOT = None   # name of the lazily created parameter tree ("transformer" / "model")
@@ -128,12 +125,7 @@ class FrozenCLIPEmbedder(AbstractEncoder, _EngineHost):
     def engine(self, B, L, precision=None):
         from upgpt_b200.clip_engine import ClipTextEngine, clip_precision
         precision = precision or clip_precision()
-        eng = self._engines.get((B, L, precision))
-        if eng is None:
-            eng = self._engines[(B, L, precision)] = ClipTextEngine(self, B, L, precision=precision)
-        if eng.weights_version != self._weights_version:
-            eng.pack_weights(self)
-        return eng
+        return self._engine_get((B, L, precision), lambda: ClipTextEngine(self, B, L, precision=precision))
 
     @torch.no_grad()
     def forward(self, text):
@@ -177,12 +169,7 @@ class FrozenClipImageEmbedder2(_EngineHost):
     def engine(self, n, precision=None):
         from upgpt_b200.clip_engine import ClipVisionEngine, clip_precision
         precision = precision or clip_precision()
-        eng = self._engines.get((n, precision))
-        if eng is None:
-            eng = self._engines[(n, precision)] = ClipVisionEngine(self, n, precision=precision)
-        if eng.weights_version != self._weights_version:
-            eng.pack_weights(self)
-        return eng
+        return self._engine_get((n, precision), lambda: ClipVisionEngine(self, n, precision=precision))
 
     @torch.no_grad()
     def forward(self, x):

@@ -19,7 +19,9 @@ class LinearProject(nn.Module):
 
 
 class DummyModel(nn.Module):
-    def __init__(self):
+    def __init__(self, *args, **kwargs):
+        # the inference facade swaps style_cond's target to this class but keeps its params ({'device': ...},
+        # generate_utils.py:139-142), so the constructor must swallow them like the reference's (poses.py:11-13)
         super().__init__()
 
     def forward(self, x):

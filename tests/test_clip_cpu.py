@@ -117,10 +117,10 @@ def test_engine_programs_record_without_a_device():
     assert tuple(ev16.w["patch.weight"].shape) == (128, 592) and tuple(e16.w["l0.qkv.weight"].shape) == (3 * 128, 128)
     L = _C.lib()
     for eng, x3 in ((e, True), (ev, True), (e16, False), (ev16, False)):
-        gemms = [a[0]._obj for f, a in eng.prog.calls if f is L.upgpt_gemm]
+        gemms = [a[0]._obj for f, a in eng.prog.kernel_calls() if f is L.upgpt_gemm]
         assert gemms and all(bool(g.flags & _C.GEMM_F_X3) == x3 for g in gemms)
         assert all(g.a and g.w and (g.out32 or g.out16) for g in gemms), "every GEMM has its operands and an output"
-        lns = [a for f, a in eng.prog.calls if f in (L.upgpt_layernorm, L.upgpt_layernorm_split3)]
+        lns = [a for f, a in eng.prog.kernel_calls() if f in (L.upgpt_layernorm, L.upgpt_layernorm_split3)]
         assert lns and all(a[0] and a[4] and a[5] and a[7] for a in lns), "every LayerNorm launch carries x, gamma, beta, out"
 
 

@@ -223,6 +223,35 @@ def test_full_size_properties_b8(dev):
     assert relerr(y1, y[:1]) < 5e-3, "batch-of-1 engine (different tiling / split-K) agrees with row 0 of the batch-of-8 engine"
 
 
+def test_unet_eps_b8_benchmarked_config_vs_oracle(dev):
+    """The configuration bench.py times (BASELINE configs[1]: bbox.yaml U-Net, B=8, 32x32x4 latent, 87x768 context) against the CPU
+    oracle AT B=8 (the B=8 engine tiles / splits differently from the B=1 engine the golden vectors pin), in the default precision
+    plan and in uniform fp16x3, at the tolerance BASELINE.json states: eps max-rel < 1e-3."""
+    import json, os
+    from conftest import ROOT
+    m, sd = _unet(BBOX_UNET_KW, 0, dev)
+    B = 8
+    x, mask, ctx = synth.synth_inputs(B, 32, 32, 87, 768, 3)
+    xc = torch.cat([x, mask], 1)
+    rec = {}
+    for t in (981, 481):
+        tt = torch.full((B,), t, dtype=torch.long)
+        with torch.no_grad():
+            ref = O.unet_forward(sd, BBOX_UNET_KW, xc, tt, ctx)
+        for prec in (None, "fp16x3"):
+            eng = m.engine(B, 32, 32, 87, precision=prec)
+            eng.set_context(ctx.to(dev)); eng.stage_inputs(xc.to(dev), tt.to(dev))
+            y = eng.run(use_graph=True).clone()
+            e = relerr(y, ref)
+            per_sample = max(relerr(y[i:i + 1], ref[i:i + 1]) for i in range(B))
+            rec[f"{eng.precision}_t{t}"] = {"batch_max_rel": e, "worst_sample_max_rel": per_sample}
+            assert e < 1e-3 and per_sample < 1e-3, (eng.precision, t, e, per_sample)
+            assert torch.equal(y, eng.run(use_graph=False)), "graph replay == eager program"
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "parity_b8.json"), "w"), indent=1)
+    print("eps parity at B=8:", rec)
+
+
 def test_config4_smpl_interpolation_sequence_cond_cache(dev):
     """BASELINE configs[3] in miniature: keyframes alpha in linspace(1, 0, K) lerp the SMPL vector and the person mask between two
     poses (app.py:298-301) with text / style tokens fixed, one DDIM sample per keyframe through ONE sampler / engine. Each keyframe's

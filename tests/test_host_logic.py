@@ -176,7 +176,7 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     eng = UNetEngine(unet, 1, 32, 32, 87, precision=precision, dry=True)
     L = _C.lib()
     fmt, n_x3, n_plain = {}, 0, 0
-    for fn, args in eng.prog.calls:
+    for fn, args in eng.prog.kernel_calls():
         if fn in (L.upgpt_prep_operand, L.upgpt_groupnorm_prep):
             a = args[0]._obj
             fmt[a.out] = bool(a.split3)
@@ -212,7 +212,65 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     # an architecture without a probed profile keeps fp16x3 everywhere in "mixed" (the probe shows its deep levels are not cheap in error)
     from oracle.make_golden import TINY_UNET_KW
     tiny = UNetEngine(UNetModel(**TINY_UNET_KW).eval(), 2, 16, 16, 87, precision="mixed", dry=True)
-    assert not tiny.mixed and all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.calls if f is L.upgpt_gemm)
+    assert not tiny.mixed and all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.kernel_calls() if f is L.upgpt_gemm)
     monkeypatch.setenv("UPGPT_MIXED_HW", "64,16")          # tuning override: thresholds for an architecture without a profile
     tiny = UNetEngine(UNetModel(**TINY_UNET_KW).eval(), 2, 16, 16, 87, precision="mixed", dry=True)
-    assert tiny.mixed and not all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.calls if f is L.upgpt_gemm)
+    assert tiny.mixed and not all(bool(a[0]._obj.flags & _C.GEMM_F_X3) for f, a in tiny.prog.kernel_calls() if f is L.upgpt_gemm)
+
+
+def test_bbox_yaml_instantiates_the_way_inference_model_rewrites_it():
+    """The reference's inference facade (ldm/data/generate_utils.py:131-146) rewrites the config before instantiating it: style_cond's
+    target becomes ldm.modules.poses.poses.DummyModel while its params stay {'device': ...}, and cond_stage_config gets params
+    {'device': ...}. Both constructors must accept that (DummyModel(*args, **kwargs) as in poses.py:11-13)."""
+    import torch
+    from ldm.util import load_config, instantiate_from_config
+    cfg = load_config(os.path.join(ROOT, "configs", "deepfashion", "bbox.yaml"))
+    p = cfg["model"]["params"]
+    p["extra_cond_stages"]["style_cond"]["params"] = {"device": "cpu"}
+    style_enc = instantiate_from_config(p["extra_cond_stages"]["style_cond"])        # clip_image_encoder of the facade
+    assert type(style_enc).__name__ == "FrozenClipImageEmbedder2"
+    p["extra_cond_stages"]["style_cond"]["target"] = "ldm.modules.poses.poses.DummyModel"
+    p["first_stage_config"]["params"]["ckpt_path"] = None
+    p["cond_stage_config"]["params"] = {"device": "cpu"}
+    p["use_ema"] = False
+    model = instantiate_from_config(cfg["model"])
+    assert type(model.extra_cond_models[0]).__name__ == "DummyModel"
+    s = torch.randn(2, 9, 768)
+    assert torch.equal(model.extra_cond_models[0](s), s)
+
+
+def test_engine_cache_is_lru_bounded_and_shares_packed_weights(monkeypatch):
+    """One packed weight copy per module (and weights tag) whatever the number of engines; the engine cache is LRU-bounded."""
+    import torch
+    from upgpt_b200.host import EngineHostMixin, WeightStore
+
+    class Eng:
+        def __init__(self, host):
+            self.weights_version = -1
+            self.packs = 0
+
+        def pack_weights(self, host):
+            self.packs += 1
+            self.weights_version = host._weights_version
+
+    class Host(EngineHostMixin):
+        def __init__(self):
+            self._host_init()
+
+    monkeypatch.setenv("UPGPT_MAX_ENGINES", "3")
+    h = Host()
+    engs = [h._engine_get((b,), lambda: Eng(h)) for b in range(5)]
+    assert len(h._engines) == 3 and list(h._engines)[0] == (2, "raw")
+    assert h._engine_get((4,), lambda: None) is engs[4] and engs[4].packs == 1
+    h.mark_weights_changed()
+    assert h._engine_get((4,), lambda: None).packs == 2          # re-pack on a version change only
+    h.use_weights_tag("ema")
+    e_ema = h._engine_get((4,), lambda: Eng(h))
+    assert e_ema is not engs[4] and list(h._engines)[-1] == (4, "ema")
+    h.use_weights_tag("raw")
+    assert h._engine_get((4,), lambda: None) is engs[4] and engs[4].packs == 2, "leaving the EMA scope costs no re-pack"
+    st = WeightStore()
+    a = st.put("w", "raw", torch.ones(4), "cpu")
+    b = st.put("w", "raw", torch.full((4,), 2.0), "cpu")
+    assert a is b and float(a[0]) == 2.0, "re-pack updates in place (stable address for recorded programs / graphs)"
+    assert st.put("w", "ema", torch.ones(4), "cpu") is not a

@@ -29,7 +29,7 @@ def main():
     from upgpt_b200.unet_engine import default_precision
     model = bench.build_model(dev, default_precision())
     eng = model.model.diffusion_model.engine(8, 32, 32, 87)
-    rows = [describe(fn, args) for fn, args in eng.prog.calls]
+    rows = [describe(fn, args) for fn, args in eng.prog.kernel_calls()]
     durs = None
     if len(sys.argv) > 1:
         lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]

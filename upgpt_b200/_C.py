@@ -120,8 +120,11 @@ _PROTOS = {
     "upgpt_capture_end": [_vp, C.POINTER(C.c_void_p)],
     "upgpt_graph_launch": [_vp, _vp],
     "upgpt_graph_destroy": [_vp],
+    "upgpt_stream_fork": [_vp, _i],
+    "upgpt_stream_join": [_vp, _i],
 }
-EXPORTS = sorted(list(_PROTOS) + ["upgpt_last_error", "upgpt_abi_version", "upgpt_launch_count", "upgpt_graph_kernel_count"])
+EXPORTS = sorted(list(_PROTOS) + ["upgpt_last_error", "upgpt_abi_version", "upgpt_launch_count", "upgpt_graph_kernel_count",
+                                  "upgpt_aux_stream"])
 
 
 def _bind(l):
@@ -131,3 +134,5 @@ def _bind(l):
         fn.restype = C.c_int
     l.upgpt_graph_kernel_count.argtypes = [_vp]
     l.upgpt_graph_kernel_count.restype = C.c_longlong
+    l.upgpt_aux_stream.argtypes = [_i]
+    l.upgpt_aux_stream.restype = C.c_void_p

@@ -33,13 +33,13 @@ def clip_precision():
 
 
 class _ClipEngineBase(EngineBase):
-    def __init__(self, device, dry=False, precision=None):
+    def __init__(self, device, dry=False, precision=None, host=None):
         """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run."""
         if device.type != "cuda" and not dry:
             raise _C.UpgptError("CLIP engines need the module on a CUDA device (no CPU fallback)")
         precision = precision or clip_precision()
         assert precision in ("fp16x3", "fp16"), precision
-        super().__init__(device, precision)
+        super().__init__(device, precision, None if dry else getattr(host, "_wstore", None), getattr(host, "_weights_tag", "raw"))
         self.s3 = int(self.split3)             # producers emit [hi | lo] planes
         self.dry = dry
         self.weights_version = -1
@@ -82,7 +82,7 @@ class _ClipEngineBase(EngineBase):
 class ClipTextEngine(_ClipEngineBase):
     def __init__(self, host, B, L, dry=False, precision=None):
         tm = host.transformer.text_model
-        super().__init__(tm.final_layer_norm.weight.device, dry, precision)
+        super().__init__(tm.final_layer_norm.weight.device, dry, precision, host)
         a = host.arch
         self.B, self.seq = B, L
         self.Cc, self.heads, self.inner, self.vocab = a["width"], a["heads"], a["mlp"], a["vocab"]
@@ -94,6 +94,9 @@ class ClipTextEngine(_ClipEngineBase):
         self._emit()
 
     def pack_weights(self, host):
+        if self.shared_pack(host._weights_version):
+            self.weights_version = host._weights_version
+            return
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in host.transformer.state_dict().items()}
         put, p = self.put, "text_model."
         put("tok", sd[p + "embeddings.token_embedding.weight"]); put("pos", sd[p + "embeddings.position_embedding.weight"])
@@ -109,6 +112,7 @@ class ClipTextEngine(_ClipEngineBase):
                 put(f"{q}.{n}.weight", sd[f"{s}.{n}.weight"]); put(f"{q}.{n}.bias", sd[f"{s}.{n}.bias"])
         put("lnf.weight", sd[p + "final_layer_norm.weight"]); put("lnf.bias", sd[p + "final_layer_norm.bias"])
         self.weights_version = host._weights_version
+        self.publish_pack(self.weights_version)
 
     def _emit(self):
         B, L, Cc, Hh, inner = self.B, self.seq, self.Cc, self.heads, self.inner
@@ -153,7 +157,7 @@ class ClipTextEngine(_ClipEngineBase):
 class ClipVisionEngine(_ClipEngineBase):
     def __init__(self, host, n, dry=False, precision=None):
         v = host.model.visual
-        super().__init__(v.proj.device, dry, precision)
+        super().__init__(v.proj.device, dry, precision, host)
         a = host.arch
         self.n, self.Cc, self.heads, self.patch, self.S, self.odim = n, a["width"], a["heads"], a["patch"], a["resolution"], a["output_dim"]
         self.n_layers = len(v.transformer.resblocks)
@@ -167,6 +171,9 @@ class ClipVisionEngine(_ClipEngineBase):
         self._emit()
 
     def pack_weights(self, host):
+        if self.shared_pack(host._weights_version):
+            self.weights_version = host._weights_version
+            return
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in host.model.visual.state_dict().items()}
         put = self.put
         w = sd["conv1.weight"].reshape(self.Cc, -1)
@@ -185,6 +192,7 @@ class ClipVisionEngine(_ClipEngineBase):
             for nm in ("ln_1", "ln_2"):
                 put(f"{q}.{nm}.weight", sd[f"{s}.{nm}.weight"]); put(f"{q}.{nm}.bias", sd[f"{s}.{nm}.bias"])
         self.weights_version = host._weights_version
+        self.publish_pack(self.weights_version)
 
     def _emit(self):
         n, Cc, Hh, T, G, Kp = self.n, self.Cc, self.heads, self.T, self.G, self.Kp

@@ -300,7 +300,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-static bool g_attn_attr = false;
+static bool g_attn_attr[64] = {};   // per device: function attributes are per device
 
 }  // namespace upgpt
 
@@ -312,10 +312,13 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   UPGPT_REQUIRE(a->dpad == 64 || a->dpad == 128, "attention: dpad must be 64 or 128 (got %d)", a->dpad);
   UPGPT_REQUIRE(a->Nq > 0 && a->Nk > 0 && a->H > 0 && a->B > 0, "attention: bad sizes");
   UPGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0, "attention: ld must be multiples of 8");
-  if (!g_attn_attr) {
+  int dev_ = 0;
+  UPGPT_CHECK_CUDA(cudaGetDevice(&dev_));
+  UPGPT_REQUIRE(dev_ >= 0 && dev_ < 64, "attention: device index %d out of range", dev_);
+  if (!g_attn_attr[dev_]) {
     UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
     UPGPT_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 204 * 1024));
-    g_attn_attr = true;
+    g_attn_attr[dev_] = true;
   }
   CUtensorMap tmQ, tmK, tmVt;
   {

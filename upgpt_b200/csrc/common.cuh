@@ -38,6 +38,7 @@ int make_tmap(CUtensorMap* out, int elem_bytes, const void* base, int rank, cons
               const uint32_t* box, bool swizzle128);
 
 bool pdl_enabled();   // programmatic dependent launch (UPGPT_PDL=0 disables)
+bool is_aux_stream(cudaStream_t s);   // one of the library's auxiliary (parallel-branch) streams of the current device
 
 #ifdef __CUDACC__
 // Launches `k` with the programmatic-stream-serialization attribute: the kernel may begin (and run its prologue) while its

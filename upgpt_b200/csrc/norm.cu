@@ -12,6 +12,7 @@
 // softmax (model.py:184).
 #include "common.cuh"
 #include <cstdlib>
+#include <mutex>
 #include "../../include/upgpt_b200.h"
 
 namespace upgpt {
@@ -542,21 +543,44 @@ static int pick_chunk(int HW, int B) {
 
 using namespace upgpt;
 
-static double* g_gn_partials = nullptr;   // [B][chunks][2*groups] per-chunk partial moments (graph-stable address)
-static int* g_gn_counters = nullptr;
+// per-device state (workspaces live on the device that runs the kernels; function attributes are per device)
 static constexpr size_t kGnPartialDoubles = (size_t)1 << 21;   // 16 MB
 static constexpr int kGnMaxBatch = 4096;
+static constexpr size_t kFusedSsFloats = (size_t)1 << 20;
+static constexpr int kNormMaxDevices = 64;
+struct NormDev {
+  double* gn_partials = nullptr;   // [B][chunks][2*groups] per-chunk partial moments (graph-stable address)
+  int* gn_counters = nullptr;
+  float* fused_ss = nullptr;       // scale/shift scratch of the two-launch fallback
+  int fused_max_cl = -1;
+  int fused_n16 = 0;               // co-resident 16-CTA clusters (occupancy API, full shared-memory carve-out)
+  int fused_smem_optin = 0;
+};
+static NormDev g_ndev[kNormMaxDevices];
+static std::mutex g_norm_mu;
+static NormDev* norm_dev() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kNormMaxDevices) return nullptr;
+  return &g_ndev[dev];
+}
 
 static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2, int B, int HW, int groups, double* stats,
                                 const float* gamma, const float* beta, float eps, float* scale_shift, cudaStream_t stream) {
   const int C = C1 + C2;
   UPGPT_REQUIRE(x1 && stats && C > 0 && C % groups == 0, "groupnorm_stats: bad args (C=%d groups=%d)", C, groups);
   UPGPT_REQUIRE(C <= 2048 && B <= kGnMaxBatch, "groupnorm_stats: C=%d > 2048 or B=%d too large", C, B);
-  if (!g_gn_partials) {
-    UPGPT_CHECK_CUDA(cudaMalloc(&g_gn_partials, kGnPartialDoubles * sizeof(double)));
-    UPGPT_CHECK_CUDA(cudaMalloc(&g_gn_counters, kGnMaxBatch * sizeof(int)));
-    UPGPT_CHECK_CUDA(cudaMemset(g_gn_counters, 0, kGnMaxBatch * sizeof(int)));
+  NormDev* nd = norm_dev();
+  UPGPT_REQUIRE(nd, "groupnorm_stats: no current CUDA device");
+  {
+    std::lock_guard<std::mutex> lk(g_norm_mu);
+    if (!nd->gn_partials) {
+      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_partials, kGnPartialDoubles * sizeof(double)));
+      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_counters, kGnMaxBatch * sizeof(int)));
+      UPGPT_CHECK_CUDA(cudaMemset(nd->gn_counters, 0, kGnMaxBatch * sizeof(int)));
+    }
   }
+  double* g_gn_partials = nd->gn_partials;
+  int* g_gn_counters = nd->gn_counters;
   // ~2 CTAs per SM in total, at least 8 pixels per CTA, at most 256 chunks per image (cross-chunk reduction cost)
   int per_img = (4 * 148 + B - 1) / B;
   if (per_img > 256) per_img = 256;
@@ -616,11 +640,6 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
 
 // GroupNorm(+SiLU) + cast in one call. Fused single-launch cluster kernel when one image's [HW][C] fp32 tile fits the shared
 // memory of a cluster (<= 16 CTAs); otherwise statistics (gn_stats) and apply (prep) as two launches.
-static float* g_fused_ss = nullptr;            // scale/shift scratch of the two-launch fallback
-static constexpr size_t kFusedSsFloats = (size_t)1 << 20;
-static int g_fused_max_cl = -1;
-static int g_fused_n16 = 0;                   // co-resident 16-CTA clusters (occupancy API, full shared-memory carve-out)
-static int g_fused_smem_optin = 0;
 
 extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -628,6 +647,13 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
   const int C = a->C1 + a->C2;
   const int HW = a->H * a->W;
   UPGPT_REQUIRE(a->groups > 0 && C > 0 && C % a->groups == 0 && a->C1 % 4 == 0 && a->C2 % 4 == 0, "groupnorm_prep: bad channels (C1=%d C2=%d groups=%d)", a->C1, a->C2, a->groups);
+  NormDev* nd = norm_dev();
+  UPGPT_REQUIRE(nd, "groupnorm_prep: no current CUDA device");
+  std::unique_lock<std::mutex> lk(g_norm_mu);
+  int& g_fused_max_cl = nd->fused_max_cl;
+  int& g_fused_n16 = nd->fused_n16;
+  int& g_fused_smem_optin = nd->fused_smem_optin;
+  float*& g_fused_ss = nd->fused_ss;
   if (g_fused_max_cl < 0) {
     int dev = 0;
     UPGPT_CHECK_CUDA(cudaGetDevice(&dev));
@@ -649,6 +675,7 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
     g_fused_max_cl = (ok16 && getenv("UPGPT_NO_CLUSTER16") == nullptr) ? 16 : 8;
     if (getenv("UPGPT_NO_FUSED_GN")) g_fused_max_cl = 0;
   }
+  lk.unlock();
   // cluster size: the smallest power of two whose chunk fits, but at least 8 px per CTA and preferably >= 8 CTAs per image
   int cl = 0, px_per_cta = 0;
   size_t smem = 0;

@@ -91,6 +91,66 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return make_tmap(out, 2, base, rank, dims, strides_bytes, box, swizzle128);
 }
 
+
+
+// ---- auxiliary streams: the parallel branch of a forked program (e.g. a ResBlock's skip 1x1 GEMM next to conv1 + GroupNorm) ----
+// One non-blocking stream per (device, index); fork / join are event edges, so they are captured into CUDA graphs as plain
+// dependencies. Events come from a small per-process ring (an event only carries the dependency between its record and the wait
+// issued right after it).
+static constexpr int kAuxStreams = 2, kAuxDevices = 64, kEventRing = 64;
+static cudaStream_t g_aux[kAuxDevices][kAuxStreams] = {};
+static cudaEvent_t g_events[kAuxDevices][kEventRing] = {};
+static int g_event_next[kAuxDevices] = {};
+static std::mutex g_aux_mu;
+
+static cudaStream_t aux_stream(int idx) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDevices || idx < 0 || idx >= kAuxStreams) return nullptr;
+  std::lock_guard<std::mutex> lk(g_aux_mu);
+  if (!g_aux[dev][idx] && cudaStreamCreateWithFlags(&g_aux[dev][idx], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  return g_aux[dev][idx];
+}
+
+bool is_aux_stream(cudaStream_t s) {
+  if (!s) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDevices) return false;
+  for (int i = 0; i < kAuxStreams; ++i) if (g_aux[dev][i] == s) return true;
+  return false;
+}
+
+static int edge(cudaStream_t from, cudaStream_t to) {
+  int dev = 0;
+  UPGPT_CHECK_CUDA(cudaGetDevice(&dev));
+  UPGPT_REQUIRE(dev >= 0 && dev < kAuxDevices, "stream edge: device index %d out of range", dev);
+  cudaEvent_t ev;
+  {
+    std::lock_guard<std::mutex> lk(g_aux_mu);
+    const int i = g_event_next[dev];
+    g_event_next[dev] = (i + 1) % kEventRing;
+    if (!g_events[dev][i]) UPGPT_CHECK_CUDA(cudaEventCreateWithFlags(&g_events[dev][i], cudaEventDisableTiming));
+    ev = g_events[dev][i];
+  }
+  UPGPT_CHECK_CUDA(cudaEventRecord(ev, from));
+  UPGPT_CHECK_CUDA(cudaStreamWaitEvent(to, ev, 0));
+  return 0;
+}
+
+}  // namespace upgpt
+
+extern "C" void* upgpt_aux_stream(int idx) { return (void*)upgpt::aux_stream(idx); }
+extern "C" int upgpt_stream_fork(void* main_stream, int aux_idx) {
+  cudaStream_t aux = upgpt::aux_stream(aux_idx);
+  UPGPT_REQUIRE(aux, "stream_fork: no auxiliary stream %d", aux_idx);
+  return upgpt::edge((cudaStream_t)main_stream, aux);
+}
+extern "C" int upgpt_stream_join(void* main_stream, int aux_idx) {
+  cudaStream_t aux = upgpt::aux_stream(aux_idx);
+  UPGPT_REQUIRE(aux, "stream_join: no auxiliary stream %d", aux_idx);
+  return upgpt::edge(aux, (cudaStream_t)main_stream);
+}
+
+namespace upgpt {
 }  // namespace upgpt
 
 extern "C" const char* upgpt_last_error(void) { return upgpt::g_err; }

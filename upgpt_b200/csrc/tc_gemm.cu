@@ -22,6 +22,7 @@
 #include "tc_gemm.cuh"
 #include <type_traits>
 #include <cstdlib>
+#include <mutex>
 #include "../../include/upgpt_b200.h"
 
 namespace upgpt {
@@ -816,39 +817,53 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int g_smem_optin = 0;
-static bool g_attr_set = false;
-static float* g_ws = nullptr;                 // split-K partial-tile workspace (allocated once: graph-stable address)
-static size_t g_ws_bytes = 0;
-static int* g_counters = nullptr;
+// Per-device state (a process may drive several GPUs: model.to('cuda:1'), one engine per device). Function attributes (the
+// > 48 KB dynamic shared memory opt-in) are per device, and the split-K workspace / arrival counters must live on the device
+// that runs the kernel. Two workspace slots per device: slot 1 serves launches on the library's auxiliary stream (the
+// parallel branch of a forked program, runtime.cu), so that concurrent GEMMs never share partials or counters.
 static constexpr int kMaxCounters = 1 << 16;
+static constexpr int kMaxDevices = 64;
+struct GemmDev {
+  bool ready = false;
+  int num_sms = 0, smem_optin = 0;
+  int max_clusters[9] = {0};         // co-resident clusters of size S (S CTAs must share a GPC), from the occupancy API
+  float* ws[2] = {nullptr, nullptr}; // split-K partial-tile workspaces (allocated once: graph-stable addresses)
+  size_t ws_bytes = 0;
+  int* counters[2] = {nullptr, nullptr};
+};
+static GemmDev g_gdev[kMaxDevices];
+static std::mutex g_gemm_mu;
 static long long* g_debug_ts = nullptr;
-static int g_max_clusters[9] = {0};           // co-resident clusters of size S (S CTAs must share a GPC), from the occupancy API
 
-static int gemm_device_setup() {
-  if (g_attr_set) return 0;
+static int gemm_device_setup(GemmDev** out) {
   int dev = 0;
   UPGPT_CHECK_CUDA(cudaGetDevice(&dev));
-  UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin));
+  UPGPT_REQUIRE(dev >= 0 && dev < kMaxDevices, "upgpt_gemm: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lk(g_gemm_mu);
+  GemmDev& d = g_gdev[dev];
+  *out = &d;
+  if (d.ready) return 0;
+  UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
   for (int S = 1; S <= 8; ++S) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(S * g_num_sms); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = g_smem_optin;
+    cfg.gridDim = dim3(S * d.num_sms); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = d.smem_optin;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = g_num_sms / (2 * S); }
-    g_max_clusters[S] = n;
+    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.num_sms / (2 * S); }
+    d.max_clusters[S] = n;
   }
-  g_ws_bytes = (size_t)96 << 20;
-  UPGPT_CHECK_CUDA(cudaMalloc(&g_ws, g_ws_bytes));
-  UPGPT_CHECK_CUDA(cudaMalloc(&g_counters, kMaxCounters * sizeof(int)));
-  UPGPT_CHECK_CUDA(cudaMemset(g_counters, 0, kMaxCounters * sizeof(int)));
-  g_attr_set = true;
+  d.ws_bytes = (size_t)96 << 20;
+  for (int i = 0; i < 2; ++i) {
+    UPGPT_CHECK_CUDA(cudaMalloc(&d.ws[i], d.ws_bytes));
+    UPGPT_CHECK_CUDA(cudaMalloc(&d.counters[i], kMaxCounters * sizeof(int)));
+    UPGPT_CHECK_CUDA(cudaMemset(d.counters[i], 0, kMaxCounters * sizeof(int)));
+  }
+  d.ready = true;
   return 0;
 }
 
@@ -858,8 +873,8 @@ static int gemm_device_setup() {
 // and a split-K tile additionally writes + re-reads its fp32 partial tile and synchronises (~2.5 us + 0.9 us per chunk).
 // Wide tiles minimise A re-reads; split-K supplies the parallelism that small-M layers lack.
 struct TileChoice { int bn; int splits; };
-static TileChoice choose_tiling(int N, int m_tiles_x_batch, int k_iters, int num_sms, int gran, bool must_divide, bool allow_split,
-                                int chunk_cols, bool x3) {
+static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_batch, int k_iters, int num_sms, int gran, bool must_divide,
+                                bool allow_split, int chunk_cols, bool x3) {
   TileChoice best{gran, 1};
   double best_t = 1e30;
   auto round_up = [](int x, int m) { return (x + m - 1) / m * m; };
@@ -897,7 +912,12 @@ using namespace upgpt;
 
 extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (gemm_device_setup()) return -2;
+  GemmDev* gd = nullptr;
+  { const int rc = gemm_device_setup(&gd); if (rc) return rc; }
+  const int g_num_sms = gd->num_sms, g_smem_optin = gd->smem_optin;
+  const int* g_max_clusters = gd->max_clusters;
+  const size_t g_ws_bytes = gd->ws_bytes;
+  const int ws_slot = is_aux_stream(stream) ? 1 : 0;
   UPGPT_REQUIRE(a && a->a && a->w, "upgpt_gemm: null operand");
   UPGPT_REQUIRE(a->out32 || a->out16, "upgpt_gemm: no output");
   UPGPT_REQUIRE(!((a->flags & UPGPT_GEMM_F_SPLIT3OUT) && (a->flags & UPGPT_GEMM_F_CHW)), "upgpt_gemm: SPLIT3OUT is not available with channel-major stores");
@@ -1011,7 +1031,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     const bool can_split = !chw_out && !geglu && a->N % 4 == 0 && splits <= 0;
     if (bn <= 0 && a->N <= 16) { bn = 16; }
     if (bn <= 0) {
-      const TileChoice tc = choose_tiling(a->N, p.num_m_tiles * p.batch, k_iters, g_num_sms, gran, /*must_divide=*/epi_mode == 0,
+      const TileChoice tc = choose_tiling(g_max_clusters, a->N, p.num_m_tiles * p.batch, k_iters, g_num_sms, gran, /*must_divide=*/epi_mode == 0,
                                           can_split, epi_mode == 2 ? 64 : 32, p.x3 != 0);
       bn = tc.bn;
       if (splits <= 0) splits = tc.splits;
@@ -1050,8 +1070,8 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
       while (splits > 1 && (splits - 1) * ((k_iters + splits - 1) / splits) >= k_iters) --splits;
       p.num_splits = splits;
     }
-    p.ws = g_ws;
-    p.counters = g_counters;
+    p.ws = gd->ws[ws_slot];
+    p.counters = gd->counters[ws_slot];
   }
   {
     const uint64_t ldw = a->ldw > 0 ? a->ldw : ld_default;  // elements between taps

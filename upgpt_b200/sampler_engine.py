@@ -86,10 +86,15 @@ class FusedSampler:
         key = (id(eng), eng.weights_version, t_key)
         tab = self._emb_tables.get(key)
         if tab is None:
-            if len(self._emb_tables) > 8:
-                self._emb_tables.clear()
             S = len(t_loop)
-            tab = torch.empty(S, eng.emb_total, device=eng.dev, dtype=torch.float32)
+            # same (engine, schedule) at a new weights version: refill the old table in place, so its address -- baked into the
+            # captured step graph -- stays valid
+            stale = [k for k in self._emb_tables if k[0] == key[0] and k[2] == key[2]]
+            tab = self._emb_tables.pop(stale[0]) if stale else None
+            if tab is None:
+                if len(self._emb_tables) > 8:
+                    self._emb_tables.clear()
+                tab = torch.empty(S, eng.emb_total, device=eng.dev, dtype=torch.float32)
             for i, t in enumerate(np.asarray(t_loop).tolist()):
                 eng.bufs["t_in"].fill_(int(t))
                 eng.run_calls(0, eng.n_emb_calls)
@@ -101,8 +106,9 @@ class FusedSampler:
         """kind: 'ddim' | 'ddpm'; noise_mode: 0 none, 1 per-step buffer refreshed by the host loop, 2 strided table.
         cfg_scale: classifier-free guidance -- the engine batch is [unconditional | conditional]; after the U-Net pass
         eps[:B] <- s*eps_c + (1-s)*eps_u, the update runs on the first half of the latent and is mirrored into the second."""
-        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), eng.weights_version, emb_tab.data_ptr(),
-               cfg_scale)
+        # weights are re-packed IN PLACE (upgpt_b200/host.py), so a captured graph stays valid across weight versions: the key holds
+        # addresses only (the timestep-embedding table, whose VALUES depend on the weights, is keyed on the version in _emb_table)
+        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), emb_tab.data_ptr(), cfg_scale)
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -161,6 +167,10 @@ class FusedSampler:
         noise_mode, noise_buf = 0, None
         if x_noise is not None:
             if isinstance(x_noise, torch.Tensor):
+                n_lat = b["x_lat"].numel() // (2 if cfg else 1)
+                if x_noise.numel() < S * n_lat or tuple(x_noise.shape[1:]) != (nB,) + tuple(b["x_lat"].shape[1:]):
+                    raise ValueError("x_noise must be (S, B, C, H, W) = %s with S >= %d, got %s (the step kernel indexes noise + step * B*C*H*W)"
+                                     % ((S, nB) + tuple(b["x_lat"].shape[1:]), S, tuple(x_noise.shape)))
                 noise_mode, noise_buf = 2, x_noise.contiguous().float()
             else:   # True -> draw on the fly into a single-step buffer
                 noise_mode, noise_buf = 1, noise1

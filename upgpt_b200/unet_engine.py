@@ -96,19 +96,58 @@ def split3_w(w):
     return torch.cat([wh, wl], dim=-1)
 
 
+class _OnAux:
+    """A launch that goes to one of the library's auxiliary streams (a parallel branch of the program, between fork and join)."""
+
+    def __init__(self, fn, idx):
+        self.fn, self.idx, self.__name__ = fn, idx, fn.__name__
+
+    def __call__(self, *a):
+        return self.fn(*a[:-1], C.c_void_p(_C.lib().upgpt_aux_stream(self.idx)))
+
+
+class _Edge:
+    """fork: the auxiliary stream waits for the main stream; join: the main stream waits for the auxiliary stream."""
+
+    def __init__(self, kind, idx):
+        self.kind, self.idx, self.__name__ = kind, idx, "upgpt_stream_" + kind
+
+    def __call__(self, stream):
+        L = _C.lib()
+        return (L.upgpt_stream_fork if self.kind == "fork" else L.upgpt_stream_join)(stream, self.idx)
+
+
 class _Program:
-    """Recorded list of (function, argument tuple) launches."""
+    """Recorded list of (function, argument tuple) launches; fork / join edges and auxiliary-stream launches mark parallel branches."""
 
     def __init__(self):
         self.calls = []
         self.keep = []   # ctypes structs must outlive the program
+        self.aux = None  # index of the auxiliary stream the following launches go to (between fork and join_point)
 
     def add(self, fn, *args):
-        self.calls.append((fn, args))
+        self.calls.append((fn if self.aux is None else _OnAux(fn, self.aux), args))
 
     def add_struct(self, fn, struct):
         self.keep.append(struct)
-        self.calls.append((fn, (C.byref(struct),)))
+        self.add(fn, C.byref(struct))
+
+    def fork(self, idx=0):
+        self.calls.append((_Edge("fork", idx), ()))
+
+    def join(self, idx=0):
+        self.calls.append((_Edge("join", idx), ()))
+
+    def kernel_calls(self):
+        """(C-ABI function, args) of every kernel launch, whatever stream it goes to."""
+        for fn, args in self.calls:
+            if isinstance(fn, _Edge):
+                continue
+            yield (fn.fn if isinstance(fn, _OnAux) else fn), args
+
+    @property
+    def n_kernels(self):
+        return sum(1 for _ in self.kernel_calls())
 
     def run(self, stream):
         for fn, args in self.calls:
@@ -120,9 +159,10 @@ class _Program:
 class EngineBase:
     """Buffer bookkeeping + emitters shared by the U-Net and VAE engines."""
 
-    def __init__(self, device, precision):
+    def __init__(self, device, precision, store=None, tag="raw"):
         self.dev = device
         self.precision = precision
+        self.store, self.tag = store, tag      # shared packed-weight store of the host module (upgpt_b200/host.py)
         assert precision in ("fp16x3", "mixed", "fp16"), precision
         self.split3 = precision in ("fp16x3", "mixed")   # engine-wide default operand format ("mixed" overrides it per layer)
         self.x3 = _C.GEMM_F_X3 if self.split3 else 0     # GEMM flag: operands carry [hi | lo] planes
@@ -138,11 +178,31 @@ class EngineBase:
     # ---- memory ----
     def put(self, name, t):
         t = t.contiguous()
-        if name in self.w and self.w[name].shape == t.shape and self.w[name].dtype == t.dtype:
+        if self.store is not None:
+            self.w[name] = self.store.put(type(self).__name__ + ':' + name, self.tag, t, self.dev)   # one packed copy per module
+        elif name in self.w and self.w[name].shape == t.shape and self.w[name].dtype == t.dtype:
             self.w[name].copy_(t)      # keep the address: captured graphs stay valid across re-packs
         else:
             self.w[name] = t.to(self.dev)
         return self.w[name]
+
+    def plan_signature(self):
+        """Engines with equal signatures pack identical weight sets (same names, formats, values)."""
+        return (type(self).__name__, self.precision)
+
+    def shared_pack(self, version):
+        """True if another engine of the module already packed this weight version in this engine's formats: bind and skip."""
+        if self.store is None:
+            return False
+        rec = self.store.plans.get((self.plan_signature(), self.tag))
+        if rec is None or rec["version"] != version:
+            return False
+        self.w = dict(rec["w"])
+        return True
+
+    def publish_pack(self, version):
+        if self.store is not None:
+            self.store.plans[(self.plan_signature(), self.tag)] = {"version": version, "w": dict(self.w)}
 
     def buf(self, name, shape, dtype=torch.float32):
         if name not in self.bufs:
@@ -196,7 +256,7 @@ class EngineBase:
         a.silu, a.layout, a.split3 = int(silu), layout, int(split3)
         a.out, a.ldo, a.raw, a.ldraw = self.p(out), 0, self.p(raw), 0
         self.prog.keep.append(a)
-        self.prog.calls.append((self.L.upgpt_groupnorm_prep, (C.byref(a), C.c_void_p(self.p(stats)))))
+        self.prog.add(self.L.upgpt_groupnorm_prep, C.byref(a), C.c_void_p(self.p(stats)))
 
     def e_gemm(self, **kw):
         if self._sizing:
@@ -242,7 +302,7 @@ class UNetEngine(EngineBase):
         dev = next(unet.parameters()).device
         if dev.type != "cuda" and not dry:
             raise _C.UpgptError("UNetEngine needs the module on a CUDA device (no CPU fallback)")
-        super().__init__(dev, precision or default_precision())
+        super().__init__(dev, precision or default_precision(), getattr(unet, "_wstore", None), getattr(unet, "_weights_tag", "raw"))
         self.dry = dry
         self.B, self.H, self.W, self.ctx_len = B, H, W, ctx_len
         self.mc = unet.model_channels
@@ -260,7 +320,16 @@ class UNetEngine(EngineBase):
             self.mixed_hw = tuple(int(v) for v in os.environ["UPGPT_MIXED_HW"].split(","))
             assert len(self.mixed_hw) == 2, "UPGPT_MIXED_HW=deep_hw,full_hw"
         self.mixed = self.mixed_hw is not None
+        # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
+        self.tf_x1 = self.mixed and os.environ.get("UPGPT_TF_PLANES", "x3") == "x1"
+        self.par_skip = os.environ.get("UPGPT_PAR_SKIP", "0") == "1"
         self.layer_hw = self._layer_resolutions(unet)
+        self.emb_off, off = {}, 0      # column of each ResBlock's timestep-embedding projection in the concatenated GEMV
+        for name, mod in unet.named_modules():
+            if isinstance(mod, om.ResBlock):
+                self.emb_off[name] = off
+                off += mod.out_channels
+        self.emb_total = off
         self.pack_weights(unet)
         # two passes over the same emitter: sizing, then recording
         self._emit(unet)
@@ -295,7 +364,7 @@ class UNetEngine(EngineBase):
         if not self.mixed:
             return self.split3
         deep_hw, full_hw = self.mixed_hw
-        if hw <= full_hw:
+        if hw <= full_hw or (kind == "tf" and self.tf_x1):
             return False
         if hw <= deep_hw:
             return kind in ("resid1x1", "conv_skipshared")
@@ -310,7 +379,14 @@ class UNetEngine(EngineBase):
         """[Cout, Cin, 3, 3] fp32 -> [Cout, 9, Cin] fp16 (x2 planes as an fp16x3 operand)."""
         return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]), x3)
 
+    def plan_signature(self):
+        return (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, tuple(sorted(self.layer_hw.items())) if self.mixed else None)
+
     def pack_weights(self, unet):
+        self._ctx_key = None   # cached context K/V depends on the weights
+        if self.shared_pack(unet._weights_version):
+            self.weights_version = unet._weights_version
+            return
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in unet.state_dict().items()}
         put = self.put
         for k in ("time_embed.0", "time_embed.2"):
@@ -319,7 +395,7 @@ class UNetEngine(EngineBase):
         w0 = sd["input_blocks.0.0.weight"]
         put("conv_in.weight", w0.permute(1, 2, 3, 0).reshape(-1, w0.shape[0]))
         put("conv_in.bias", sd["input_blocks.0.0.bias"])
-        emb_w, emb_b, self.emb_off, off = [], [], {}, 0
+        emb_w, emb_b = [], []
         for name, mod in unet.named_modules():
             if isinstance(mod, om.ResBlock):
                 p = name
@@ -335,8 +411,6 @@ class UNetEngine(EngineBase):
                     ws = sd[p + ".skip_connection.weight"]
                     put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]), x3a)); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
                 emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
-                self.emb_off[p] = off
-                off += mod.out_channels
             elif isinstance(mod, (om.Downsample, om.Upsample)):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
                 w = sd[name + sub + ".weight"]
@@ -376,11 +450,10 @@ class UNetEngine(EngineBase):
         from .ops import timestep_freqs
         put("temb.freqs", timestep_freqs(self.mc))
         put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
-        self.emb_total = off
         put("out.0.weight", sd["out.0.weight"]); put("out.0.bias", sd["out.0.bias"])
         put("out.conv.weight", self._conv_w(sd["out.2.weight"])); put("out.conv.bias", sd["out.2.bias"])
         self.weights_version = unet._weights_version
-        self._ctx_key = None   # cached context K/V depends on the weights
+        self.publish_pack(self.weights_version)
 
     # ------------------------------------------------------------------------------------------------ program
     def _res_block(self, p, mod, x1, C1, x2, C2, B, H, W, out):
@@ -393,11 +466,24 @@ class UNetEngine(EngineBase):
         op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=x3a)
         h32 = self.scratch("res_h", B * HW * Cout, torch.float32)
         emb = None if self._sizing else self.bufs["emb_all"][:, self.emb_off[p]:]
+        par_skip = has_skip and self.par_skip and not self._sizing
+        if has_skip:
+            skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
+        if par_skip:
+            # the skip 1x1 (openaimodel.py:241) only needs the un-normalised operand planes: it runs on an auxiliary stream beside
+            # conv1 and the second GroupNorm and is joined in front of conv2, which consumes it as its residual
+            self.prog.fork(0)
+            self.prog.aux = 0
+            self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
+                        bias=self.w.get(p + ".skip.bias"), flags=fa)
+            self.prog.aux = None
         self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W,
                     out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=fa)
         op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=x3b)
-        if has_skip:
-            skip32 = self.scratch("res_skip", B * HW * Cout, torch.float32)
+        if par_skip:
+            self.prog.join(0)
+            res = skip32
+        elif has_skip:
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
                         bias=self.w.get(p + ".skip.bias"), flags=fa)
             res = skip32
@@ -496,7 +582,7 @@ class UNetEngine(EngineBase):
             P.add(L_.upgpt_linear_small_m, emb.data_ptr(), 4 * self.mc, B, self.w["emb_all.weight"].data_ptr(),
                   self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 0, 0, emb_all.data_ptr(), self.emb_total)
         # the launches above depend on the timestep only: samplers may run them once per schedule (sampler_engine.py)
-        self.n_emb_calls = 0 if self._sizing else len(self.prog.calls)
+        self.n_emb_calls = 0 if self._sizing else len(self.prog.calls)     # (no fork / join edges among them)
         # ---- input blocks ----
         hs = []
         h = self.buf("h_in0", (B, H * W, self.mc))
@@ -637,4 +723,4 @@ class UNetEngine(EngineBase):
 
     @property
     def launches_per_step(self):
-        return len(self.prog.calls)
+        return self.prog.n_kernels

@@ -17,7 +17,7 @@ class VAEDecoderEngine(EngineBase):
         dev = next(ae.parameters()).device
         if dev.type != "cuda":
             raise _C.UpgptError("VAEDecoderEngine needs the module on a CUDA device (no CPU fallback)")
-        super().__init__(dev, precision or default_precision())
+        super().__init__(dev, precision or default_precision(), getattr(ae, '_wstore', None), getattr(ae, '_weights_tag', 'raw'))
         self.B, self.H, self.W = B, H, W
         self.dec = ae.decoder
         self.zc = ae.post_quant_conv.in_channels
@@ -32,6 +32,9 @@ class VAEDecoderEngine(EngineBase):
         return w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]).half()
 
     def pack_weights(self, ae):
+        if self.shared_pack(ae._weights_version):
+            self.weights_version = ae._weights_version
+            return
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in ae.state_dict().items()}
         put = self.put
         w = sd["post_quant_conv.weight"]
@@ -51,6 +54,7 @@ class VAEDecoderEngine(EngineBase):
             else:
                 put(n, v)
         self.weights_version = ae._weights_version
+        self.publish_pack(self.weights_version)
 
     def _resnet(self, p, cin, cout, x, B, H, W, out):
         HW = H * W
@@ -182,7 +186,7 @@ class VAEEncoderEngine(VAEDecoderEngine):
         dev = next(ae.parameters()).device
         if dev.type != "cuda":
             raise _C.UpgptError("VAEEncoderEngine needs the module on a CUDA device (no CPU fallback)")
-        EngineBase.__init__(self, dev, "fp16")
+        EngineBase.__init__(self, dev, "fp16", getattr(ae, '_wstore', None), getattr(ae, '_weights_tag', 'raw'))
         self.B, self.H, self.W = B, H, W
         self.enc = ae.encoder
         nres = self.enc.num_resolutions
@@ -195,6 +199,9 @@ class VAEEncoderEngine(VAEDecoderEngine):
         self._emit()
 
     def pack_weights(self, ae):
+        if self.shared_pack(ae._weights_version):
+            self.weights_version = ae._weights_version
+            return
         sd = {k: v.detach().to(self.dev, torch.float32) for k, v in ae.state_dict().items()}
         put = self.put
         w = sd["encoder.conv_in.weight"]
@@ -212,6 +219,7 @@ class VAEEncoderEngine(VAEDecoderEngine):
             else:
                 put(n, v)
         self.weights_version = ae._weights_version
+        self.publish_pack(self.weights_version)
 
     def _emit(self):
         B, H, W = self.B, self.H, self.W
