@@ -74,8 +74,23 @@ typedef struct upgpt_gemm_args {
   int ldT;                  /* CHW stores: elements between channels (0 = rows_per_group) */
   unsigned flags;           /* UPGPT_GEMM_F_* */
   float out_scale;          /* accumulator scale before bias (0 = 1.0) */
+  /* ---- LayerNorm folded into the GEMMs around it (attention.py:203-205,211-215: x + attn(LN(x)), x + ff(LN(x))) ----
+   * producer (the GEMM that writes the residual stream x): rowstats_out[row][t][2] = {sum, sum of squares} of the fp32 result row over
+   * the columns of N tile t (t < n_tiles of upgpt_gemm_plan), written with plain stores in a fixed order (bit-reproducible).
+   * consumer (the GEMM that reads LN(x)): a = fp16 planes of the RAW x, w = gamma-scaled weights W'[n][k] = gamma[k] W[n][k],
+   * ln_colsum[n] = sum_k W'[n][k] (of the fp16-rounded planes), bias[n] = b[n] + sum_k beta[k] W[n][k]; per row the epilogue forms
+   *   mean = sum / K, rstd = rsqrt(sumsq / K - mean^2 + ln_eps),   D = rstd * (acc - mean * ln_colsum[n]) + bias[n]
+   * which equals LN(x) W^T + b with the statistics of the fp32 x: no LayerNorm kernel and no normalised copy of x exist. */
+  float* rowstats_out;      /* [rows][n_tiles][2] or NULL */
+  const float* ln_stats;    /* the producer's rowstats_out, or NULL (no folded LayerNorm) */
+  int ln_slots;             /* partial slots per row of ln_stats (= the producer's n_tiles) */
+  float ln_eps;
+  const float* ln_colsum;   /* [N] */
 } upgpt_gemm_args;
 int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
+/* the tiling upgpt_gemm picks for these arguments on the current device, without launching: plan[0] = block_n, plan[1] = n_tiles
+ * (N tiles = rowstats slots per row), plan[2] = split-K factor, plan[3] = pipeline stages */
+int upgpt_gemm_plan(const upgpt_gemm_args* args, int plan[4]);
 /* bring-up instrumentation: CTA c of every following upgpt_gemm stamps %globaltimer (ns) into buf[c*16 + slot]; NULL = off */
 int upgpt_debug_set_gemm_timestamps(long long* buf);
 

@@ -77,6 +77,73 @@ def test_conv3x3_stride2_phases_and_nchw_out(dev):
     assert relerr(o, F.conv2d(x.half().float().permute(0, 3, 1, 2), w4.float(), padding=1)) < 2e-5
 
 
+@pytest.mark.parametrize("M,C,N,x3,prod_splits,cons", [(8192, 224, 768, 1, 0, "f16"), (300, 224, 1792, 0, 0, "geglu"), (128, 896, 1024, 0, 4, "f16"),
+                                                       (512, 896, 3072, 1, 2, "f16"), (128, 896, 896, 0, 0, "split"), (2048, 448, 512, 1, 0, "f32")])
+def test_layernorm_folded_into_gemms(dev, M, C, N, x3, prod_splits, cons):
+    """x = A0 W0^T + b0 + r (the GEMM that writes the residual stream) emits fp16 planes of the raw x and per-row {sum, sumsq} partials
+    per N tile (TMA-store epilogue or the cluster split-K reduction); the consumer GEMM runs on those planes with gamma-scaled weights
+    and applies mean / rstd in its epilogue (fp16 TMA-store, GEGLU, fp32, split-K reduction): result == LayerNorm(x) W^T + b."""
+    import ctypes as C_
+    from upgpt_b200 import ops, _C
+    from upgpt_b200.unet_engine import pack_geglu, geglu_half, split3_w
+    g = torch.Generator().manual_seed(M + C + N)
+    K0 = 256
+    A0 = (torch.randn(M, K0, generator=g) * 0.5).half(); W0 = (torch.randn(C, K0, generator=g) * 0.1).half()
+    b0 = torch.randn(C, generator=g) + 0.7; r = torch.randn(M, C, generator=g)          # rows with a non-zero mean
+    x_ref = A0.float() @ W0.float().t() + b0 + r
+    gamma = 1 + 0.2 * torch.randn(C, generator=g); beta = 0.3 * torch.randn(C, generator=g)
+    W = torch.randn(N, C, generator=g) * C ** -0.5; b = 0.1 * torch.randn(N, generator=g)
+    y_ref = F.layer_norm(x_ref, (C,), gamma, beta, 1e-5) @ W.t() + b
+    # ---- producer ----
+    x32 = torch.full((M, C), float("nan"), device=dev)
+    planes = 2 if x3 else 1
+    raw16 = torch.zeros(M, planes * C, device=dev, dtype=torch.half)
+    stats = torch.full((M, 16, 2), float("nan"), device=dev)
+    pa = _C.GemmArgs()
+    kw = dict(a=A0.to(dev), w=W0.to(dev), mode=0, M=M, N=C, K=K0, splits=prod_splits, out32=x32, out16=raw16, bias=b0.to(dev), res32=r.to(dev),
+              rowstats_out=stats, flags=_C.GEMM_F_SPLIT3OUT if x3 else 0)
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v); v = v.data_ptr()
+        setattr(pa, k, v)
+    plan = (C_.c_int * 4)()
+    _C.check(_C.lib().upgpt_gemm_plan(C_.byref(pa), C_.byref(plan)), "plan")
+    slots = int(plan[1])
+    assert 1 <= slots <= 16 and (prod_splits == 0 or int(plan[2]) == prod_splits)
+    _C.check(_C.lib().upgpt_gemm(C_.byref(pa), ops.stream()), "producer")
+    torch.cuda.synchronize()
+    assert relerr(x32, x_ref) < 2e-5
+    st = stats[:, :slots].double().sum(1).cpu()
+    assert relerr(st[:, 0], x_ref.double().sum(1)) < 1e-5 and relerr(st[:, 1], (x_ref.double() ** 2).sum(1)) < 1e-5
+    # ---- consumer ----
+    wg = W * gamma[None, :]
+    bias_f = (b.double() + W.double() @ beta.double()).float()
+    if cons == "geglu":
+        inner = N // 2; half = geglu_half(inner, bool(x3))
+        wg, bias_f = pack_geglu(wg, bias_f, inner, half)
+        yr = y_ref[:, :inner] * F.gelu(y_ref[:, inner:])
+    wp = split3_w(wg) if x3 else wg.half()
+    colsum = wp.double().sum(-1).float()
+    ck = dict(a=raw16, w=wp.to(dev), mode=0, M=M, N=N, K=C, bias=bias_f.to(dev), ln_stats=stats, ln_slots=slots, ln_eps=1e-5, ln_colsum=colsum.to(dev),
+              flags=_C.GEMM_F_X3 if x3 else 0)
+    if cons == "geglu":
+        o16 = torch.zeros(M, inner, device=dev, dtype=torch.half)
+        ops.gemm(out16=o16, block_n=2 * half, **dict(ck, flags=ck["flags"] | _C.GEMM_F_GEGLU))
+        torch.cuda.synchronize()
+        assert relerr(o16, yr) < 3e-3
+    elif cons == "f16":
+        o16 = torch.zeros(M, N, device=dev, dtype=torch.half)
+        ops.gemm(out16=o16, **ck)
+        torch.cuda.synchronize()
+        assert relerr(o16, y_ref) < (2e-3 if x3 else 3e-3)
+    else:
+        o32 = torch.full((M, N), float("nan"), device=dev)
+        ops.gemm(out32=o32, splits=4 if cons == "split" else 0, **ck)
+        torch.cuda.synchronize()
+        assert relerr(o32, y_ref) < (1e-4 if x3 else 2e-3)     # single-plane operands: x rounded to fp16 (relative to |x|, not |x - mean|)
+
+
 def test_geglu_epilogue(dev):
     from upgpt_b200 import ops, _C
     from upgpt_b200.unet_engine import pack_geglu, geglu_half
@@ -282,6 +349,47 @@ def test_flash_attention(dev, B, Hh, Nq, Nk, d):
         torch.cuda.synchronize()
         assert relerr(out2[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
         assert torch.equal(out2, out), "same arithmetic whichever way V is laid out"
+
+
+@pytest.mark.parametrize("B,Hh,Nq,Nk,d,ramp,split3", [(2, 8, 1024, 1024, 28, 1.0, 1), (1, 8, 1024, 87, 28, 1.0, 1), (1, 2, 256, 300, 32, 20.0, 0),
+                                                      (2, 4, 100, 100, 16, 1.0, 0), (1, 8, 4096, 4096, 28, 1.0, 0)])
+def test_flash_attention_head_pairs_d32(dev, B, Hh, Nq, Nk, d, ramp, split3):
+    """dpad = 32: q / k / v rows hold head PAIRS in 64-wide (128-byte swizzled) rows, head h at columns 32 h. The S MMA of head h covers
+    the two 16-wide k-steps of its half-row, P V runs over the pair's 64 V columns and the head keeps its own 32 (the level-0 shape of
+    bbox.yaml: 8 heads of 28). Self (K ring, one V slot, one S buffer, two CTAs per SM) and cross (87 keys, one tile); the lo plane of
+    the [hi | lo] output; rows whose max keeps growing (rescale path)."""
+    from upgpt_b200 import ops
+    g = torch.Generator().manual_seed(Nq + Nk + d)
+    dpad = 32
+    q = torch.randn(B, Hh, Nq, d, generator=g).half()
+    k = (torch.randn(B, Hh, Nk, d, generator=g) * torch.linspace(1.0, ramp, Nk)[None, None, :, None]).half()
+    v = torch.randn(B, Hh, Nk, d, generator=g).half()
+    ref = torch.softmax(torch.einsum("bhid,bhjd->bhij", q.float(), k.float()) * d ** -0.5, -1) @ v.float()
+    HD = Hh * dpad
+    Q = torch.zeros(B, Nq, Hh, dpad, dtype=torch.half); Q[..., :d] = q.permute(0, 2, 1, 3)
+    KV = torch.zeros(B, Nk, 2, Hh, dpad, dtype=torch.half); KV[:, :, 0, :, :d] = k.permute(0, 2, 1, 3); KV[:, :, 1, :, :d] = v.permute(0, 2, 1, 3)
+    Qd, KVd = Q.to(dev), KV.to(dev)
+    planes = 2 if split3 else 1
+    out = torch.full((B, Nq, planes, Hh, dpad), float("nan"), device=dev, dtype=torch.half)
+    ops.attention(q=Qd, ldq=HD, k=KVd, ldk=2 * HD, k_batch_stride=Nk * 2 * HD, vt=KVd.reshape(-1)[HD:], ldvt=2 * HD, v_rowmajor=1,
+                  v_batch_stride=Nk * 2 * HD, out=out, ldo=planes * HD, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=dpad, scale=d ** -0.5, split3_out=split3)
+    torch.cuda.synchronize()
+    hi = out[:, :, 0]
+    assert relerr(hi[..., :d].permute(0, 2, 1, 3), ref) < 3e-3
+    if d < dpad:
+        assert float(hi[..., d:].float().abs().max()) == 0.0      # padded head columns stay exactly zero
+    if split3:
+        full = hi.float() + out[:, :, 1].float()
+        assert relerr(full[..., :d].permute(0, 2, 1, 3), ref) < 1.5e-3     # the lo plane refines the fp16 rounding of O
+    # the same problem through the 64-wide single-head path must agree to fp16 rounding of P / O
+    Q64 = torch.zeros(B, Nq, Hh, 64, dtype=torch.half); Q64[..., :d] = q.permute(0, 2, 1, 3)
+    KV64 = torch.zeros(B, Nk, 2, Hh, 64, dtype=torch.half); KV64[:, :, 0, :, :d] = k.permute(0, 2, 1, 3); KV64[:, :, 1, :, :d] = v.permute(0, 2, 1, 3)
+    out64 = torch.full((B, Nq, Hh, 64), float("nan"), device=dev, dtype=torch.half)
+    KVd64 = KV64.to(dev)
+    ops.attention(q=Q64.to(dev), ldq=Hh * 64, k=KVd64, ldk=2 * Hh * 64, k_batch_stride=Nk * 2 * Hh * 64, vt=KVd64.reshape(-1)[Hh * 64:], ldvt=2 * Hh * 64,
+                  v_rowmajor=1, v_batch_stride=Nk * 2 * Hh * 64, out=out64, ldo=Hh * 64, B=B, H=Hh, Nq=Nq, Nk=Nk, dpad=64, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    assert relerr(hi[..., :d], out64[..., :d]) < 2e-3
 
 
 @pytest.mark.parametrize("Nk,ramp", [(1024, 12.0), (1024, 1.0), (300, 30.0)])

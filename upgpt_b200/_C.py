@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int), ("rows_per_group", C.c_int),
         ("res32", C.c_void_p), ("ldres", C.c_int), ("ldT", C.c_int),
         ("flags", C.c_uint), ("out_scale", C.c_float),
+        ("rowstats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
     ]
 
 
@@ -90,6 +91,7 @@ class AttnArgs(C.Structure):
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _PROTOS = {
     "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
+    "upgpt_gemm_plan": [C.POINTER(GemmArgs), C.POINTER(C.c_int * 4)],
     "upgpt_debug_set_gemm_timestamps": [_vp],
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
     "upgpt_groupnorm_affine": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp],

@@ -15,6 +15,7 @@
 // Replaces CrossAttention.forward's einsum / softmax / einsum (attention.py:178-192) for both attn1 (self) and attn2
 // (keys = [text | style | SMPL] context, attention.py:213).
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/upgpt_b200.h"
 
 namespace upgpt {
@@ -28,8 +29,12 @@ struct AttnParams {
   int ldo;
   int plane;           // > 0: also write the lo plane at column offset plane (fp16x3 operand layout [hi | lo])
   int v_mn;            // V is row-major [Nk][d] (same layout as K): the P V MMA reads it as an MN-major B operand
-  int kv_stages;       // K / V ring depth: 2, or 1 when all keys fit one tile (cross-attention over the 87-token context, 8x8 / 4x4 self)
-  uint32_t tmem_cols;  // TMEM columns to allocate: 512 (two S buffers + O), or 256 for the single-tile form (S + O) so that two CTAs
+  int k_stages;        // K ring depth: 2, or 1 when all keys fit one tile (cross-attention over the 87-token context, 8x8 / 4x4 self)
+  int v_stages;        // V ring depth (1 in the compact two-CTAs-per-SM forms)
+  int s_bufs;          // S accumulators in TMEM: 2 (ping-pong) or 1 (compact forms: the co-resident CTA fills the gap instead)
+  int d32;             // head dim padded to 32: q / k / v hold head PAIRS in 64-wide rows (head h at columns 32 h); the S MMA of head h
+                       // runs over the two 16-wide k-steps of its half of the row, P V over the pair's 64 V columns (its own 32 are kept)
+  uint32_t tmem_cols;  // TMEM columns to allocate: 512 (two S buffers + O), or 256 for the compact forms (S + O) so that two CTAs
   uint32_t o_col;      // share an SM; first column of the O accumulator
 };
 
@@ -55,28 +60,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t qk_bytes = (uint32_t)dch * kTileBytes;      // Q tile or K tile
   const uint32_t vt_chunk = (uint32_t)p.dpad * 128u;          // V^T chunk: [dpad rows][64 keys]
   const uint32_t vt_bytes = 2u * vt_chunk;
-  const uint32_t nst = (uint32_t)p.kv_stages;
+  const uint32_t nks = (uint32_t)p.k_stages, nvs = (uint32_t)p.v_stages;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + qk_bytes;                        // nst stages
-  uint8_t* sV = sK + nst * qk_bytes;                  // nst stages
-  uint8_t* sP = sV + nst * vt_bytes;                  // [2 key chunks][128][64] fp16
-  const uint32_t off_bar = (1 + nst) * qk_bytes + nst * vt_bytes + 2 * kTileBytes;
+  uint8_t* sK = sQ + qk_bytes;                        // nks stages
+  uint8_t* sV = sK + nks * qk_bytes;                  // nvs stages
+  uint8_t* sP = sV + nvs * vt_bytes;                  // [2 key chunks][128][64] fp16
+  const uint32_t off_bar = (1 + nks) * qk_bytes + nvs * vt_bytes + 2 * kTileBytes;
   uint64_t* bars = (uint64_t*)(smem + off_bar);
   uint64_t* bar_q = bars;
-  uint64_t* bar_kv_full = bars + 1;    // [2]
-  uint64_t* bar_kv_empty = bars + 3;   // [2]
-  uint64_t* bar_s = bars + 5;          // [2] S buffer b written by the tensor core
-  uint64_t* bar_sfree = bars + 7;      // [2] S buffer b consumed by all softmax warps
-  uint64_t* bar_p = bars + 9;          // P tile staged (and O rescaled)
-  uint64_t* bar_o = bars + 10;         // O += P V finished
-  uint32_t* tmem_base_smem = (uint32_t*)(bars + 11);
+  uint64_t* bar_k_full = bars + 1;     // [2]
+  uint64_t* bar_k_empty = bars + 3;    // [2] K slot read by the S MMA
+  uint64_t* bar_v_full = bars + 5;     // [2]
+  uint64_t* bar_v_empty = bars + 7;    // [2] V slot read by the P V MMA
+  uint64_t* bar_s = bars + 9;          // [2] S buffer b written by the tensor core
+  uint64_t* bar_sfree = bars + 11;     // [2] S buffer b consumed by all softmax warps
+  uint64_t* bar_p = bars + 13;         // P tile staged (and O rescaled)
+  uint64_t* bar_o = bars + 14;         // O += P V finished
+  uint32_t* tmem_base_smem = (uint32_t*)(bars + 15);
   float* xch = (float*)(smem + off_bar + 128);   // [2 tiles parity][2 halves][128 rows] row-max exchange, then row-sum exchange
+  // ring slot / use count of tile j in a ring of `n` (1 or 2) slots
+  auto slot = [](int j, int n) { return n == 2 ? (j & 1) : 0; };
+  auto use = [](int j, int n) { return n == 2 ? (j >> 1) : j; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   const int qt = blockIdx.x % p.num_q_tiles;
   const int bh = blockIdx.x / p.num_q_tiles;
   const int h = bh % p.H, b = bh / p.H;
+  const int hc = p.d32 ? (h >> 1) : h;      // head coordinate of the TMA boxes (a 64-wide box holds a head pair when d32)
   const int q0 = qt * 128;
   const int n_kv = (p.Nk + 127) >> 7;
 
@@ -84,7 +95,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(bar_q, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_kv_full[s], 1); mbar_init(&bar_kv_empty[s], 1);
+      mbar_init(&bar_k_full[s], 1); mbar_init(&bar_k_empty[s], 1);
+      mbar_init(&bar_v_full[s], 1); mbar_init(&bar_v_empty[s], 1);
       mbar_init(&bar_s[s], 1); mbar_init(&bar_sfree[s], 8);
     }
     mbar_init(bar_p, 8);
@@ -100,22 +112,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tO = tmem_base + p.o_col;    // dpad columns; S buffers at columns [0,128) and (two-stage form) [128,256)
 
   if (warp == 0) {
+    // two independent producer lanes: lane 0 feeds Q and the K ring, lane 1 the V ring (a V slot only frees when its P V MMA has
+    // completed, long after the next K tile is wanted)
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_q, qk_bytes);
-      for (int c = 0; c < dch; ++c) tma_load_4d(sQ + c * kTileBytes, &tmQ, bar_q, c * 64, h, q0, b);
+      for (int c = 0; c < dch; ++c) tma_load_4d(sQ + c * kTileBytes, &tmQ, bar_q, c * 64, hc, q0, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&bar_kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bar_kv_full[s], qk_bytes + vt_bytes);
+        const int s = slot(j, p.k_stages);
+        mbar_wait(&bar_k_empty[s], (use(j, p.k_stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bar_k_full[s], qk_bytes);
         for (int c = 0; c < dch; ++c)
-          tma_load_4d(sK + s * qk_bytes + c * kTileBytes, &tmK, &bar_kv_full[s], c * 64, h, j * 128, b);
+          tma_load_4d(sK + s * qk_bytes + c * kTileBytes, &tmK, &bar_k_full[s], c * 64, hc, j * 128, b);
+      }
+    } else if (lane == 1) {
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = slot(j, p.v_stages);
+        mbar_wait(&bar_v_empty[s], (use(j, p.v_stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bar_v_full[s], vt_bytes);
         if (p.v_mn) {
           // row-major V: the same [128 keys][64 d] swizzled boxes as K
           for (int c = 0; c < dch; ++c)
-            tma_load_4d(sV + s * vt_bytes + c * kTileBytes, &tmVt, &bar_kv_full[s], c * 64, h, j * 128, b);
+            tma_load_4d(sV + s * vt_bytes + c * kTileBytes, &tmVt, &bar_v_full[s], c * 64, hc, j * 128, b);
         } else {
           for (int c = 0; c < 2; ++c)
-            tma_load_3d(sV + s * vt_bytes + c * vt_chunk, &tmVt, &bar_kv_full[s], j * 128 + c * 64, h * p.dpad, b);
+            tma_load_3d(sV + s * vt_bytes + c * vt_chunk, &tmVt, &bar_v_full[s], j * 128 + c * 64, h * p.dpad, b);
         }
       }
     }
@@ -124,7 +144,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_s = make_idesc_f16(128, 128);
       const uint32_t idesc_o = make_idesc_f16(128, (uint32_t)p.dpad, false, p.v_mn != 0);
       auto issue_pv = [&](int jj) {   // O (+)= P(jj) V(jj)
-        const int sp = jj & 1;
+        const int sp = slot(jj, p.v_stages);
+        mbar_wait(&bar_v_full[sp], use(jj, p.v_stages) & 1);
+        tc_fence_after();
         for (int c = 0; c < 2; ++c) {
           const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sP + c * kTileBytes));
           if (p.v_mn) {
@@ -142,24 +164,26 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tO, ad + 2 * k, bd + 2 * k, idesc_o, (jj > 0 || c > 0 || k > 0) ? 1u : 0u);
           }
         }
-        tc_commit(&bar_kv_empty[sp]);
+        tc_commit(&bar_v_empty[sp]);
         tc_commit(bar_o);
       };
       mbar_wait(bar_q, 0);
+      // d32: head h owns the 16-wide k-steps {2 (h & 1), 2 (h & 1) + 1} of the pair's 64-wide rows
+      const int k_lo = p.d32 ? 2 * (h & 1) : 0, k_hi = p.d32 ? k_lo + 2 : 4;
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&bar_kv_full[s], (j >> 1) & 1);
-        mbar_wait(&bar_sfree[s], ((j >> 1) & 1) ^ 1);     // softmax is done with what S buffer s held two tiles ago
+        const int s = slot(j, p.k_stages), sb = slot(j, p.s_bufs);
+        mbar_wait(&bar_k_full[s], use(j, p.k_stages) & 1);
+        mbar_wait(&bar_sfree[sb], (use(j, p.s_bufs) & 1) ^ 1);     // softmax has loaded what S buffer sb held before
         tc_fence_after();
-        // S(j) = Q K(j)^T into S buffer s -- issued before waiting for P(j-1), so it overlaps softmax(j-1)
-        const uint32_t tS = tmem_base + (uint32_t)(s * 128);
+        // S(j) = Q K(j)^T into S buffer sb -- issued before waiting for P(j-1), so it overlaps softmax(j-1)
+        const uint32_t tS = tmem_base + (uint32_t)(sb * 128);
         for (int c = 0; c < dch; ++c) {
           const uint64_t ad = make_desc_kmajor_sw128(smem_u32(sQ + c * kTileBytes));
           const uint64_t bd = make_desc_kmajor_sw128(smem_u32(sK + s * qk_bytes + c * kTileBytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16_ss(tS, ad + 2 * k, bd + 2 * k, idesc_s, (c > 0 || k > 0) ? 1u : 0u);
+          for (int k = k_lo; k < k_hi; ++k) tc_mma_f16_ss(tS, ad + 2 * k, bd + 2 * k, idesc_s, (c > 0 || k > k_lo) ? 1u : 0u);
         }
-        tc_commit(&bar_s[s]);
+        tc_commit(&bar_k_empty[s]);
+        tc_commit(&bar_s[sb]);
         if (j > 0) {
           mbar_wait(bar_p, (j - 1) & 1);
           tc_fence_after();
@@ -181,8 +205,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float c2 = p.scale_log2e;
     const int ocols = p.dpad >> 1;          // O columns owned by this thread
     for (int j = 0; j < n_kv; ++j) {
-      const int sb = j & 1;
-      mbar_wait(&bar_s[sb], (j >> 1) & 1);
+      const int sb = slot(j, p.s_bufs);
+      mbar_wait(&bar_s[sb], use(j, p.s_bufs) & 1);
       tc_fence_after();
       uint32_t v[64];
       {
@@ -263,13 +287,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_wait(bar_o, (n_kv - 1) & 1);
     tc_fence_after();
     const int q = q0 + r;
-    __half* orow = p.out + ((size_t)b * p.Nq + q) * p.ldo + h * p.dpad + hf * ocols;
+    // d32: the O accumulator holds P_h times the V columns of BOTH heads of the pair; head h's are columns [32 (h & 1), +32), i.e.
+    // exactly the half owned by the threads with hf == (h & 1) -- they store, the other half of the threads has nothing to write
+    const bool writer = !p.d32 || hf == (h & 1);
+    __half* orow = p.out + ((size_t)b * p.Nq + q) * p.ldo + (p.d32 ? h * 32 : h * p.dpad + hf * ocols);
 #pragma unroll 1
     for (int cc = 0; cc < ocols; cc += 32) {
       uint32_t o[32];
       tmem_ld32(tO + lane_off + (uint32_t)(hf * ocols + cc), o);
       tmem_ld_wait();
-      if (q < p.Nq) {
+      if (q < p.Nq && writer) {
         uint32_t pk[16], pl[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -309,7 +336,11 @@ using namespace upgpt;
 extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   UPGPT_REQUIRE(a && a->q && a->k && a->vt && a->out, "attention: null pointer");
-  UPGPT_REQUIRE(a->dpad == 64 || a->dpad == 128, "attention: dpad must be 64 or 128 (got %d)", a->dpad);
+  UPGPT_REQUIRE(a->dpad == 32 || a->dpad == 64 || a->dpad == 128, "attention: dpad must be 32, 64 or 128 (got %d)", a->dpad);
+  const bool d32 = a->dpad == 32;
+  UPGPT_REQUIRE(!d32 || (a->H % 2 == 0 && a->v_rowmajor), "attention: dpad 32 runs on head pairs (even H) with row-major V");
+  const int dpad = d32 ? 64 : a->dpad;      // width of the loaded rows (a head pair when d32)
+  const int Hc = d32 ? a->H / 2 : a->H;     // head coordinate range of the TMA boxes
   UPGPT_REQUIRE(a->Nq > 0 && a->Nk > 0 && a->H > 0 && a->B > 0, "attention: bad sizes");
   UPGPT_REQUIRE(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldvt % 8 == 0 && a->ldo % 8 == 0, "attention: ld must be multiples of 8");
   int dev_ = 0;
@@ -322,49 +353,54 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   }
   CUtensorMap tmQ, tmK, tmVt;
   {
-    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nq, (uint64_t)a->B};
-    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->Nq};
+    uint64_t dims[4] = {(uint64_t)dpad, (uint64_t)Hc, (uint64_t)a->Nq, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)dpad * 2, (uint64_t)a->ldq * 2, (uint64_t)a->ldq * 2 * a->Nq};
     uint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap_f16(&tmQ, a->q, 4, dims, str, box, true)) return -3;
   }
   {
-    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nk, (uint64_t)a->B};
-    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldk * 2,
+    uint64_t dims[4] = {(uint64_t)dpad, (uint64_t)Hc, (uint64_t)a->Nk, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)dpad * 2, (uint64_t)a->ldk * 2,
                        (uint64_t)(a->k_batch_stride > 0 ? a->k_batch_stride : (long long)a->ldk * a->Nk) * 2};
     uint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap_f16(&tmK, a->k, 4, dims, str, box, true)) return -3;
   }
   if (a->v_rowmajor) {
     // V row-major [B][Nk][ldvt], head h at columns [h*dpad, (h+1)*dpad): same addressing as K
-    uint64_t dims[4] = {(uint64_t)a->dpad, (uint64_t)a->H, (uint64_t)a->Nk, (uint64_t)a->B};
-    uint64_t str[3] = {(uint64_t)a->dpad * 2, (uint64_t)a->ldvt * 2,
+    uint64_t dims[4] = {(uint64_t)dpad, (uint64_t)Hc, (uint64_t)a->Nk, (uint64_t)a->B};
+    uint64_t str[3] = {(uint64_t)dpad * 2, (uint64_t)a->ldvt * 2,
                        (uint64_t)(a->v_batch_stride > 0 ? a->v_batch_stride : (long long)a->ldvt * a->Nk) * 2};
     uint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap_f16(&tmVt, a->vt, 4, dims, str, box, true)) return -3;
   } else {
     // V^T: [B][H*dpad][ldvt], valid keys = Nk
-    uint64_t dims[3] = {(uint64_t)a->Nk, (uint64_t)a->H * a->dpad, (uint64_t)a->B};
-    uint64_t str[2] = {(uint64_t)a->ldvt * 2, (uint64_t)a->ldvt * 2 * a->H * a->dpad};
-    uint32_t box[3] = {64, (uint32_t)a->dpad, 1};
+    uint64_t dims[3] = {(uint64_t)a->Nk, (uint64_t)a->H * dpad, (uint64_t)a->B};
+    uint64_t str[2] = {(uint64_t)a->ldvt * 2, (uint64_t)a->ldvt * 2 * a->H * dpad};
+    uint32_t box[3] = {64, (uint32_t)dpad, 1};
     if (make_tmap_f16(&tmVt, a->vt, 3, dims, str, box, true)) return -3;
   }
   AttnParams p{};
-  p.Nq = a->Nq; p.Nk = a->Nk; p.H = a->H; p.B = a->B; p.dpad = a->dpad;
+  p.Nq = a->Nq; p.Nk = a->Nk; p.H = a->H; p.B = a->B; p.dpad = dpad; p.d32 = d32 ? 1 : 0;
   p.num_q_tiles = (a->Nq + 127) / 128;
   p.scale_log2e = a->scale * 1.4426950408889634f;
   p.out = (__half*)a->out; p.ldo = a->ldo;
-  p.plane = a->split3_out ? a->H * a->dpad : 0;
+  p.plane = a->split3_out ? a->H * a->dpad : 0;      // (dpad 32: the planes are H * 32 columns apart)
   p.v_mn = a->v_rowmajor ? 1 : 0;
   UPGPT_REQUIRE(!a->split3_out || a->ldo >= 2 * a->H * a->dpad, "attention: split3_out needs ldo >= 2*H*dpad");
-  const int dch = a->dpad / 64;
+  const int dch = dpad / 64;
   const bool one_tile = a->Nk <= 128;      // all keys in one tile: no K/V ring, one S buffer
-  p.kv_stages = one_tile ? 1 : 2;
-  p.tmem_cols = one_tile ? 256u : 512u;
-  p.o_col = one_tile ? 128u : 256u;
-  const size_t smem = 1024 + (size_t)dch * kTileBytes * (1 + p.kv_stages) + (size_t)p.kv_stages * 2 * a->dpad * 128 + 2 * kTileBytes + 128 +
+  // compact multi-tile form (64-wide rows): K ring of 2, ONE V slot, ONE S buffer -> 96 KB of shared memory and 256 TMEM columns, so two
+  // CTAs share an SM and fill each other's S -> softmax -> P -> PV bubbles (the per-tile chain, not a pipe, bounded the one-CTA form)
+  const bool compact = one_tile || (dpad == 64 && a->v_rowmajor && getenv("UPGPT_ATTN_NO_COMPACT") == nullptr);
+  p.k_stages = one_tile ? 1 : 2;
+  p.v_stages = one_tile ? 1 : (compact ? 1 : 2);
+  p.s_bufs = compact ? 1 : 2;
+  p.tmem_cols = compact ? 256u : 512u;
+  p.o_col = compact ? 128u : 256u;
+  const size_t smem = 1024 + (size_t)dch * kTileBytes * (1 + p.k_stages) + (size_t)p.v_stages * 2 * dpad * 128 + 2 * kTileBytes + 128 +
                       2 * 256 * 4 + 64;
   const unsigned grid = (unsigned)(p.num_q_tiles * a->H * a->B);
-  if (one_tile) UPGPT_CHECK_CUDA(launch_k(attention_kernel<2>, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
+  if (compact) UPGPT_CHECK_CUDA(launch_k(attention_kernel<2>, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
   else UPGPT_CHECK_CUDA(launch_k(attention_kernel<1>, dim3(grid), dim3(kAttnThreads), smem, stream, tmQ, tmK, tmVt, p));
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());

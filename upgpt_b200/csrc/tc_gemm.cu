@@ -46,7 +46,10 @@ __device__ __forceinline__ void store_h4(__half* dst, float4 v, int plane) {
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// MINB = 2: the two-CTAs-per-SM form (<= 102 registers, <= ~110 KB shared memory, <= 256 TMEM columns): the CTAs of a short GEMM
+// overlap each other's epilogue latency, and a PDL successor's prologue overlaps its predecessor's tail.
+template <int MINB>
+__global__ void __launch_bounds__(kGemmThreads, MINB)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ GemmParams p) {
@@ -74,6 +77,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   long long* row_tab = (long long*)(smem + off_tab);         // 2 x [128] global output row of each tile row (-1 = not stored)
   int* grp_tab = (int*)(smem + off_tab + 2 * 128 * 8);       // 2 x [128] row group (image / batch entry) of each tile row
   float* bias_s = (float*)(smem + off_tab + 2 * 128 * 8 + 2 * 128 * 4);   // 2 x [256] bias of this tile's columns
+  float* ln_tab = bias_s + 2 * 256;            // 2 x {mean[128], rstd[128]} per-row LayerNorm statistics (folded LN consumer)
+  float* lns_s = ln_tab + 2 * 256;             // 2 x [256] column sums s[n] of this tile's columns (folded LN consumer)
+  float* rsx = lns_s + 2 * 256;                // [2 tile parities][128 rows][2] row-stat exchange between the epilogue groups (producer)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -272,6 +278,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
+    int tile_ctr = 0;
     const bool conv = (p.flags & GEMM_CONV) != 0;
     const bool chw = (p.flags & GEMM_CHW) != 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -308,9 +315,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float* bs = p.bias;
       // publish this thread's row bookkeeping for the flat (coalesced) passes: first wait until every thread of the group has
       // finished reading the previous tile's tables / residual chunk; a later group barrier orders the writes before the reads
+      // folded LayerNorm (consumer): this row's mean / rstd from the producer's per-tile partial sums, summed in slot order
+      const bool ln = p.ln_stats != nullptr;
+      float ln_mu = 0.f, ln_rs = 1.f;
+      if (ln && valid) {
+        const float2* sp = (const float2*)(p.ln_stats + (size_t)grow * p.ln_slots * 2);
+        float su = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_slots; ++i) { const float2 t = sp[i]; su += t.x; sq += t.y; }
+        ln_mu = su * p.ln_inv_c;
+        const float var = fmaxf(fmaf(-ln_mu, ln_mu, sq * p.ln_inv_c), 0.f);
+        ln_rs = rsqrtf(var + p.ln_eps);
+      }
+      float* const lnmu_t = ln_tab + grp * 256;
+      float* const lnrs_t = lnmu_t + 128;
+      float* const lns_g = lns_s + grp * 256;
       named_bar_sync(gbar, 128);
       rtab[r] = valid ? grow : -1;
       gtab[r] = group;
+      if (ln) { lnmu_t[r] = ln_mu; lnrs_t[r] = ln_rs; }
+      float rs_sum = 0.f, rs_sq = 0.f;       // producer: this row's {sum, sum of squares} over the chunks this thread handles
       const bool tma_epi = p.epi_mode != 0 && p.num_splits == 1;
       const bool f16out = p.epi_mode == 2;
       const int cw = f16out ? 64 : 32;                 // chunk width of the TMA-store epilogue
@@ -321,6 +344,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = r; i < p.block_n; i += 128) {
           const int n = nt * p.block_n + i;
           bias_g[i] = (p.bias && n < p.N_total) ? p.bias[n] : 0.f;
+          if (ln) lns_g[i] = n < p.N_total ? p.ln_colsum[n] : 0.f;
         }
         if (p.res_tma && r == 0 && grp < nch) {
           // prefetch the residual of this group's first chunk while the main loop is still running
@@ -395,6 +419,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n >= p.N_total) return;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) b4 = *(const float4*)(p.bias + n);
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ln) s4 = *(const float4*)(p.ln_colsum + n);
         long long gr[8];
         float4 v[8], e1[8], e2[8];
 #pragma unroll
@@ -414,6 +440,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < 8; ++k) {
           if (k >= iters || gr[k] < 0) continue;
           float4 o = v[k];
+          if (ln) {
+            const int rr = rr0 + k * rstep;
+            const float mu = lnmu_t[rr], rsd = lnrs_t[rr];
+            o.x = rsd * fmaf(-mu, s4.x, o.x); o.y = rsd * fmaf(-mu, s4.y, o.y); o.z = rsd * fmaf(-mu, s4.z, o.z); o.w = rsd * fmaf(-mu, s4.w, o.w);
+          }
           o.x += b4.x + e1[k].x + e2[k].x; o.y += b4.y + e1[k].y + e2[k].y; o.z += b4.z + e1[k].z + e2[k].z; o.w += b4.w + e1[k].w + e2[k].w;
           if (p.out32) *(float4*)(p.out32 + (size_t)gr[k] * p.ld32 + n) = o;
           if (p.out16) store_h4(p.out16 + (size_t)gr[k] * p.ld16 + n, o, p.out16_plane);
@@ -439,8 +470,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld32(t_acc + (uint32_t)j0, v);
             tmem_ld_wait();
             float f[32];
+            if (ln) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + i]);
+              for (int i = 0; i < 32; ++i)
+                f[i] = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + i], __uint_as_float(v[i]) * p.out_scale), bias_g[j0 + i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + i]);
+            }
 #pragma unroll
             for (int q = 0; q < 8; ++q) { f[4 * q] += e[q].x; f[4 * q + 1] += e[q].y; f[4 * q + 2] += e[q].z; f[4 * q + 3] += e[q].w; }
             if (p.res_tma) {
@@ -461,6 +498,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
               }
             }
+            if (p.rowstats) {
+              // columns past N_total carry exact zeros (zero-filled operands, bias, row vector and residual): no mask needed
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { rs_sum += f[i]; rs_sq = fmaf(f[i], f[i], rs_sq); }
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = __float_as_uint(f[i]);
           } else {
@@ -471,8 +513,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                const float a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + 32 * h + i]);
-                const float a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_g[j0 + 32 * h + i + 1]);
+                float a0, a1;
+                if (ln) {
+                  a0 = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + 32 * h + i], __uint_as_float(v[i]) * p.out_scale), bias_g[j0 + 32 * h + i]);
+                  a1 = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + 32 * h + i + 1], __uint_as_float(v[i + 1]) * p.out_scale), bias_g[j0 + 32 * h + i + 1]);
+                } else {
+                  a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + 32 * h + i]);
+                  a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_g[j0 + 32 * h + i + 1]);
+                }
                 __half2 hh = __floats2half2_rn(a0, a1);
                 pk[16 * h + (i >> 1)] = *(uint32_t*)&hh;
               }
@@ -514,6 +562,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        if (p.rowstats) {
+          // the two groups drained alternate chunks of the same rows: group 1 hands its partial over, group 0 adds in a fixed order
+          float2* const xs = (float2*)rsx + ((tile_ctr & 1) * 128);
+          if (grp == 1) xs[r] = make_float2(rs_sum, rs_sq);
+          named_bar_sync(3, 256);
+          if (grp == 0 && valid) {
+            const float2 o = xs[r];
+            *(float2*)(p.rowstats + ((size_t)grow * p.num_n_tiles + nt) * 2) = make_float2(rs_sum + o.x, rs_sq + o.y);
+          }
+          ++tile_ctr;
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         if (stamp) TS(9);
         continue;
@@ -534,8 +593,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int ncol_g = ncol_x + half_n;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float xv = __uint_as_float(xr[i]) + (bs ? bs[ncol_x + i] : 0.f);
-              const float gv = __uint_as_float(gr_[i]) + (bs ? bs[ncol_g + i] : 0.f);
+              float xa = __uint_as_float(xr[i]), ga = __uint_as_float(gr_[i]);
+              if (ln) {
+                xa = ln_rs * fmaf(-ln_mu, p.ln_colsum[ncol_x + i], xa);
+                ga = ln_rs * fmaf(-ln_mu, p.ln_colsum[ncol_g + i], ga);
+              }
+              const float xv = xa + (bs ? bs[ncol_x + i] : 0.f);
+              const float gv = ga + (bs ? bs[ncol_g + i] : 0.f);
               f[h0 + i] = xv * gelu_erf_f(gv);
             }
           }
@@ -742,21 +806,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t rbase[SS];
 #pragma unroll
         for (int j = 0; j < SS; ++j) rbase[j] = mapa_shared(p_base, (uint32_t)j);
+        const bool ln = p.ln_stats != nullptr;
+        const float* lnmu_t = ln_tab + grp * 256;
+        const float* lnrs_t = lnmu_t + 128;
+        float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};   // producer row stats: <= 4 rows of this slice per thread
         // UC column chunks of a row are processed together: all their partial / row-vector / residual loads are issued before the
         // first use, so one DSMEM + L2 round trip (~450 cycles under load) is paid per UC elements instead of per element
         constexpr int UC = SS <= 3 ? 4 : 2;
         for (int c0 = 0; c0 < nchunks; c0 += UC) {
           int n[UC];
           bool ok[UC];
-          float4 b4[UC];
+          float4 b4[UC], s4[UC];
 #pragma unroll
           for (int u = 0; u < UC; ++u) {
             const int ncol = (c0 + u) * 32 + q * 4;
             n[u] = nt * p.block_n + ncol;
             ok[u] = ncol < p.block_n && n[u] < p.N_total;
             b4[u] = (ok[u] && p.bias) ? *(const float4*)(p.bias + n[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s4[u] = (ok[u] && ln) ? *(const float4*)(p.ln_colsum + n[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          for (int rr = row_lo + (tid2 >> 3); rr < row_hi; rr += 32) {
+          int it = 0;
+          for (int rr = row_lo + (tid2 >> 3); rr < row_hi; rr += 32, ++it) {
             const long long g = rtab[rr];
             if (g < 0) continue;
             const uint32_t off0 = (uint32_t)(c0 * 16384 + rr * 128 + ((q ^ (rr & 7)) << 4));
@@ -781,10 +851,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float4 o = t[u][0];   // partials are summed in rank order whoever owns the row => bit-reproducible, batch-order independent
 #pragma unroll
               for (int j = 1; j < SS; ++j) { o.x += t[u][j].x; o.y += t[u][j].y; o.z += t[u][j].z; o.w += t[u][j].w; }
+              if (ln) {
+                const float mu = lnmu_t[rr], rsd = lnrs_t[rr];
+                o.x = rsd * fmaf(-mu, s4[u].x, o.x); o.y = rsd * fmaf(-mu, s4[u].y, o.y);
+                o.z = rsd * fmaf(-mu, s4[u].z, o.z); o.w = rsd * fmaf(-mu, s4[u].w, o.w);
+              }
               o.x += b4[u].x + e1[u].x + e2[u].x; o.y += b4[u].y + e1[u].y + e2[u].y;
               o.z += b4[u].z + e1[u].z + e2[u].z; o.w += b4[u].w + e1[u].w + e2[u].w;
               if (p.out32) *(float4*)(p.out32 + (size_t)g * p.ld32 + n[u]) = o;
               if (p.out16) store_h4(p.out16 + (size_t)g * p.ld16 + n[u], o, p.out16_plane);
+              if (p.rowstats && it < 4) {
+                st_s[it] += (o.x + o.y) + (o.z + o.w);
+                st_q[it] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, st_q[it]))));
+              }
+            }
+          }
+        }
+        if (p.rowstats) {
+          // a row's 8 column quads of every chunk sit in 8 consecutive lanes: butterfly over them (fixed order), lane q == 0 stores
+          int it = 0;
+          for (int rr = row_lo + (tid2 >> 3); rr < row_lo + ((rows_per + 31) & ~31) && it < 4; rr += 32, ++it) {
+            float a = st_s[it], b = st_q[it];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if (q == 0 && rr < row_hi) {
+              const long long g = rtab[rr];
+              if (g >= 0) *(float2*)(p.rowstats + ((size_t)g * p.num_n_tiles + nt) * 2) = make_float2(a, b);
             }
           }
         }
@@ -845,7 +937,8 @@ static int gemm_device_setup(GemmDev** out) {
   if (d.ready) return 0;
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
+  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
+  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
   for (int S = 1; S <= 8; ++S) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(S * d.num_sms); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = d.smem_optin;
@@ -854,7 +947,7 @@ static int gemm_device_setup(GemmDev** out) {
     attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.num_sms / (2 * S); }
+    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<1>, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.num_sms / (2 * S); }
     d.max_clusters[S] = n;
   }
   d.ws_bytes = (size_t)96 << 20;
@@ -910,15 +1003,15 @@ static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_
 
 using namespace upgpt;
 
-extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out) {
+  const bool dry = plan_out != nullptr;      // upgpt_gemm_plan: same decisions, no tensor maps, no launch
   GemmDev* gd = nullptr;
   { const int rc = gemm_device_setup(&gd); if (rc) return rc; }
   const int g_num_sms = gd->num_sms, g_smem_optin = gd->smem_optin;
   const int* g_max_clusters = gd->max_clusters;
   const size_t g_ws_bytes = gd->ws_bytes;
   const int ws_slot = is_aux_stream(stream) ? 1 : 0;
-  UPGPT_REQUIRE(a && a->a && a->w, "upgpt_gemm: null operand");
+  UPGPT_REQUIRE(a && (dry || (a->a && a->w)), "upgpt_gemm: null operand");
   UPGPT_REQUIRE(a->out32 || a->out16, "upgpt_gemm: no output");
   UPGPT_REQUIRE(!((a->flags & UPGPT_GEMM_F_SPLIT3OUT) && (a->flags & UPGPT_GEMM_F_CHW)), "upgpt_gemm: SPLIT3OUT is not available with channel-major stores");
   UPGPT_REQUIRE(a->K > 0 && a->N > 0, "upgpt_gemm: bad K/N");
@@ -972,7 +1065,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a_imgs, n_planes};
     const uint64_t lda = a->lda > 0 ? a->lda : ld_default;
     uint64_t strides[4] = {lda * 2, lda * 2 * a->W, lda * 2 * a->W * a->H, (uint64_t)a->K * 2};
-    if (make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
+    if (!dry && make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = p.tap_dx[t] = p.tap_dn[t] = 0; }
     if (a->mode == UPGPT_GEMM_CONV3X3) {
       for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; }
@@ -1004,7 +1097,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)a->M, 1, (uint64_t)p.batch, n_planes};
     uint64_t strides[4] = {lda * 2, abs_ * 2, abs_ * 2, (uint64_t)a->K * 2};
     uint32_t box[5] = {64, 128, 1, 1, 1};
-    if (make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
+    if (!dry && make_tmap_f16(&tmA, a->a, 5, dims, strides, box, true)) return -3;
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = p.tap_dx[t] = p.tap_dn[t] = 0; }
     m_rows_total = a->M;
     p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : a->M;
@@ -1025,6 +1118,17 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   const int k_iters = p.taps * p.kblocks_per_tap;
   int bn = a->block_n;
   int splits = a->splits;
+  // two CTAs per SM (experiment, UPGPT_GEMM_2CTA=1): short single-plane GEMMs with row-major output, tiles <= 128 columns, no split-K
+  static const bool two_env = getenv("UPGPT_GEMM_2CTA") != nullptr && getenv("UPGPT_GEMM_2CTA")[0] == '1';
+  bool two_cta = two_env && !p.x3 && !chw_out && !geglu && bn <= 0 && splits <= 0 && k_iters <= 32 && p.num_m_tiles * p.batch >= 16;
+  if (two_cta) {
+    const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
+    // as many tiles as fit 2 x SMs at once, widest first
+    bn = 128;
+    while (bn > 64 && p.num_m_tiles * p.batch * ((a->N + bn - 1) / bn) < 2 * g_num_sms - g_num_sms / 2) bn -= gran;
+    if (epi_mode == 0) { while (bn > 16 && a->N % bn) bn -= 16; }
+    splits = 1;
+  }
   if (bn > 0 && ((epi_mode == 1 && bn % 32) || (epi_mode == 2 && bn % 64))) epi_mode = 0;   // explicit tile width wins
   if (bn <= 0 || splits <= 0) {
     const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
@@ -1080,10 +1184,21 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     uint64_t dims[5] = {(uint64_t)a->K, (uint64_t)p.taps, (uint64_t)a->N, (uint64_t)p.batch, n_planes};
     uint64_t strides[4] = {ldw * 2, n_stride * 2, wbs * 2, (uint64_t)a->K * 2};
     uint32_t box[5] = {64, 1, (uint32_t)bn, 1, 1};
-    if (make_tmap_f16(&tmB, a->w, 5, dims, strides, box, true)) return -3;
+    if (!dry && make_tmap_f16(&tmB, a->w, 5, dims, strides, box, true)) return -3;
   }
 
   p.debug_ts = g_debug_ts;
+  p.rowstats = a->rowstats_out;
+  p.ln_stats = a->ln_stats; p.ln_slots = a->ln_slots; p.ln_eps = a->ln_eps; p.ln_colsum = a->ln_colsum;
+  p.ln_inv_c = 1.f / (float)a->K;
+  if (p.ln_stats) {
+    UPGPT_REQUIRE(p.ln_slots > 0 && p.ln_colsum && !conv && p.batch == 1, "upgpt_gemm: folded LayerNorm needs ln_slots > 0, ln_colsum and a plain GEMM");
+    UPGPT_REQUIRE(!(p.flags & GEMM_CHW), "upgpt_gemm: folded LayerNorm is not available with channel-major stores");
+    UPGPT_REQUIRE(((uintptr_t)p.ln_stats & 7) == 0 && ((uintptr_t)p.ln_colsum & 15) == 0, "upgpt_gemm: ln_stats / ln_colsum alignment");
+  }
+  if (p.rowstats) {
+    UPGPT_REQUIRE(((uintptr_t)p.rowstats & 7) == 0 && !(p.flags & (GEMM_CHW | GEMM_GEGLU)) && a->out32, "upgpt_gemm: rowstats_out needs an fp32 row-major result");
+  }
   p.out32 = a->out32; p.ld32 = a->ld32 > 0 ? a->ld32 : a->N;
   const int n_out16 = (p.flags & GEMM_GEGLU) ? a->N / 2 : a->N;
   p.out16_plane = (a->flags & UPGPT_GEMM_F_SPLIT3OUT) ? n_out16 : 0;
@@ -1121,12 +1236,12 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
       strides[0] = ldc * eb; strides[1] = ldc * eb * a->M; strides[2] = ldc * eb * a->M;
       box[0] = cw; box[1] = 128; box[2] = 1; box[3] = 1;
     }
-    if (make_tmap(&tmC, eb, cbase, 4, dims, strides, box, true)) return -3;
+    if (!dry && make_tmap(&tmC, eb, cbase, 4, dims, strides, box, true)) return -3;
     if (p.epi_mode == 1 && p.res32 && p.ldres % 4 == 0 && ((uintptr_t)p.res32 & 15) == 0) {
       const uint64_t ldr = p.ldres;
       if (conv) { strides[0] = ldr * 4; strides[1] = ldr * 4 * a->W; strides[2] = ldr * 4 * a->W * a->H; }
       else { strides[0] = ldr * 4; strides[1] = ldr * 4 * a->M; strides[2] = ldr * 4 * a->M; }
-      if (make_tmap(&tmR, 4, p.res32, 4, dims, strides, box, true)) return -3;
+      if (!dry && make_tmap(&tmR, 4, p.res32, 4, dims, strides, box, true)) return -3;
       p.res_tma = 1;
     }
   }
@@ -1136,13 +1251,19 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   size_t epi_bytes = 0;
   int stages = 0;
   for (int pass = 0; pass < 2; ++pass) {
-    epi_bytes = 2 * 16384 + (p.res_tma ? 2 * 16384 : 0) + 2 * (128 * 8 + 128 * 4 + 256 * 4) + 1024 /*alignment slack*/;
+    epi_bytes = 2 * 16384 + (p.res_tma ? 2 * 16384 : 0) + 2 * (128 * 8 + 128 * 4 + 256 * 4) + 3 * 2048 /*LayerNorm tables*/ + 1024 /*alignment slack*/;
     stages = (int)(((size_t)g_smem_optin - 1024 - 256 - epi_bytes) / stage_bytes);
     // x3 needs two slot pairs in flight to overlap loads with MMAs: give up the residual TMA prefetch buffers first
     if (p.x3 && stages < 4 && p.res_tma) { p.res_tma = 0; continue; }
     break;
   }
   const int loads_per_split = (p.x3 ? 2 : 1) * ((k_iters + splits - 1) / splits);
+  if (two_cta) {
+    p.res_tma = 0;
+    epi_bytes = 2 * 16384 + 2 * (128 * 8 + 128 * 4 + 256 * 4) + 3 * 2048 + 1024;
+    stages = (int)(((size_t)110 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
+    if (stages < 2) two_cta = false;
+  }
   if (stages > (p.x3 ? 8 : 6)) stages = p.x3 ? 8 : 6;
   if (stages > loads_per_split + 1) stages = loads_per_split + 1;
   if (p.x3) stages &= ~1;
@@ -1159,11 +1280,20 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
   p.fd_tiles_per_img = make_fastdiv(p.tiles_per_img);
   p.fd_tiles_per_row = make_fastdiv(p.tiles_per_row);
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
+  if (two_cta) grid = num_tiles < 2 * g_num_sms ? num_tiles : 2 * g_num_sms;
   // split-K flavour: the splits of a tile as one thread-block cluster reducing over DSMEM (one tile per CTA; the fp32 partial
   // tile [128][bn] is laid over the drained operand slots), else the global-workspace reduction
   p.cluster_reduce = (p.num_splits > 1 && p.num_splits <= 8 && (size_t)stages * stage_bytes >= (size_t)512 * bn &&
                       getenv("UPGPT_NO_CLUSTER_SPLITK") == nullptr) ? 1 : 0;
   p.coop_reduce = (!p.cluster_reduce && p.num_splits > 1 && num_tiles <= grid) ? 1 : 0;
+  if (p.ln_stats || p.rowstats)
+    UPGPT_REQUIRE(p.num_splits == 1 || p.cluster_reduce, "upgpt_gemm: folded LayerNorm needs the cluster split-K reduction (splits=%d)", p.num_splits);
+  if (p.rowstats)
+    UPGPT_REQUIRE(p.cluster_reduce || p.epi_mode == 1, "upgpt_gemm: rowstats_out needs the TMA-store epilogue (16-byte aligned fp32 rows)");
+  if (dry) {
+    plan_out[0] = p.block_n; plan_out[1] = p.num_n_tiles; plan_out[2] = p.num_splits; plan_out[3] = p.stages;
+    return 0;
+  }
   if (p.cluster_reduce) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_tiles); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
@@ -1178,7 +1308,7 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
       ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, p));
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, tmA, tmB, tmC, tmR, p));
   } else if (p.coop_reduce) {
     // the distributed split-K reduction spins on the arrival of sibling CTAs: a cooperative launch guarantees (or refuses)
     // co-residency instead of risking a deadlock
@@ -1187,13 +1317,21 @@ extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, p));
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, tmA, tmB, tmC, tmR, p));
   } else {
-    UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
+    if (two_cta) UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel<2>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
+    else UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel<1>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
   }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) { return gemm_run(a, (cudaStream_t)stream_, nullptr); }
+
+extern "C" int upgpt_gemm_plan(const upgpt_gemm_args* a, int plan[4]) {
+  UPGPT_REQUIRE(plan, "upgpt_gemm_plan: null plan");
+  return gemm_run(a, nullptr, plan);
 }
 
 // bring-up instrumentation: when set, every CTA of tc_gemm_kernel stamps %globaltimer at 12 points into buf[cta][16]

@@ -70,6 +70,12 @@ struct GemmParams {
   int ldres;
   int ldT;              // CHW: stride between channels (>= rows_per_group)
   float out_scale;      // applied to the accumulator before bias (1.0 default)
+  // ---- folded LayerNorm (include/upgpt_b200.h) ----
+  float* rowstats;          // producer: [rows][num_n_tiles][2] {sum, sumsq} of the final fp32 row over this N tile
+  const float* ln_stats;    // consumer: [rows][ln_slots][2]
+  int ln_slots;
+  float ln_eps, ln_inv_c;   // 1 / K
+  const float* ln_colsum;   // [N_total]
   // ---- deterministic split-K ----
   float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
   int ws_rows, ws_ld;

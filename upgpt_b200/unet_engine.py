@@ -68,6 +68,15 @@ def pad_heads_cols(w, heads, d, dpad):
     return out.reshape(N, heads * dpad)
 
 
+def head_pad(d, heads):
+    """Padded head width of the attention operands: 32 (two heads share one 64-wide row of q / k / v; needs an even head count),
+    64 or 128 columns. d = 28 / 56 / 112 at bbox.yaml -> 32 / 64 / 128."""
+    if d <= 32 and heads % 2 == 0 and os.environ.get("UPGPT_ATTN_D32", "1") != "0":
+        return 32
+    assert d <= 128, "head dim > 128 not supported by the attention kernel"
+    return 64 if d <= 64 else 128
+
+
 def geglu_half(inner, x3=False):
     """Half-width of a GEGLU accumulator tile ([x | gate] = 2*half columns). In the fp16x3 mode a 256-column tile leaves shared
     memory for a single {hi, lo} slot pair (no load / MMA overlap: measured 47 us for M=8192, N=1792, K=224), so 224 is preferred;
@@ -179,7 +188,8 @@ class EngineBase:
     def put(self, name, t):
         t = t.contiguous()
         if self.store is not None:
-            self.w[name] = self.store.put(type(self).__name__ + ':' + name, self.tag, t, self.dev)   # one packed copy per module
+            # one packed copy per (module, operand-format plan, weights tag), shared by every engine with that plan
+            self.w[name] = self.store.put((self.plan_signature(), name), self.tag, t, self.dev)
         elif name in self.w and self.w[name].shape == t.shape and self.w[name].dtype == t.dtype:
             self.w[name].copy_(t)      # keep the address: captured graphs stay valid across re-packs
         else:
@@ -259,12 +269,21 @@ class EngineBase:
         self.prog.add(self.L.upgpt_groupnorm_prep, C.byref(a), C.c_void_p(self.p(stats)))
 
     def e_gemm(self, **kw):
+        """Records one upgpt_gemm launch; returns the number of N tiles the library picks for it (= rowstats slots per row)."""
         if self._sizing:
-            return
+            return 1
         a = _C.GemmArgs()
         for k, v in kw.items():
             setattr(a, k, self.p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
+        n_tiles = 1
+        if a.rowstats_out and not getattr(self, "dry", False):
+            plan = (C.c_int * 4)()
+            if self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan)) != 0:
+                a.splits = 1        # the row statistics need the TMA-store or the cluster split-K epilogue: drop split-K if the pick has neither
+                _C.check(self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan)), "upgpt_gemm_plan")
+            n_tiles = int(plan[1])
         self.prog.add_struct(self.L.upgpt_gemm, a)
+        return n_tiles
 
     def e_layernorm(self, x, rows, Cc, gamma, beta, out16, split3=None, ldx=None):
         if self._sizing:
@@ -323,6 +342,8 @@ class UNetEngine(EngineBase):
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and os.environ.get("UPGPT_TF_PLANES", "x3") == "x1"
         self.par_skip = os.environ.get("UPGPT_PAR_SKIP", "0") == "1"
+        # LayerNorm folded into the GEMMs around it (include/upgpt_b200.h: rowstats_out / ln_stats): no LayerNorm launches
+        self.ln_fold = os.environ.get("UPGPT_LN_FOLD", "1") != "0"
         self.layer_hw = self._layer_resolutions(unet)
         self.emb_off, off = {}, 0      # column of each ResBlock's timestep-embedding projection in the concatenated GEMV
         for name, mod in unet.named_modules():
@@ -380,7 +401,10 @@ class UNetEngine(EngineBase):
         return self._w16(w.permute(0, 2, 3, 1).contiguous().reshape(w.shape[0], 9, w.shape[1]), x3)
 
     def plan_signature(self):
-        return (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, tuple(sorted(self.layer_hw.items())) if self.mixed else None)
+        if getattr(self, "_plan_sig", None) is None:
+            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.ln_fold,
+                              tuple(sorted(self.layer_hw.items())) if self.mixed else None)
+        return self._plan_sig
 
     def pack_weights(self, unet):
         self._ctx_key = None   # cached context K/V depends on the weights
@@ -419,8 +443,7 @@ class UNetEngine(EngineBase):
             elif isinstance(mod, SpatialTransformer):
                 p = name
                 Cc, Hh, d = mod.in_channels, mod.n_heads, mod.d_head
-                dpad = 64 if d <= 64 else 128
-                assert d <= 128, "head dim > 128 not supported by the attention kernel"
+                dpad = head_pad(d, Hh)
                 x3p, x3t = self.use_x3("resid1x1", self.layer_hw[p]), self.use_x3("tf", self.layer_hw[p])
                 put(p + ".norm.weight", sd[p + ".norm.weight"]); put(p + ".norm.bias", sd[p + ".norm.bias"])
                 wpi = sd[p + ".proj_in.weight"]
@@ -434,18 +457,31 @@ class UNetEngine(EngineBase):
                     wq = pad_heads_rows(sd[q + ".attn1.to_q.weight"], Hh, d, dpad)
                     wk = pad_heads_rows(sd[q + ".attn1.to_k.weight"], Hh, d, dpad)
                     wv = pad_heads_rows(sd[q + ".attn1.to_v.weight"], Hh, d, dpad)
-                    put(q + ".attn1.qkv.weight", self._w16(torch.cat([wq, wk, wv], 0), x3t))    # one fused q | k | v projection
+                    wqkv = torch.cat([wq, wk, wv], 0)                                            # one fused q | k | v projection
+                    wq2 = pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad)
+                    if self.ln_fold:
+                        # LN(x) W^T = rstd (x (gamma o W)^T - mean colsum) + W beta: gamma goes into the weights, beta into a bias
+                        wqkv = self._put_ln_folded(q + ".attn1.qkv", wqkv, None, sd[q + ".norm1.weight"], sd[q + ".norm1.bias"], x3t)
+                        wq2 = self._put_ln_folded(q + ".attn2.q", wq2, None, sd[q + ".norm2.weight"], sd[q + ".norm2.bias"], x3t)
+                    put(q + ".attn1.qkv.weight", self._w16(wqkv, x3t))
                     put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad), x3t))
                     put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
-                    put(q + ".attn2.q.weight", self._w16(pad_heads_rows(sd[q + ".attn2.to_q.weight"], Hh, d, dpad), x3t))
+                    put(q + ".attn2.q.weight", self._w16(wq2, x3t))
                     put(q + ".attn2.kv.weight", self._w16(torch.cat([pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad),
                                                                      pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)], 0)))
                     put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad), x3t))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
                     half = geglu_half(inner, x3t)
-                    w1, b1 = pack_geglu(sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"], inner, half)
+                    w1, b1 = sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"]
+                    if self.ln_fold:
+                        g3, be3 = sd[q + ".norm3.weight"], sd[q + ".norm3.bias"]
+                        b1 = (b1.double() + w1.double() @ be3.double()).float()
+                        w1 = w1 * g3[None, :]
+                    w1, b1 = pack_geglu(w1, b1, inner, half)
                     put(q + ".ff1.weight", self._w16(w1, x3t)); put(q + ".ff1.bias", b1)
+                    if self.ln_fold:
+                        put(q + ".ff1.colsum", self.w[q + ".ff1.weight"].double().sum(-1).float())
                     put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"], x3t)); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
         from .ops import timestep_freqs
         put("temb.freqs", timestep_freqs(self.mc))
@@ -454,6 +490,18 @@ class UNetEngine(EngineBase):
         put("out.conv.weight", self._conv_w(sd["out.2.weight"])); put("out.conv.bias", sd["out.2.bias"])
         self.weights_version = unet._weights_version
         self.publish_pack(self.weights_version)
+
+    def _put_ln_folded(self, name, w, b, gamma, beta, x3):
+        """LayerNorm(gamma, beta) folded into the Linear (w, b) that consumes it: stores bias' = b + W beta and the column sums of the
+        gamma-scaled weight, returns that weight for the caller to pack."""
+        bias = w.double() @ beta.double()
+        if b is not None:
+            bias = bias + b.double()
+        self.put(name + ".bias", bias.float())
+        w = w * gamma[None, :]
+        # column sums of the weights AS THE TENSOR CORE SEES THEM (fp16-rounded planes), so the mean term cancels exactly
+        self.put(name + ".colsum", self._w16(w, x3).double().sum(-1).float())
+        return w
 
     # ------------------------------------------------------------------------------------------------ program
     def _res_block(self, p, mod, x1, C1, x2, C2, B, H, W, out):
@@ -496,7 +544,7 @@ class UNetEngine(EngineBase):
     def _transformer(self, p, mod, x, Cc, B, H, W, out):
         HW, M = H * W, B * H * W
         Hh, d = mod.n_heads, mod.d_head
-        dpad = 64 if d <= 64 else 128
+        dpad = head_pad(d, Hh)
         HD = Hh * dpad
         L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
         x3p, x3t = self.use_x3("resid1x1", HW), self.use_x3("tf", HW)    # proj_in / proj_out ; attention projections + feed-forward
@@ -511,45 +559,63 @@ class UNetEngine(EngineBase):
         tok16 = self.scratch("tok16", M * Cc * kx, torch.float16)
         qkv16 = self.scratch("qkv16", M * 3 * HD, torch.float16)
         att16 = self.scratch("att16", M * HD * kx, torch.float16)
-        self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
-                    bias=self.w.get(p + ".proj_in.bias"), flags=fp)
+        fold = self.ln_fold
+        # folded LayerNorm: the GEMM that writes the residual stream also emits its raw fp16 planes and per-row {sum, sumsq}; the GEMM
+        # that consumes LN(x) reads those planes with gamma-scaled weights and applies mean / rstd in its epilogue
+        lnst = self.scratch("lnstats", M * 16 * 2, torch.float32) if fold else None
+        rawkw = (lambda: dict(out16=tok16, rowstats_out=lnst)) if fold else (lambda: {})
+        slots = self.e_gemm(a=op, w=self.w.get(p + ".proj_in.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=tokA,
+                            bias=self.w.get(p + ".proj_in.bias"), flags=fp | (s3 if fold else 0), **rawkw())
+        lnkw = lambda n, sl: dict(ln_stats=lnst, ln_slots=sl, ln_eps=1e-5, ln_colsum=self.w.get(n + ".colsum"), bias=self.w.get(n + ".bias"))
         cur, nxt = tokA, tokB
         for bi in range(len(mod.transformer_blocks)):
             q = f"{p}.transformer_blocks.{bi}"
             g = lambda n: self.w.get(q + n)
             inner = mod.transformer_blocks[bi].ff.net[2].in_features
             ff16 = self.scratch("ff16", M * inner * kxt, torch.float16)
+            last = bi == len(mod.transformer_blocks) - 1
+            assert slots <= 16
             # --- self attention ---
-            self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16, x3t)
+            if not fold:
+                self.e_layernorm(cur, M, Cc, g(".norm1.weight"), g(".norm1.bias"), tok16, x3t)
             # one q | k | v projection (row-major fp16); the attention kernel reads V row-major as an MN-major operand (no V^T)
-            self.e_gemm(a=tok16, w=g(".attn1.qkv.weight"), mode=_C.GEMM_PLAIN, M=M, N=3 * HD, K=Cc, out16=qkv16, flags=x3)
+            self.e_gemm(a=tok16, w=g(".attn1.qkv.weight"), mode=_C.GEMM_PLAIN, M=M, N=3 * HD, K=Cc, out16=qkv16, flags=x3,
+                        **(lnkw(q + ".attn1.qkv", slots) if fold else {}))
             kptr = None if self._sizing else qkv16[HD:]
             vptr = None if self._sizing else qkv16[2 * HD:]
             self.e_attention(q=qkv16, ldq=3 * HD, k=kptr, ldk=3 * HD, k_batch_stride=HW * 3 * HD, vt=vptr, ldvt=3 * HD, v_rowmajor=1,
                              v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
                              scale=float(d) ** -0.5, split3_out=int(x3t))
-            self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
-                        bias=g(".attn1.out.bias"), res32=cur, flags=x3)
+            slots = self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                                bias=g(".attn1.out.bias"), res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
-            self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16, x3t)
-            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qkv16, flags=x3)
+            if not fold:
+                self.e_layernorm(cur, M, Cc, g(".norm2.weight"), g(".norm2.bias"), tok16, x3t)
+            self.e_gemm(a=tok16, w=g(".attn2.q.weight"), mode=_C.GEMM_PLAIN, M=M, N=HD, K=Cc, out16=qkv16, flags=x3,
+                        **(lnkw(q + ".attn2.q", slots) if fold else {}))
             kvc = self.buf(q + ".ctx_kv", (B * L, 2 * HD), torch.float16)       # cond-cache: K | V of the context, row-major
             vcp = None if self._sizing else kvc.reshape(-1)[HD:]
             self.e_attention(q=qkv16, ldq=HD, k=kvc, ldk=2 * HD, k_batch_stride=L * 2 * HD, vt=vcp, ldvt=2 * HD, v_rowmajor=1,
                              v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
                              scale=float(d) ** -0.5, split3_out=int(x3t))
-            self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
-                        bias=g(".attn2.out.bias"), res32=cur, flags=x3)
+            slots = self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
+                                bias=g(".attn2.out.bias"), res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
-            self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16, x3t)
+            if not fold:
+                self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16, x3t)
             self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner, x3t),
-                        out16=ff16, bias=g(".ff1.bias"), flags=_C.GEMM_F_GEGLU | s3 | x3)
-            last = bi == len(mod.transformer_blocks) - 1
-            # the last block's feed-forward also emits the fp16 operand of proj_out, in proj_out's operand format
-            self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
-                        res32=cur, out16=tok16 if last else None, flags=(_C.GEMM_F_SPLIT3OUT if (last and x3p) else 0) | x3)
+                        out16=ff16, flags=_C.GEMM_F_GEGLU | s3 | x3,
+                        **(lnkw(q + ".ff1", slots) if fold else dict(bias=g(".ff1.bias"))))
+            # the last block's feed-forward also emits the fp16 operand of proj_out, in proj_out's operand format; an inner block's emits
+            # the raw planes + row statistics of the next block's first LayerNorm
+            if last:
+                self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
+                            res32=cur, out16=tok16, flags=(_C.GEMM_F_SPLIT3OUT if x3p else 0) | x3)
+            else:
+                slots = self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
+                                    res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
         self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
                     bias=self.w.get(p + ".proj_out.bias"), res32=x, flags=fp)
@@ -653,7 +719,7 @@ class UNetEngine(EngineBase):
         self.e_prep(ctx32, self.ctx_dim, None, 0, B, 1, L, None, None, None, 0.0, False, 0, ctx16, split3=self.split3)
         for name, mod in unet.named_modules():
             if isinstance(mod, SpatialTransformer):
-                dpad = 64 if mod.d_head <= 64 else 128
+                dpad = head_pad(mod.d_head, mod.n_heads)
                 HD = mod.n_heads * dpad
                 for bi in range(len(mod.transformer_blocks)):
                     q = f"{name}.transformer_blocks.{bi}"
