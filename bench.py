@@ -1,8 +1,10 @@
 """Headline benchmark: images/sec @256x256, 50-step DDIM, bs=8 per GPU, random-init U-Net + KL-f8 decode (BASELINE.json
 configs[1]), synthetic 32x32x4 latents / (B, 87, 768) context / bbox person mask.
 
-    python bench.py [--gpus N --steps K --warmup W]             # this repo's B200 path
-    python bench.py --impl reference [...]                     # the reference algorithm on the host CPU (oracle port)
+    python bench.py [--gpus N --steps K --warmup W]             # this repo's B200 path, BASELINE configs[1]
+    python bench.py --config c4|c5                              # BASELINE configs[3] (16 SMPL-interpolation keyframes x bs=4) / configs[4] (64x64 latent, bs=4)
+    python bench.py --impl reference [...]                     # the reference's own code on the host CPU (baseline/_ref, else the oracle port)
+    python bench.py --impl reference --full                    # ... one complete 50-step + decode job instead of a bounded sample
     torchrun --nproc-per-node N bench.py --gpus N ...          # one rank per GPU, batch sharded (weak scaling)
 
 One "step" = one full pass of the hot path over one batch: 50 DDIM steps through the U-Net (one CUDA graph replay per
@@ -19,11 +21,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "images/sec @256x256, 50-step DDIM, bs=8"
 UNIT = "images/s"
-B_PER_GPU, LAT, CTX_LEN, CTX_DIM, DDIM_STEPS = 8, 32, 87, 768, 50
-GF_UNET_PER_SAMPLE_STEP = 91.03      # SURVEY.md 8(d), FlopCounterMode on the reference U-Net, 32x32 latent
-GF_VAE_PER_IMAGE = 622.19
+CTX_LEN, CTX_DIM, DDIM_STEPS = 87, 768, 50
+# BASELINE.json configs: batch per GPU, latent size, keyframes per step (c4: one step = the whole interpolation sequence),
+# algorithmic GFLOP of one U-Net pass per sample and of one VAE decode per image (FlopCounterMode on the reference)
+WORKLOADS = {
+    "c2": dict(B=8, lat=32, keyframes=1, gf_unet=91.03, gf_vae=622.19, metric="images/sec @256x256, 50-step DDIM, bs=8",
+               what="configs[1]: bbox.yaml U-Net (425.29M params, random init) 32x32x4 latent, 87x768 context, 50-step DDIM eta=%g, bs=8 per GPU, "
+                    "+ KL-f8 decode to 256x256 uint8"),
+    "c4": dict(B=4, lat=32, keyframes=16, gf_unet=91.03, gf_vae=622.19, metric="images/sec @256x256, 50-step DDIM, 16 SMPL-interpolation keyframes x bs=4",
+               what="configs[3]: bbox.yaml U-Net, 16 keyframes x bs=4 (SMPL vector + person mask lerped between two poses, text / style tokens "
+                    "fixed: the cond-cache refreshes 1 of 87 context rows per keyframe), 50-step DDIM eta=%g per keyframe, + KL-f8 decode to 256x256 uint8"),
+    "c5": dict(B=4, lat=64, keyframes=1, gf_unet=421.34, gf_vae=2514.5, metric="images/sec @512x512, 50-step DDIM, bs=4",
+               what="configs[4]: bbox.yaml U-Net on a 64x64x4 latent (4096-token self-attention), 87x768 context, 50-step DDIM eta=%g, bs=4 per GPU, "
+                    "+ KL-f8 decode to 512x512 uint8"),
+}
+METRIC = WORKLOADS["c2"]["metric"]
+B_PER_GPU, LAT = WORKLOADS["c2"]["B"], WORKLOADS["c2"]["lat"]
+GF_UNET_PER_SAMPLE_STEP = WORKLOADS["c2"]["gf_unet"]
+GF_VAE_PER_IMAGE = WORKLOADS["c2"]["gf_vae"]
+
+
+def workload_string(cfg, eta):
+    return WORKLOADS[cfg]["what"] % eta
 
 
 def parse():
@@ -38,6 +58,9 @@ def parse():
                          "except the deep low-resolution levels (both meet the 1e-3 eps tolerance); fp16 = fast mode")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the additional fp16 fast-mode measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json workload: c2 = configs[1] (headline), c4 = configs[3], c5 = configs[4]")
+    ap.add_argument("--full", action="store_true", help="--impl reference: time ONE complete 50-step + decode job (minutes) instead of bounded samples")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline (outside the timed region)")
     return ap.parse_args()
 
 

@@ -184,7 +184,17 @@ int upgpt_step_state(int* step_ptr, int op, int value, long long* t_buf, int B, 
  * once per schedule, e.g. emb_layers(SiLU(time_embed(timestep_embedding(t_step)))) of all 22 ResBlocks (openaimodel.py:218-224,723-724) --
  * t is the same for every sample of a batch in ddim.py:142 / ddpm.py:1271, so the 4 embedding launches leave the step graph */
 int upgpt_gather_step_row(const float* table, long long row_stride, const int* step_ptr, float* dst, int B, int n, void* stream);
-/* out = a*sa + b*sb (b may be NULL): q_sample / mask blend helpers (ddpm.py:281-284, ddim.py:144-147) */
+/* q_sample with an optional known-region blend, one launch:
+ *   q = sqrt_acp[t] * x0 + sqrt_1m_acp[t] * noise                  (DDPM.q_sample ddpm.py:281-284; stochastic_encode ddim.py:207-221)
+ *   out = mask ? q * mask + (1 - mask) * img : q                    (ddim.py:144-147, ddpm.py:1281-1284)
+ * x0 / noise / img / out: [B][C][HW] fp32; mask: [B][mask_c][HW] with mask_c = 1 (broadcast over channels) or C.
+ * t: per sample from t_per_sample[B] (int64), else t_table[*step_ptr] (device-side step counter of the sampler graphs; noise is then
+ * read at noise + *step_ptr * noise_step_stride), else t_imm. sqrt_acp / sqrt_1m_acp: the schedule buffers (device, fp32). */
+int upgpt_qsample_blend(const float* x0, const float* noise, long long noise_step_stride, const float* mask, int mask_c,
+                        const float* img, float* out, const float* sqrt_acp, const float* sqrt_1m_acp,
+                        const long long* t_per_sample, const long long* t_table, const int* step_ptr, int t_imm, int B, int C, int HW,
+                        void* stream);
+/* out = a*sa + b*sb (b may be NULL): classifier-free guidance combine, latent mirror */
 int upgpt_axpby(const float* a, float sa, const float* b, float sb, float* out, long long n, void* stream);
 /* out = (wa*a + wb*b + wc*c + wd*d) / den, terms with a NULL pointer skipped: the pseudo linear multistep eps combinations of
  * PLMSSampler.p_sample_plms (plms.py:211-229), e.g. (55 e_t - 59 e_1 + 37 e_2 - 9 e_3) / 24 */

@@ -93,13 +93,15 @@ class DDIMSampler(object):
                                   corrector_kwargs=corrector_kwargs, x_T=x_T, log_every_t=log_every_t,
                                   unconditional_guidance_scale=unconditional_guidance_scale,
                                   unconditional_conditioning=unconditional_conditioning,
-                                  x_noise=kwargs.get("x_noise"), fused=kwargs.get("fused"))
+                                  x_noise=kwargs.get("x_noise"), fused=kwargs.get("fused"), x0_noise=kwargs.get("x0_noise"))
 
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
                       quantize_denoised=False, mask=None, x0=None, img_callback=None, log_every_t=100, temperature=1.,
                       noise_dropout=0., score_corrector=None, corrector_kwargs=None, unconditional_guidance_scale=1.,
-                      unconditional_conditioning=None, x_noise=None, fused=None):
+                      unconditional_conditioning=None, x_noise=None, fused=None, x0_noise=None):
+        """x_noise (S, B, C, H, W): the per-step noise of eta > 0 (the reference draws it inside the loop, util.py:264-267).
+        x0_noise (S, B, C, H, W): the noise of q_sample(x0, t) in the mask / x0 branch (ddim.py:144-147), drawn up front when None."""
         device = self.model.betas.device
         b = shape[0]
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device=device, dtype=torch.float32)
@@ -113,7 +115,12 @@ class DDIMSampler(object):
         intermediates = {"x_inter": [img], "pred_x0": [img]}
 
         cfg = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
-        plain = mask is None and score_corrector is None and not quantize_denoised and noise_dropout == 0.
+        if mask is not None:
+            assert x0 is not None
+            if x0_noise is None:
+                x0_noise = torch.randn((total_steps,) + tuple(shape), device=device)
+        # the known-region blend stays on the fused graph path (one more launch per step); with guidance it takes the general loop
+        plain = (mask is None or not cfg) and score_corrector is None and not quantize_denoised and noise_dropout == 0.
         can_fuse = plain and hasattr(self.model, "fused_sampler") and self.model.fused_sampler(cond) is not None
         if can_fuse and cfg:   # guidance runs as one [unconditional | conditional] 2B-batch step graph
             can_fuse = self.model.fused_sampler(cond).cfg_fusable(cond, unconditional_conditioning)
@@ -133,7 +140,8 @@ class DDIMSampler(object):
             img, intermediates = eng.run_ddim(img, cond, np.asarray(time_range), coef, x_noise if eta_on else None,
                                               log_every_t, callback, img_callback, intermediates,
                                               ucond=unconditional_conditioning if cfg else None,
-                                              cfg_scale=float(unconditional_guidance_scale) if cfg else None)
+                                              cfg_scale=float(unconditional_guidance_scale) if cfg else None,
+                                              mask=mask, x0=x0, x0_noise=x0_noise)
             return img, intermediates
 
         from upgpt_b200 import ops
@@ -141,10 +149,8 @@ class DDIMSampler(object):
         for i, step in enumerate(time_range):
             index = total_steps - i - 1
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
-            if mask is not None:
-                assert x0 is not None
-                img_orig = self.model.q_sample(x0, ts)
-                img = img_orig * mask + (1. - mask) * img
+            if mask is not None:     # img <- q_sample(x0, ts) * mask + (1 - mask) * img (ddim.py:144-147), one kernel
+                img = self.model.q_sample_blend(x0, ts, mask, img, noise=x0_noise[i])
             noise_i = None
             if eta_on:
                 noise_i = x_noise[i]
@@ -207,15 +213,12 @@ class DDIMSampler(object):
         if use_original_steps:
             sa, s1m = self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod
         else:
-            sa = torch.sqrt(torch.as_tensor(self.ddim_alphas, device=x0.device))
-            s1m = torch.as_tensor(self.ddim_sqrt_one_minus_alphas, device=x0.device)
+            sa = torch.sqrt(torch.as_tensor(self.ddim_alphas, dtype=torch.float32, device=x0.device))
+            s1m = torch.as_tensor(self.ddim_sqrt_one_minus_alphas, dtype=torch.float32, device=x0.device)
         if noise is None:
             noise = torch.randn_like(x0)
-        tt = t.reshape(-1)
-        assert bool((tt == tt[0]).all()), "stochastic_encode: one timestep per call on the CUDA path"
-        out = torch.empty_like(x0)
-        ops.axpby(x0.contiguous(), float(sa[tt[0]]), noise.contiguous(), float(s1m[tt[0]]), out)
-        return out
+        # t indexes the (DDIM-grid or original) alpha tables per sample, as extract_into_tensor does in the reference
+        return ops.qsample_blend(x0, noise, sa.contiguous(), s1m.contiguous(), t=t.reshape(-1))
 
     @torch.no_grad()
     def decode(self, x_latent, cond, t_start, unconditional_guidance_scale=1.0, unconditional_conditioning=None,
@@ -225,6 +228,16 @@ class DDIMSampler(object):
         timesteps = timesteps[:t_start]
         total_steps = timesteps.shape[0]
         coef = self._coef_rows(use_original_steps, 1.)
+        cfg = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+        eng = self.model.fused_sampler(cond) if hasattr(self.model, "fused_sampler") else None
+        if eng is not None and (not cfg or eng.cfg_fusable(cond, unconditional_conditioning)):
+            # the last t_start steps of the schedule as step-graph replays, like ddim_sampling's fused path
+            sig = coef[:total_steps, 2]
+            x_noise = torch.randn((total_steps,) + tuple(x_latent.shape), device=x_latent.device) if bool((sig != 0).any()) else None
+            x_dec, _ = eng.run_ddim(x_latent.to(torch.float32), cond, np.flip(timesteps), coef[:total_steps], x_noise, 10 ** 9, None, None,
+                                    {"x_inter": [], "pred_x0": []}, ucond=unconditional_conditioning if cfg else None,
+                                    cfg_scale=float(unconditional_guidance_scale) if cfg else None)
+            return x_dec
         x_dec = x_latent
         for i, step in enumerate(np.flip(timesteps)):
             index = total_steps - i - 1

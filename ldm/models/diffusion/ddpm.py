@@ -204,9 +204,18 @@ class DDPM(nn.Module):
                 extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape))
 
     def q_sample(self, x_start, t, noise=None):
+        """sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise with a per-sample t (ddpm.py:281-284): one upgpt_qsample_blend launch."""
         noise = default(noise, lambda: torch.randn_like(x_start))
-        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
-                extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+        if not x_start.is_cuda:
+            raise RuntimeError("upgpt_b200: q_sample runs on the CUDA extension only (no CPU fallback)")
+        from upgpt_b200 import ops
+        return ops.qsample_blend(x_start, noise, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, t=t)
+
+    def q_sample_blend(self, x0, t, mask, img, noise=None):
+        """img_orig * mask + (1 - mask) * img with img_orig = q_sample(x0, t) (ddim.py:144-147, ddpm.py:1281-1284), fused."""
+        from upgpt_b200 import ops
+        noise = default(noise, lambda: torch.randn_like(x0))
+        return ops.qsample_blend(x0, noise, self.sqrt_alphas_cumprod, self.sqrt_one_minus_alphas_cumprod, t=t, mask=mask, img=img)
 
     def get_input(self, batch, k):
         x = batch[k]
@@ -425,8 +434,7 @@ class LatentDiffusion(DDPM):
                 ts = torch.full((shape[0],), i, device=device, dtype=torch.long)
                 img = self.p_sample(img, cond, ts, clip_denoised=self.clip_denoised)
                 if mask is not None:
-                    img_orig = self.q_sample(x0, ts)
-                    img = img_orig * mask + (1. - mask) * img
+                    img = self.q_sample_blend(x0, ts, mask, img)
                 if i % log_every_t == 0 or i == timesteps - 1:
                     inter["x_inter"].append(img)
                 if callback:

@@ -290,20 +290,41 @@ def ddim_step(x, e_t, a_t, a_prev, sigma_t, sqrt_one_minus_at, noise=None, tempe
     return a_prev.sqrt() * pred_x0 + dir_xt + nz, pred_x0
 
 
-def ddim_sample(apply_model, x_T, S, eta, sched, noises=None, temperature=1., return_all=False):
-    """DDIMSampler.ddim_sampling loop (ddim.py:114-163). apply_model(x, t) -> eps. noises: (S,B,C,H,W) indexed by loop i."""
+def q_sample(x_start, t, sched, noise):
+    """DDPM.q_sample (ddpm.py:281-284): sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise, per-sample t."""
+    ex = lambda a: a[t].reshape(-1, 1, 1, 1)
+    return ex(sched["sqrt_alphas_cumprod"]) * x_start + ex(sched["sqrt_one_minus_alphas_cumprod"]) * noise
+
+
+def ddim_sample(apply_model, x_T, S, eta, sched, noises=None, temperature=1., return_all=False, mask=None, x0=None, q_noises=None,
+                t_start=None):
+    """DDIMSampler.ddim_sampling loop (ddim.py:114-163). apply_model(x, t) -> eps. noises: (S,B,C,H,W) indexed by loop i.
+    mask / x0 (ddim.py:144-147): before every step img <- q_sample(x0, t) * mask + (1 - mask) * img, q_sample's noise = q_noises[i].
+    t_start: DDIMSampler.decode (ddim.py:223-240) -- only the first t_start timesteps of the schedule, i.e. the LAST t_start steps."""
     ts, alphas, alphas_prev, sigmas, s1m = ddim_schedule(sched["alphas_cumprod"], S, eta, sched["betas"].shape[0])
+    if t_start is not None:
+        ts = ts[:t_start]
     img, b = x_T, x_T.shape[0]
     traj = []
     for i, step in enumerate(np.flip(ts)):
         index = len(ts) - i - 1
         t = torch.full((b,), int(step), dtype=torch.long)
+        if mask is not None:
+            img = q_sample(x0, t, sched, q_noises[i]) * mask + (1. - mask) * img
         e_t = apply_model(img, t)
         img, pred_x0 = ddim_step(img, e_t, alphas[index], alphas_prev[index], sigmas[index], s1m[index],
                                  None if noises is None else noises[i], temperature)
         if return_all:
             traj.append(img)
     return (img, traj) if return_all else img
+
+
+def stochastic_encode(x0, t_index, S, sched, noise):
+    """DDIMSampler.stochastic_encode (ddim.py:207-221) on the DDIM grid: t_index (B,) indexes ddim_alphas."""
+    ts, alphas, _, _, s1m = ddim_schedule(sched["alphas_cumprod"], S, 0.0, sched["betas"].shape[0])
+    sa = torch.sqrt(alphas)[t_index].reshape(-1, 1, 1, 1)
+    sm = torch.as_tensor(s1m)[t_index].reshape(-1, 1, 1, 1)
+    return sa * x0 + sm * noise
 
 
 def ddpm_step(x, e_t, t, sched, noise):

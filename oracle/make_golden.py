@@ -81,6 +81,11 @@ def main():
             with torch.no_grad():
                 return m_tiny(torch.cat([x, self.mask], 1), t, self.ctx)
 
+        def q_sample(self, x_start, t, noise=None):      # DDPM.q_sample (ddpm.py:281-284) with injected noise (mask / x0 path)
+            noise = next(self.q_noise) if noise is None else noise
+            e = lambda a: a[t].reshape(-1, 1, 1, 1)
+            return e(sched["sqrt_alphas_cumprod"]) * x_start + e(sched["sqrt_one_minus_alphas_cumprod"]) * noise
+
     x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, 0)
     shim = Shim(mask, ctx)
     for S, eta in ((50, 0.0), (10, 1.0)):
@@ -105,6 +110,37 @@ def main():
         out[f"ddim_S{S}_eta{int(eta)}_alphas"] = np.asarray(sampler.ddim_alphas, dtype=np.float64)
         out[f"ddim_S{S}_eta{int(eta)}_alphas_prev"] = np.asarray(sampler.ddim_alphas_prev, dtype=np.float64)
         out[f"ddim_S{S}_eta{int(eta)}_sigmas"] = np.asarray(sampler.ddim_sigmas, dtype=np.float64)
+
+    # ---- DDIM mask / x0 blending (ddim.py:144-147), stochastic_encode -> decode (ddim.py:207-240): reference DDIMSampler, S = 10 ----
+    g = torch.Generator().manual_seed(321)
+    S = 10
+    x0 = torch.randn(*x.shape, generator=g) * 0.8
+    keep = (torch.rand(2, 1, 16, 16, generator=g) > 0.5).float()          # 1 = keep the known latent x0, 0 = generate
+    q_noises = torch.randn(S, *x.shape, generator=g)
+    shim.q_noise = iter(q_noises)
+    # p_sample_ddim always calls noise_like (times sigma = 0 here): the iterator injected above for the eta = 1 case is exhausted
+    ref.DDIMSampler.make_schedule.__globals__["noise_like"] = lambda shape, device, repeat=False: torch.zeros(shape)
+    sampler = ref.DDIMSampler(shim)
+    with torch.no_grad():
+        samples, _ = sampler.sample(S, 2, (4, 16, 16), conditioning=None, eta=0.0, x_T=x, mask=keep, x0=x0, verbose=False)
+        apply = lambda xx, tt: O.unet_forward(sd_tiny, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, ctx)
+        mine = O.ddim_sample(apply, x, S, 0.0, sched, mask=keep, x0=x0, q_noises=q_noises)
+    e = relerr(mine, samples)
+    print(f"[ddim mask/x0 S={S}] oracle-vs-reference max-rel={e:.2e}")
+    assert e < 1e-4
+    out["ddim_mask_S10_x0"] = samples.numpy()
+    enc_noise = torch.randn(*x.shape, generator=g)
+    t_enc = 6
+    with torch.no_grad():
+        z_enc = sampler.stochastic_encode(x0, torch.tensor([t_enc] * 2), noise=enc_noise)
+        z_dec = sampler.decode(z_enc, None, t_enc)
+        mine_enc = O.stochastic_encode(x0, torch.tensor([t_enc] * 2), S, sched, enc_noise)
+        mine_dec = O.ddim_sample(apply, mine_enc, S, 0.0, sched, t_start=t_enc)
+    e1, e2 = relerr(mine_enc, z_enc), relerr(mine_dec, z_dec)
+    print(f"[ddim stochastic_encode t={t_enc} -> decode] oracle-vs-reference max-rel={e1:.2e} / {e2:.2e}")
+    assert e1 < 1e-5 and e2 < 1e-4
+    out["ddim_encode_S10_t6"] = z_enc.numpy()
+    out["ddim_decode_S10_t6"] = z_dec.numpy()
 
     # ---- PLMS ('next' row 8(f)-3): reference PLMSSampler over the tiny U-Net, S = 10 (exercises all four multistep orders) ----
     sampler = ref.PLMSSampler(shim)

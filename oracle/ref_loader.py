@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *real* reference modules (soon-yau/upgpt @ /root/reference).
 
-Only usable inside the build container (the GPU box has no /root/reference).  Used by
-oracle/make_golden.py to (1) validate the CPU restatement in oracle/ldm_oracle.py and (2) generate
-the committed golden vectors under tests/golden/.  Never imported by the product package.
+Used by oracle/make_golden.py (build container) to (1) validate the CPU restatement in oracle/ldm_oracle.py and (2) generate the
+committed golden vectors under tests/golden/, and by `bench.py --impl reference` to time the reference's own code on the host cores
+(on the GPU box from the unmodified copy oracle/vendor_reference.py leaves under the git-ignored baseline/_ref/).  Never imported by
+the product package.
 
 Shims:
   * omegaconf is absent -> stub `omegaconf.listconfig.ListConfig` (openaimodel.py:476 imports it)
@@ -12,7 +13,9 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("UPGPT_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_VENDORED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")      # oracle/vendor_reference.py (git-ignored, travels with gpurun)
+REF_ROOT = os.environ.get("UPGPT_REFERENCE") or ("/root/reference" if os.path.isdir("/root/reference/ldm") else _VENDORED)
 
 
 def available() -> bool:

@@ -107,3 +107,31 @@ def test_ddpm_step_closed_form():
     xt = sched["sqrt_alphas_cumprod"][t].reshape(-1, 1, 1, 1) * x0 + sched["sqrt_one_minus_alphas_cumprod"][t].reshape(-1, 1, 1, 1) * eps
     x_prev, x0_hat = O.ddpm_step(xt, eps, t, sched, torch.zeros_like(xt))
     assert relerr(x0_hat, x0) < 1e-4
+
+
+def _mask_case():
+    """The inputs oracle/make_golden.py drew for the mask / x0 and stochastic_encode -> decode cases (generator seed 321)."""
+    g = torch.Generator().manual_seed(321)
+    x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, 0)
+    x0 = torch.randn(*x.shape, generator=g) * 0.8
+    keep = (torch.rand(2, 1, 16, 16, generator=g) > 0.5).float()
+    q_noises = torch.randn(10, *x.shape, generator=g)
+    enc_noise = torch.randn(*x.shape, generator=g)
+    return x, mask, ctx, x0, keep, q_noises, enc_noise
+
+
+def test_ddim_mask_blend_and_encode_decode_match_reference_golden(golden):
+    """ddim.py:144-147 (img <- q_sample(x0, t) * mask + (1 - mask) * img before every step) and ddim.py:207-240 (stochastic_encode on
+    the DDIM grid, decode = the last t_start steps) vs the reference DDIMSampler's own outputs."""
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    sd = synth.synth_state_dict(UNetModel(**TINY_UNET_KW).state_dict(), 0)
+    x, mask, ctx, x0, keep, q_noises, enc_noise = _mask_case()
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    apply = lambda xx, tt: O.unet_forward(sd, TINY_UNET_KW, torch.cat([xx, mask], 1), tt, ctx)
+    with torch.no_grad():
+        got = O.ddim_sample(apply, x, 10, 0.0, sched, mask=keep, x0=x0, q_noises=q_noises)
+        enc = O.stochastic_encode(x0, torch.tensor([6, 6]), 10, sched, enc_noise)
+        dec = O.ddim_sample(apply, enc, 10, 0.0, sched, t_start=6)
+    assert relerr(got, torch.from_numpy(golden["ddim_mask_S10_x0"])) < 1e-4
+    assert relerr(enc, torch.from_numpy(golden["ddim_encode_S10_t6"])) < 1e-6
+    assert relerr(dec, torch.from_numpy(golden["ddim_decode_S10_t6"])) < 1e-4

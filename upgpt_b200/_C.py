@@ -108,6 +108,7 @@ _PROTOS = {
     "upgpt_ddpm_step": [_vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp, _ll, _vp],
     "upgpt_step_state": [_vp, _i, _i, _vp, _i, _vp, _vp],
     "upgpt_axpby": [_vp, _f, _vp, _f, _vp, _ll, _vp],
+    "upgpt_qsample_blend": [_vp, _vp, _ll, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "upgpt_gather_step_row": [_vp, _ll, _vp, _vp, _i, _i, _vp],
     "upgpt_to_uint8_nhwc": [_vp, _i, _i, _i, _vp, _vp],
     "upgpt_embed_tokens": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp],

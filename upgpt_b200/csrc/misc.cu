@@ -394,6 +394,51 @@ extern "C" int upgpt_lincomb4(const float* a, float wa, const float* b, float wb
   return 0;
 }
 
+// q_sample (+ mask blend): out = q * m + (1 - m) * img with q = sqrt(acp[t]) x0 + sqrt(1 - acp[t]) noise (ddpm.py:281-284, the
+// known-region blend of ddim.py:144-147 / ddpm.py:1281-1284); mask == NULL: out = q (q_sample, stochastic_encode ddim.py:207-221).
+// t per sample (t_per_sample), or one t for the batch read from t_table[*step_ptr] (device-side step counter: graph replays need no
+// host data), or t_imm. noise is indexed + step * noise_step_stride (a [S][B][C][HW] table) when the step counter is used.
+namespace upgpt {
+__global__ void __launch_bounds__(256)
+qsample_blend_kernel(const float* __restrict__ x0, const float* __restrict__ noise, long long noise_step_stride, const float* __restrict__ mask,
+                     int mask_c, const float* __restrict__ img, float* __restrict__ out, const float* __restrict__ sqrt_acp,
+                     const float* __restrict__ sqrt_1m_acp, const long long* __restrict__ t_per_sample, const long long* __restrict__ t_table,
+                     const int* __restrict__ step_ptr, int t_imm, int C, int HW, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step = step_ptr ? *step_ptr : 0;
+  const long long t_all = t_table ? t_table[step] : (long long)t_imm;
+  const float* nz = noise + (step_ptr ? (size_t)step * (size_t)noise_step_stride : 0);
+  const size_t chw = (size_t)C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / chw, r = i - b * chw;
+    const long long t = t_per_sample ? t_per_sample[b] : t_all;
+    const float q = sqrt_acp[t] * x0[i] + sqrt_1m_acp[t] * nz[i];
+    if (mask) {
+      const float m = mask[mask_c == 1 ? b * HW + (r % HW) : i];
+      out[i] = q * m + (1.f - m) * img[i];
+    } else {
+      out[i] = q;
+    }
+  }
+}
+}  // namespace upgpt
+
+extern "C" int upgpt_qsample_blend(const float* x0, const float* noise, long long noise_step_stride, const float* mask, int mask_c,
+                                   const float* img, float* out, const float* sqrt_acp, const float* sqrt_1m_acp,
+                                   const long long* t_per_sample, const long long* t_table, const int* step_ptr, int t_imm, int B, int C,
+                                   int HW, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(x0 && noise && out && sqrt_acp && sqrt_1m_acp && B > 0 && C > 0 && HW > 0, "qsample_blend: bad args");
+  UPGPT_REQUIRE(!mask || (img && (mask_c == 1 || mask_c == C)), "qsample_blend: mask needs img and 1 or C mask channels");
+  const size_t n = (size_t)B * C * HW;
+  UPGPT_CHECK_CUDA(launch_k(qsample_blend_kernel, dim3(ew_grid(n)), dim3(256), 0, stream, x0, noise, noise_step_stride, mask, mask_c, img, out,
+                            sqrt_acp, sqrt_1m_acp, t_per_sample, t_table, step_ptr, t_imm, C, HW, n));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * noise) * out_scale from NCHW moments [B][2C][HW] = {mean | logvar}
 // (DiagonalGaussianDistribution.sample / .mode, distributions.py:24-37; x scale_factor of get_first_stage_encoding, ddpm.py:569-576)
 namespace upgpt {

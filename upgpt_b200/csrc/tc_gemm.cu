@@ -352,6 +352,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_4d(rbuf, &tmR, rbar, nt * p.block_n + grp * 32, oc1, oc2, oc3);
         }
       }
+      if (p.flags & GEMM_GEGLU) {     // (filled while the main loop is still running; read after the group barrier below)
+        for (int i = r; i < p.block_n; i += 128) {
+          const int n = nt * p.block_n + i;
+          bias_g[i] = bs ? bs[n] : 0.f;
+          lns_g[i] = ln ? p.ln_colsum[n] : 0.f;
+        }
+      }
 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
@@ -581,6 +588,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // tile columns are [x (half) | gate (half)]; out16[:, nt*half + j] = (x + bx) * gelu(gate + bg)
         const int half_n = p.block_n >> 1;
         bool first = true;
+        // this tile's bias (and, with a folded LayerNorm, column sums) staged once in shared memory: the per-element global loads
+        // of the inner loop made this epilogue -- which already bounds the GEGLU projections -- a third slower
+        named_bar_sync(gbar, 128);
+        const float ln_ms = ln_mu * ln_rs;         // D = rstd acc - (mean rstd) colsum + bias; rstd = 1, mean = 0 without a folded LayerNorm
         for (int j0 = grp * 32; j0 < half_n; j0 += 64) {
           const int ncols = min(32, half_n - j0);
           float f[32];
@@ -589,17 +600,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld16(t_acc + (uint32_t)(j0 + h0), xr);
             tmem_ld16(t_acc + (uint32_t)(half_n + j0 + h0), gr_);
             tmem_ld_wait();
-            const int ncol_x = nt * p.block_n + j0 + h0;
-            const int ncol_g = ncol_x + half_n;
+            const int cx = j0 + h0, cg = cx + half_n;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              float xa = __uint_as_float(xr[i]), ga = __uint_as_float(gr_[i]);
+              float xv, gv;
               if (ln) {
-                xa = ln_rs * fmaf(-ln_mu, p.ln_colsum[ncol_x + i], xa);
-                ga = ln_rs * fmaf(-ln_mu, p.ln_colsum[ncol_g + i], ga);
+                xv = fmaf(ln_rs, __uint_as_float(xr[i]), fmaf(-ln_ms, lns_g[cx + i], bias_g[cx + i]));
+                gv = fmaf(ln_rs, __uint_as_float(gr_[i]), fmaf(-ln_ms, lns_g[cg + i], bias_g[cg + i]));
+              } else {
+                xv = __uint_as_float(xr[i]) + bias_g[cx + i];
+                gv = __uint_as_float(gr_[i]) + bias_g[cg + i];
               }
-              const float xv = xa + (bs ? bs[ncol_x + i] : 0.f);
-              const float gv = ga + (bs ? bs[ncol_g + i] : 0.f);
               f[h0 + i] = xv * gelu_erf_f(gv);
             }
           }

@@ -130,6 +130,31 @@ def axpby(a, sa, b, sb, out):
     _C.check(_C.lib().upgpt_axpby(_p(a), float(sa), _p(b), float(sb), _p(out), a.numel(), stream()), "upgpt_axpby")
 
 
+def qsample_blend(x0, noise, sqrt_acp, sqrt_1m_acp, t=None, t_imm=0, mask=None, img=None, out=None, t_table=None, step_ptr=None,
+                  noise_step_stride=0):
+    """out = q (* mask + (1 - mask) * img) with q = sqrt_acp[t] x0 + sqrt_1m_acp[t] noise (upgpt_qsample_blend). t: (B,) int64 tensor,
+    or (t_table, step_ptr) for the sampler graphs, or the immediate t_imm."""
+    x0 = _req(x0.contiguous().float(), torch.float32, "x0")
+    B, Cc = x0.shape[0], x0.shape[1]
+    HW = x0.numel() // (B * Cc)
+    noise = _req(noise.contiguous().float(), torch.float32, "noise")
+    if out is None:
+        out = torch.empty_like(x0)
+    mask_c = 0
+    if mask is not None:
+        mask = _req(mask.contiguous().float(), torch.float32, "mask")
+        mask_c = mask.shape[1]
+        if mask.shape[0] != B:
+            mask = mask.expand(B, *mask.shape[1:]).contiguous()
+        img = _req(img.contiguous().float(), torch.float32, "img")
+    if t is not None:
+        t = _req(t.to(device=x0.device, dtype=torch.int64).contiguous(), torch.int64, "t")
+    _C.check(_C.lib().upgpt_qsample_blend(_p(x0), _p(noise), int(noise_step_stride), _p(mask), mask_c, _p(img), _p(out), _p(sqrt_acp),
+                                          _p(sqrt_1m_acp), _p(t), _p(t_table), _p(step_ptr), int(t_imm), B, Cc, HW, stream()),
+             "upgpt_qsample_blend")
+    return out
+
+
 def softmax_rows(x, n, scale, out16):
     rows = x.numel() // x.shape[-1]
     _C.check(_C.lib().upgpt_softmax_rows(_p(x), x.shape[-1], rows, n, float(scale), _p(out16), out16.shape[-1], stream()),

@@ -102,13 +102,14 @@ class FusedSampler:
             self._emb_tables[key] = tab
         return tab
 
-    def _step_graph(self, eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale=None):
+    def _step_graph(self, eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale=None, blend=None):
         """kind: 'ddim' | 'ddpm'; noise_mode: 0 none, 1 per-step buffer refreshed by the host loop, 2 strided table.
         cfg_scale: classifier-free guidance -- the engine batch is [unconditional | conditional]; after the U-Net pass
         eps[:B] <- s*eps_c + (1-s)*eps_u, the update runs on the first half of the latent and is mirrored into the second."""
         # weights are re-packed IN PLACE (upgpt_b200/host.py), so a captured graph stays valid across weight versions: the key holds
         # addresses only (the timestep-embedding table, whose VALUES depend on the weights, is keyed on the version in _emb_table)
-        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), emb_tab.data_ptr(), cfg_scale)
+        key = (id(eng), kind, noise_mode, 0 if noise_buf is None else noise_buf.data_ptr(), emb_tab.data_ptr(), cfg_scale,
+               None if blend is None else tuple(t.data_ptr() for t in blend))
         g = self._graphs.get(key)
         if g is not None:
             return g
@@ -129,6 +130,14 @@ class FusedSampler:
 
         def body():
             s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if blend is not None:
+                # known-region blend in front of the step (ddim.py:144-147): x <- q_sample(x0, t) * mask + (1 - mask) * x, with t and this
+                # step's q_sample noise found through the device-side step counter
+                bx0, bnoise, bmask, sa, s1m = blend
+                Bn, Cn = x.shape[0], x.shape[1]
+                _C.check(L.upgpt_qsample_blend(bx0.data_ptr(), bnoise.data_ptr(), n, bmask.data_ptr(), bmask.shape[1], x.data_ptr(), x.data_ptr(),
+                                               sa.data_ptr(), s1m.data_ptr(), 0, b["s_ttable"].data_ptr(), b["s_step"].data_ptr(), 0, Bn, Cn,
+                                               x.numel() // (Bn * Cn), s), "qsample_blend")
             # this step's timestep-embedding rows from the per-schedule table (replaces 4 launches + 43 MB of fp32 weights per step)
             _C.check(L.upgpt_gather_step_row(emb_tab.data_ptr(), emb_tab.shape[1], b["s_step"].data_ptr(), b["emb_all"].data_ptr(),
                                              x.shape[0], emb_tab.shape[1], s), "gather_step_row")
@@ -152,7 +161,7 @@ class FusedSampler:
         self._graphs[key] = g
         return g
 
-    def _loop(self, eng, kind, S, t_loop, coef_loop, x_noise, log_idx, callback, img_callback, intermediates, cfg_scale=None):
+    def _loop(self, eng, kind, S, t_loop, coef_loop, x_noise, log_idx, callback, img_callback, intermediates, cfg_scale=None, blend=None):
         b = eng.bufs
         cfg = cfg_scale is not None
         nB = b["x_lat"].shape[0] // 2 if cfg else b["x_lat"].shape[0]
@@ -177,7 +186,17 @@ class FusedSampler:
         x_saved = b["x_lat"].clone()
         emb_tab = self._emb_table(eng, t_loop)
         ops.step_state(b["s_step"], 0, 0)
-        g = self._step_graph(eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale)   # warm-up run inside mutates x_lat / step: restore
+        if blend is not None:
+            bx0, bnoise, bmask = blend
+            shp = tuple(b["x_lat"].shape)
+            if tuple(bnoise.shape) != (S,) + shp or tuple(bx0.shape) != shp or bmask.shape[1] not in (1, shp[1]):
+                raise ValueError("mask / x0 blend: x0 %s, x0_noise (S,)+%s and mask (B, 1|C, H, W) expected, got %s / %s / %s"
+                                 % (shp, shp, tuple(bx0.shape), tuple(bnoise.shape), tuple(bmask.shape)))
+            m = self.model
+            blend = (bx0.contiguous().float(), bnoise.contiguous().float(), bmask.expand(shp[0], *bmask.shape[1:]).contiguous().float(),
+                     m.sqrt_alphas_cumprod.contiguous(), m.sqrt_one_minus_alphas_cumprod.contiguous())
+            self._blend_ref = blend       # the graph bakes these addresses: keep the tensors alive with the sampler
+        g = self._step_graph(eng, kind, noise_mode, noise_buf, emb_tab, cfg_scale, blend)   # warm-up run inside mutates x_lat / step: restore
         b["x_lat"].copy_(x_saved)
         ops.step_state(b["s_step"], 0, 0)
         for i in range(S):
@@ -195,13 +214,17 @@ class FusedSampler:
 
     # ---- DDIM (ddim.py:114-163) ----
     def run_ddim(self, x_T, cond, time_range, coef_by_index, x_noise, log_every_t, callback, img_callback, intermediates,
-                 ucond=None, cfg_scale=None):
+                 ucond=None, cfg_scale=None, mask=None, x0=None, x0_noise=None):
         eng = self._prepare(x_T, cond, ucond)
         S = len(time_range)
         coef_loop = coef_by_index[:S].flip(0).contiguous()     # loop i uses index S-1-i
         log_idx = {i for i in range(S) if (S - i - 1) % log_every_t == 0 or (S - i - 1) == S - 1}
+        blend = None
+        if mask is not None:
+            assert ucond is None, "the known-region blend with guidance runs on the general loop"
+            blend = (x0, x0_noise, mask)
         return self._loop(eng, "ddim", S, np.asarray(time_range), coef_loop, x_noise, log_idx, callback, img_callback, intermediates,
-                          cfg_scale if ucond is not None else None)
+                          cfg_scale if ucond is not None else None, blend)
 
     # ---- DDPM ancestral (ddpm.py:1244-1292) ----
     def run_ddpm(self, x_T, cond, timesteps, coef_by_t, x_noise, log_every_t, callback, img_callback, intermediates):
