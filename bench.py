@@ -115,74 +115,131 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------- CPU arm
+def _reference_modules(cfg):
+    """The reference's own hot path on the CPU: (kind, unet_step(x) -> x', decode(z) -> image, full(x) -> image).
+    kind "reference": the UNMODIFIED reference modules (UNetModel, DDIMSampler, Decoder of soon-yau/upgpt, from /root/reference or
+    its vendored copy baseline/_ref, oracle/vendor_reference.py) driven through DDIMSampler.sample / p_sample_ddim.
+    kind "port": the oracle's functional restatement (oracle/ldm_oracle.py) when the reference files are not present."""
+    import torch
+    from oracle import ldm_oracle as O
+    from oracle import ref_loader
+    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+    from upgpt_b200 import synth
+    wl = WORKLOADS[cfg]
+    B, lat = wl["B"], wl["lat"]
+    x, mask, ctx = synth.synth_inputs(B, lat, lat, CTX_LEN, CTX_DIM, 0)
+    sched = O.register_schedule(1000, 0.00085, 0.012)
+    if ref_loader.available():
+        ref = ref_loader.load_reference()
+        torch.manual_seed(0)
+        unet = ref.UNetModel(**BBOX_UNET_KW).eval()
+        unet.load_state_dict(synth.synth_state_dict(unet.state_dict(), 0))
+        dec = ref.Decoder(**BBOX_VAE_KW).eval()
+        pq = torch.nn.Conv2d(4, 4, 1)
+        full_sd = {("decoder." + k): v for k, v in dec.state_dict().items()}
+        full_sd.update({("post_quant_conv." + k): v for k, v in pq.state_dict().items()})
+        vsd = synth.synth_state_dict(full_sd, 0)
+        dec.load_state_dict({k[len("decoder."):]: v for k, v in vsd.items() if k.startswith("decoder.")})
+        pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in vsd.items() if k.startswith("post_quant_conv.")})
+
+        class Shim:      # the duck-typed `model` the reference DDIMSampler drives (LatentDiffusion's surface, ddpm.py:962,1567-1570)
+            num_timesteps = 1000
+            betas, alphas_cumprod, alphas_cumprod_prev = sched["betas"], sched["alphas_cumprod"], sched["alphas_cumprod_prev"]
+            device = torch.device("cpu")
+            parameterization = "eps"
+
+            def apply_model(self, xx, t, c):
+                return unet(torch.cat([xx, mask[:xx.shape[0]]], 1), t, context=ctx[:xx.shape[0]])
+
+        sampler = ref.DDIMSampler(Shim())
+        sampler.make_schedule(ddim_num_steps=DDIM_STEPS, ddim_eta=1.0, verbose=False)
+
+        def unet_step(xx):       # one iteration of ddim_sampling's loop (ddim.py:140-161) at the middle of the schedule
+            ts = torch.full((xx.shape[0],), int(sampler.ddim_timesteps[25]), dtype=torch.long)
+            return sampler.p_sample_ddim(xx, None, ts, index=25)[0]
+
+        def decode(z):           # AutoencoderKL.decode (autoencoder.py:330-333) after decode_first_stage's 1 / scale_factor (ddpm.py:779)
+            return dec(pq(z / 0.18215))
+
+        def full(xx):
+            z, _ = sampler.sample(DDIM_STEPS, xx.shape[0], tuple(xx.shape[1:]), conditioning=None, eta=1.0, x_T=xx, verbose=False)
+            return decode(z)
+
+        return "reference", x, unet_step, decode, full
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.models.autoencoder import AutoencoderKL
+    unet = UNetModel(**BBOX_UNET_KW); sd_u = synth.synth_state_dict(unet.state_dict(), 0); del unet
+    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4); sd_v = synth.synth_state_dict(ae.state_dict(), 0); del ae
+    t = torch.full((B,), 501, dtype=torch.long)
+
+    def unet_step(xx):
+        e = O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([xx, mask[:xx.shape[0]]], 1), t[:xx.shape[0]], ctx[:xx.shape[0]])
+        ts, al, alp, sg, s1m = O.ddim_schedule(sched["alphas_cumprod"], DDIM_STEPS, 1.0)
+        return O.ddim_step(xx, e, al[25], alp[25], sg[25], s1m[25], torch.randn_like(xx))[0]
+
+    def decode(z):
+        return O.decode_first_stage(sd_v, BBOX_VAE_KW, z, 0.18215)
+
+    def full(xx):
+        z = O.ddim_sample(lambda a, tt: O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([a, mask], 1), tt, ctx), xx, DDIM_STEPS, 1.0, sched,
+                          torch.randn(DDIM_STEPS, *xx.shape))
+        return decode(z)
+
+    return "port", x, unet_step, decode, full
+
+
+def _cpu_sample(cfg, warmup, steps, full_job):
+    """Times the reference's CPU path: bounded samples (1 denoising step at the config's batch + 1 single-image decode, scaled to the
+    full job), or with full_job ONE complete 50-step + batch decode. -> (kind, cores, value img/s, actual seconds per bench step, note)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kind, x, unet_step, decode, full = _reference_modules(cfg)
+    wl = WORKLOADS[cfg]
+    B, n_img = wl["B"], wl["B"] * wl["keyframes"]
+    with torch.no_grad():
+        if full_job:
+            t0 = time.perf_counter(); full(x); dt = time.perf_counter() - t0
+            dt_job = dt * wl["keyframes"]
+            return kind, cores, n_img / dt_job, dt, ("ONE complete job measured: %d-step DDIM at B=%d + decode of the batch in %.1f s"
+                                                     % (DDIM_STEPS, B, dt)) + (" (x%d keyframes)" % wl["keyframes"] if wl["keyframes"] > 1 else ""), False
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter(); unet_step(x); tu = time.perf_counter() - t0
+            t0 = time.perf_counter(); decode(x[:1]); tv = time.perf_counter() - t0
+            if i >= warmup:
+                times.append((tu, tv))
+    tu = sum(a for a, _ in times) / len(times)
+    tv = sum(b for _, b in times) / len(times)
+    t_job = wl["keyframes"] * (DDIM_STEPS * tu + B * tv)
+    note = ("bounded sample per bench step: 1 denoising step at B=%d (%.2f s) + 1 single-image VAE decode (%.2f s); value = images of the "
+            "full job / (%d keyframe(s) x (50 x step + %d x decode)) -- EXTRAPOLATED, `python bench.py --impl reference --full` measures one "
+            "complete job" % (B, tu, tv, wl["keyframes"], B))
+    return kind, cores, n_img / t_job, tu + tv, note, True
+
+
 def cpu_reference_arm(args, rank):
-    """--impl reference: the reference's algorithm (oracle port of its PyTorch fp32 path) on the host cores.
-    Each 'step' is a bounded sample of the workload: ONE U-Net denoising step at B=8 plus ONE single-image VAE decode,
-    extrapolated to images/s of the full 50-step + decode job."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     import torch
-    from oracle import ldm_oracle as O
-    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
-    from upgpt_b200 import synth
-    from ldm.modules.diffusionmodules.openaimodel import UNetModel
-    from ldm.models.autoencoder import AutoencoderKL
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    unet = UNetModel(**BBOX_UNET_KW)
-    sd_u = synth.synth_state_dict(unet.state_dict(), 0)
-    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4)
-    sd_v = synth.synth_state_dict(ae.state_dict(), 0)
-    del unet, ae
-    x, mask, ctx = synth.synth_inputs(B_PER_GPU, LAT, LAT, CTX_LEN, CTX_DIM, 0)
-    t = torch.full((B_PER_GPU,), 501, dtype=torch.long)
-    times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx)
-            t_unet = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            O.decode_first_stage(sd_v, BBOX_VAE_KW, x[:1], 0.18215)
-            t_vae = time.perf_counter() - t0
-            if i >= args.warmup:
-                times.append((t_unet, t_vae))
-    tu = sum(a for a, _ in times) / len(times)
-    tv = sum(b for _, b in times) / len(times)
-    t_batch = DDIM_STEPS * tu + B_PER_GPU * tv
-    val = B_PER_GPU / t_batch
-    sample = "1 U-Net step at B=8 (%.2f s) + 1 single-image VAE decode (%.2f s) per bench step; extrapolated x50 steps, x8 decodes" % (tu, tv)
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    kind, cores, val, sec_per_step, note, extrap = _cpu_sample(args.config, args.warmup, args.steps, args.full)
+    wl = WORKLOADS[args.config]
+    line = {"impl": "reference", "metric": wl["metric"], "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "bbox.yaml U-Net 32x32x4 latent, 87x768 context, 50-step DDIM, bs=8, + KL-f8 decode to 256x256",
-                       "host": "CPU, torch %s, %d threads" % (torch.__version__, cores)},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": workload_string(args.config, args.eta), "host": "CPU, torch %s, %d threads" % (torch.__version__, cores),
+                       "extrapolated": extrap, "ms_per_step_is": "wall time of one bench step as run (the bounded sample, or the complete job with --full)",
+                       "implementation": "unmodified reference modules (UNetModel / DDIMSampler / Decoder)" if kind == "reference" else "oracle port"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": note},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_quick():
-    """cpu_baseline for the b200 arm (rank 0, N=1): ~10-30 s of oracle work on the host cores."""
-    import torch
-    from oracle import ldm_oracle as O
-    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
-    from upgpt_b200 import synth
-    from ldm.modules.diffusionmodules.openaimodel import UNetModel
-    from ldm.models.autoencoder import AutoencoderKL
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    unet = UNetModel(**BBOX_UNET_KW); sd_u = synth.synth_state_dict(unet.state_dict(), 0); del unet
-    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4); sd_v = synth.synth_state_dict(ae.state_dict(), 0); del ae
-    x, mask, ctx = synth.synth_inputs(B_PER_GPU, LAT, LAT, CTX_LEN, CTX_DIM, 0)
-    t = torch.full((B_PER_GPU,), 501, dtype=torch.long)
-    with torch.no_grad():
-        O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x[:1], mask[:1]], 1), t[:1], ctx[:1])   # warm-up
-        t0 = time.perf_counter(); O.unet_forward(sd_u, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx); tu = time.perf_counter() - t0
-        t0 = time.perf_counter(); O.decode_first_stage(sd_v, BBOX_VAE_KW, x[:1], 0.18215); tv = time.perf_counter() - t0
-    val = B_PER_GPU / (DDIM_STEPS * tu + B_PER_GPU * tv)
-    return {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "1 U-Net step at B=8 (%.2f s) + 1 single-image VAE decode (%.2f s), extrapolated to 50 steps + 8 decodes" % (tu, tv)}
+def cpu_baseline_quick(cfg="c2"):
+    """cpu_baseline for the b200 arm (rank 0, N=1): ~10-30 s of the reference's CPU path on the host cores."""
+    kind, cores, val, _, note, _ = _cpu_sample(cfg, 1, 1, False)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": note}
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU arm
@@ -273,13 +330,13 @@ def roofline_hbm_kernel(dev, pk):
 
 
 def roofline_attention(dev, pk):
-    """The attention cores of the level-0 SpatialTransformer (B=8, 8 heads, d=28 padded to 64, 1024 queries), timed alone with CUDA
-    events as a graph of 8 launches rotating over 8 operand sets: self-attention (1024 keys, q|k|v slices of one fused projection,
-    V row-major) and cross-attention over the 87-token context cache. Algorithmic flops = 4*B*Nq*Nk*(H*d) (attention.py:178-192;
+    """The attention cores of the level-0 SpatialTransformer (B=8, 8 heads, d=28 padded to 32 = head pairs in 64-wide rows, 1024 queries),
+    timed alone with CUDA events as a graph of 8 launches rotating over 8 operand sets: self-attention (1024 keys, q|k|v slices of one fused
+    projection, V row-major) and cross-attention over the 87-token context cache. Algorithmic flops = 4*B*Nq*Nk*(H*d) (attention.py:178-192;
     the zero-padded head columns are not counted); the standalone cross-attention is HBM-bound, so its GB/s is given too."""
     import torch
     from upgpt_b200 import ops
-    B, Hh, Nq, d, dpad = B_PER_GPU, 8, LAT * LAT, 28, 64
+    B, Hh, Nq, d, dpad = B_PER_GPU, 8, LAT * LAT, 28, 32
     HD, NC, REP = Hh * dpad, 8, 8
     res = {}
     for name, Nk in (("self", Nq), ("cross", CTX_LEN)):
@@ -308,7 +365,7 @@ def roofline_attention(dev, pk):
         flops = 4.0 * B * Nq * Nk * Hh * d
         nbytes = 2.0 * (B * Nq * HD + 2 * B * Nk * HD) + 2.0 * B * Nq * 2 * HD     # fp16 q, k, v in; [hi | lo] fp16 planes out
         ach = flops / (ms * 1e-3) / 1e12
-        res[name] = {"kernel": "attention_kernel (%s, B=8, 8 heads, d=28->64, Nq=1024, Nk=%d)" % (name, Nk), "bound": "tensor", "achieved": ach,
+        res[name] = {"kernel": "attention_kernel (%s, B=8, 8 heads, d=28->32 head pairs, Nq=1024, Nk=%d)" % (name, Nk), "bound": "tensor", "achieved": ach,
                      "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "us_per_launch": ms * 1e3,
                      "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
                      "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
@@ -317,20 +374,65 @@ def roofline_attention(dev, pk):
 
 
 def parity_spot_check(model, dev):
-    """eps of the bbox.yaml U-Net (B=1, t=501) on the GPU vs the CPU oracle, in the benchmark's precision mode."""
+    """eps of the bbox.yaml U-Net AT THE BENCHMARKED SHAPE (B=8, 32x32, t=501) on the GPU vs the CPU oracle, in the benchmark's precision
+    mode (the B=8 engine tiles and splits differently from a B=1 engine)."""
     import torch
     from oracle import ldm_oracle as O
     from oracle.ref_loader import BBOX_UNET_KW
     from upgpt_b200 import synth
     unet = model.model.diffusion_model
     sd = {k: v.detach().float().cpu() for k, v in unet.state_dict().items()}
-    x, mask, ctx = synth.synth_inputs(1, LAT, LAT, CTX_LEN, CTX_DIM, 11)
-    t = torch.full((1,), 501, dtype=torch.long)
+    B = B_PER_GPU
+    x, mask, ctx = synth.synth_inputs(B, LAT, LAT, CTX_LEN, CTX_DIM, 11)
+    t = torch.full((B,), 501, dtype=torch.long)
     with torch.no_grad():
         ref = O.unet_forward(sd, BBOX_UNET_KW, torch.cat([x, mask], 1), t, ctx)
         got = unet(torch.cat([x, mask], 1).to(dev), t.to(dev), ctx.to(dev)).cpu()
-    return {"eps_max_rel_vs_oracle": float((got - ref).abs().max() / ref.abs().max()), "eps_l2_rel": float((got - ref).norm() / ref.norm()),
-            "case": "bbox.yaml U-Net, B=1, 32x32, t=501, synthetic weights", "tolerance": 1e-3}
+    worst = max(float((got[i] - ref[i]).abs().max() / ref[i].abs().max()) for i in range(B))
+    return {"eps_max_rel_vs_oracle": float((got - ref).abs().max() / ref.abs().max()), "eps_max_rel_worst_sample": worst,
+            "eps_l2_rel": float((got - ref).norm() / ref.norm()),
+            "case": "bbox.yaml U-Net, B=8, 32x32, t=501, synthetic weights (the benchmarked engine)", "tolerance": 1e-3}
+
+
+def gpu_eager_baseline(dev):
+    """Like-for-like GPU baseline, OUTSIDE the timed region: the reference algorithm as plain PyTorch eager ops on this
+    GPU (the oracle's functional restatement moved to the device) at configs[1], strict fp32 and TF32-allowed."""
+    import torch
+    from oracle import ldm_oracle as O
+    from oracle.ref_loader import BBOX_UNET_KW, BBOX_VAE_KW
+    from upgpt_b200 import synth
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from ldm.models.autoencoder import AutoencoderKL
+    unet = UNetModel(**BBOX_UNET_KW); sd_u = {k: v.to(dev) for k, v in synth.synth_state_dict(unet.state_dict(), 0).items()}; del unet
+    ae = AutoencoderKL(BBOX_VAE_KW, embed_dim=4); sd_v = {k: v.to(dev) for k, v in synth.synth_state_dict(ae.state_dict(), 0).items()}; del ae
+    x, mask, ctx = [t.to(dev) for t in synth.synth_inputs(B_PER_GPU, LAT, LAT, CTX_LEN, CTX_DIM, 0)]
+    xin, t = torch.cat([x, mask], 1), torch.full((B_PER_GPU,), 501, dtype=torch.long, device=dev)
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    res = {"what": "PyTorch %s eager ops on this GPU running the oracle's restatement of the reference U-Net / decoder at configs[1]" % torch.__version__}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    prev_dev = torch.get_default_device()
+    torch.set_default_device(dev)      # the oracle builds its small tables (timestep frequencies) on the default device
+    try:
+        with torch.no_grad():
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32; torch.backends.cudnn.allow_tf32 = tf32
+                ms_u = timed(lambda: O.unet_forward(sd_u, BBOX_UNET_KW, xin, t, ctx), 3)
+                ms_v = timed(lambda: O.decode_first_stage(sd_v, BBOX_VAE_KW, x, 0.18215), 2)
+                res[name] = {"unet_step_ms_b8": ms_u, "vae_decode_ms_b8": ms_v, "images_per_s": B_PER_GPU / ((DDIM_STEPS * ms_u + ms_v) * 1e-3)}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        torch.set_default_device(prev_dev)
+    return res
 
 
 def gpu_arm(args, rank, world):
@@ -342,35 +444,60 @@ def gpu_arm(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from upgpt_b200 import _C, ops, synth
+    from upgpt_b200.distributed import gather_frames
     from ldm.models.diffusion.ddim import DDIMSampler
     L = _C.lib()
     pk = peaks()
     model = build_model(dev, args.precision)
-    B = B_PER_GPU
-    # synthetic inputs: resident copies (kernel-only `value`) and pinned host copies (`e2e`)
-    x_T, mask, ctx = synth.synth_inputs(B, LAT, LAT, CTX_LEN, CTX_DIM, 100 + rank)
-    x_dev, mask_dev, ctx_dev = x_T.to(dev), mask.to(dev), ctx.to(dev)
-    x_pin, mask_pin, ctx_pin = x_T.pin_memory(), mask.pin_memory(), ctx.pin_memory()
-    out_pin = torch.empty(B, 256, 256, 3, dtype=torch.uint8).pin_memory()
-    gathered = torch.empty(world * B, 256, 256, 3, dtype=torch.uint8, device=dev) if world > 1 else None
+    wl = WORKLOADS[args.config]
+    B, lat, KF = wl["B"], wl["lat"], wl["keyframes"]
+    px = 8 * lat
+    # synthetic inputs: resident copies (kernel-only `value`) and pinned host copies (`e2e`). Per-rank seeds: a sample's inputs depend on
+    # its global index (rank * B + i), not on how many ranks share the job
+    parts = [synth.synth_inputs(1, lat, lat, CTX_LEN, CTX_DIM, 1000 + rank * B + i) for i in range(B)]
+    x_T, mask, ctx = (torch.cat([p[j] for p in parts], 0) for j in range(3))
+    if KF > 1:
+        # configs[3]: keyframes alpha in linspace(1, 0, KF) lerp the SMPL vector and the person mask between two poses (app.py:296-301)
+        g = torch.Generator().manual_seed(1000 + rank)
+        smpl_a, smpl_b = torch.randn(B, 1, 85, generator=g) * 0.5, torch.randn(B, 1, 85, generator=g) * 0.5
+        _, mask_b, _ = synth.synth_inputs(B, lat, lat, CTX_LEN, CTX_DIM, 200 + rank)
+        alphas = torch.linspace(1, 0, KF).tolist()
+        smpl_kf = torch.stack([a * smpl_a + (1 - a) * smpl_b for a in alphas])            # (KF, B, 1, 85)
+        mask_kf = torch.stack([a * mask + (1 - a) * mask_b for a in alphas])              # (KF, B, 1, lat, lat)
+    else:
+        smpl_kf, mask_kf = None, mask[None]
+    x_dev, ctx_dev, mask_kf_dev = x_T.to(dev), ctx.to(dev), mask_kf.to(dev)
+    smpl_kf_dev = None if smpl_kf is None else smpl_kf.to(dev)
+    x_pin, ctx_pin, mask_kf_pin = x_T.pin_memory(), ctx.pin_memory(), mask_kf.pin_memory()
+    smpl_kf_pin = None if smpl_kf is None else smpl_kf.pin_memory()
+    out_pin = torch.empty(KF, B, px, px, 3, dtype=torch.uint8).pin_memory()
     sampler = DDIMSampler(model)
 
     def hot_path(xT, m, c):
         cond = {"c_crossattn": c, "c_concat": [m]}
-        z, _ = sampler.sample(DDIM_STEPS, B, (4, LAT, LAT), conditioning=cond, eta=args.eta, x_T=xT, verbose=False, log_every_t=1000)
+        z, _ = sampler.sample(DDIM_STEPS, B, (4, lat, lat), conditioning=cond, eta=args.eta, x_T=xT, verbose=False, log_every_t=1000)
         img = model.decode_first_stage(z)
         frames = ops.to_uint8_nhwc(img)
         if world > 1:   # the one collective of the path: all-gather of decoded frames over NVLink
-            dist.all_gather_into_tensor(gathered, frames)
+            gather_frames(frames, sizes=[B] * world)
         return frames
 
+    def sequence(xT, c, masks, smpls, sink=None):
+        """One bench step: KF keyframes (1 except configs[3]); per keyframe the SMPL token is projected on the device (LinearProject,
+        poses.py:3-9) and replaces context row 86 -- the cond-cache refreshes that row of the 16 K | V caches only."""
+        for k in range(KF):
+            ck = c if smpls is None else torch.cat([c[:, :CTX_LEN - 1], model.extra_cond_models[1](smpls[k])], 1)
+            frames = hot_path(xT, masks[k], ck)
+            if sink is not None:
+                sink[k].copy_(frames, non_blocking=True)
+
     def step_resident():
-        return hot_path(x_dev, mask_dev, ctx_dev)
+        sequence(x_dev, ctx_dev, mask_kf_dev, smpl_kf_dev)
 
     def step_e2e():
-        xd = x_pin.to(dev, non_blocking=True); md = mask_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True)
-        frames = hot_path(xd, md, cd)
-        out_pin.copy_(frames, non_blocking=True)
+        xd = x_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True); md = mask_kf_pin.to(dev, non_blocking=True)
+        sd = None if smpl_kf_pin is None else smpl_kf_pin.to(dev, non_blocking=True)
+        sequence(xd, cd, md, sd, out_pin)
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -406,11 +533,21 @@ def gpu_arm(args, rank, world):
     clk = clocks.stop()
     ms_e2e, wall_e2e, _ = timed(step_e2e, 1, args.steps)
     ms_e2e = max(ms_e2e, wall_e2e * 1e3)   # host copies are part of the end-to-end figure: take the host clock if larger
-    n_img = world * B * args.steps
+    n_img = world * B * KF * args.steps
     value = n_img / (ms * 1e-3)
     e2e_val = n_img / (ms_e2e * 1e-3)
+    cond_cache = None
+    if KF > 1:
+        eng0 = next(iter(model.model.diffusion_model._engines.values()))
+        st = dict(eng0.cond.stats)
+        os.environ["UPGPT_COND_CACHE_ROWS"] = "0"          # the same sequence with a full K | V rebuild (16 GEMMs) per keyframe
+        ms_full, _, _ = timed(step_resident, 1, args.steps)
+        del os.environ["UPGPT_COND_CACHE_ROWS"]
+        cond_cache = {"row_refresh_images_per_s": value, "full_rebuild_images_per_s": n_img / (ms_full * 1e-3), "stats_row_refresh_run": st,
+                      "note": "per keyframe: 1 changed context row x 16 layers as M=B GEMMs vs one (B*87)-row k|v GEMM per layer; both are "
+                              "~0.2 ms against ~%.0f ms of sampling per keyframe" % (ms / args.steps / KF)}
     fast = None
-    if args.precision != "fp16" and not args.no_fast_mode:
+    if args.precision != "fp16" and not args.no_fast_mode and args.config == "c2":
         # opt-in fast mode (single fp16 operand plane, eps ~1.5e-3): same workload, reported beside the headline
         os.environ["UPGPT_PRECISION"] = "fp16"
         ms_f, _, _ = timed(step_resident, max(1, args.warmup - 1), args.steps)
@@ -424,20 +561,21 @@ def gpu_arm(args, rank, world):
             roof_attn = roofline_attention(dev, pk)
         except Exception as e:      # an auxiliary measurement must never take the headline line down
             roof_attn = {"error": repr(e)[:300]}
-        alg_tf_per_step = world * B * (DDIM_STEPS * GF_UNET_PER_SAMPLE_STEP + GF_VAE_PER_IMAGE) / 1e3
-        eng = [e for k, e in model.model.diffusion_model._engines.items() if k[-1] == args.precision][0]
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        alg_tf_per_step = world * B * KF * (DDIM_STEPS * wl["gf_unet"] + wl["gf_vae"]) / 1e3
+        eng = [e for k, e in model.model.diffusion_model._engines.items() if args.precision in k][0]
+        h2d = x_pin.numel() * 4 + ctx_pin.numel() * 4 + mask_kf_pin.numel() * 4 + (0 if smpl_kf_pin is None else smpl_kf_pin.numel() * 4)
+        line = {"metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": PRECISION_NOTES[args.precision][0],
                 "data": "synthetic",
-                "config": {"workload": "configs[1]: bbox.yaml U-Net (425.29M params, random init) 32x32x4 latent, 87x768 context, "
-                                       "50-step DDIM eta=%g, bs=%d per GPU, + KL-f8 decode to 256x256 uint8" % (args.eta, B),
-                           "global_batch": world * B, "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
+                "config": {"workload": workload_string(args.config, args.eta),
+                           "global_batch": world * B, "images_per_step": world * B * KF,
+                           "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
                            "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
                            "kernels_per_unet_step": eng.launches_per_step - eng.n_emb_calls + 3, "precision_mode": args.precision,
+                           "precision_plan": {"name": eng.plan_name, "calibration": next((v[2] for v in getattr(model.model.diffusion_model, "_plans", {}).values()), None)},
                            "eps_tolerance": PRECISION_NOTES[args.precision][1]},
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_pin.numel() * 4 + mask_pin.numel() * 4 + ctx_pin.numel() * 4),
-                        "d2h_bytes_per_step": int(out_pin.numel())},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_pin.numel())},
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 "roofline": roof,
@@ -446,11 +584,21 @@ def gpu_arm(args, rank, world):
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
                                "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},
                 "fast_mode": fast}
+        if cond_cache is not None:
+            line["cond_cache"] = cond_cache
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_quick()
-            line["parity"] = parity_spot_check(model, dev)
+            line["cpu_baseline"] = cpu_baseline_quick(args.config)
+            if args.config == "c2":
+                line["parity"] = parity_spot_check(model, dev)
         else:
             line["cpu_baseline"] = None
+        if world == 1 and not args.no_eager_baseline and args.config == "c2":
+            try:
+                del model, sampler
+                torch.cuda.empty_cache()
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev)
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": repr(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -144,10 +144,27 @@ class UNetModel(nn.Module, EngineHostMixin):
         self._host_reset()
         return out
 
+    def precision_plan(self, H, W, ctx_len):
+        """The calibrated "mixed" plan of the CURRENT weights at this latent size (upgpt_b200/precision.py): measured on the device at the
+        first request after a weight change, cached per (weights tag, version, size). None: calibration disabled -> static profile."""
+        from upgpt_b200 import precision as P
+        if not P.enabled() or not next(self.parameters()).is_cuda:
+            return None
+        plans = self.__dict__.setdefault("_plans", {})
+        key = (self._weights_tag, H, W, ctx_len)
+        hit = plans.get(key)
+        if hit is None or hit[0] != self._weights_version:
+            plan, report = P.calibrate(self, H, W, ctx_len)
+            hit = plans[key] = (self._weights_version, plan, report)
+        return hit[1]
+
     def engine(self, B, H, W, ctx_len, precision=None):
         from upgpt_b200.unet_engine import UNetEngine, default_precision
         precision = precision or default_precision()
-        return self._engine_get((B, H, W, ctx_len, precision), lambda: UNetEngine(self, B, H, W, ctx_len, precision=precision))
+        plan = self.precision_plan(H, W, ctx_len) if precision == "mixed" else None
+        pname = None if plan is None else plan["name"]
+        return self._engine_get((B, H, W, ctx_len, precision, pname),
+                                lambda: UNetEngine(self, B, H, W, ctx_len, precision=precision, plan=plan))
 
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """x (B, in_channels, H, W) fp32 NCHW, timesteps (B,) int64, context (B, L, context_dim) -> eps (B, out, H, W)."""

@@ -10,6 +10,10 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `pytest -m gpu`")
+    # The tests build dozens of U-Nets: they run the STATIC "mixed" profile (unet_engine.MIXED_PROFILES) instead of paying the load-time
+    # precision calibration (upgpt_b200/precision.py, ~3 s per model) each time; tests/test_gpu_hotpath.py::test_precision_calibration*
+    # and the benchmarked-configuration parity test switch it back on.
+    os.environ.setdefault("UPGPT_CALIBRATE", "0")
 
 
 @pytest.fixture(scope="session")

@@ -21,7 +21,11 @@ def test_reference_arm_prints_one_json_line():
     d = _line(out.stdout)
     assert d["impl"] == "reference" and d["metric"].startswith("images/sec @256x256, 50-step DDIM, bs=8") and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference": the unmodified reference modules (/root/reference here, its vendored copy baseline/_ref on the GPU box); "port": the oracle
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["extrapolated"] is True and "workload" in d["config"]
+    import bench
+    assert d["config"]["workload"] == bench.workload_string("c2", 1.0), "both arms name the workload with the same string"
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # under torchrun only rank 0 works and prints
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")

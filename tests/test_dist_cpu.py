@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from upgpt_b200.distributed import gather_frames, shard_batch, shard_range
+from upgpt_b200.distributed import gather_frames, per_sample_noise, shard_batch, shard_range
 
 
 def _free_port():
@@ -24,6 +24,12 @@ def _worker(rank, world, port, n_total, q):
     ok = torch.equal(mine["c_crossattn"], cond["c_crossattn"][lo:hi]) and torch.equal(mine["c_concat"][0], cond["c_concat"][0][lo:hi])
     out = gather_frames(frames_all[lo:hi].clone())
     ok = ok and torch.equal(out, frames_all)
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    ok = ok and torch.equal(gather_frames(frames_all[lo:hi].clone(), sizes=sizes), frames_all)     # known shard sizes: one collective
+    # per-sample noise: what rank r draws for its shard equals the corresponding slice of a single-process draw
+    whole = per_sample_noise((4, 2, 2), range(n_total), seed=5, steps=3)
+    mine_n = per_sample_noise((4, 2, 2), range(lo, hi), seed=5, steps=3)
+    ok = ok and torch.equal(mine_n, whole[:, lo:hi]) and tuple(whole.shape) == (3, n_total, 4, 2, 2)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

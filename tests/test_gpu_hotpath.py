@@ -272,12 +272,14 @@ def test_full_size_properties_b8(dev):
     assert relerr(y1, y[:1]) < 5e-3, "batch-of-1 engine (different tiling / split-K) agrees with row 0 of the batch-of-8 engine"
 
 
-def test_unet_eps_b8_benchmarked_config_vs_oracle(dev):
+def test_unet_eps_b8_benchmarked_config_vs_oracle(dev, monkeypatch):
     """The configuration bench.py times (BASELINE configs[1]: bbox.yaml U-Net, B=8, 32x32x4 latent, 87x768 context) against the CPU
     oracle AT B=8 (the B=8 engine tiles / splits differently from the B=1 engine the golden vectors pin), in the default precision
-    plan and in uniform fp16x3, at the tolerance BASELINE.json states: eps max-rel < 1e-3."""
+    plan -- CALIBRATED on these weights exactly as bench.py gets it (upgpt_b200/precision.py) -- and in uniform fp16x3, at the tolerance
+    BASELINE.json states: eps max-rel < 1e-3."""
     import json, os
     from conftest import ROOT
+    monkeypatch.setenv("UPGPT_CALIBRATE", "1")
     m, sd = _unet(BBOX_UNET_KW, 0, dev)
     B = 8
     x, mask, ctx = synth.synth_inputs(B, 32, 32, 87, 768, 3)
@@ -293,12 +295,40 @@ def test_unet_eps_b8_benchmarked_config_vs_oracle(dev):
             y = eng.run(use_graph=True).clone()
             e = relerr(y, ref)
             per_sample = max(relerr(y[i:i + 1], ref[i:i + 1]) for i in range(B))
-            rec[f"{eng.precision}_t{t}"] = {"batch_max_rel": e, "worst_sample_max_rel": per_sample}
+            rec[f"{eng.precision}_t{t}"] = {"batch_max_rel": e, "worst_sample_max_rel": per_sample, "plan": eng.plan_name}
             assert e < 1e-3 and per_sample < 1e-3, (eng.precision, t, e, per_sample)
             assert torch.equal(y, eng.run(use_graph=False)), "graph replay == eager program"
+    rec["calibration"] = m._plans[("raw", 32, 32, 87)][2]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "parity_b8.json"), "w"), indent=1)
     print("eps parity at B=8:", rec)
+
+
+def test_precision_calibration_falls_back_when_the_limit_is_tight(dev, monkeypatch):
+    """upgpt_b200/precision.py: the "mixed" plan is measured per checkpoint against the fp16x3 eps of the same weights; a tighter limit (a
+    checkpoint that is more sensitive) must walk down the candidate list to a safer plan, a limit of 0 must end at uniform fp16x3, and
+    new weights must trigger a new calibration."""
+    from upgpt_b200 import precision as P
+    monkeypatch.setenv("UPGPT_CALIBRATE", "1")
+    m, sd = _unet(TINY_UNET_KW, 0, dev)
+    x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, 0)
+    xc, tt, c = torch.cat([x, mask], 1).to(dev), torch.full((2,), 481, dtype=torch.long, device=dev), ctx.to(dev)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, TINY_UNET_KW, xc.cpu(), tt.cpu(), ctx)
+    y = m(xc, tt, c)
+    ver, plan, rep = m._plans[("raw", 16, 16, 87)]
+    assert rep["chosen"] == plan["name"] and all(v >= 0 for v in rep["deviation_vs_fp16x3"].values())
+    assert relerr(y, ref) < 1e-3
+    assert len(m._engines) == 1, "calibration engines are throw-away: one engine (and one packed weight set) remains"
+    plan0, rep0 = P.calibrate(m, 16, 16, 87, limit=0.0)
+    assert plan0["name"] == "fp16x3" and len(rep0["deviation_vs_fp16x3"]) == len(P.candidates(16, 16, len(m.channel_mult))) - 1
+    devs = rep0["deviation_vs_fp16x3"]
+    first = next(iter(devs))
+    plan1, _ = P.calibrate(m, 16, 16, 87, limit=devs[first] * 0.999)      # just too tight for the fastest candidate
+    assert plan1["name"] != first
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), 7))
+    m(xc, tt, c)
+    assert m._plans[("raw", 16, 16, 87)][0] == m._weights_version != ver, "new weights -> new calibration"
 
 
 def test_config4_smpl_interpolation_sequence_cond_cache(dev):

@@ -316,12 +316,16 @@ class EngineBase:
 
 
 class UNetEngine(EngineBase):
-    def __init__(self, unet, B, H, W, ctx_len, precision=None, dry=False):
-        """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run."""
+    def __init__(self, unet, B, H, W, ctx_len, precision=None, dry=False, plan=None, store=None):
+        """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run.
+        plan: {"mixed_hw": (deep_hw, full_hw) | None, "tf_x1": bool} of the "mixed" precision mode (upgpt_b200/precision.py calibrates
+        it per checkpoint); default: the static profile of MIXED_PROFILES / the UPGPT_MIXED_HW, UPGPT_TF_PLANES overrides.
+        store: packed-weight store to use instead of the module's (throw-away engines of the calibration)."""
         dev = next(unet.parameters()).device
         if dev.type != "cuda" and not dry:
             raise _C.UpgptError("UNetEngine needs the module on a CUDA device (no CPU fallback)")
-        super().__init__(dev, precision or default_precision(), getattr(unet, "_wstore", None), getattr(unet, "_weights_tag", "raw"))
+        super().__init__(dev, precision or default_precision(), store if store is not None else getattr(unet, "_wstore", None),
+                         getattr(unet, "_weights_tag", "raw"))
         self.dry = dry
         self.B, self.H, self.W, self.ctx_len = B, H, W, ctx_len
         self.mc = unet.model_channels
@@ -338,9 +342,13 @@ class UNetEngine(EngineBase):
         if self.precision == "mixed" and os.environ.get("UPGPT_MIXED_HW"):    # tuning override "deep_hw,full_hw" for any architecture
             self.mixed_hw = tuple(int(v) for v in os.environ["UPGPT_MIXED_HW"].split(","))
             assert len(self.mixed_hw) == 2, "UPGPT_MIXED_HW=deep_hw,full_hw"
+        tf_x1 = os.environ.get("UPGPT_TF_PLANES", "x3") == "x1"
+        if plan is not None and self.precision == "mixed":
+            self.mixed_hw, tf_x1 = plan["mixed_hw"], bool(plan["tf_x1"])
         self.mixed = self.mixed_hw is not None
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
-        self.tf_x1 = self.mixed and os.environ.get("UPGPT_TF_PLANES", "x3") == "x1"
+        self.tf_x1 = self.mixed and tf_x1
+        self.plan_name = (plan or {}).get("name", "static")
         self.par_skip = os.environ.get("UPGPT_PAR_SKIP", "0") == "1"
         # LayerNorm folded into the GEMMs around it (include/upgpt_b200.h: rowstats_out / ln_stats): no LayerNorm launches
         self.ln_fold = os.environ.get("UPGPT_LN_FOLD", "1") != "0"
