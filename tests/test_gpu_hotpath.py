@@ -320,7 +320,7 @@ def test_precision_calibration_falls_back_when_the_limit_is_tight(dev, monkeypat
     assert rep["chosen"] == plan["name"] and all(v >= 0 for v in rep["deviation_vs_fp16x3"].values())
     assert relerr(y, ref) < 1e-3
     assert len(m._engines) == 1, "calibration engines are throw-away: one engine (and one packed weight set) remains"
-    plan0, rep0 = P.calibrate(m, 16, 16, 87, limit=0.0)
+    plan0, rep0 = P.calibrate(m, 16, 16, 87, limit=-1.0)     # nothing passes (a plan that changes no layer of this U-Net deviates by exactly 0)
     assert plan0["name"] == "fp16x3" and len(rep0["deviation_vs_fp16x3"]) == len(P.candidates(16, 16, len(m.channel_mult))) - 1
     devs = rep0["deviation_vs_fp16x3"]
     first = next(iter(devs))

@@ -46,7 +46,7 @@ def calibrate(unet, H, W, ctx_len, limit=None):
     """-> (plan dict for UNetEngine(plan=...), report dict). Engines built here pack into a throw-away weight store."""
     from .host import WeightStore
     from .unet_engine import UNetEngine
-    limit = float(os.environ.get("UPGPT_CALIBRATE_LIMIT", limit or LIMIT))
+    limit = float(os.environ.get("UPGPT_CALIBRATE_LIMIT", LIMIT if limit is None else limit))
     dev = next(unet.parameters()).device
     g = torch.Generator().manual_seed(20261017)
     lat = min(unet.in_channels, unet.out_channels)
