@@ -293,6 +293,18 @@ def facade_arm(dev, precision, eta, steps):
             "engines": len(unet._engines), "packed_weight_sets": len(unet._wstore.plans), "repacks_during_timed_requests": len(unet._wstore.plans) - packs0}
 
 
+def _traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of the kernel
+    (profiles/r02_roofline_traffic.json <- profiles/r02_ncu_set_full_summary.txt); None when no capture of this case is committed."""
+    for name in ("r02_roofline_traffic.json", "r01_roofline_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            d = json.load(open(tp)).get(key)
+            if d:
+                return d.get("dram_bytes")
+    return None
+
+
 def roofline_dominant_kernel(dev, pk, precision):
     """Dominant kernel = tc_gemm_kernel (tcgen05 implicit-GEMM conv); its largest single class is the 224->224 3x3 conv at
     32x32, B=8 (14 launches per U-Net step).  Timed with CUDA events on the launching stream as a graph of 16 launches that
@@ -323,10 +335,7 @@ def roofline_dominant_kernel(dev, pk, precision):
     ms = sorted(ts)[len(ts) // 2]
     flops = 2.0 * B * H * W * 9 * C * C
     ach = flops / (ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")      # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch,
-    if os.path.exists(tp):                                                 # from the committed `ncu --set full` capture of this kernel
-        traffic = json.load(open(tp)).get("conv224_" + ("fp16x3" if x3 else "fp16"), {}).get("dram_bytes")
+    traffic = _traffic("conv224_" + ("fp16x3" if x3 else "fp16"))
     exe = flops * (3 if x3 else 1)
     return {"kernel": "tc_gemm_kernel (conv3x3 224->224 @32x32, B=8, %s)" % ("fp16x3" if x3 else "fp16"), "bound": "tensor", "achieved": ach, "peak": pk["tf_burst"],
             "unit": "TFLOP/s", "frac": ach / pk["tf_burst"], "traffic": traffic, "peak_source": pk["src"] + " (burst: kernel timed alone)",
@@ -362,8 +371,40 @@ def roofline_hbm_kernel(dev, pk):
     nbytes = B * H * W * C * 6.0
     ach = nbytes / (ms * 1e-3) / 1e9
     return {"kernel": "prep_kernel (GroupNorm apply + swish + fp16 cast, VAE level 256x256x128, B=8)", "bound": "hbm", "achieved": ach,
-            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "us_per_launch": ms * 1e3,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic("prep_256x256x128"), "us_per_launch": ms * 1e3,
             "algorithmic_bytes_per_launch": nbytes, "peak_source": pk["src"] + " (copy bandwidth)"}
+
+
+def roofline_weight_bound_conv(dev, pk):
+    """The HBM-bound ResBlock conv north_star names (896 -> 896 3x3 at the 4x4 level, B = 8: M = 128 rows against 14.5 MB of fp16
+    weights): timed alone as a graph of 16 launches rotating over 16 weight sets (231 MB > L2, so every launch streams its
+    weights from HBM). Algorithmic bytes = activations in + weights + fp32 result out; single-plane operands as in the calibrated plan."""
+    import torch
+    from upgpt_b200 import _C, ops
+    B, H, W, C = B_PER_GPU, 4, 4, 896
+    REP = 16
+    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half()
+    ws = [(torch.randn(C, 9, C, device=dev) * 0.02).half() for _ in range(REP)]
+    bias, e = torch.randn(C, device=dev), torch.randn(B, C, device=dev)
+    out = torch.empty(B * H * W, C, device=dev)
+    call = lambda i: ops.gemm(a=x, w=ws[i], mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, rowvec=e)
+    for i in range(3):
+        call(i)
+    torch.cuda.synchronize()
+    g = ops.Graph().capture(lambda: [call(i) for i in range(REP)])
+    g.launch(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.launch(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / REP)
+    ms = sorted(ts)[len(ts) // 2]
+    nbytes = B * H * W * C * 2.0 + C * 9 * C * 2.0 + B * H * W * C * 4.0
+    ach = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "tc_gemm_kernel (conv3x3 896->896 @4x4, B=8, fp16: weight-streaming, split-K over an 8-CTA cluster)", "bound": "hbm", "achieved": ach,
+            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": _traffic("conv_deep_896_4x4"), "us_per_launch": ms * 1e3,
+            "algorithmic_bytes_per_launch": nbytes, "peak_source": pk["src"] + " (copy bandwidth)",
+            "limiter": "latency, not bandwidth: ~1.7 us prologue + 16 k-blocks per CTA + DSMEM split-K reduction and drain (~4.5 us) for 14.5 MB of weights"}
 
 
 def roofline_attention(dev, pk):
@@ -595,6 +636,10 @@ def gpu_arm(args, rank, world):
         roof = roofline_dominant_kernel(dev, pk, args.precision)
         roof_hbm = roofline_hbm_kernel(dev, pk)
         try:
+            roof_wconv = roofline_weight_bound_conv(dev, pk)
+        except Exception as e:
+            roof_wconv = {"error": repr(e)[:300]}
+        try:
             roof_attn = roofline_attention(dev, pk)
         except Exception as e:      # an auxiliary measurement must never take the headline line down
             roof_attn = {"error": repr(e)[:300]}
@@ -617,6 +662,7 @@ def gpu_arm(args, rank, world):
                 "clocks": clk,
                 "roofline": roof,
                 "roofline_hbm": roof_hbm,
+                "roofline_weight_bound_conv": roof_wconv,
                 "roofline_attention": roof_attn,
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
                                "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},

@@ -274,3 +274,31 @@ def test_engine_cache_is_lru_bounded_and_shares_packed_weights(monkeypatch):
     b = st.put("w", "raw", torch.full((4,), 2.0), "cpu")
     assert a is b and float(a[0]) == 2.0, "re-pack updates in place (stable address for recorded programs / graphs)"
     assert st.put("w", "ema", torch.ones(4), "cpu") is not a
+
+
+def test_inference_model_facade_builds_and_mixes_styles():
+    """ldm/data/generate_utils.py mirror (reference generate_utils.py:131-190): config rewrite, create_batch, mix_style on pre-computed
+    style embeddings (masked slots -> the empty style, per-slot overrides), bbox-mask interpolation helpers."""
+    import torch
+    from ldm.data.generate_utils import InferenceModel, style_names, interp_mask
+    from ldm.util import load_config
+    cfg = load_config(os.path.join(ROOT, "configs", "deepfashion", "bbox.yaml"))
+    cfg["model"]["params"]["use_ema"] = False
+    im = InferenceModel(cfg, None, "cpu")
+    assert type(im.model.extra_cond_models[0]).__name__ == "DummyModel" and type(im.clip_image_encoder).__name__ == "FrozenClipImageEmbedder2"
+    b = im.create_batch({"smpl": torch.zeros(1, 85), "txt": "a person"}, repeat=3)
+    assert tuple(b["smpl"].shape) == (3, 1, 85) and b["txt"] == ["a person"] * 3
+    s = torch.randn(9, 768)
+    empty, hat = torch.zeros(768), torch.ones(768)
+    out = im.mix_style(s, {"headwear": hat, "top": ""}, mask=["shoes"], empty_style=empty)
+    assert tuple(out.shape) == (9, 768)
+    assert torch.equal(out[style_names.index("headwear")], hat) and torch.equal(out[style_names.index("shoes")], empty)
+    keep = [i for i, n in enumerate(style_names) if n not in ("headwear", "shoes")]
+    assert torch.equal(out[keep], s[keep])
+    with pytest.raises(NotImplementedError):
+        im.mix_style(s, {"top": "a red shirt"})
+    a = torch.full((1, 32, 24), -1.0); a[0, 4:20, 6:18] = -0.99215686
+    c = torch.full((1, 32, 24), -1.0); c[0, 8:28, 2:10] = -0.99215686
+    mid = interp_mask(a, c, 0.5)
+    ys, xs = torch.nonzero(mid[0] > -1.0, as_tuple=True)
+    assert (int(ys.min()), int(ys.max()), int(xs.min()), int(xs.max())) == (6, 23, 4, 13)

@@ -13,6 +13,17 @@ if which == "conv224":
     x = (torch.randn(B, H, W, C * kx, device=dev) * 0.5).half(); w = (torch.randn(C, 9, C * kx, device=dev) * 0.02).half()
     out = torch.empty(B * H * W, C, device=dev); bias = torch.randn(C, device=dev)
     fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, flags=_C.GEMM_F_X3 if x3 else 0)
+elif which == "conv_deep":
+    # the weight-bandwidth-bound ResBlock conv of the 4x4 level (896 -> 896, M = 8 x 16 = 128 rows, K = 9 x 896): 14.5 MB of fp16 weights
+    # (single plane in the calibrated plan) against 0.23 MB of activations. 8 weight sets (116 MB) rotate so the weights come from HBM.
+    B, H, W, C = 8, 4, 4, 896
+    x = (torch.randn(B, H, W, C, device=dev) * 0.5).half()
+    ws = [(torch.randn(C, 9, C, device=dev) * 0.02).half() for _ in range(8)]
+    out = torch.empty(B * H * W, C, device=dev); bias = torch.randn(C, device=dev); e = torch.randn(B, C, device=dev)
+    it = [0]
+    def fn():
+        it[0] += 1
+        ops.gemm(a=x, w=ws[it[0] % 8], mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, rowvec=e)
 elif which == "gemm_small":
     M, N, K = 128, 896, 896
     a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)

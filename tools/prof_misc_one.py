@@ -12,17 +12,28 @@ if which == "gn_fused":
     st = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64); out = torch.zeros(B * H * W * 2 * C, device=dev, dtype=torch.half)
     fn = lambda: ops.groupnorm_prep(st, x1=x, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, gamma=gamma, beta=beta, eps=1e-5, silu=1, layout=0,
                                     split3=1, out=out, raw=None)
+elif which == "prep":
+    # GroupNorm apply + swish + fp16 cast at the VAE decoder's 256x256x128 level, B = 8 (bench.py's roofline_hbm kernel)
+    B, H, W, C = 8, 256, 256, 128
+    x = torch.randn(B, H * W, C, device=dev); ss = torch.randn(B, 2, C, device=dev)
+    out = torch.empty(B * H * W * C, device=dev, dtype=torch.half)
+    fn = lambda: ops.prep(x1=x, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, stats=None, gamma=None, beta=None, eps=1e-6, silu=1,
+                          layout=0, split3=0, out=out, raw=None, scale_shift=ss)
 else:
-    B, Hh, Nq, d, dpad = 8, 8, 1024, 28, 64
-    Nk = 1024 if which == "attn_self" else 87
-    Nkp = (Nk + 7) // 8 * 8
-    q = (torch.randn(B, Nq, Hh * dpad, device=dev) * 0.5).half(); k = (torch.randn(B, Nk, Hh * dpad, device=dev) * 0.5).half()
-    vt = (torch.randn(B, Hh * dpad, Nkp, device=dev) * 0.5).half(); o = torch.zeros(B, Nq, 2 * Hh * dpad, device=dev, dtype=torch.half)
-    a = _C.AttnArgs()
-    a.q, a.ldq, a.k, a.ldk, a.k_batch_stride, a.vt, a.ldvt, a.out, a.ldo = q.data_ptr(), Hh * dpad, k.data_ptr(), Hh * dpad, 0, vt.data_ptr(), Nkp, o.data_ptr(), 2 * Hh * dpad
-    a.B, a.H, a.Nq, a.Nk, a.dpad, a.scale, a.split3_out = B, Hh, Nq, Nk, dpad, d ** -0.5, 1
-    import ctypes as C
-    fn = lambda: _C.check(_C.lib().upgpt_attention(C.byref(a), ops.stream()), "attn")
+    # level-0 attention cores as the engine runs them: 8 heads of 28 padded to 32 (head pairs in 64-wide rows), V row-major
+    B, Hh, Nq, d, dpad = 8, 8, 1024, 28, 32
+    HD = Hh * dpad
+    if which == "attn_self":
+        qkv = (torch.randn(B * Nq, 3 * HD, device=dev) * 0.5).half()
+        kw = dict(q=qkv, ldq=3 * HD, k=qkv.reshape(-1)[HD:], ldk=3 * HD, k_batch_stride=Nq * 3 * HD, vt=qkv.reshape(-1)[2 * HD:], ldvt=3 * HD,
+                  v_rowmajor=1, v_batch_stride=Nq * 3 * HD, Nk=Nq)
+    else:
+        Nk = 87
+        qq = (torch.randn(B * Nq, HD, device=dev) * 0.5).half(); kv = (torch.randn(B * Nk, 2 * HD, device=dev) * 0.5).half()
+        kw = dict(q=qq, ldq=HD, k=kv, ldk=2 * HD, k_batch_stride=Nk * 2 * HD, vt=kv.reshape(-1)[HD:], ldvt=2 * HD, v_rowmajor=1,
+                  v_batch_stride=Nk * 2 * HD, Nk=Nk)
+    o = torch.zeros(B * Nq, 2 * HD, device=dev, dtype=torch.half)
+    fn = lambda: ops.attention(out=o, ldo=2 * HD, B=B, H=Hh, Nq=Nq, dpad=dpad, scale=float(d) ** -0.5, split3_out=1, **kw)
 for _ in range(6):
     fn()
 torch.cuda.synchronize()

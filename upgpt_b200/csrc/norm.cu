@@ -11,6 +11,7 @@
 // F.interpolate nearest x2 (openaimodel.py:116; model.py:53), th.cat([h, hs.pop()]) (openaimodel.py:736),
 // softmax (model.py:184).
 #include "common.cuh"
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include "../../include/upgpt_b200.h"
@@ -674,6 +675,7 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
     g_fused_n16 = ok16 ? n : 0;
     g_fused_max_cl = (ok16 && getenv("UPGPT_NO_CLUSTER16") == nullptr) ? 16 : 8;
     if (getenv("UPGPT_NO_FUSED_GN")) g_fused_max_cl = 0;
+    if (getenv("UPGPT_GN_VERBOSE")) fprintf(stderr, "[upgpt] fused GroupNorm: max cluster %d, co-resident 16-CTA clusters %d\n", g_fused_max_cl, g_fused_n16);
   }
   lk.unlock();
   // cluster size: the smallest power of two whose chunk fits, but at least 8 px per CTA and preferably >= 8 CTAs per image
@@ -688,7 +690,7 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
       const int px = (HW + c - 1) / c;
       const size_t need = (size_t)px * C * 4 + scratch;
       if (c > 1 && px < 8) break;
-      if (c == 16 && a->B > g_fused_n16 && cl != 0) break;
+      if (c == 16 && a->B > g_fused_n16 && cl != 0 && getenv("UPGPT_GN_FORCE16") == nullptr) break;
       if (need + 256 > (size_t)g_fused_smem_optin) continue;
       cl = c; px_per_cta = px; smem = need + 128;
     }

@@ -46,13 +46,12 @@ __device__ __forceinline__ void store_h4(__half* dst, float4 v, int plane) {
   }
 }
 
-// MINB = 2: the two-CTAs-per-SM form (<= 102 registers, <= ~110 KB shared memory, <= 256 TMEM columns): the CTAs of a short GEMM
-// overlap each other's epilogue latency, and a PDL successor's prologue overlaps its predecessor's tail.
-template <int MINB>
-__global__ void __launch_bounds__(kGemmThreads, MINB)
+// (A two-CTAs-per-SM variant -- <= 102 registers, <= 110 KB shared memory, so that a PDL successor's prologue overlaps its predecessor's
+// tail -- was measured in round 2: the spills and the 2-stage pipeline cost more than the overlap gained, 4.27 -> 4.53 ms per U-Net step.)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ GemmParams p) {
+               const __grid_constant__ CUtensorMap tmH, const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // carve-up by integer offsets from the __shared__ array, so that every access below compiles to LDS/STS (casting
   // through uintptr_t would demote the pointers to the generic address space)
@@ -61,7 +60,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)p.stages * kABytes;
-  const uint32_t off_bar = (uint32_t)p.stages * (kABytes + b_bytes);
+  const uint32_t off_bar = (uint32_t)p.stages * (kABytes + b_bytes) + p.pipe_pad;
   uint64_t* bar_full = (uint64_t*)(smem + off_bar);
   uint64_t* bar_empty = bar_full + p.stages;
   uint64_t* bar_tfull = bar_empty + p.stages;
@@ -363,6 +362,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
       if (stamp) TS(8);
+      if (tma_epi && p.res_bulk && r == 0 && grp < nch) {
+        // every MMA of this CTA's only tile has completed: the operand slots are dead. All residual chunks of this group are fetched
+        // into them in one go (the per-chunk fetch exposed one L2 round trip per 32 columns).
+        int cnt = 0;
+        for (int c = grp; c < nch; c += 2) ++cnt;
+        mbar_arrive_expect_tx(rbar, p.a_bytes * (uint32_t)cnt);
+        for (int c = grp; c < nch; c += 2)
+          tma_load_4d(smem + p.off_resb + (uint32_t)c * 16384u, &tmR, rbar, nt * p.block_n + c * 32, oc1, oc2, oc3);
+      }
+      bool bulk_waited = false;
       const uint32_t t_acc = tmem_base + (uint32_t)(acc * p.block_n) + ((uint32_t)(quad * 32) << 16);
       // all TMEM reads of this warp for this tile are done: hand the accumulator stage back to the MMA issuer
       auto release_acc = [&]() {
@@ -476,6 +485,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld32(t_acc + (uint32_t)j0, v);
             tmem_ld_wait();
+            if (stamp && c == 0) TS(12);
             float f[32];
             if (ln) {
 #pragma unroll
@@ -491,6 +501,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               mbar_wait(rbar, res_phase);
               res_phase ^= 1;
               const float* rb = rbuf + r * 32;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 x = *(const float4*)(rb + ((q ^ (r & 7)) << 2));
+                f[4 * q] += x.x; f[4 * q + 1] += x.y; f[4 * q + 2] += x.z; f[4 * q + 3] += x.w;
+              }
+            } else if (p.res_bulk) {
+              if (!bulk_waited) { mbar_wait(rbar, 0); bulk_waited = true; }
+              const float* rb = (const float*)(smem + p.off_resb + (uint32_t)c * 16384u) + r * 32;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const float4 x = *(const float4*)(rb + ((q ^ (r & 7)) << 2));
@@ -533,9 +551,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (stamp && c == 0) TS(13);
           if (c + 2 >= nch) release_acc();            // last chunk of this group: its TMEM reads are done
           if (r == 0) tma_store_wait_read<0>();       // the group's previous bulk store has finished reading `st`
           named_bar_sync(gbar, 128);                  // ... and every thread has finished reading `rbuf`
+          if (stamp && c == 0) TS(14);
           if (p.res_tma && r == 0 && c + 2 < nch) {
             mbar_arrive_expect_tx(rbar, p.a_bytes);
             tma_load_4d(rbuf, &tmR, rbar, n0 + 64, oc1, oc2, oc3);
@@ -546,13 +566,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 8; ++q)
               *(uint4*)(rowp + ((q ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
+          uint8_t* const hst = smem + p.off_hst + (uint32_t)grp * 16384u;
+          if (!f16out && p.h_tma) {
+            // fp16 copy of this thread's 32 finished columns as [plane][row][32 halves] (64-byte rows, no swizzle): hi, then the
+            // error-compensation plane lo = fp16(x - hi)
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float a0 = __uint_as_float(pk[i]), a1 = __uint_as_float(pk[i + 1]);
+              __half2 h2 = __floats2half2_rn(a0, a1);
+              hh[i >> 1] = *(uint32_t*)&h2;
+              const float2 fh = __half22float2(h2);
+              __half2 l2 = __floats2half2_rn(a0 - fh.x, a1 - fh.y);
+              ll[i >> 1] = *(uint32_t*)&l2;
+            }
+            uint4* hp = (uint4*)(hst + r * 64);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hp[q] = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+            if (p.h_planes == 2) {
+              uint4* lp = (uint4*)(hst + 8192 + r * 64);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) lp[q] = make_uint4(ll[4 * q], ll[4 * q + 1], ll[4 * q + 2], ll[4 * q + 3]);
+            }
+          }
           fence_proxy_async_smem();
           named_bar_sync(gbar, 128);
           if (r == 0) {
             tma_store_4d(&tmC, st, n0, oc1, oc2, oc3);
+            if (!f16out && p.h_tma) tma_store_4d(&tmH, hst, n0, oc1, 0, oc3);
             tma_store_commit();
           }
-          if (!f16out && p.out16) {
+          if (stamp && c == 0) TS(15);
+          if (!f16out && p.out16 && !p.h_tma) {
             // secondary fp16 copy of the finished fp32 chunk: coalesced flat pass over the staged values (the next chunk's
             // staging writes come after the next group barrier, i.e. after every thread has left this pass)
             const int q = r & 7, rr0 = r >> 3;
@@ -948,8 +993,7 @@ static int gemm_device_setup(GemmDev** out) {
   if (d.ready) return 0;
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev));
   UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
-  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
+  UPGPT_CHECK_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin));
   for (int S = 1; S <= 8; ++S) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(S * d.num_sms); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = d.smem_optin;
@@ -958,7 +1002,7 @@ static int gemm_device_setup(GemmDev** out) {
     attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<1>, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.num_sms / (2 * S); }
+    if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = d.num_sms / (2 * S); }
     d.max_clusters[S] = n;
   }
   d.ws_bytes = (size_t)96 << 20;
@@ -1129,17 +1173,6 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   const int k_iters = p.taps * p.kblocks_per_tap;
   int bn = a->block_n;
   int splits = a->splits;
-  // two CTAs per SM (experiment, UPGPT_GEMM_2CTA=1): short single-plane GEMMs with row-major output, tiles <= 128 columns, no split-K
-  static const bool two_env = getenv("UPGPT_GEMM_2CTA") != nullptr && getenv("UPGPT_GEMM_2CTA")[0] == '1';
-  bool two_cta = two_env && !p.x3 && !chw_out && !geglu && bn <= 0 && splits <= 0 && k_iters <= 32 && p.num_m_tiles * p.batch >= 16;
-  if (two_cta) {
-    const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
-    // as many tiles as fit 2 x SMs at once, widest first
-    bn = 128;
-    while (bn > 64 && p.num_m_tiles * p.batch * ((a->N + bn - 1) / bn) < 2 * g_num_sms - g_num_sms / 2) bn -= gran;
-    if (epi_mode == 0) { while (bn > 16 && a->N % bn) bn -= 16; }
-    splits = 1;
-  }
   if (bn > 0 && ((epi_mode == 1 && bn % 32) || (epi_mode == 2 && bn % 64))) epi_mode = 0;   // explicit tile width wins
   if (bn <= 0 || splits <= 0) {
     const int gran = epi_mode == 2 ? 64 : (epi_mode == 1 ? 32 : 16);
@@ -1257,6 +1290,14 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     }
   }
 
+  // ---- one tile per CTA: the dead operand pipeline serves the epilogue (bulk residual prefetch, TMA-stored fp16 planes) ----
+  const bool tmR_valid = p.res_tma == 1;
+  const bool single_tile = p.num_splits == 1 && p.num_m_tiles * p.num_n_tiles * p.batch <= g_num_sms;
+  static const bool epi2_env = getenv("UPGPT_GEMM_NO_EPI2") == nullptr;
+  const bool want_bulk = epi2_env && single_tile && p.epi_mode == 1 && tmR_valid;
+  const bool want_h = epi2_env && single_tile && p.epi_mode == 1 && !conv && p.out16 != nullptr && p.ld16 % 8 == 0;
+  if (want_bulk) p.res_tma = 0;      // no dedicated per-chunk residual buffers: more pipeline stages instead
+
   // ---- pipeline depth from the smem budget ----
   const size_t stage_bytes = (size_t)kABytes + (size_t)bn * 128;
   size_t epi_bytes = 0;
@@ -1269,18 +1310,30 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     break;
   }
   const int loads_per_split = (p.x3 ? 2 : 1) * ((k_iters + splits - 1) / splits);
-  if (two_cta) {
-    p.res_tma = 0;
-    epi_bytes = 2 * 16384 + 2 * (128 * 8 + 128 * 4 + 256 * 4) + 3 * 2048 + 1024;
-    stages = (int)(((size_t)110 * 1024 - 1024 - 256 - epi_bytes) / stage_bytes);
-    if (stages < 2) two_cta = false;
-  }
   if (stages > (p.x3 ? 8 : 6)) stages = p.x3 ? 8 : 6;
   if (stages > loads_per_split + 1) stages = loads_per_split + 1;
   if (p.x3) stages &= ~1;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * 8 + 16 + epi_bytes;
+  CUtensorMap tmH = tmA;
+  {
+    const size_t pipe_bytes = (size_t)stages * stage_bytes;
+    const int nch32 = (bn + 31) / 32;
+    auto pad_for = [&](int units) { const size_t need = (size_t)units * 16384; return need > pipe_bytes ? need - pipe_bytes : (size_t)0; };
+    auto fits = [&](int units) { return 1024 + pipe_bytes + pad_for(units) + (2 * stages + 6) * 8 + 16 + epi_bytes <= (size_t)g_smem_optin; };
+    int units = 0;
+    if (want_bulk && fits(nch32)) { p.res_bulk = 1; p.off_resb = 0; units = nch32; }
+    if (want_h && fits(units + 2)) {
+      p.h_tma = 1; p.off_hst = (uint32_t)units * 16384u; units += 2;
+      p.h_planes = p.out16_plane > 0 ? 2 : 1;
+      uint64_t dims[4] = {(uint64_t)a->N, (uint64_t)a->M, (uint64_t)p.h_planes, (uint64_t)p.batch};
+      uint64_t strides[3] = {(uint64_t)p.ld16 * 2, (uint64_t)(p.out16_plane > 0 ? p.out16_plane : a->N) * 2, (uint64_t)p.ld16 * 2 * a->M};
+      uint32_t box[4] = {32, 128, (uint32_t)p.h_planes, 1};
+      if (!dry && make_tmap(&tmH, 2, p.out16, 4, dims, strides, box, false)) return -3;
+    }
+    p.pipe_pad = (uint32_t)pad_for(units);
+  }
+  const size_t smem = 1024 + stages * stage_bytes + p.pipe_pad + (2 * stages + 6) * 8 + 16 + epi_bytes;
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.num_splits * p.batch;
@@ -1291,7 +1344,6 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   p.fd_tiles_per_img = make_fastdiv(p.tiles_per_img);
   p.fd_tiles_per_row = make_fastdiv(p.tiles_per_row);
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  if (two_cta) grid = num_tiles < 2 * g_num_sms ? num_tiles : 2 * g_num_sms;
   // split-K flavour: the splits of a tile as one thread-block cluster reducing over DSMEM (one tile per CTA; the fp32 partial
   // tile [128][bn] is laid over the drained operand slots), else the global-workspace reduction
   p.cluster_reduce = (p.num_splits > 1 && p.num_splits <= 8 && (size_t)stages * stage_bytes >= (size_t)512 * bn &&
@@ -1319,7 +1371,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
       ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, tmA, tmB, tmC, tmR, p));
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, tmH, p));
   } else if (p.coop_reduce) {
     // the distributed split-K reduction spins on the arrival of sibling CTAs: a cooperative launch guarantees (or refuses)
     // co-residency instead of risking a deadlock
@@ -1328,10 +1380,9 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, tmA, tmB, tmC, tmR, p));
+    UPGPT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, tmA, tmB, tmC, tmR, tmH, p));
   } else {
-    if (two_cta) UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel<2>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
-    else UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel<1>, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, p));
+    UPGPT_CHECK_CUDA(launch_k(tc_gemm_kernel, dim3(grid), dim3(kGemmThreads), smem, stream, tmA, tmB, tmC, tmR, tmH, p));
   }
   count_launch();
   UPGPT_CHECK_CUDA(cudaGetLastError());

@@ -85,6 +85,13 @@ struct GemmParams {
   // ---- TMA epilogue ----
   int epi_mode;         // 0 flat stores; 1 fp32 tile chunks [rows][32] by TMA store; 2 fp16 chunks [rows][64] by TMA store
   int res_tma;          // residual tile chunks prefetched by TMA load (epi_mode 1)
+  // one tile per CTA: after the main loop the operand pipeline's shared memory is dead and serves the epilogue
+  int res_bulk;         // ALL residual chunks of the tile are fetched at once (one TMA round trip instead of one per chunk) into
+  uint32_t off_resb;    //   the dead pipeline region at this byte offset, chunk c at + c * 16 KB
+  int h_tma;            // the fp16 copy ([hi | lo] planes) of a chunk is staged at off_hst + group * 16 KB as [plane][128 rows][32 halves]
+  uint32_t off_hst;     //   and stored by TMA (tmH) instead of the flat pass
+  int h_planes;         // 1 or 2
+  uint32_t pipe_pad;    // bytes appended to the operand pipeline region so that the epilogue buffers above fit it
   long long* debug_ts;  // optional [gridDim.x][16] globaltimer stamps (bring-up instrumentation), null in production
   // ---- fast division for the tile decode ----
   FastDiv fd_splits, fd_tiles_mn, fd_tiles_per_batch, fd_m_tiles, fd_tiles_per_img, fd_tiles_per_row;

@@ -349,7 +349,8 @@ class UNetEngine(EngineBase):
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and tf_x1
         self.plan_name = (plan or {}).get("name", "static")
-        self.par_skip = os.environ.get("UPGPT_PAR_SKIP", "0") == "1"
+        # a ResBlock's skip 1x1 GEMM runs on an auxiliary stream beside conv1 + GroupNorm (fork / join edges in the step graph)
+        self.par_skip = os.environ.get("UPGPT_PAR_SKIP", "1") != "0"
         # LayerNorm folded into the GEMMs around it (include/upgpt_b200.h: rowstats_out / ln_stats): no LayerNorm launches
         self.ln_fold = os.environ.get("UPGPT_LN_FOLD", "1") != "0"
         self.layer_hw = self._layer_resolutions(unet)
