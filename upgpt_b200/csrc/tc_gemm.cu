@@ -659,12 +659,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               f[h0 + i] = xv * gelu_erf_f(gv);
             }
           }
-          if (!first) named_bar_sync(gbar, 128);   // the previous chunk's flat pass has left the staging buffer
+          if (stamp && j0 == 0) TS(12);
+          if (p.geglu_tma && ncols == 32) {
+            // fp16 [hi | lo] planes of this thread's 32 finished columns -> staging [plane][row][32 halves] -> one TMA store per chunk
+            // (the flat coalesced pass cost ~1 us per chunk: as much as two thirds of the GELU arithmetic)
+            uint32_t hh[16], ll[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              __half2 h2 = __floats2half2_rn(f[i], f[i + 1]);
+              hh[i >> 1] = *(uint32_t*)&h2;
+              const float2 fh = __half22float2(h2);
+              __half2 l2 = __floats2half2_rn(f[i] - fh.x, f[i + 1] - fh.y);
+              ll[i >> 1] = *(uint32_t*)&l2;
+            }
+            if (r == 0) tma_store_wait_read<0>();      // the group's previous bulk store has finished reading the staging buffer
+            named_bar_sync(gbar, 128);
+            uint8_t* const hst = (uint8_t*)st;
+            uint4* hp = (uint4*)(hst + r * 64);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hp[q] = make_uint4(hh[4 * q], hh[4 * q + 1], hh[4 * q + 2], hh[4 * q + 3]);
+            if (p.h_planes == 2) {
+              uint4* lp = (uint4*)(hst + 8192 + r * 64);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) lp[q] = make_uint4(ll[4 * q], ll[4 * q + 1], ll[4 * q + 2], ll[4 * q + 3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(gbar, 128);
+            if (r == 0) {
+              tma_store_4d(&tmH, hst, nt * half_n + j0, mt * 128, 0, bidx);
+              tma_store_commit();
+            }
+            first = true;     // the staging buffer is guarded by the bulk-store wait above, not by the flat pass's barrier
+            if (stamp && j0 == 0) TS(14);
+            continue;
+          }
+          if (p.geglu_tma && r == 0) tma_store_wait_read<0>();
+          if (!first || p.geglu_tma) named_bar_sync(gbar, 128);   // the previous chunk's flat pass / bulk store has left the staging buffer
           first = false;
           stage_row(f, ncols);
           named_bar_sync(gbar, 128);
+          if (stamp && j0 == 0) TS(13);
           flush_chunk(nt * half_n + j0, ncols, 2);
+          if (stamp && j0 == 0) TS(14);
         }
+        if (stamp) TS(15);
       } else if (chw) {
         for (int j0 = grp * 16; j0 < p.block_n; j0 += 32) {
           uint32_t v[16];
@@ -1332,6 +1370,16 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
       if (!dry && make_tmap(&tmH, 2, p.out16, 4, dims, strides, box, false)) return -3;
     }
     p.pipe_pad = (uint32_t)pad_for(units);
+    if (epi2_env && geglu && !conv && p.out16 && p.ld16 % 8 == 0 && ((uintptr_t)p.out16 & 15) == 0 && (bn / 2) % 32 == 0) {
+      // GEGLU: every chunk of the tile's 'x' half is 32 columns wide -> TMA-stored fp16 planes from the groups' staging buffers
+      p.geglu_tma = 1;
+      p.h_planes = p.out16_plane > 0 ? 2 : 1;
+      const int n_out = a->N / 2;
+      uint64_t dims[4] = {(uint64_t)n_out, (uint64_t)a->M, (uint64_t)p.h_planes, (uint64_t)p.batch};
+      uint64_t strides[3] = {(uint64_t)p.ld16 * 2, (uint64_t)(p.out16_plane > 0 ? p.out16_plane : n_out) * 2, (uint64_t)p.ld16 * 2 * a->M};
+      uint32_t box[4] = {32, 128, (uint32_t)p.h_planes, 1};
+      if (!dry && make_tmap(&tmH, 2, p.out16, 4, dims, strides, box, false)) return -3;
+    }
   }
   const size_t smem = 1024 + stages * stage_bytes + p.pipe_pad + (2 * stages + 6) * 8 + 16 + epi_bytes;
   UPGPT_REQUIRE(smem <= (size_t)g_smem_optin, "upgpt_gemm: smem %zu > %d", smem, g_smem_optin);

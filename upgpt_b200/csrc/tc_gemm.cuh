@@ -91,6 +91,7 @@ struct GemmParams {
   int h_tma;            // the fp16 copy ([hi | lo] planes) of a chunk is staged at off_hst + group * 16 KB as [plane][128 rows][32 halves]
   uint32_t off_hst;     //   and stored by TMA (tmH) instead of the flat pass
   int h_planes;         // 1 or 2
+  int geglu_tma;        // GEGLU epilogue: finished 32-column chunks are staged as [plane][128 rows][32 halves] and stored by TMA (tmH)
   uint32_t pipe_pad;    // bytes appended to the operand pipeline region so that the epilogue buffers above fit it
   long long* debug_ts;  // optional [gridDim.x][16] globaltimer stamps (bring-up instrumentation), null in production
   // ---- fast division for the tile decode ----
