@@ -44,6 +44,8 @@ enum {
   UPGPT_GEMM_F_CHW = 1u << 2,   /* store channel-major: out[(group*N + n)*ldT + row_in_group] (NCHW images, V^T for attention) */
   UPGPT_GEMM_F_SPLIT3OUT = 1u << 4, /* out16 rows = [hi | lo] fp16 planes (N columns each, ld16 default 2N; x ~= hi + lo to ~22 bits):
                                       the A operand of a following UPGPT_GEMM_F_X3 GEMM */
+  UPGPT_GEMM_F_W_STATIC = 1u << 6,  /* w holds model weights, i.e. nothing a preceding launch of the stream writes: the kernel may fetch it
+                                      before its programmatic-dependency wait (weight stream overlaps the predecessor's tail) */
   UPGPT_GEMM_F_X3 = 1u << 5         /* error-compensated fp16x3 product (the precision mode that meets the 1e-3 eps tolerance):
                                       A rows = [Ah | Al] planes of K columns (lda default 2K), W rows per tap = [Wh | Wl] (ldw
                                       default 2K); D = Ah*Wh + Al*Wh + Ah*Wl in fp32: 3 MMAs per k-step on 2 loaded plane pairs */
@@ -86,13 +88,28 @@ typedef struct upgpt_gemm_args {
   int ln_slots;             /* partial slots per row of ln_stats (= the producer's n_tiles) */
   float ln_eps;
   const float* ln_colsum;   /* [N] */
+  /* ---- GroupNorm statistics from the epilogue (openaimodel.py:201-203,225-227; attention.py:254): the kernel that PRODUCES a tensor a
+   * GroupNorm will read adds the per-(image, group) moments of its fp32 result to 64-bit fixed-point accumulators
+   *   gn_acc[(img * gn_groups + g) * 2 + {0, 1}] += {sum * 2^24, sumsq * 2^20},   g = (gn_choff + n) / gn_cpg,  img = row / rows_per_group
+   * (per-tile partial sums in fp32 in a fixed order, then integer atomics: associative, hence bit-reproducible). The GroupNorm itself
+   * is then upgpt_prep_operand(gn_acc = ...): apply only, no statistics pass. gn_acc2: a second consumer with its own grouping (an
+   * encoder output also feeds a decoder ResBlock's concatenated input). Needs an fp32 row-major result and rows_per_group = H*W. */
+  long long* gn_acc;
+  int gn_groups, gn_cpg, gn_choff;
+  long long* gn_acc2;
+  int gn_cpg2, gn_choff2;
 } upgpt_gemm_args;
 int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
 /* the tiling upgpt_gemm picks for these arguments on the current device, without launching: plan[0] = block_n, plan[1] = n_tiles
- * (N tiles = rowstats slots per row), plan[2] = split-K factor, plan[3] = pipeline stages */
-int upgpt_gemm_plan(const upgpt_gemm_args* args, int plan[4]);
+ * (N tiles = rowstats slots per row), plan[2] = split-K factor, plan[3] = pipeline stages, plan[4] = epilogue path (1 TMA-store,
+ * 2 cluster split-K reduction, 0 other: only 1 and 2 can emit rowstats_out / gn_acc), plan[5..7] reserved */
+int upgpt_gemm_plan(const upgpt_gemm_args* args, int plan[8]);
 /* bring-up instrumentation: CTA c of every following upgpt_gemm stamps %globaltimer (ns) into buf[c*16 + slot]; NULL = off */
 int upgpt_debug_set_gemm_timestamps(long long* buf);
+/* bring-up instrumentation: launch trace inside dependent chains / graph replays. buf (device memory, 8-byte words): buf[0] = counter
+ * (zero it), buf[1] = capacity, buf[2 + i] = (%globaltimer ns << 2) | kind; kind 0 = block 0 of a kernel entered, kind 1 = its
+ * griddepcontrol.wait returned (predecessor drained). Differences of consecutive kind-1 stamps = effective cost per launch. NULL = off */
+int upgpt_trace_set(unsigned long long* buf);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Normalisation / operand preparation (HBM-bound elementwise + reductions)
@@ -119,8 +136,17 @@ typedef struct upgpt_prep_args {
   void* out; int ldo;        /* fp16 output, ldo elements per pixel (0 = C or 2C) */
   void* raw; int ldraw;      /* optional un-normalised fp16 copy (layout 0) */
   const float* scale_shift;  /* optional [B][2][C] affine from upgpt_groupnorm_affine (then stats/gamma/beta/eps are ignored) */
+  const long long* gn_acc;   /* optional [B][groups][2] fixed-point group moments {sum * 2^24, sumsq * 2^20} accumulated by the kernels that
+                                PRODUCED x1 / x2 (upgpt_gemm's gn_acc, upgpt_gn_accumulate): GroupNorm(gamma, beta, eps) is applied from
+                                them -- no statistics pass over the tensor, no reduction in this kernel */
 } upgpt_prep_args;
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
+/* Adds the per-(image, group) moments of x [B][HW][C] (channels choff .. choff + C of a GroupNorm over `groups` groups of `cpg` channels)
+ * to acc[b][g] = {sum * 2^24, sumsq * 2^20} with 64-bit integer atomics: integer addition is associative, so the accumulated moments
+ * are bit-reproducible whatever the arrival order. For tensors no GEMM epilogue produced (the input convolution). */
+int upgpt_gn_accumulate(const float* x, int C, int B, int HW, int groups, int cpg, int choff, long long* acc, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (graph-capturable): re-arms the moment accumulators at the start of a pass */
+int upgpt_zero(void* ptr, long long bytes, void* stream);
 /* GroupNorm(gamma, beta, eps) [+ SiLU] + cast of `args` in ONE call (args->stats / scale_shift are ignored; `stats` receives the
  * {sum, sumsq} moments). One launch when an image's [H*W][C] fp32 tile fits the shared memory of a thread-block cluster (one
  * cluster per image: TMA bulk load, moments exchanged over distributed shared memory, normalised out of shared memory), else

@@ -107,7 +107,7 @@ def test_layernorm_folded_into_gemms(dev, M, C, N, x3, prod_splits, cons):
         if isinstance(v, torch.Tensor):
             keep.append(v); v = v.data_ptr()
         setattr(pa, k, v)
-    plan = (C_.c_int * 4)()
+    plan = (C_.c_int * 8)()
     _C.check(_C.lib().upgpt_gemm_plan(C_.byref(pa), C_.byref(plan)), "plan")
     slots = int(plan[1])
     assert 1 <= slots <= 16 and (prod_splits == 0 or int(plan[2]) == prod_splits)
@@ -142,6 +142,72 @@ def test_layernorm_folded_into_gemms(dev, M, C, N, x3, prod_splits, cons):
         ops.gemm(out32=o32, splits=4 if cons == "split" else 0, **ck)
         torch.cuda.synchronize()
         assert relerr(o32, y_ref) < (1e-4 if x3 else 2e-3)     # single-plane operands: x rounded to fp16 (relative to |x|, not |x - mean|)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,x3,splits", [(8, 32, 32, 224, 224, 1, 0), (8, 32, 32, 224, 224, 0, 1), (8, 16, 16, 448, 448, 1, 0), (8, 8, 8, 896, 896, 0, 0),
+                                                      (8, 4, 4, 896, 896, 0, 0), (8, 4, 4, 1792, 896, 0, 4), (2, 32, 24, 224, 224, 0, 0), (3, 8, 8, 448, 896, 0, 2)])
+def test_groupnorm_moments_from_conv_epilogue(dev, B, H, W, Cin, Cout, x3, splits):
+    """upgpt_gemm(gn_acc=...): the conv that produces a tensor adds its per-(image, group) moments to int64 fixed-point accumulators
+    (TMA-store epilogue and cluster split-K reduction; 1 .. 8 images per tile; two consumers with different groupings: the next block's
+    GroupNorm over the tensor alone and a decoder GroupNorm over a concatenation it is the first part of). upgpt_prep_operand(gn_acc=...)
+    then applies GroupNorm + SiLU without a statistics pass: same operand as the fused one-launch GroupNorm kernel; accumulators are
+    bit-identical across runs and equal to upgpt_gn_accumulate on the stored tensor up to fixed-point rounding."""
+    from upgpt_b200 import ops, _C
+    from upgpt_b200.unet_engine import split3_w
+    g = torch.Generator().manual_seed(B * H + Cin + Cout)
+    HW = H * W
+    x = torch.randn(B, H, W, Cin, generator=g) * 0.5
+    w = torch.randn(Cout, 9, Cin, generator=g) * (9 * Cin) ** -0.5
+    b = torch.randn(Cout, generator=g); e = torch.randn(B, Cout, generator=g)
+    xa = (split3_w(x) if x3 else x.half()).to(dev); wa = (split3_w(w) if x3 else w.half()).to(dev)
+    out = torch.full((B * HW, Cout), float("nan"), device=dev)
+    groups = 32
+    cpg1 = Cout // groups
+    C2 = Cout // 2                                   # second consumer: GroupNorm over [this tensor | C2 more channels]
+    cpg2 = (Cout + C2) // groups
+    acc1 = torch.zeros(B, groups, 2, device=dev, dtype=torch.int64)
+    acc2 = torch.zeros(B, groups, 2, device=dev, dtype=torch.int64)
+    kw = dict(a=xa, w=wa, mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W, out32=out, bias=b.to(dev), rowvec=e.to(dev), splits=splits,
+              flags=_C.GEMM_F_X3 if x3 else 0, gn_acc=acc1, gn_groups=groups, gn_cpg=cpg1, gn_choff=0, gn_acc2=acc2, gn_cpg2=cpg2, gn_choff2=0)
+    try:
+        ops.gemm(**kw)
+    except _C.UpgptError as ex:
+        # the tiling picked a split factor of 3 / 5 / 6 / 7: the moments need power-of-two row slices -> the caller pins one (the engine
+        # does the same through upgpt_gemm_plan, unet_engine.py:_gn_from_epilogues)
+        assert "power-of-two" in str(ex) and splits == 0
+        kw["splits"] = 4
+        ops.gemm(**kw)
+    torch.cuda.synchronize()
+    y = out.reshape(B, HW, Cout).double().cpu()
+    ref1 = torch.stack([y.reshape(B, HW, groups, cpg1).sum((1, 3)), (y ** 2).reshape(B, HW, groups, cpg1).sum((1, 3))], -1)
+    got1 = torch.stack([acc1[..., 0].double() / 2 ** 24, acc1[..., 1].double() / 2 ** 20], -1).cpu()
+    assert relerr(got1[..., 1], ref1[..., 1]) < 1e-5 and float((got1[..., 0] - ref1[..., 0]).abs().max()) < 1e-3 * float(ref1[..., 1].max()) ** 0.5
+    # second consumer: only the groups the tensor's channels fall into carry anything
+    ch = torch.arange(Cout) // cpg2
+    ref2 = torch.zeros(B, groups, 2, dtype=torch.float64)
+    ref2[..., 0].index_add_(1, ch, y.sum(1)); ref2[..., 1].index_add_(1, ch, (y ** 2).sum(1))
+    got2 = torch.stack([acc2[..., 0].double() / 2 ** 24, acc2[..., 1].double() / 2 ** 20], -1).cpu()
+    assert relerr(got2[..., 1], ref2[..., 1]) < 1e-5
+    # bit-reproducible, and equal to the stand-alone accumulation kernel on the stored tensor up to fixed-point rounding of the partials
+    a1b = torch.zeros_like(acc1)
+    ops.gemm(**dict(kw, gn_acc=a1b, gn_acc2=None))
+    torch.cuda.synchronize()
+    assert torch.equal(a1b, acc1)
+    a1c = torch.zeros_like(acc1)
+    _C.check(_C.lib().upgpt_gn_accumulate(out.data_ptr(), Cout, B, HW, groups, cpg1, 0, a1c.data_ptr(), ops.stream()), "gn_accumulate")
+    torch.cuda.synchronize()
+    assert float((a1c - acc1).abs().max()) <= 2e-7 * float(acc1.abs().max())     # fp32 partial sums taken in a different (fixed) order
+    # apply from the accumulators == the fused one-launch GroupNorm(+SiLU) operand
+    gamma = (1 + 0.1 * torch.randn(Cout, generator=g)).to(dev); beta = (0.1 * torch.randn(Cout, generator=g)).to(dev)
+    o_acc = torch.zeros(B * HW, 2 * Cout, device=dev, dtype=torch.half); o_fused = torch.zeros_like(o_acc)
+    ops.prep(x1=out, C1=Cout, x2=None, C2=0, B=B, H=H, W=W, groups=groups, stats=None, gamma=gamma, beta=beta, eps=1e-5, silu=1, layout=0, split3=1,
+             out=o_acc, raw=None, gn_acc=acc1)
+    st = torch.zeros(B, groups, 2, device=dev, dtype=torch.float64)
+    ops.groupnorm_prep(st, x1=out, C1=Cout, x2=None, C2=0, B=B, H=H, W=W, groups=groups, gamma=gamma, beta=beta, eps=1e-5, silu=1, layout=0, split3=1,
+                       out=o_fused, raw=None)
+    torch.cuda.synchronize()
+    full = lambda t: t[:, :Cout].float() + t[:, Cout:].float()
+    assert relerr(full(o_acc), full(o_fused)) < 2e-6
 
 
 def test_geglu_epilogue(dev):

@@ -16,7 +16,13 @@ def describe(fn, args):
         taps = 9 if a.mode in (1, 2, 4) else 1
         fl = 2.0 * M * a.N * a.K * taps
         x3 = bool(a.flags & _C.GEMM_F_X3)
-        return "gemm", "%-10s M=%5d N=%4d K=%4d%s%s%s" % (mode, M, a.N, a.K * taps, " x3" if x3 else "", " geglu" if a.flags & 2 else "", " chw" if a.flags & 4 else ""), fl * (3 if x3 else 1)
+        return "gemm", "%-10s M=%5d N=%4d K=%4d%s%s%s" % (mode, M, a.N, a.K * taps, " x3" if x3 else "", " geglu" if a.flags & 2 else "", " chw" if a.flags & 4 else "") + (" +res" if a.res32 else "") + (" +rv" if a.rowvec else "") + (" ln" if a.ln_stats else "") + (" rs" if a.rowstats_out else "") + (" h16" if (a.out16 and a.out32) else (" f16" if a.out16 else "")), fl * (3 if x3 else 1)
+    if name == "upgpt_attention":
+        a = C.cast(args[0], C.POINTER(_C.AttnArgs)).contents
+        return "attention", "B=%d H=%2d Nq=%4d Nk=%4d dpad=%3d" % (a.B, a.H, a.Nq, a.Nk, a.dpad), 4.0 * a.B * a.H * a.Nq * a.Nk * a.dpad
+    if name in ("upgpt_groupnorm_prep", "upgpt_prep_operand"):
+        a = C.cast(args[0], C.POINTER(_C.PrepArgs)).contents
+        return name.replace("upgpt_", ""), "C=%4d+%4d HW=%4d layout=%d silu=%d%s" % (a.C1, a.C2, a.H * a.W, a.layout, a.silu, " x3" if a.split3 else ""), 0.0
     return name.replace("upgpt_", ""), "", 0.0
 
 

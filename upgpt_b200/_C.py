@@ -28,11 +28,14 @@ class GemmArgs(C.Structure):
         ("res32", C.c_void_p), ("ldres", C.c_int), ("ldT", C.c_int),
         ("flags", C.c_uint), ("out_scale", C.c_float),
         ("rowstats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
+        ("gn_acc", C.c_void_p), ("gn_groups", C.c_int), ("gn_cpg", C.c_int), ("gn_choff", C.c_int),
+        ("gn_acc2", C.c_void_p), ("gn_cpg2", C.c_int), ("gn_choff2", C.c_int),
     ]
 
 
 GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1, GEMM_CONV3X3_S2PHASE_ASYM = 0, 1, 2, 3, 4
 GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT, GEMM_F_X3 = 1 << 1, 1 << 2, 1 << 4, 1 << 5
+GEMM_F_W_STATIC = 1 << 6
 
 
 def lib():
@@ -76,6 +79,7 @@ class PrepArgs(C.Structure):
         ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("silu", C.c_int), ("layout", C.c_int), ("split3", C.c_int),
         ("out", C.c_void_p), ("ldo", C.c_int), ("raw", C.c_void_p), ("ldraw", C.c_int), ("scale_shift", C.c_void_p),
+        ("gn_acc", C.c_void_p),
     ]
 
 
@@ -91,11 +95,14 @@ class AttnArgs(C.Structure):
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _PROTOS = {
     "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
-    "upgpt_gemm_plan": [C.POINTER(GemmArgs), C.POINTER(C.c_int * 4)],
+    "upgpt_gemm_plan": [C.POINTER(GemmArgs), C.POINTER(C.c_int * 8)],
     "upgpt_debug_set_gemm_timestamps": [_vp],
+    "upgpt_trace_set": [_vp],
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],
     "upgpt_groupnorm_affine": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _f, _vp, _vp],
     "upgpt_prep_operand": [C.POINTER(PrepArgs), _vp],
+    "upgpt_gn_accumulate": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp],
+    "upgpt_zero": [_vp, _ll, _vp],
     "upgpt_groupnorm_prep": [C.POINTER(PrepArgs), _vp, _vp],
     "upgpt_layernorm": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],
     "upgpt_layernorm_split3": [_vp, _i, _i, _i, _vp, _vp, _f, _vp, _i, _vp],

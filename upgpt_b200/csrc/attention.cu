@@ -406,3 +406,5 @@ extern "C" int upgpt_attention(const upgpt_attn_args* a, void* stream_) {
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+UPGPT_TRACE_TU(attention)

@@ -318,3 +318,5 @@ extern "C" int upgpt_attention_small(const float* qkv, int ld, int koff, int vof
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+UPGPT_TRACE_TU(clip)

@@ -57,8 +57,37 @@ inline cudaError_t launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cu
   cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
 }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// In-graph launch trace (bring-up instrumentation, upgpt_trace_set): thread 0 of block 0 of every kernel of the library stamps
+// %globaltimer when it enters (kind 0) and when its griddepcontrol.wait returns = its predecessor has drained (kind 1) into
+// buf[2 + i] = (ns << 2 | kind), i = atomic counter buf[0], capacity buf[1]. Consecutive kind-1 stamps are the EFFECTIVE cost of a
+// launch inside a dependent chain (graph replay included), which ncu's serialised cold-cache durations cannot show.
+// One pointer per translation unit (no relocatable device code): UPGPT_TRACE_TU(name) defines its setter.
+static __device__ unsigned long long* g_trace_tu = nullptr;
+__device__ __forceinline__ void trace_stamp(unsigned kind) {
+  if ((threadIdx.x | threadIdx.y | blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    unsigned long long* tb = g_trace_tu;
+    if (tb) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const unsigned long long i = atomicAdd(tb, 1ULL);
+      if (i < tb[1]) tb[2 + i] = (t << 2) | kind;
+    }
+  }
+}
+#define UPGPT_TRACE_TU(name)                                                                                       \
+  namespace upgpt {                                                                                                \
+  int trace_set_##name(unsigned long long* buf) {                                                                  \
+    return cudaMemcpyToSymbol(g_trace_tu, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;                              \
+  }                                                                                                                \
+  }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  trace_stamp(0);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_stamp(1);
+}
 
 // ----------------------------------------------------------------------------------------------
 // device helpers
@@ -142,6 +171,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
           "r"(smem_u32(dst)),
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// TMA prefetch of a 5-D box into L2 (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
 }
 
 // TMA store smem -> global (bulk-group completion); OOB parts of the box are clipped

@@ -543,3 +543,5 @@ extern "C" int upgpt_graph_destroy(void* graph_exec) {
   }
   return 0;
 }
+
+UPGPT_TRACE_TU(misc)

@@ -178,6 +178,7 @@ struct PrepParams {
   int groups;
   const double* stats;     // null -> no normalisation
   const float* scale_shift;   // optional [B][2][C] precomputed affine (from gn_stats); replaces stats/gamma/beta
+  const long long* gn_acc;    // optional [B][groups][2] fixed-point moments accumulated by the producers of x1 / x2
   const float* gamma; const float* beta;
   float eps;
   int silu;
@@ -260,13 +261,19 @@ prep_kernel(const PrepParams p) {
     const float* ss = p.scale_shift + (size_t)b * 2 * C;
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) shf[c] = ss[c];
     __syncthreads();
-  } else if (p.stats) {
+  } else if (p.stats || p.gn_acc) {
     const int cpg = C / p.groups;
     const double inv_n = 1.0 / ((double)cpg * HW);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       const int g = c / cpg;
-      const double su = p.stats[((size_t)b * p.groups + g) * 2];
-      const double sq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+      double su, sq;
+      if (p.gn_acc) {     // fixed-point moments from the producers' epilogues (kGnSumScale / kGnSqScale)
+        su = (double)p.gn_acc[((size_t)b * p.groups + g) * 2] * (1.0 / 16777216.0);
+        sq = (double)p.gn_acc[((size_t)b * p.groups + g) * 2 + 1] * (1.0 / 1048576.0);
+      } else {
+        su = p.stats[((size_t)b * p.groups + g) * 2];
+        sq = p.stats[((size_t)b * p.groups + g) * 2 + 1];
+      }
       const double mean = su * inv_n;
       double var = sq * inv_n - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -303,7 +310,7 @@ prep_kernel(const PrepParams p) {
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (ipx[u] < npx) prep_emit(p, b, p0 + ipx[u], ic[u], vin[u], scale, shift, p.stats || p.scale_shift);
+      if (ipx[u] < npx) prep_emit(p, b, p0 + ipx[u], ic[u], vin[u], scale, shift, p.stats || p.scale_shift || p.gn_acc);
   }
 }
 
@@ -529,6 +536,42 @@ softmax_rows_kernel(const float* __restrict__ x, int ldx, int n, float scale, __
   for (int i = threadIdx.x; i < n; i += 256) orow[i] = __float2half_rn(expf((xr[i] - m) * scale) * inv);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Group moments of a tensor as 64-bit fixed-point accumulators (see include/upgpt_b200.h: upgpt_gn_accumulate).
+// grid = (pixel chunks, B), 256 threads: thread = (channel quad, row lane) like gn_stats; per-channel chunk sums -> integer atomics.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gn_accumulate_kernel(const float* __restrict__ x, int C, int HW, int chunk, int groups, int cpg, int choff, long long* __restrict__ acc) {
+  extern __shared__ float shc[];   // [lanes][2][C]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C4 = C >> 2;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+  const int lanes = max(1, 256 / C4);
+  const int qi = threadIdx.x % C4, lane = threadIdx.x / C4;
+  if (lane < lanes && C4 <= 256) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    for (int px = p0 + lane; px < p1; px += lanes) {
+      const float4 v = __ldg((const float4*)(x + ((size_t)b * HW + px) * C + 4 * qi));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* mine = shc + (size_t)lane * 2 * C;
+    *(float4*)(mine + 4 * qi) = s;
+    *(float4*)(mine + C + 4 * qi) = q;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) { s += shc[(size_t)l * 2 * C + c]; q += shc[(size_t)l * 2 * C + C + c]; }
+    const int g = (choff + c) / cpg;
+    unsigned long long* a = (unsigned long long*)(acc + ((size_t)b * groups + g) * 2);
+    atomicAdd(a, (unsigned long long)__float2ll_rn(s * 16777216.f));
+    atomicAdd(a + 1, (unsigned long long)__float2ll_rn(q * 1048576.f));
+  }
+}
+
 static int pick_chunk(int HW, int B) {
   // aim for >= ~4 CTAs per SM without making chunks tiny
   int chunk = (int)(((long long)HW * B + 591) / 592);
@@ -619,12 +662,13 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   UPGPT_REQUIRE(a && a->x1 && a->out, "prep_operand: null");
   const int C = a->C1 + a->C2;
   UPGPT_REQUIRE(a->C1 % 4 == 0 && a->C2 % 4 == 0 && C > 0, "prep_operand: channels must be multiples of 4");
-  UPGPT_REQUIRE(!a->stats || a->scale_shift || (a->groups > 0 && C % a->groups == 0), "prep_operand: bad groups");
+  UPGPT_REQUIRE(!(a->stats || a->gn_acc) || a->scale_shift || (a->groups > 0 && C % a->groups == 0), "prep_operand: bad groups");
   UPGPT_REQUIRE(a->layout != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "prep_operand: stride-2 phases need even H, W");
   UPGPT_REQUIRE(!a->raw || a->layout == 0, "prep_operand: raw copy only with layout 0");
   PrepParams p{};
   p.x1 = a->x1; p.C1 = a->C1; p.x2 = a->x2; p.C2 = a->C2; p.H = a->H; p.W = a->W; p.B = a->B;
   p.scale_shift = a->scale_shift;
+  p.gn_acc = a->gn_acc;
   p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
   p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
@@ -770,3 +814,27 @@ extern "C" int upgpt_softmax_rows(const float* x, int ldx, long long rows, int n
   UPGPT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+extern "C" int upgpt_gn_accumulate(const float* x, int C, int B, int HW, int groups, int cpg, int choff, long long* acc, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  UPGPT_REQUIRE(x && acc && C > 0 && C % 4 == 0 && C <= 1024 && B > 0 && HW > 0 && groups > 0 && cpg > 0, "gn_accumulate: bad args (C=%d)", C);
+  UPGPT_REQUIRE((choff + C + cpg - 1) / cpg <= groups, "gn_accumulate: channels %d..%d exceed %d groups of %d", choff, choff + C, groups, cpg);
+  int per_img = (2 * 148 + B - 1) / B;
+  int chunk = (HW + per_img - 1) / per_img;
+  if (chunk < 16) chunk = 16;
+  if (chunk > HW) chunk = HW;
+  dim3 grid((HW + chunk - 1) / chunk, B);
+  const int lanes = 256 / (C / 4) < 1 ? 1 : 256 / (C / 4);
+  UPGPT_CHECK_CUDA(launch_k(gn_accumulate_kernel, grid, dim3(256), sizeof(float) * 2 * C * lanes, stream, x, C, HW, chunk, groups, cpg, choff, acc));
+  count_launch();
+  UPGPT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int upgpt_zero(void* ptr, long long bytes, void* stream_) {
+  UPGPT_REQUIRE(ptr && bytes > 0, "upgpt_zero: bad args");
+  UPGPT_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream_));
+  return 0;
+}
+
+UPGPT_TRACE_TU(norm)

@@ -156,3 +156,16 @@ namespace upgpt {
 extern "C" const char* upgpt_last_error(void) { return upgpt::g_err; }
 extern "C" int upgpt_abi_version(void) { return 1; }
 extern "C" long long upgpt_launch_count(void) { return upgpt::g_launches.load(); }
+
+// ---- in-graph launch trace (common.cuh: trace_stamp): one device pointer per translation unit ----
+namespace upgpt {
+int trace_set_attention(unsigned long long*); int trace_set_clip(unsigned long long*); int trace_set_misc(unsigned long long*);
+int trace_set_norm(unsigned long long*); int trace_set_tc_gemm(unsigned long long*);
+}
+extern "C" int upgpt_trace_set(unsigned long long* buf) {
+  int rc = 0;
+  rc |= upgpt::trace_set_attention(buf); rc |= upgpt::trace_set_clip(buf); rc |= upgpt::trace_set_misc(buf);
+  rc |= upgpt::trace_set_norm(buf); rc |= upgpt::trace_set_tc_gemm(buf);
+  if (rc) { upgpt::set_last_error("upgpt_trace_set: cudaMemcpyToSymbol failed"); return -2; }
+  return 0;
+}

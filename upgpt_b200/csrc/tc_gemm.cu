@@ -79,6 +79,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* ln_tab = bias_s + 2 * 256;            // 2 x {mean[128], rstd[128]} per-row LayerNorm statistics (folded LN consumer)
   float* lns_s = ln_tab + 2 * 256;             // 2 x [256] column sums s[n] of this tile's columns (folded LN consumer)
   float* rsx = lns_s + 2 * 256;                // [2 tile parities][128 rows][2] row-stat exchange between the epilogue groups (producer)
+  const bool gn = p.gn_acc[0] != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,6 +109,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_base_smem, tmem_cols);
 
   const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  // image (row group) index of tile row 0 of M tile `mt`, and this CTA's moments -> shared accumulators / shared -> global
+  auto tile_img_base = [&](int mt, int bidx) -> int {
+    if (p.flags & GEMM_CONV) return p.tile_imgs > 1 ? mt * p.tile_imgs : p.fd_tiles_per_img.div(mt);
+    return (int)(((long long)bidx * p.M_total + (long long)mt * 128) / p.rows_per_group);
+  };
+  // GroupNorm moments (include/upgpt_b200.h: gn_acc). The lanes of a warp hold the {sum, sumsq} of 32 consecutive result columns
+  // (lane = column) over some rows of image `img`; columns of one GroupNorm group are contiguous, so a segmented shuffle reduction
+  // (fixed order) leaves each group's total in the first lane of its run, which adds it to the global 64-bit fixed-point accumulator
+  // with a fire-and-forget integer atomic (associative: the accumulated value does not depend on the arrival order).
+  // Must be called by all 32 lanes; n < 0 marks a lane without a column.
+  auto gn_commit = [&](int img, int n, float sv, float qv) {
+#pragma unroll
+    for (int cns = 0; cns < 2; ++cns) {
+      if (!p.gn_acc[cns]) continue;
+      const int g = n >= 0 ? (p.gn_choff[cns] + n) / p.gn_cpg[cns] : -1;
+      float a = sv, b = qv;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const float a2 = __shfl_down_sync(0xffffffffu, a, off), b2 = __shfl_down_sync(0xffffffffu, b, off);
+        const int g2 = __shfl_down_sync(0xffffffffu, g, off);
+        if (lane + off < 32 && g2 == g) { a += a2; b += b2; }
+      }
+      const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
+      if (g >= 0 && (lane == 0 || gprev != g)) {
+        unsigned long long* acc = (unsigned long long*)(p.gn_acc[cns] + ((size_t)img * p.gn_groups + g) * 2);
+        atomicAdd(acc, (unsigned long long)__float2ll_rn(a * 16777216.f));
+        atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(b * 1048576.f));
+      }
+    }
+  };
+
   const int tiles_per_batch = tiles_mn * p.num_splits;
   const int num_tiles = tiles_per_batch * p.batch;
   const int k_iters_total = p.taps * p.kblocks_per_tap;
@@ -160,7 +192,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
+  // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail. The producer lane goes further when W
+  // is static (model weights): it issues the W boxes of its first tile's leading k-blocks into the operand ring -- and L2 prefetches of
+  // the following ones -- BEFORE the dependency wait, so the weight stream from HBM overlaps the predecessor too; only the A boxes
+  // (activations written by the predecessor) are issued after the wait.
+  int pre_slots = 0;
+  if (threadIdx.x == 0 && p.w_prefetch && (int)blockIdx.x < num_tiles) {
+    const int k_begin = f_split * k_per_split;
+    const int k_end = min(k_begin + k_per_split, k_iters_total);
+    int tap = k_begin / p.kblocks_per_tap;
+    int kb = k_begin - tap * p.kblocks_per_tap;
+    int kit = k_begin;
+    for (; kit < k_end && pre_slots + p.x3 < p.stages; ++kit, ++kb) {
+      if (kb == p.kblocks_per_tap) { kb = 0; ++tap; }
+      for (int plane = 0; plane <= p.x3; ++plane) {
+        mbar_arrive_expect_tx(&bar_full[pre_slots], p.a_bytes + b_bytes);
+        tma_load_5d(sB + (size_t)pre_slots * b_bytes, &tmB, &bar_full[pre_slots], kb * 64, tap, f_nt * p.block_n, f_bidx, plane);
+        ++pre_slots;
+      }
+    }
+    if (p.w_prefetch > 1) {
+      for (int n = 0; kit < k_end && n < p.w_prefetch; ++kit, ++kb, ++n) {
+        if (kb == p.kblocks_per_tap) { kb = 0; ++tap; }
+        for (int plane = 0; plane <= p.x3; ++plane) tma_prefetch_l2_5d(&tmB, kb * 64, tap, f_nt * p.block_n, f_bidx, plane);
+      }
+    }
+  }
+  pdl_wait();
   if (threadIdx.x == 0) TS(1);
 
   if (warp == 0) {
@@ -182,11 +240,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kb == p.kblocks_per_tap) { kb = 0; ++tap; }
           for (int plane = 0; plane <= p.x3; ++plane) {   // x3: slot pair {(Ah, Wh), (Al, Wl)}
             if (kit == k_begin && plane == 0) TS(2);       // coordinates decoded, about to issue the first TMA
-            mbar_wait(&bar_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
-            tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
-                        c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
-            tma_load_5d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx, plane);
+            if (pre_slots > 0) {
+              // first pass over this slot: its W box and the barrier's byte count were issued before the dependency wait
+              --pre_slots;
+              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
+                          c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
+            } else {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
+              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
+                          c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
+              tma_load_5d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx, plane);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -597,21 +662,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_commit();
           }
           if (stamp && c == 0) TS(15);
-          if (!f16out && p.out16 && !p.h_tma) {
-            // secondary fp16 copy of the finished fp32 chunk: coalesced flat pass over the staged values (the next chunk's
-            // staging writes come after the next group barrier, i.e. after every thread has left this pass)
-            const int q = r & 7, rr0 = r >> 3;
-            const int n = n0 + (q << 2);
-            if (n < p.N_total) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int rr = rr0 + k * 16;
-                const long long gr = rtab[rr];
-                if (gr < 0) continue;
-                const float4 o = *(const float4*)(st + rr * 32 + ((q ^ (rr & 7)) << 2));
-                store_h4(p.out16 + (size_t)gr * p.ld16 + n, o, p.out16_plane);
+          if (gn && !f16out) {
+            // GroupNorm moments of this chunk: warp = one 32-row block of the staged fp32 values, lane = column; a lane sums its column
+            // over the block's rows of one image (fixed order), gn_commit reduces the columns of a group and adds the total
+            const int n = n0 + lane;
+            const bool cok = n < p.N_total;
+            const int sw = lane >> 2, el = lane & 3;
+            float sv = 0.f, qv = 0.f;
+            int cur = -1;
+            for (int rr = quad * 32; rr < quad * 32 + 32; ++rr) {     // rtab / gtab: the same for every lane -> uniform control flow
+              if (rtab[rr] < 0) continue;
+              const int img = gtab[rr];
+              if (img != cur) {
+                if (cur >= 0) gn_commit(cur, cok ? n : -1, sv, qv);
+                cur = img; sv = 0.f; qv = 0.f;
+              }
+              if (cok) {
+                const float v = st[rr * 32 + (((sw ^ (rr & 7)) << 2) | el)];
+                sv += v; qv = fmaf(v, v, qv);
               }
             }
+            if (cur >= 0) gn_commit(cur, cok ? n : -1, sv, qv);
           }
         }
         if (p.rowstats) {
@@ -922,7 +993,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int it = 0;
           for (int rr = row_lo + (tid2 >> 3); rr < row_hi; rr += 32, ++it) {
             const long long g = rtab[rr];
-            if (g < 0) continue;
+            float4 go[UC];
+#pragma unroll
+            for (int u = 0; u < UC; ++u) go[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g < 0 && !gn) continue;
+            if (g >= 0) {
             const uint32_t off0 = (uint32_t)(c0 * 16384 + rr * 128 + ((q ^ (rr & 7)) << 4));
             float4 t[UC][SS], e1[UC], e2[UC];
             const float* rvp = p.rowvec ? p.rowvec + (size_t)gtab[rr] * p.ld_rowvec : nullptr;
@@ -957,6 +1032,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.rowstats && it < 4) {
                 st_s[it] += (o.x + o.y) + (o.z + o.w);
                 st_q[it] = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, st_q[it]))));
+              }
+              go[u] = o;
+            }
+            }
+            if (gn) {
+              // GroupNorm moments: the 4 rows a warp handles per iteration (4 row lanes x 8 column quads) belong to one image. Butterfly
+              // over the row lanes (every lane ends with its column quad's totals), lane (j, q) keeps column 4q + j, one shuffle
+              // brings column c to lane c, gn_commit reduces the columns of a group and adds the total.
+              const int img = __shfl_sync(0xffffffffu, g >= 0 ? gtab[rr] : -1, 0);      // row lane 0's row: valid if any of the 4 is
+#pragma unroll
+              for (int u = 0; u < UC; ++u) {
+                float sv[4] = {go[u].x, go[u].y, go[u].z, go[u].w}, qv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  qv[k] = sv[k] * sv[k];
+                  sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], 8); qv[k] += __shfl_xor_sync(0xffffffffu, qv[k], 8);
+                  sv[k] += __shfl_xor_sync(0xffffffffu, sv[k], 16); qv[k] += __shfl_xor_sync(0xffffffffu, qv[k], 16);
+                }
+                const int j = lane >> 3;
+                const float ms = j == 0 ? sv[0] : (j == 1 ? sv[1] : (j == 2 ? sv[2] : sv[3]));
+                const float mq = j == 0 ? qv[0] : (j == 1 ? qv[1] : (j == 2 ? qv[2] : qv[3]));
+                const int src = ((lane & 3) << 3) | (lane >> 2);          // lane holding column `lane` of this chunk
+                const float cs = __shfl_sync(0xffffffffu, ms, src), cq = __shfl_sync(0xffffffffu, mq, src);
+                const int ncol = nt * p.block_n + (c0 + u) * 32 + lane;
+                const bool cok = img >= 0 && (c0 + u) * 32 + lane < p.block_n && ncol < p.N_total;
+                gn_commit(img < 0 ? 0 : img, cok ? ncol : -1, cs, cq);
               }
             }
           }
@@ -1270,6 +1371,13 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   }
 
   p.debug_ts = g_debug_ts;
+  {
+    // UPGPT_GEMM_WPREFETCH: 0 = off, 1 = operand ring only (default), n > 1 = ring + L2 prefetch of up to n further k-blocks.
+    // Measured on the bbox.yaml step at B = 8 (gpurun_out/r2r_probe.jsonl): 4.32 / 4.29 / 4.36 ms for 0 / 1 / 64 -- inside the run-to-run
+    // noise: the chain is not bound by the weight stream (the CTA that starts last has no lead time to use).
+    static const int wp_env = getenv("UPGPT_GEMM_WPREFETCH") ? atoi(getenv("UPGPT_GEMM_WPREFETCH")) : 1;
+    p.w_prefetch = (a->flags & UPGPT_GEMM_F_W_STATIC) ? wp_env : 0;
+  }
   p.rowstats = a->rowstats_out;
   p.ln_stats = a->ln_stats; p.ln_slots = a->ln_slots; p.ln_eps = a->ln_eps; p.ln_colsum = a->ln_colsum;
   p.ln_inv_c = 1.f / (float)a->K;
@@ -1280,6 +1388,22 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   }
   if (p.rowstats) {
     UPGPT_REQUIRE(((uintptr_t)p.rowstats & 7) == 0 && !(p.flags & (GEMM_CHW | GEMM_GEGLU)) && a->out32, "upgpt_gemm: rowstats_out needs an fp32 row-major result");
+  }
+  p.gn_acc[0] = a->gn_acc; p.gn_acc[1] = a->gn_acc ? a->gn_acc2 : nullptr;
+  p.gn_groups = a->gn_groups; p.gn_cpg[0] = a->gn_cpg; p.gn_cpg[1] = a->gn_cpg2; p.gn_choff[0] = a->gn_choff; p.gn_choff[1] = a->gn_choff2;
+  if (p.gn_acc[0]) {
+    UPGPT_REQUIRE(a->out32 && !(p.flags & (GEMM_CHW | GEMM_GEGLU)) && !p.ln_stats && !p.rowstats,
+                  "upgpt_gemm: gn_acc needs an fp32 row-major result and no folded LayerNorm on the same launch");
+    UPGPT_REQUIRE(p.gn_groups > 0 && p.gn_cpg[0] > 0 && (!p.gn_acc[1] || p.gn_cpg[1] > 0) && p.rows_per_group % 4 == 0,
+                  "upgpt_gemm: gn_acc needs gn_groups, gn_cpg > 0 and rows_per_group %% 4 == 0");
+    const int imgs_per_tile = conv ? (p.tile_imgs > 1 ? p.tile_imgs : 1)
+                                   : (p.rows_per_group % 128 == 0 ? 1 : (128 + p.rows_per_group - 1) / p.rows_per_group + 1);
+    for (int c = 0; c < 2; ++c) {
+      if (!p.gn_acc[c]) continue;
+      p.gn_gt[c] = (bn + p.gn_cpg[c] - 1) / p.gn_cpg[c] + 1;
+      UPGPT_REQUIRE(imgs_per_tile * p.gn_gt[c] <= 128, "upgpt_gemm: gn_acc: %d images x %d groups per tile exceed the 128 accumulator slots", imgs_per_tile, p.gn_gt[c]);
+      UPGPT_REQUIRE((p.gn_choff[c] + a->N + p.gn_cpg[c] - 1) / p.gn_cpg[c] <= p.gn_groups, "upgpt_gemm: gn_acc: channels exceed gn_groups x gn_cpg");
+    }
   }
   p.out32 = a->out32; p.ld32 = a->ld32 > 0 ? a->ld32 : a->N;
   const int n_out16 = (p.flags & GEMM_GEGLU) ? a->N / 2 : a->N;
@@ -1401,8 +1525,14 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     UPGPT_REQUIRE(p.num_splits == 1 || p.cluster_reduce, "upgpt_gemm: folded LayerNorm needs the cluster split-K reduction (splits=%d)", p.num_splits);
   if (p.rowstats)
     UPGPT_REQUIRE(p.cluster_reduce || p.epi_mode == 1, "upgpt_gemm: rowstats_out needs the TMA-store epilogue (16-byte aligned fp32 rows)");
+  const int epi_path = (p.num_splits == 1 && p.epi_mode == 1) ? 1 : (p.cluster_reduce ? 2 : 0);
+  if (p.gn_acc[0]) {
+    UPGPT_REQUIRE(epi_path != 0, "upgpt_gemm: gn_acc needs the TMA-store epilogue or the cluster split-K reduction (block_n=%d splits=%d)", p.block_n, p.num_splits);
+    UPGPT_REQUIRE(epi_path != 2 || 128 % p.num_splits == 0, "upgpt_gemm: gn_acc with split-K needs a power-of-two split factor (got %d)", p.num_splits);
+  }
   if (dry) {
-    plan_out[0] = p.block_n; plan_out[1] = p.num_n_tiles; plan_out[2] = p.num_splits; plan_out[3] = p.stages;
+    plan_out[0] = p.block_n; plan_out[1] = p.num_n_tiles; plan_out[2] = p.num_splits; plan_out[3] = p.stages; plan_out[4] = epi_path;
+    plan_out[5] = plan_out[6] = plan_out[7] = 0;
     return 0;
   }
   if (p.cluster_reduce) {
@@ -1439,7 +1569,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
 
 extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) { return gemm_run(a, (cudaStream_t)stream_, nullptr); }
 
-extern "C" int upgpt_gemm_plan(const upgpt_gemm_args* a, int plan[4]) {
+extern "C" int upgpt_gemm_plan(const upgpt_gemm_args* a, int plan[8]) {
   UPGPT_REQUIRE(plan, "upgpt_gemm_plan: null plan");
   return gemm_run(a, nullptr, plan);
 }
@@ -1449,3 +1579,5 @@ extern "C" int upgpt_debug_set_gemm_timestamps(long long* buf) {
   g_debug_ts = buf;
   return 0;
 }
+
+UPGPT_TRACE_TU(tc_gemm)

@@ -9,6 +9,7 @@ enum GemmFlags : uint32_t {
   GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
   GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
   GEMM_CONV = 1u << 3,
+  GEMM_W_STATIC = 1u << 6, // W holds model weights (independent of the stream's preceding launches): fetched BEFORE the PDL dependency wait
   GEMM_SPLIT3OUT = 1u << 4,  // (public flag) out16 written as error-compensated [hi | lo] planes
   GEMM_X3 = 1u << 5,         // (public flag) operands carry [hi | lo] planes; D = Ah*Wh + Al*Wh + Ah*Wl
 };
@@ -76,6 +77,11 @@ struct GemmParams {
   int ln_slots;
   float ln_eps, ln_inv_c;   // 1 / K
   const float* ln_colsum;   // [N_total]
+  // ---- GroupNorm moments of the result for up to two consumers (include/upgpt_b200.h: gn_acc) ----
+  long long* gn_acc[2];
+  int gn_groups, gn_cpg[2], gn_choff[2];
+  int gn_gt[2];             // accumulator slots per image of a tile: the groups an N tile can touch
+  int w_prefetch;           // > 0: W boxes of the first tile are issued before the PDL wait (GEMM_W_STATIC); > 1: + L2 prefetch depth
   // ---- deterministic split-K ----
   float* ws;            // [num_splits][ws_rows][ws_ld] partial tiles
   int ws_rows, ws_ld;

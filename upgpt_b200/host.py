@@ -73,4 +73,7 @@ class EngineHostMixin:
         self._engines.move_to_end(key)
         if eng.weights_version != self._weights_version:
             eng.pack_weights(self)
+            # upgpt_gemm(UPGPT_GEMM_F_W_STATIC) streams weights ahead of its stream dependency: the (rare) re-pack must have landed
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
         return eng

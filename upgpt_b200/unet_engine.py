@@ -148,9 +148,9 @@ class _Program:
         self.calls.append((_Edge("join", idx), ()))
 
     def kernel_calls(self):
-        """(C-ABI function, args) of every kernel launch, whatever stream it goes to."""
+        """(C-ABI function, args) of every kernel launch, whatever stream it goes to (stream edges and memset nodes are not kernels)."""
         for fn, args in self.calls:
-            if isinstance(fn, _Edge):
+            if isinstance(fn, _Edge) or getattr(fn, "__name__", "") == "upgpt_zero":
                 continue
             yield (fn.fn if isinstance(fn, _OnAux) else fn), args
 
@@ -183,6 +183,11 @@ class EngineBase:
         self._scratch = {}
         self._sizing = True
         self.prog = _Program()
+        # GroupNorm statistics from the producing GEMM's epilogue (include/upgpt_b200.h: gn_acc): out32 pointer -> recorded args struct of
+        # the launch that produces the tensor; accumulator slots of [B][32][2] int64 from one pool that the program zeroes first
+        self.gn_epi = os.environ.get("UPGPT_GN_EPILOGUE", "0") != "0"
+        self._producers = {}
+        self._gn_slots = 0
 
     # ---- memory ----
     def put(self, name, t):
@@ -243,11 +248,12 @@ class EngineBase:
         self.prog.add(self.L.upgpt_groupnorm_affine, self.p(x1), C1, self.p(x2), C2, B, HW, 32, self.p(stats), self.p(gamma), self.p(beta),
                       eps, self.p(ss))
 
-    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, ss=None):
+    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, ss=None, gn_acc=0):
         if self._sizing:
             return
         a = _C.PrepArgs()
         a.scale_shift = self.p(ss)
+        a.gn_acc = gn_acc
         a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
         a.B, a.H, a.W, a.groups = B, H, W, 32
         a.stats, a.gamma, a.beta, a.eps = self.p(stats), self.p(gamma), self.p(beta), eps
@@ -275,15 +281,91 @@ class EngineBase:
         a = _C.GemmArgs()
         for k, v in kw.items():
             setattr(a, k, self.p(v) if (isinstance(v, torch.Tensor) or v is None) else v)
+        if a.batch <= 1:
+            # every unbatched GEMM of the engines multiplies by model weights (only the VAE attention's q k^T / p v products have an
+            # activation as W): the kernel may stream W ahead of its dependency wait
+            a.flags |= _C.GEMM_F_W_STATIC
         n_tiles = 1
         if a.rowstats_out and not getattr(self, "dry", False):
-            plan = (C.c_int * 4)()
+            plan = (C.c_int * 8)()
             if self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan)) != 0:
                 a.splits = 1        # the row statistics need the TMA-store or the cluster split-K epilogue: drop split-K if the pick has neither
                 _C.check(self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan)), "upgpt_gemm_plan")
             n_tiles = int(plan[1])
         self.prog.add_struct(self.L.upgpt_gemm, a)
+        if a.out32:
+            self._producers[a.out32] = a
         return n_tiles
+
+    GN_MAX_SLOTS = 96
+
+    def gn_begin(self):
+        """Start of a recorded pass: one memset node re-arms the GroupNorm moment accumulators (its byte count is patched by gn_end)."""
+        if self._sizing or not self.gn_epi or getattr(self, "dry", False):
+            return
+        self._producers, self._gn_slots = {}, 0
+        pool = self.buf("gn_acc_pool", (self.GN_MAX_SLOTS, self.B, 32, 2), torch.int64)
+        self._gn_zero_idx = len(self.prog.calls)
+        self.prog.add(self.L.upgpt_zero, pool.data_ptr(), pool.numel() * 8)
+
+    def gn_end(self):
+        if self._sizing or not self.gn_epi or getattr(self, "dry", False):
+            return
+        fn, args = self.prog.calls[self._gn_zero_idx]
+        if self._gn_slots == 0:
+            del self.prog.calls[self._gn_zero_idx]
+        else:
+            self.prog.calls[self._gn_zero_idx] = (fn, (args[0], self._gn_slots * self.B * 32 * 2 * 8))
+
+    def _gn_from_epilogues(self, sources, B, HW):
+        """sources: [(tensor, channels, channel offset in the GroupNorm's input)]. If every source tensor was produced by a recorded
+        upgpt_gemm launch that can emit GroupNorm moments from its epilogue, wires them to a fresh accumulator slot and returns its
+        address; else None (the caller uses the one-launch fused GroupNorm kernel)."""
+        if not self.gn_epi or getattr(self, "dry", False) or self._gn_slots >= self.GN_MAX_SLOTS:
+            return None
+        Cc = sum(c for _, c, _ in sources)
+        if Cc % 32:
+            return None
+        prods = []
+        for t, c, off in sources:
+            a = self._producers.get(self.p(t))
+            if a is None or (a.gn_acc and a.gn_acc2) or HW % 4:
+                return None
+            prods.append((a, off))
+        if "gn_acc_pool" not in self.bufs:
+            return None       # no gn_begin() in this program
+        acc = self.bufs["gn_acc_pool"].data_ptr() + self._gn_slots * B * 32 * 2 * 8
+        saved = []
+        ok = True
+        for a, off in prods:
+            saved.append((a, a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits))
+            if a.mode == _C.GEMM_PLAIN:
+                a.rows_per_group = HW
+            if not a.gn_acc:
+                a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff = acc, 32, Cc // 32, off
+            else:
+                a.gn_acc2, a.gn_cpg2, a.gn_choff2 = acc, Cc // 32, off
+            plan = (C.c_int * 8)()
+            rc = self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan))
+            if rc != 0 and a.splits <= 0:
+                # e.g. a split factor of 3 / 5 / 6 / 7: the moments need equal power-of-two row slices -> pin the next lower power of two
+                probe = _C.GemmArgs.from_buffer_copy(a)
+                probe.gn_acc, probe.gn_acc2 = 0, 0
+                if self.L.upgpt_gemm_plan(C.byref(probe), C.byref(plan)) == 0 and plan[2] > 1:
+                    sp = 1
+                    while sp * 2 <= plan[2]:
+                        sp *= 2
+                    a.splits = sp
+                    rc = self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan))
+            if rc != 0:
+                ok = False
+                break
+        if not ok:
+            for a, g0, g1, g2, g3, g4, g5, g6, rpg, sp in saved:
+                a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits = g0, g1, g2, g3, g4, g5, g6, rpg, sp
+            return None
+        self._gn_slots += 1
+        return acc
 
     def e_layernorm(self, x, rows, Cc, gamma, beta, out16, split3=None, ldx=None):
         if self._sizing:
@@ -307,9 +389,17 @@ class EngineBase:
         op = self.scratch("op16", B * H * W * mult * Cc * (2 if split3 else 1), torch.float16)
         raw = self.scratch("raw16", B * H * W * Cc * (2 if split3 else 1), torch.float16) if want_raw else None
         if gname is not None:
-            # GroupNorm(+SiLU) + cast: one fused cluster launch per GroupNorm (two launches internally for VAE-sized images)
-            self.e_gn_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
-                           raw, split3)
+            acc = None
+            if not self._sizing:
+                acc = self._gn_from_epilogues([(x1, C1, 0)] + ([(x2, C2, C1)] if C2 else []), B, H * W)
+            if acc is not None:
+                # the moments come from the epilogues of the launches that produced x1 / x2: GroupNorm(+SiLU) + cast is apply-only
+                self.e_prep(x1, C1, x2, C2, B, H, W, None, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
+                            raw, split3, gn_acc=acc)
+            else:
+                # GroupNorm(+SiLU) + cast: one fused cluster launch per GroupNorm (two launches internally for VAE-sized images)
+                self.e_gn_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
+                               raw, split3)
         else:
             self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3)
         return op, raw
@@ -660,6 +750,7 @@ class UNetEngine(EngineBase):
                   self.w["emb_all.bias"].data_ptr(), self.emb_total, 4 * self.mc, 0, 0, emb_all.data_ptr(), self.emb_total)
         # the launches above depend on the timestep only: samplers may run them once per schedule (sampler_engine.py)
         self.n_emb_calls = 0 if self._sizing else len(self.prog.calls)     # (no fork / join edges among them)
+        self.gn_begin()
         # ---- input blocks ----
         hs = []
         h = self.buf("h_in0", (B, H * W, self.mc))
@@ -718,6 +809,7 @@ class UNetEngine(EngineBase):
         op, _ = self.norm_operand(h, ch, None, 0, B, H, W, "out.0", 1e-5, True, split3=self.split3)
         self.e_gemm(a=op, w=self.w.get("out.conv.weight"), mode=_C.GEMM_CONV3X3, N=self.out_ch, K=ch,
                     n_imgs=B, H=H, W=W, block_n=16, splits=1, out32=eps, bias=self.w.get("out.conv.bias"), flags=_C.GEMM_F_CHW | self.x3)
+        self.gn_end()
 
     def _emit_context(self, unet):
         """Program that fills the per-layer context K / V^T caches (timestep-invariant: attention.py:162-163,175-176)."""
