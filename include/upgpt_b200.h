@@ -36,8 +36,14 @@ enum {
   UPGPT_GEMM_CONV3X3 = 1,         /* A NHWC [n_imgs][H][W][K], W [N][9][K], stride 1, zero pad 1 */
   UPGPT_GEMM_CONV3X3_S2PHASE = 2, /* stride-2 conv; A holds the 4 stride-2 phases [4][n_imgs][H][W][K] (H,W = OUTPUT size) */
   UPGPT_GEMM_CONV1X1 = 3,         /* A NHWC, W [N][K] (image addressing, used when the epilogue needs per-image rows) */
-  UPGPT_GEMM_CONV3X3_S2PHASE_ASYM = 4 /* stride-2 conv with zero pad (0,1,0,1) = right/bottom only (VAE Encoder Downsample, model.py:59-79):
+  UPGPT_GEMM_CONV3X3_S2PHASE_ASYM = 4, /* stride-2 conv with zero pad (0,1,0,1) = right/bottom only (VAE Encoder Downsample, model.py:59-79):
                                       out(y,x) tap (r,s) reads in(2y+r, 2x+s); A = the 4 stride-2 phases as in S2PHASE */
+  UPGPT_GEMM_CONV3X3_UP2 = 5      /* nearest x2 upsample + 3x3 conv (Upsample, openaimodel.py:116-118; model.py:49-52) WITHOUT the upsampled
+                                      tensor: A = the LOW-resolution NHWC operand [n_imgs][H][W][K] (H, W = INPUT size), the result is
+                                      [n_imgs][2H * 2W][N]. Output pixel (2y+a, 2x+b) only sees the 2x2 source pixels (y+a-1+u, x+b-1+v):
+                                      four parity-wise 2x2 convolutions, 16 instead of 36 tap products per source pixel (2.25x fewer MACs).
+                                      W = [4 parities a*2+b][N][4 taps u*2+v][K]: the sums of the 3x3 taps that land on one source pixel
+                                      (rows {0 | 1+2} for a = 0, {0+1 | 2} for a = 1; same for columns), made by the caller */
 };
 enum {
   UPGPT_GEMM_F_GEGLU = 1u << 1, /* W rows packed per tile as [x | gate]; out16 = x * gelu(gate)   (attention.py:37-44) */

@@ -210,6 +210,30 @@ def test_groupnorm_moments_from_conv_epilogue(dev, B, H, W, Cin, Cout, x3, split
     assert relerr(full(o_acc), full(o_fused)) < 2e-6
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,x3,splits", [(8, 4, 4, 896, 896, 0, 0), (8, 8, 8, 896, 448, 1, 0), (8, 16, 16, 448, 448, 1, 0), (2, 16, 16, 448, 224, 0, 1),
+                                                      (3, 6, 10, 64, 96, 1, 0), (1, 64, 64, 128, 128, 0, 0), (2, 5, 3, 32, 48, 0, 2)])
+def test_upsample_fold_conv(dev, B, H, W, Cin, Cout, x3, splits):
+    """UPGPT_GEMM_CONV3X3_UP2 == conv3x3(nearest x2 upsample) (openaimodel.py:116-118, model.py:49-52) from the LOW-resolution operand:
+    several images per tile (4x4, 8x8), one image over several tiles, ragged tiles, split-K through the cluster and the flat path."""
+    from upgpt_b200 import ops, _C
+    from upgpt_b200.unet_engine import split3_w, up2_conv_w
+    g = torch.Generator().manual_seed(B * H + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, generator=g) * 0.5
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5
+    b = torch.randn(Cout, generator=g)
+    wp = up2_conv_w(w)
+    xa = (split3_w(x) if x3 else x.half()).to(dev); wa = (split3_w(wp) if x3 else wp.half()).to(dev)
+    out = torch.full((B * 4 * H * W, Cout), float("nan"), device=dev)
+    ops.gemm(a=xa, w=wa, mode=_C.GEMM_CONV3X3_UP2, N=Cout, K=Cin, n_imgs=B, H=H, W=W, out32=out, bias=b.to(dev), splits=splits,
+             flags=(_C.GEMM_F_X3 if x3 else 0) | _C.GEMM_F_W_STATIC)
+    torch.cuda.synchronize()
+    xr = x if x3 else x.half().float()
+    ref = F.conv2d(F.interpolate(xr.permute(0, 3, 1, 2).double(), scale_factor=2, mode="nearest"), w.double(), b.double(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * 4 * H * W, Cout).float()
+    assert not torch.isnan(out).any()
+    assert relerr(out.cpu(), ref) < (2e-5 if x3 else 2e-3)       # single plane: the folded weights are rounded to fp16
+
+
 def test_geglu_epilogue(dev):
     from upgpt_b200 import ops, _C
     from upgpt_b200.unet_engine import pack_geglu, geglu_half

@@ -157,6 +157,31 @@ def test_lr_scheduler_stub_matches_reference_formula():
     assert abs(s(0) - 1e-6) < 1e-12 and abs(s(50) - (1e-6 + (1 - 1e-6) * 0.5)) < 1e-9 and s(1000) == 1.0
 
 
+def test_upsample_fold_weights_reproduce_interpolate_conv():
+    """up2_conv_w (UPGPT_GEMM_CONV3X3_UP2): four parity-wise 2x2 kernels over the low-resolution input == conv3x3(nearest x2 upsample),
+    openaimodel.py:116-118 / model.py:49-52, including the zero padding at the borders of the UPSAMPLED image."""
+    import torch.nn.functional as F
+    from upgpt_b200.unet_engine import up2_conv_w
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 5, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 6, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wp = up2_conv_w(w)                                   # [4][Cout][4][Cin]
+    assert wp.shape == (4, 4, 4, 6)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = 0
+            for u in (0, 1):
+                for v in (0, 1):
+                    # source pixel (y + a - 1 + u, x + b - 1 + v); +1 for the zero pad of xp
+                    src = xp[:, :, a + u:a + u + 5, b + v:b + v + 7]
+                    acc = acc + torch.einsum("bchw,oc->bohw", src, wp[a * 2 + b, :, u * 2 + v, :])
+            out[:, :, a::2, b::2] = acc
+    torch.testing.assert_close(out, ref, rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("precision", ["fp16x3", "mixed", "fp16"])
 def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     """Host logic of the per-layer precision plan (recorded without a device): every tensor-core GEMM must find its A operand in the

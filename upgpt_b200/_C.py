@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
 
 
 GEMM_PLAIN, GEMM_CONV3X3, GEMM_CONV3X3_S2PHASE, GEMM_CONV1X1, GEMM_CONV3X3_S2PHASE_ASYM = 0, 1, 2, 3, 4
+GEMM_CONV3X3_UP2 = 5
 GEMM_F_GEGLU, GEMM_F_CHW, GEMM_F_SPLIT3OUT, GEMM_F_X3 = 1 << 1, 1 << 2, 1 << 4, 1 << 5
 GEMM_F_W_STATIC = 1 << 6
 

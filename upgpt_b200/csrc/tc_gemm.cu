@@ -236,6 +236,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int k_end = min(k_begin + k_per_split, k_iters_total);
         int tap = k_begin / p.kblocks_per_tap;
         int kb = k_begin - tap * p.kblocks_per_tap;
+        const int tofs = (p.flags & GEMM_UP2) ? bidx * 4 : 0;   // parity-wise tap offsets (bidx = output parity)
         for (int kit = k_begin; kit < k_end; ++kit, ++kb) {
           if (kb == p.kblocks_per_tap) { kb = 0; ++tap; }
           for (int plane = 0; plane <= p.x3; ++plane) {   // x3: slot pair {(Ah, Wh), (Al, Wl)}
@@ -243,13 +244,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (pre_slots > 0) {
               // first pass over this slot: its W box and the barrier's byte count were issued before the dependency wait
               --pre_slots;
-              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
-                          c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
+              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tofs + tap],
+                          c2 + p.tap_dy[tofs + tap], c3 + p.tap_dn[tofs + tap], plane);
             } else {
               mbar_wait(&bar_empty[stage], phase ^ 1);
               mbar_arrive_expect_tx(&bar_full[stage], p.a_bytes + b_bytes);
-              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tap],
-                          c2 + p.tap_dy[tap], c3 + p.tap_dn[tap], plane);
+              tma_load_5d(sA + (size_t)stage * kABytes, &tmA, &bar_full[stage], kb * 64, c1 + p.tap_dx[tofs + tap],
+                          c2 + p.tap_dy[tofs + tap], c3 + p.tap_dn[tofs + tap], plane);
               tma_load_5d(sB + (size_t)stage * b_bytes, &tmB, &bar_full[stage], kb * 64, tap, nt * p.block_n, bidx, plane);
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -356,6 +357,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int img = mt * p.tile_imgs + r / p.HW;
           valid = (r < p.tile_imgs * p.HW) && (img < p.n_imgs);
           grow = (long long)mt * p.tile_imgs * p.HW + r;
+          if (p.flags & GEMM_UP2) {
+            // low-resolution pixel (y, x) of image img -> pixel (2y + a, 2x + b) of the 2H x 2W result, (a, b) = this tile's parity
+            const int pix = r - (r / p.HW) * p.HW;
+            const int y = pix / p.W;
+            grow = (long long)img * 4 * p.HW + (long long)(2 * y + (bidx >> 1)) * (2 * p.W) + 2 * (pix - y * p.W) + (bidx & 1);
+          }
         } else {
           // tile = tile_rows x tile_cols pixels of one image (tile_cols divides W; the last row tile may be ragged)
           const int img = mt / p.tiles_per_img;
@@ -366,6 +373,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int y = ty * p.tile_rows + ry;
           valid = (r < p.tile_rows * p.tile_cols) && (y < p.H);
           grow = (long long)img * p.HW + (long long)y * p.W + x0 + (r - ry * p.tile_cols);
+          if (p.flags & GEMM_UP2)
+            grow = (long long)img * 4 * p.HW + (long long)(2 * y + (bidx >> 1)) * (2 * p.W) + 2 * (x0 + (r - ry * p.tile_cols)) + (bidx & 1);
         }
       } else {
         const int m = mt * 128 + r;
@@ -1211,15 +1220,16 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   UPGPT_REQUIRE(a->K > 0 && a->N > 0, "upgpt_gemm: bad K/N");
   UPGPT_REQUIRE(a->K % 8 == 0, "upgpt_gemm: K (=%d) must be a multiple of 8 (16-byte TMA rows)", a->K);
   const bool s2 = a->mode == UPGPT_GEMM_CONV3X3_S2PHASE || a->mode == UPGPT_GEMM_CONV3X3_S2PHASE_ASYM;
-  const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || s2 || a->mode == UPGPT_GEMM_CONV1X1;
+  const bool up2 = a->mode == UPGPT_GEMM_CONV3X3_UP2;
+  const bool conv = a->mode == UPGPT_GEMM_CONV3X3 || s2 || a->mode == UPGPT_GEMM_CONV1X1 || up2;
   GemmParams p{};
   p.flags = a->flags;
   p.x3 = (a->flags & UPGPT_GEMM_F_X3) ? 1 : 0;
   const uint64_t n_planes = p.x3 ? 2 : 1;          // operand planes [hi | lo] = 5th tensor-map dimension, K elements apart
   const uint64_t ld_default = n_planes * (uint64_t)a->K;
-  p.batch = conv ? 1 : (a->batch > 0 ? a->batch : 1);
+  p.batch = up2 ? 4 : (conv ? 1 : (a->batch > 0 ? a->batch : 1));   // UP2: the "batch" index of a tile is its output parity (a, b)
   p.N_total = a->N;
-  p.taps = (a->mode == UPGPT_GEMM_CONV3X3 || s2) ? 9 : 1;
+  p.taps = (a->mode == UPGPT_GEMM_CONV3X3 || s2) ? 9 : (up2 ? 4 : 1);
   p.kblocks_per_tap = (a->K + 63) / 64;
   p.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
 
@@ -1263,6 +1273,12 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     for (int t = 0; t < 9; ++t) { p.tap_dy[t] = p.tap_dx[t] = p.tap_dn[t] = 0; }
     if (a->mode == UPGPT_GEMM_CONV3X3) {
       for (int t = 0; t < 9; ++t) { p.tap_dy[t] = t / 3 - 1; p.tap_dx[t] = t % 3 - 1; }
+    } else if (up2) {
+      // out(2y + a, 2x + b) reads the upsampled rows 2y + a + {-1, 0, 1} = source rows y + {a - 1, a}: tap (u, v) of parity (a, b)
+      // sits at source offset (a - 1 + u, b - 1 + v) and carries the sum of the 3x3 weights that land on that source pixel
+      p.flags |= GEMM_UP2;
+      for (int par = 0; par < 4; ++par)
+        for (int t = 0; t < 4; ++t) { p.tap_dy[par * 4 + t] = (par >> 1) - 1 + (t >> 1); p.tap_dx[par * 4 + t] = (par & 1) - 1 + (t & 1); }
     } else if (a->mode == UPGPT_GEMM_CONV3X3_S2PHASE) {
       // out(y,x) tap (r,s) reads in(2y+r-1, 2x+s-1) = phase[(r+1)&1][(s+1)&1] at (y + (r==0 ? -1 : 0), x + (s==0 ? -1 : 0))
       for (int t = 0; t < 9; ++t) {
@@ -1280,7 +1296,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     }
     m_rows_total = a->n_imgs * p.HW;
     p.M_total = m_rows_total;
-    p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : p.HW;
+    p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : (up2 ? 4 * p.HW : p.HW);
   } else {
     UPGPT_REQUIRE(a->M > 0, "upgpt_gemm: bad M");
     p.M_total = a->M;
@@ -1302,7 +1318,8 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   const bool chw_out = (p.flags & GEMM_CHW) != 0;
   const bool geglu = (p.flags & GEMM_GEGLU) != 0;
   int epi_mode = 0;
-  if (!chw_out && !geglu) {
+  if (up2) UPGPT_REQUIRE(!chw_out && !geglu && !a->rowstats_out && !a->ln_stats && !a->gn_acc, "upgpt_gemm(UP2): plain row-major epilogue only");
+  if (!chw_out && !geglu && !up2) {      // UP2 scatters a tile's rows over the 2H x 2W image: flat row-table stores, no box store
     const int ld32 = a->ld32 > 0 ? a->ld32 : a->N;
     const int ld16 = a->ld16 > 0 ? a->ld16 : a->N;
     if (a->out32 && ld32 % 4 == 0 && ((uintptr_t)a->out32 & 15) == 0) epi_mode = 1;

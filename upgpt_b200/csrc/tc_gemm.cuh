@@ -9,6 +9,7 @@ enum GemmFlags : uint32_t {
   GEMM_GEGLU = 1u << 1,    // tile columns are [x | gate] halves; out16 gets x * gelu(gate)
   GEMM_CHW = 1u << 2,      // outputs stored channel-major: out[(group * N_total + n) * ldT + row_in_group]
   GEMM_CONV = 1u << 3,
+  GEMM_UP2 = 1u << 7,      // conv over the nearest-x2 upsampled image as four parity-wise 2x2 convolutions over the low-resolution operand
   GEMM_W_STATIC = 1u << 6, // W holds model weights (independent of the stream's preceding launches): fetched BEFORE the PDL dependency wait
   GEMM_SPLIT3OUT = 1u << 4,  // (public flag) out16 written as error-compensated [hi | lo] planes
   GEMM_X3 = 1u << 5,         // (public flag) operands carry [hi | lo] planes; D = Ah*Wh + Al*Wh + Ah*Wl
@@ -56,7 +57,7 @@ struct GemmParams {
   int tiles_per_row;    // column tiles per image row (W / tile_cols)
   int tile_cols;        // pixels per tile row (divides W)
   int n_imgs;           // number of images addressed by the output
-  int tap_dy[9], tap_dx[9], tap_dn[9];
+  int tap_dy[16], tap_dx[16], tap_dn[16];   // per tap; GEMM_UP2: per (parity, tap) = [parity * 4 + tap]
   // ---- epilogue ----
   float* out32;         // [rows, ld32] (or CHW)
   int ld32;

@@ -105,6 +105,27 @@ def split3_w(w):
     return torch.cat([wh, wl], dim=-1)
 
 
+def up2_conv_w(w):
+    """[Cout, Cin, 3, 3] fp32 weights of the conv behind a nearest-x2 upsample (openaimodel.py:116-118, model.py:49-52) -> the four
+    parity-wise 2x2 kernels [4 (a*2+b), Cout, 4 (u*2+v), Cin] of UPGPT_GEMM_CONV3X3_UP2: output pixel (2y+a, 2x+b) reads the upsampled
+    rows 2y+a-1 .. 2y+a+1, i.e. source rows y+a-1 and y+a; the 3x3 taps that land on the same source pixel are summed (in fp32)."""
+    rows = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}      # parity -> 3x3 tap indices of source offset u = 0 / 1
+    out = w.new_zeros(4, w.shape[0], 4, w.shape[1])
+    for a in (0, 1):
+        for b in (0, 1):
+            for u in (0, 1):
+                for v in (0, 1):
+                    acc = 0
+                    for i in rows[a][u]:
+                        for j in rows[b][v]:
+                            acc = acc + w[:, :, i, j]
+                    out[a * 2 + b, :, u * 2 + v, :] = acc
+    return out
+
+
+UP2_FOLD = os.environ.get("UPGPT_UP2_FOLD", "1") != "0"
+
+
 class _OnAux:
     """A launch that goes to one of the library's auxiliary streams (a parallel branch of the program, between fork and join)."""
 
@@ -539,7 +560,10 @@ class UNetEngine(EngineBase):
             elif isinstance(mod, (om.Downsample, om.Upsample)):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
                 w = sd[name + sub + ".weight"]
-                put(name + ".weight", self._conv_w(w, self.use_x3("conv", self.layer_hw[name])))
+                if isinstance(mod, om.Upsample) and UP2_FOLD:
+                    put(name + ".weight", self._w16(up2_conv_w(w), self.use_x3("conv", self.layer_hw[name])))
+                else:
+                    put(name + ".weight", self._conv_w(w, self.use_x3("conv", self.layer_hw[name])))
                 put(name + ".bias", sd[name + sub + ".bias"])
             elif isinstance(mod, SpatialTransformer):
                 p = name
@@ -787,11 +811,18 @@ class UNetEngine(EngineBase):
                     h, ch = out, mod.out_channels
                 elif isinstance(mod, om.Upsample):
                     x3c = self.use_x3("conv", hh * ww * 4)
-                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=x3c)
-                    hh, ww = hh * 2, ww * 2
-                    out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
-                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
-                                W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
+                    out = self.buf(p + ".out", (B, hh * ww * 4, mod.out_channels))
+                    if UP2_FOLD:
+                        # the x2 replicate is never materialised: four parity-wise 2x2 convolutions over the low-resolution operand
+                        op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=0, split3=x3c)
+                        self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_UP2, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
+                                    W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
+                        hh, ww = hh * 2, ww * 2
+                    else:
+                        op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1, split3=x3c)
+                        hh, ww = hh * 2, ww * 2
+                        self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=mod.out_channels, K=ch, n_imgs=B, H=hh,
+                                    W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
                     h, ch = out, mod.out_channels
                 else:
                     raise NotImplementedError(type(mod))

@@ -9,7 +9,7 @@ import ctypes as C
 import torch
 
 from . import _C
-from .unet_engine import EngineBase, _Program, default_precision
+from .unet_engine import EngineBase, _Program, default_precision, up2_conv_w, UP2_FOLD
 
 
 class VAEDecoderEngine(EngineBase):
@@ -47,7 +47,9 @@ class VAEDecoderEngine(EngineBase):
             n = k[len("decoder."):]
             if n.startswith("conv_in."):
                 continue
-            if v.dim() == 4 and v.shape[-1] == 3:
+            if v.dim() == 4 and v.shape[-1] == 3 and ".upsample." in n and UP2_FOLD:
+                put(n, up2_conv_w(v).half())
+            elif v.dim() == 4 and v.shape[-1] == 3:
                 put(n, self._conv_w(v))
             elif v.dim() == 4:
                 put(n, v.reshape(v.shape[0], v.shape[1]).half())
@@ -132,11 +134,18 @@ class VAEDecoderEngine(EngineBase):
                 h, ch = out, cout
             if i_level != 0:
                 p = f"up.{i_level}.upsample.conv"
-                op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1)
-                hh, ww = hh * 2, ww * 2
-                out = self.buf(f"lvl{i_level}.up", (B, hh * ww, ch))
-                self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=ch, K=ch, n_imgs=B, H=hh, W=ww, out32=out,
-                            bias=self.w.get(p + ".bias"))
+                out = self.buf(f"lvl{i_level}.up", (B, hh * ww * 4, ch))
+                if UP2_FOLD:
+                    # Upsample (model.py:49-52) without the x2 replicate: four parity-wise 2x2 convolutions over the low-resolution operand
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=0)
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3_UP2, N=ch, K=ch, n_imgs=B, H=hh, W=ww, out32=out,
+                                bias=self.w.get(p + ".bias"))
+                    hh, ww = hh * 2, ww * 2
+                else:
+                    op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=1)
+                    hh, ww = hh * 2, ww * 2
+                    self.e_gemm(a=op, w=self.w.get(p + ".weight"), mode=_C.GEMM_CONV3X3, N=ch, K=ch, n_imgs=B, H=hh, W=ww, out32=out,
+                                bias=self.w.get(p + ".bias"))
                 h = out
         img = self.buf("img", (B, dec.out_ch, hh, ww))
         op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, "norm_out", 1e-6, True)
