@@ -11,9 +11,9 @@ def describe(fn, args):
     name = fn.__name__ if hasattr(fn, "__name__") else str(fn)
     if name == "upgpt_gemm":
         a = C.cast(args[0], C.POINTER(_C.GemmArgs)).contents
-        mode = {0: "gemm", 1: "conv3x3", 2: "conv3x3s2", 3: "conv1x1", 4: "conv3x3s2a"}[a.mode]
-        M = a.M * max(a.batch, 1) if a.mode == 0 else a.n_imgs * a.H * a.W
-        taps = 9 if a.mode in (1, 2, 4) else 1
+        mode = {0: "gemm", 1: "conv3x3", 2: "conv3x3s2", 3: "conv1x1", 4: "conv3x3s2a", 5: "conv3x3up2"}[a.mode]
+        M = a.M * max(a.batch, 1) if a.mode == 0 else a.n_imgs * a.H * a.W * (4 if a.mode == 5 else 1)
+        taps = 9 if a.mode in (1, 2, 4) else (4 if a.mode == 5 else 1)
         fl = 2.0 * M * a.N * a.K * taps
         x3 = bool(a.flags & _C.GEMM_F_X3)
         return "gemm", "%-10s M=%5d N=%4d K=%4d%s%s%s" % (mode, M, a.N, a.K * taps, " x3" if x3 else "", " geglu" if a.flags & 2 else "", " chw" if a.flags & 4 else "") + (" +res" if a.res32 else "") + (" +rv" if a.rowvec else "") + (" ln" if a.ln_stats else "") + (" rs" if a.rowstats_out else "") + (" h16" if (a.out16 and a.out32) else (" f16" if a.out16 else "")), fl * (3 if x3 else 1)

@@ -120,6 +120,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // with a fire-and-forget integer atomic (associative: the accumulated value does not depend on the arrival order).
   // Must be called by all 32 lanes; n < 0 marks a lane without a column.
   auto gn_commit = [&](int img, int n, float sv, float qv) {
+    if (p.gn_dbg & 2) return;
 #pragma unroll
     for (int cns = 0; cns < 2; ++cns) {
       if (!p.gn_acc[cns]) continue;
@@ -132,7 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane + off < 32 && g2 == g) { a += a2; b += b2; }
       }
       const int gprev = __shfl_up_sync(0xffffffffu, g, 1);
-      if (g >= 0 && (lane == 0 || gprev != g)) {
+      if (g >= 0 && (lane == 0 || gprev != g) && !(p.gn_dbg & 1)) {
         unsigned long long* acc = (unsigned long long*)(p.gn_acc[cns] + ((size_t)img * p.gn_groups + g) * 2);
         atomicAdd(acc, (unsigned long long)__float2ll_rn(a * 16777216.f));
         atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(b * 1048576.f));
@@ -1407,6 +1408,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     UPGPT_REQUIRE(((uintptr_t)p.rowstats & 7) == 0 && !(p.flags & (GEMM_CHW | GEMM_GEGLU)) && a->out32, "upgpt_gemm: rowstats_out needs an fp32 row-major result");
   }
   p.gn_acc[0] = a->gn_acc; p.gn_acc[1] = a->gn_acc ? a->gn_acc2 : nullptr;
+  { static const int dbg = getenv("UPGPT_GN_DBG") ? atoi(getenv("UPGPT_GN_DBG")) : 0; p.gn_dbg = dbg; }
   p.gn_groups = a->gn_groups; p.gn_cpg[0] = a->gn_cpg; p.gn_cpg[1] = a->gn_cpg2; p.gn_choff[0] = a->gn_choff; p.gn_choff[1] = a->gn_choff2;
   if (p.gn_acc[0]) {
     UPGPT_REQUIRE(a->out32 && !(p.flags & (GEMM_CHW | GEMM_GEGLU)) && !p.ln_stats && !p.rowstats,

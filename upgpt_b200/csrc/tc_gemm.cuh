@@ -81,6 +81,7 @@ struct GemmParams {
   // ---- GroupNorm moments of the result for up to two consumers (include/upgpt_b200.h: gn_acc) ----
   long long* gn_acc[2];
   int gn_groups, gn_cpg[2], gn_choff[2];
+  int gn_dbg;               // bring-up (UPGPT_GN_DBG): bit 0 = skip the atomics, bit 1 = skip the whole commit
   int gn_gt[2];             // accumulator slots per image of a tile: the groups an N tile can touch
   int w_prefetch;           // > 0: W boxes of the first tile are issued before the PDL wait (GEMM_W_STATIC); > 1: + L2 prefetch depth
   // ---- deterministic split-K ----

@@ -359,7 +359,7 @@ class EngineBase:
         saved = []
         ok = True
         for a, off in prods:
-            saved.append((a, a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits))
+            saved.append((a, a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits, a.block_n))
             if a.mode == _C.GEMM_PLAIN:
                 a.rows_per_group = HW
             if not a.gn_acc:
@@ -376,14 +376,14 @@ class EngineBase:
                     sp = 1
                     while sp * 2 <= plan[2]:
                         sp *= 2
-                    a.splits = sp
+                    a.splits, a.block_n = sp, int(plan[0])     # (a pinned split alone would re-pick the tile width for an unsplit launch)
                     rc = self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan))
             if rc != 0:
                 ok = False
                 break
         if not ok:
-            for a, g0, g1, g2, g3, g4, g5, g6, rpg, sp in saved:
-                a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits = g0, g1, g2, g3, g4, g5, g6, rpg, sp
+            for a, g0, g1, g2, g3, g4, g5, g6, rpg, sp, bn in saved:
+                a.gn_acc, a.gn_groups, a.gn_cpg, a.gn_choff, a.gn_acc2, a.gn_cpg2, a.gn_choff2, a.rows_per_group, a.splits, a.block_n = g0, g1, g2, g3, g4, g5, g6, rpg, sp, bn
             return None
         self._gn_slots += 1
         return acc
