@@ -223,11 +223,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) mbar_arrive(&bar_sfree[sb]);
       const int kbase = j * 128 + hf * 64;
       float m_loc = -INFINITY;
+      if (kbase + 64 > p.Nk) {       // only the ragged last half-tile carries keys past Nk (warp-uniform branch)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float sv = (kbase + i < p.Nk) ? __uint_as_float(v[i]) : -INFINITY;
-        v[i] = __float_as_uint(sv);
-        m_loc = fmaxf(m_loc, sv);
+        for (int i = 0; i < 64; ++i) {
+          const float sv = (kbase + i < p.Nk) ? __uint_as_float(v[i]) : -INFINITY;
+          v[i] = __float_as_uint(sv);
+          m_loc = fmaxf(m_loc, sv);
+        }
+      } else {
+        // two independent max chains (a single 64-deep chain of dependent FMNMX exposes its latency at two warps per scheduler)
+        float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]);
+#pragma unroll
+        for (int i = 2; i < 64; i += 2) { m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1])); }
+        m_loc = fmaxf(m0, m1);
       }
       float* mx = xch + (j & 1) * 256;
       mx[hf * 128 + r] = m_loc;
@@ -238,16 +246,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float m_new = ((m_cand - m_run) * c2 > 8.f) ? m_cand : m_run;
       const float alpha = ex2_approx((m_run - m_new) * c2);
       const float mc = m_new * c2;
-      float l_tile = 0.f;
+      float l_tile = 0.f, l_tile1 = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 64; i += 2) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), c2, -mc));
         const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), c2, -mc));
-        l_tile += p0 + p1;
+        l_tile += p0; l_tile1 += p1;
         __half2 hh = __floats2half2_rn(p0, p1);
         pk[i >> 1] = *(uint32_t*)&hh;
       }
+      l_tile += l_tile1;
       l_part = l_part * alpha + l_tile;
       m_run = m_new;
       // P smem and the O accumulator are busy until PV(j-1) has completed

@@ -8,6 +8,8 @@ synthetic latent / context -- the eps of each candidate plan against the fp16x3 
 candidate whose deviation stays under `LIMIT`:
 
     deep+tf1 : single plane in the two deepest levels (weight-bandwidth bound) and in every attention projection / feed-forward GEMM
+    deep+tf1s: the same, but the attention / feed-forward GEMMs of the full-resolution level (the most sensitive ones:
+               profiles/r01_precision_sensitivity.txt) keep [hi | lo] planes
     deep     : single plane in the two deepest levels only (the round-1 plan)
     deepest  : single plane in the deepest level only
     fp16x3   : error-compensated operands everywhere
@@ -19,7 +21,8 @@ import os
 
 import torch
 
-LIMIT = 7e-4          # max |eps_plan - eps_fp16x3| / max |eps_fp16x3|; + fp16x3's own <= 2e-4 stays inside the 1e-3 tolerance
+LIMIT = 6.5e-4        # max |eps_plan - eps_fp16x3| / max |eps_fp16x3|; + fp16x3's own <= 2e-4 stays inside the 1e-3 tolerance (the
+                      # per-sample maximum at B = 8 runs ~1.3x the B = 1 probe: 7.5e-4 for a probe deviation of 5.8e-4)
 TIMESTEPS = (981, 481)
 
 
@@ -29,6 +32,7 @@ def candidates(H, W, n_levels):
     out = []
     if deep is not None:
         out.append(("deep+tf1", dict(mixed_hw=deep, tf_x1=True)))
+        out.append(("deep+tf1s", dict(mixed_hw=deep, tf_x1=True, tf_hw=max(hw0 // 4, 1))))
         out.append(("deep", dict(mixed_hw=deep, tf_x1=False)))
         out.append(("deepest", dict(mixed_hw=(deep[1], deep[1]), tf_x1=False)))
     else:

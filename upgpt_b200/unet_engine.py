@@ -429,7 +429,7 @@ class EngineBase:
 class UNetEngine(EngineBase):
     def __init__(self, unet, B, H, W, ctx_len, precision=None, dry=False, plan=None, store=None):
         """dry: record the program over host buffers without a device (CPU unit tests of the host logic); it can never run.
-        plan: {"mixed_hw": (deep_hw, full_hw) | None, "tf_x1": bool} of the "mixed" precision mode (upgpt_b200/precision.py calibrates
+        plan: {"mixed_hw": (deep_hw, full_hw) | None, "tf_x1": bool[, "tf_hw": int]} of the "mixed" precision mode (upgpt_b200/precision.py calibrates
         it per checkpoint); default: the static profile of MIXED_PROFILES / the UPGPT_MIXED_HW, UPGPT_TF_PLANES overrides.
         store: packed-weight store to use instead of the module's (throw-away engines of the calibration)."""
         dev = next(unet.parameters()).device
@@ -456,6 +456,8 @@ class UNetEngine(EngineBase):
         tf_x1 = os.environ.get("UPGPT_TF_PLANES", "x3") == "x1"
         if plan is not None and self.precision == "mixed":
             self.mixed_hw, tf_x1 = plan["mixed_hw"], bool(plan["tf_x1"])
+        # tf_hw: the attention / feed-forward GEMMs run on single planes up to this many tokens per image (None = every level)
+        self.tf_hw = (plan or {}).get("tf_hw") if self.precision == "mixed" else None
         self.mixed = self.mixed_hw is not None
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and tf_x1
@@ -505,7 +507,7 @@ class UNetEngine(EngineBase):
         if not self.mixed:
             return self.split3
         deep_hw, full_hw = self.mixed_hw
-        if hw <= full_hw or (kind == "tf" and self.tf_x1):
+        if hw <= full_hw or (kind == "tf" and self.tf_x1 and (self.tf_hw is None or hw <= self.tf_hw)):
             return False
         if hw <= deep_hw:
             return kind in ("resid1x1", "conv_skipshared")
@@ -522,7 +524,7 @@ class UNetEngine(EngineBase):
 
     def plan_signature(self):
         if getattr(self, "_plan_sig", None) is None:
-            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.ln_fold,
+            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.ln_fold,
                               tuple(sorted(self.layer_hw.items())) if self.mixed else None)
         return self._plan_sig
 
