@@ -37,18 +37,31 @@ class LitEma(nn.Module):
                 self.register_buffer(s_name, p.clone().detach().data)
         self.collected_params = []
 
+    # copy_to / store / restore move every parameter of the model: ~700 tensors, three times per `ema_scope`, i.e. per request through
+    # log_images. One multi-tensor copy per call (torch._foreach_copy_) instead of ~2000 single-tensor launches keeps the scope's host
+    # cost out of the request latency (same values, same semantics as ema.py:55-76).
     def copy_to(self, model):
         shadow = dict(self.named_buffers())
+        dst, src = [], []
         for name, p in model.named_parameters():
             if p.requires_grad:
-                p.data.copy_(shadow[self.m_name2s_name[name]].data)
+                dst.append(p.data); src.append(shadow[self.m_name2s_name[name]].data)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def store(self, parameters):
-        self.collected_params = [p.clone() for p in parameters]
+        params = [p.data for p in parameters]
+        keep = self.collected_params
+        if len(keep) != len(params) or any(k.shape != p.shape or k.dtype != p.dtype or k.device != p.device for k, p in zip(keep, params)):
+            keep = [torch.empty_like(p) for p in params]
+        if params:
+            torch._foreach_copy_(keep, params)
+        self.collected_params = keep
 
     def restore(self, parameters):
-        for c, p in zip(self.collected_params, parameters):
-            p.data.copy_(c.data)
+        params = [p.data for p in parameters]
+        if params:
+            torch._foreach_copy_(params, [c.data for c in self.collected_params])
 
 
 class DiffusionWrapper(nn.Module):

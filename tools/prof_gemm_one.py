@@ -24,6 +24,13 @@ elif which == "conv_deep":
     def fn():
         it[0] += 1
         ops.gemm(a=x, w=ws[it[0] % 8], mode=_C.GEMM_CONV3X3, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, rowvec=e)
+elif which == "up2":
+    # Upsample of the 16x16 -> 32x32 level (448 -> 448, fp16x3) as four parity-wise 2x2 convolutions over the low-resolution operand
+    from upgpt_b200.unet_engine import split3_w, up2_conv_w
+    B, H, W, C = 8, 16, 16, 448
+    x = split3_w(torch.randn(B, H, W, C, device=dev) * 0.5); w = split3_w(up2_conv_w(torch.randn(C, C, 3, 3, device=dev) * 0.02))
+    out = torch.empty(B * 4 * H * W, C, device=dev); bias = torch.randn(C, device=dev)
+    fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3_UP2, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, flags=_C.GEMM_F_X3 | _C.GEMM_F_W_STATIC)
 elif which == "gemm_small":
     M, N, K = 128, 896, 896
     a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)
