@@ -1,9 +1,9 @@
 """Cuts an ncu launch list of tools/prof_hot_path.py (2 eager U-Net steps + 1 VAE decode) into its parts and prints per-kernel shares.
-usage: python tools/summarize_hot_path.py <csv> [unet_launches_per_step=422] [vae_launches=106]"""
+usage: python tools/summarize_hot_path.py <csv> [unet_launches_per_step=297] [vae_launches=95]"""
 import collections, csv, re, sys
 path = sys.argv[1]
-n_unet = int(sys.argv[2]) if len(sys.argv) > 2 else 422
-n_vae = int(sys.argv[3]) if len(sys.argv) > 3 else 106
+n_unet = int(sys.argv[2]) if len(sys.argv) > 2 else 297
+n_vae = int(sys.argv[3]) if len(sys.argv) > 3 else 95
 lines = [l for l in open(path) if not l.startswith("==")]
 rows = [r for r in csv.DictReader(lines) if r["Metric Name"] == "gpu__time_duration.sum"]
 d = [(re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", ""), float(r["Metric Value"]) / 1e3) for r in rows]
