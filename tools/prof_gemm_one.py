@@ -31,6 +31,14 @@ elif which == "up2":
     x = split3_w(torch.randn(B, H, W, C, device=dev) * 0.5); w = split3_w(up2_conv_w(torch.randn(C, C, 3, 3, device=dev) * 0.02))
     out = torch.empty(B * 4 * H * W, C, device=dev); bias = torch.randn(C, device=dev)
     fn = lambda: ops.gemm(a=x, w=w, mode=_C.GEMM_CONV3X3_UP2, N=C, K=C, n_imgs=B, H=H, W=W, out32=out, bias=bias, flags=_C.GEMM_F_X3 | _C.GEMM_F_W_STATIC)
+elif which == "geglu":
+    # GEGLU feed-forward projection of the 32x32 level (attention.py:37-44): M 8192, N 2 x 896, K 224, single-plane operands, folded LayerNorm
+    M3, K3, inner = 8192, 224, 896
+    a3 = (torch.randn(M3, K3, device=dev) * 0.5).half(); w3 = (torch.randn(2 * inner, K3, device=dev) * 0.05).half()
+    b3 = torch.randn(2 * inner, device=dev); o3 = torch.empty(M3, inner, device=dev, dtype=torch.half); cs = torch.randn(2 * inner, device=dev)
+    st = torch.rand(M3 * 2 * 2, device=dev) + 1.0
+    fn = lambda: ops.gemm(a=a3, w=w3, mode=0, M=M3, N=2 * inner, K=K3, out16=o3, bias=b3, ln_stats=st, ln_slots=2, ln_eps=1e-5, ln_colsum=cs,
+                          flags=_C.GEMM_F_GEGLU | _C.GEMM_F_W_STATIC)
 elif which == "gemm_small":
     M, N, K = 128, 896, 896
     a = (torch.randn(M, K, device=dev) * 0.5).half(); w = (torch.randn(N, K, device=dev) * 0.02).half(); out = torch.empty(M, N, device=dev)

@@ -49,7 +49,7 @@ def lib():
         _build.build()
     if not os.path.exists(_LIB_PATH):
         raise UpgptError("libupgpt_b200.so missing at %s; run `python -m upgpt_b200.build`" % _LIB_PATH)
-    l = C.CDLL(_LIB_PATH)
+    l = C.CDLL(os.environ.get("UPGPT_LIB_PATH") or _LIB_PATH)     # UPGPT_LIB_PATH: bring-up (A/B of two builds inside one GPU call)
     l.upgpt_last_error.restype = C.c_char_p
     l.upgpt_launch_count.restype = C.c_longlong
     _bind(l)

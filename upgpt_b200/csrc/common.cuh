@@ -336,14 +336,27 @@ __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + _
 // Exact-erf GELU (attention.py:37-44 uses F.gelu's default erf form). The GEGLU epilogues evaluate it 7.3 M times per level-0
 // projection on 8 warps per SM, so erf is a branch-free Abramowitz-Stegun 7.1.26 form: erf(z) = 1 - (a1 t + .. + a5 t^5) e^(-z^2),
 // t = 1 / (1 + p z), |error| <= 1.5e-7 (fp32 erff: ~1e-7) in ~14 instructions with two MUFU ops instead of erff's ~30 with branches.
+// (raw MUFU.RCP / MUFU.EX2: __fdividef and exp2f wrap them in range checks and denormal scaling -- 7 more instructions per element, and the
+// GEGLU epilogue is instruction-fetch bound: ncu attributes a third of its stall samples to no_instructions. 1 + p z >= 1 and
+// -z^2 log2(e) <= 0, so neither wrapper's special cases can occur; ex2.approx.ftz flushes to 0 below 2^-126, as erf needs.)
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float erf_as_f(float z) {
   const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  const float t = rcp_approx_f(fmaf(0.3275911f, az, 1.0f));
   float pl = fmaf(1.061405429f, t, -1.453152027f);
   pl = fmaf(pl, t, 1.421413741f);
   pl = fmaf(pl, t, -0.284496736f);
   pl = fmaf(pl, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * az * az);
+  const float e = ex2_approx_f(-1.4426950408889634f * az * az);
   return copysignf(fmaf(-pl * t, e, 1.0f), z);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f)); }

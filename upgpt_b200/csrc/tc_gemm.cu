@@ -562,13 +562,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_wait();
             if (stamp && c == 0) TS(12);
             float f[32];
-            if (ln) {
+            {
+              // bias (and column sums) of the chunk's 32 columns as 16-byte shared-memory loads (j0 is a multiple of 32)
+              const float4* b4p = (const float4*)(bias_g + j0);
+              const float4* s4p = (const float4*)(lns_g + j0);
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                f[i] = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + i], __uint_as_float(v[i]) * p.out_scale), bias_g[j0 + i]);
-            } else {
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = b4p[i4];
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                if (ln) {
+                  const float4 ss = s4p[i4];
+                  const float sv[4] = {ss.x, ss.y, ss.z, ss.w};
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + i]);
+                  for (int e = 0; e < 4; ++e)
+                    f[4 * i4 + e] = fmaf(ln_rs, fmaf(-ln_mu, sv[e], __uint_as_float(v[4 * i4 + e]) * p.out_scale), bv[e]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) f[4 * i4 + e] = fmaf(__uint_as_float(v[4 * i4 + e]), p.out_scale, bv[e]);
+                }
+              }
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) { f[4 * q] += e[q].x; f[4 * q + 1] += e[q].y; f[4 * q + 2] += e[q].z; f[4 * q + 3] += e[q].w; }
@@ -611,18 +623,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               uint32_t v[32];
               tmem_ld32(t_acc + (uint32_t)(j0 + 32 * h), v);
               tmem_ld_wait();
+              const float4* b4p = (const float4*)(bias_g + j0 + 32 * h);
+              const float4* s4p = (const float4*)(lns_g + j0 + 32 * h);
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                float a0, a1;
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = b4p[i4];
+                const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                float o[4];
                 if (ln) {
-                  a0 = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + 32 * h + i], __uint_as_float(v[i]) * p.out_scale), bias_g[j0 + 32 * h + i]);
-                  a1 = fmaf(ln_rs, fmaf(-ln_mu, lns_g[j0 + 32 * h + i + 1], __uint_as_float(v[i + 1]) * p.out_scale), bias_g[j0 + 32 * h + i + 1]);
+                  const float4 ss = s4p[i4];
+                  const float sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o[e] = fmaf(ln_rs, fmaf(-ln_mu, sv[e], __uint_as_float(v[4 * i4 + e]) * p.out_scale), bv[e]);
                 } else {
-                  a0 = fmaf(__uint_as_float(v[i]), p.out_scale, bias_g[j0 + 32 * h + i]);
-                  a1 = fmaf(__uint_as_float(v[i + 1]), p.out_scale, bias_g[j0 + 32 * h + i + 1]);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) o[e] = fmaf(__uint_as_float(v[4 * i4 + e]), p.out_scale, bv[e]);
                 }
-                __half2 hh = __floats2half2_rn(a0, a1);
-                pk[16 * h + (i >> 1)] = *(uint32_t*)&hh;
+                __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+                pk[16 * h + 2 * i4] = *(uint32_t*)&h0;
+                pk[16 * h + 2 * i4 + 1] = *(uint32_t*)&h1;
               }
             }
           }
@@ -727,17 +746,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld16(t_acc + (uint32_t)(half_n + j0 + h0), gr_);
             tmem_ld_wait();
             const int cx = j0 + h0, cg = cx + half_n;
+            // per-column constants as 16-byte shared-memory loads (cx, cg are multiples of 16 columns): one LDS.128 per 4 elements and
+            // array instead of 4 scalar broadcasts per element
+            const float4* bx4 = (const float4*)(bias_g + cx);
+            const float4* bg4 = (const float4*)(bias_g + cg);
+            const float4* sx4 = (const float4*)(lns_g + cx);
+            const float4* sg4 = (const float4*)(lns_g + cg);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float xv, gv;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bx = bx4[i4], bg = bg4[i4];
+              float cxv[4] = {bx.x, bx.y, bx.z, bx.w}, cgv[4] = {bg.x, bg.y, bg.z, bg.w};
               if (ln) {
-                xv = fmaf(ln_rs, __uint_as_float(xr[i]), fmaf(-ln_ms, lns_g[cx + i], bias_g[cx + i]));
-                gv = fmaf(ln_rs, __uint_as_float(gr_[i]), fmaf(-ln_ms, lns_g[cg + i], bias_g[cg + i]));
-              } else {
-                xv = __uint_as_float(xr[i]) + bias_g[cx + i];
-                gv = __uint_as_float(gr_[i]) + bias_g[cg + i];
+                const float4 sx = sx4[i4], sg = sg4[i4];
+                cxv[0] = fmaf(-ln_ms, sx.x, cxv[0]); cxv[1] = fmaf(-ln_ms, sx.y, cxv[1]); cxv[2] = fmaf(-ln_ms, sx.z, cxv[2]); cxv[3] = fmaf(-ln_ms, sx.w, cxv[3]);
+                cgv[0] = fmaf(-ln_ms, sg.x, cgv[0]); cgv[1] = fmaf(-ln_ms, sg.y, cgv[1]); cgv[2] = fmaf(-ln_ms, sg.z, cgv[2]); cgv[3] = fmaf(-ln_ms, sg.w, cgv[3]);
               }
-              f[h0 + i] = xv * gelu_erf_f(gv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * i4 + e;
+                // rstd = 1 and (mean rstd) = 0 without a folded LayerNorm: the same two FMAs serve both forms
+                const float xv = fmaf(ln_rs, __uint_as_float(xr[i]), cxv[e]);
+                const float gv = fmaf(ln_rs, __uint_as_float(gr_[i]), cgv[e]);
+                f[h0 + i] = xv * gelu_erf_f(gv);
+              }
             }
           }
           if (stamp && j0 == 0) TS(12);
