@@ -327,3 +327,27 @@ def test_inference_model_facade_builds_and_mixes_styles():
     mid = interp_mask(a, c, 0.5)
     ys, xs = torch.nonzero(mid[0] > -1.0, as_tuple=True)
     assert (int(ys.min()), int(ys.max()), int(xs.min()), int(xs.max())) == (6, 23, 4, 13)
+
+
+def test_ema_scope_swaps_and_restores_parameters():
+    """LitEma.store / copy_to / restore (reference ldm/modules/ema.py:55-76) as multi-tensor copies: inside the scope the module holds the
+    EMA weights, afterwards exactly the training weights; the stash buffers are reused across scopes (no per-request allocation)."""
+    from ldm.models.diffusion.ddpm import LitEma
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.LayerNorm(5), torch.nn.Linear(5, 3))
+    ema = LitEma(m)
+    train = [p.detach().clone() for p in m.parameters()]
+    shadow = dict(ema.named_buffers())
+    for name, _ in m.named_parameters():
+        shadow[ema.m_name2s_name[name]].mul_(0.5).add_(0.25)          # EMA weights that differ from the training weights
+    want = [shadow[ema.m_name2s_name[n]].clone() for n, _ in m.named_parameters()]
+    for rep in range(2):
+        ema.store(m.parameters())
+        stash = [c.data_ptr() for c in ema.collected_params]
+        ema.copy_to(m)
+        assert all(torch.equal(p, w) for p, w in zip(m.parameters(), want))
+        ema.restore(m.parameters())
+        assert all(torch.equal(p, w) for p, w in zip(m.parameters(), train))
+        if rep:
+            assert stash == stash0, "the second scope reuses the first scope's stash"
+        stash0 = stash
