@@ -545,3 +545,43 @@ def test_ddim_and_ddpm_update_kernels(dev, eta):
         xp, p0 = torch.empty(2, 4, 32, 32, device=dev), torch.empty(2, 4, 32, 32, device=dev)
         ops.ddpm_step(x.to(dev), e.to(dev), model_rows, xp, p0, noise=nz.to(dev), step_imm=tt)
         assert relerr(xp, ref_prev) < 5e-6 and relerr(p0, ref_x0) < 5e-6
+
+
+def test_launch_trace_stamps_every_kernel_in_order(dev):
+    """upgpt_trace_set: block 0 of every kernel of the library stamps %globaltimer on entry (kind 0) and when its dependency wait returns
+    (kind 1): a chain of n launches leaves n stamps of each kind, the kind-1 stamps are non-decreasing (completion order of a dependent
+    chain), nothing is written when the trace is off, and the capacity word bounds the writes."""
+    from upgpt_b200 import ops, _C
+    L = _C.lib()
+    M, N, K = 256, 128, 128
+    a = (torch.randn(M, K) * 0.5).half().to(dev); w = (torch.randn(N, K) * 0.05).half().to(dev)
+    out = torch.empty(M, N, device=dev); o16 = torch.empty(M, N, device=dev, dtype=torch.half)
+
+    def chain():
+        ops.gemm(a=a, w=w, mode=0, M=M, N=N, K=K, out32=out)
+        _C.check(L.upgpt_axpby(out.data_ptr(), 2.0, out.data_ptr(), 0.5, out.data_ptr(), out.numel(), ops.stream()), "axpby")
+        ops.gemm(a=a, w=w, mode=0, M=M, N=N, K=K, out16=o16)
+    chain(); torch.cuda.synchronize()
+    cap = 64
+    buf = torch.zeros(cap + 2, dtype=torch.int64, device=dev); buf[1] = cap
+    torch.cuda.synchronize()
+    _C.check(L.upgpt_trace_set(buf.data_ptr()), "trace_set")
+    chain(); chain(); torch.cuda.synchronize()
+    _C.check(L.upgpt_trace_set(None), "trace_set")
+    chain(); torch.cuda.synchronize()                      # trace off: no further stamps
+    h = buf.cpu()
+    n = int(h[0])
+    assert n == 12, "6 launches x {entry, dependency wait returned}"
+    st = h[2:2 + n]
+    kind, t = st & 3, st >> 2
+    assert int((kind == 0).sum()) == 6 and int((kind == 1).sum()) == 6
+    tw = t[kind == 1]
+    assert bool((tw[1:] >= tw[:-1]).all()) and int(tw[-1] - tw[0]) < 10_000_000      # ns; a handful of small launches
+    assert int(h[2 + n:].abs().sum()) == 0
+    small = torch.zeros(2 + 2, dtype=torch.int64, device=dev); small[1] = 2       # capacity 2: the counter runs on, the writes stop
+    torch.cuda.synchronize()
+    _C.check(L.upgpt_trace_set(small.data_ptr()), "trace_set")
+    chain(); torch.cuda.synchronize()
+    _C.check(L.upgpt_trace_set(None), "trace_set")
+    hs = small.cpu()
+    assert int(hs[0]) == 6 and int((hs[2:] != 0).sum()) == 2
