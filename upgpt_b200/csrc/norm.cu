@@ -11,6 +11,7 @@
 // F.interpolate nearest x2 (openaimodel.py:116; model.py:53), th.cat([h, hs.pop()]) (openaimodel.py:736),
 // softmax (model.py:184).
 #include "common.cuh"
+#include "tc_gemm.cuh"   // FastDiv
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -323,6 +324,107 @@ prep_kernel(const PrepParams p) {
 //   last-CTA cross-chunk reduction, then prep) cost ~9 us + ~9 us per GroupNorm at the U-Net's sizes, almost all of it latency.
 // grid = (CL, B), cluster = (CL, 1, 1), 512 threads; dynamic smem = chunk + reduction scratch.
 // ------------------------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU)+cast with ONE CTA PER (image, 4 groups). The groups of a GroupNorm are independent: a CTA that owns whole groups
+// needs no exchange with any other CTA -- no cluster, no distributed shared memory, no second pass over memory. It loads its
+// HW x 4 cpg values into registers (float4 items, <= MAXI <= 7 per thread at 1024 threads), reduces the moments inside the block in a fixed order, and
+// normalises out of registers through prep_emit. grid = (groups / 4, B). A pixel contributes a run of 4 cpg channels (112 B .. 896 B):
+// full sectors at the 8x8 / 4x4 levels; at 32x32 (cpg = 7: 112-byte loads, 56-byte plane stores shared between CTAs) the partial
+// sectors make this form slower than the pixel-parallel cluster kernel below, which keeps those levels (measured).
+// ------------------------------------------------------------------------------------------------------------------
+static constexpr int kGroupThreads = 1024, kGroupG = 4;   // 32 warps: the emit is latency-bound per thread (SiLU, stores)
+template <int MAXI>
+__global__ void __launch_bounds__(kGroupThreads)
+gn_group_kernel(const PrepParams p, double* __restrict__ stats_out, const FastDiv fd_ip, const FastDiv fd_cpg) {
+  constexpr int G = kGroupG;
+  __shared__ double red[kGroupThreads / 32][2 * G];
+  __shared__ __align__(16) float sc[256], sh[256];
+  __shared__ float ms[G][2];
+  pdl_launch_dependents();
+  const int C = p.C1 + p.C2, HW = p.H * p.W;
+  const int cpg = C / p.groups;
+  const int gq = blockIdx.x, b = blockIdx.y;
+  const int cbase = gq * G * cpg;
+  const int IP = (G * cpg) >> 2;            // float4 items per pixel
+  const int n_items = HW * IP;
+  pdl_wait();
+  float4 v[MAXI];
+  float s[G], q[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { s[g] = 0.f; q[g] = 0.f; }
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int j = (int)threadIdx.x + kGroupThreads * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n_items) {
+      const int px = fd_ip.div(j);
+      const int c4 = j - px * IP;
+      const int c = cbase + 4 * c4;
+      const size_t row = (size_t)b * HW + px;
+      v[i] = c < p.C1 ? *(const float4*)(p.x1 + row * p.C1 + c) : *(const float4*)(p.x2 + row * p.C2 + (c - p.C1));
+      const int g0 = fd_cpg.div(4 * c4), g3 = fd_cpg.div(4 * c4 + 3);
+      if (g0 == g3) {       // the item lies inside one group (always when cpg % 4 == 0)
+        const float vs = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        const float vq = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, v[i].w * v[i].w)));
+#pragma unroll
+        for (int g = 0; g < G; ++g) { s[g] += g == g0 ? vs : 0.f; q[g] += g == g0 ? vq : 0.f; }
+      } else {
+        const float e[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int gk = fd_cpg.div(4 * c4 + k);
+#pragma unroll
+          for (int g = 0; g < G; ++g) { s[g] += g == gk ? e[k] : 0.f; q[g] += g == gk ? e[k] * e[k] : 0.f; }
+        }
+      }
+    }
+  }
+  // block moments in a fixed order: butterfly inside the warp, then the 32 warp partials in double
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s[g] += __shfl_xor_sync(0xffffffffu, s[g], o); q[g] += __shfl_xor_sync(0xffffffffu, q[g], o); }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) { red[threadIdx.x >> 5][2 * g] = (double)s[g]; red[threadIdx.x >> 5][2 * g + 1] = (double)q[g]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    double S = 0.0, Q = 0.0;
+#pragma unroll
+    for (int w = 0; w < kGroupThreads / 32; ++w) { S += red[w][2 * g]; Q += red[w][2 * g + 1]; }
+    const double inv_n = 1.0 / ((double)cpg * HW);
+    const double mean = S * inv_n;
+    double var = Q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    ms[g][0] = (float)mean;
+    ms[g][1] = (float)(1.0 / sqrt(var + (double)p.eps));
+    if (stats_out) {
+      stats_out[((size_t)b * p.groups + gq * G + g) * 2] = S;
+      stats_out[((size_t)b * p.groups + gq * G + g) * 2 + 1] = Q;
+    }
+  }
+  __syncthreads();
+  for (int cl = threadIdx.x; cl < G * cpg; cl += kGroupThreads) {
+    const int g = fd_cpg.div(cl);
+    const float ga = p.gamma ? p.gamma[cbase + cl] : 1.f, be = p.beta ? p.beta[cbase + cl] : 0.f;
+    const float scl = ms[g][1] * ga;
+    sc[cl] = scl;
+    sh[cl] = be - ms[g][0] * scl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int j = (int)threadIdx.x + kGroupThreads * i;
+    if (j >= n_items) continue;
+    const int px = fd_ip.div(j);
+    const int c = cbase + 4 * (j - px * IP);
+    prep_emit(p, b, px, c, v[i], sc - cbase, sh - cbase, true);      // (scale / shift tables are indexed by the global channel)
+  }
+}
+
 static constexpr int kFusedThreads = 1024;   // 32 warps per SM: the emit phase is instruction-latency bound
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
@@ -692,6 +794,36 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
   const int C = a->C1 + a->C2;
   const int HW = a->H * a->W;
   UPGPT_REQUIRE(a->groups > 0 && C > 0 && C % a->groups == 0 && a->C1 % 4 == 0 && a->C2 % 4 == 0, "groupnorm_prep: bad channels (C1=%d C2=%d groups=%d)", a->C1, a->C2, a->groups);
+  {
+    // one CTA per (image, 4 groups) when that fits the registers of a block and the level is small enough for the short channel runs
+    // to be whole sectors (UPGPT_GN_GROUP_HW: largest H*W that takes this form, 0 = never; default from the measurements in DESIGN.md)
+    static const int group_hw = getenv("UPGPT_GN_GROUP_HW") ? atoi(getenv("UPGPT_GN_GROUP_HW")) : 64;
+    const int cpg = C / a->groups;
+    const long long n_items = (long long)HW * cpg;      // = HW * (4 cpg) / 4
+    if (HW <= group_hw && a->groups % kGroupG == 0 && kGroupG * cpg <= 256 && n_items <= (long long)kGroupThreads * 7 &&
+        ((uintptr_t)a->x1 & 15) == 0 && (!a->x2 || ((uintptr_t)a->x2 & 15) == 0) && a->B <= 65535) {
+      UPGPT_REQUIRE(a->layout != 2 || (a->H % 2 == 0 && a->W % 2 == 0), "groupnorm_prep: stride-2 phases need even H, W");
+      UPGPT_REQUIRE(!a->raw || a->layout == 0, "groupnorm_prep: raw copy only with layout 0");
+      PrepParams p{};
+      p.x1 = a->x1; p.C1 = a->C1; p.x2 = a->x2; p.C2 = a->C2; p.H = a->H; p.W = a->W; p.B = a->B;
+      p.groups = a->groups; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
+      p.layout = a->layout; p.split3 = a->split3;
+      p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
+      p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
+      UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "groupnorm_prep: ld must be a multiple of 4");
+      const FastDiv fd_ip = make_fastdiv(cpg), fd_cpg = make_fastdiv(cpg);      // items per pixel = 4 cpg / 4 = cpg
+      const dim3 grid(a->groups / kGroupG, a->B), block(kGroupThreads);
+      const int per = (int)((n_items + kGroupThreads - 1) / kGroupThreads);
+      cudaError_t e;
+      if (per <= 1) e = launch_k(gn_group_kernel<1>, grid, block, 0, stream, p, stats, fd_ip, fd_cpg);
+      else if (per <= 4) e = launch_k(gn_group_kernel<4>, grid, block, 0, stream, p, stats, fd_ip, fd_cpg);
+      else e = launch_k(gn_group_kernel<7>, grid, block, 0, stream, p, stats, fd_ip, fd_cpg);
+      UPGPT_CHECK_CUDA(e);
+      count_launch();
+      UPGPT_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   NormDev* nd = norm_dev();
   UPGPT_REQUIRE(nd, "groupnorm_prep: no current CUDA device");
   std::unique_lock<std::mutex> lk(g_norm_mu);
