@@ -145,6 +145,8 @@ typedef struct upgpt_prep_args {
   const long long* gn_acc;   /* optional [B][groups][2] fixed-point group moments {sum * 2^24, sumsq * 2^20} accumulated by the kernels that
                                 PRODUCED x1 / x2 (upgpt_gemm's gn_acc, upgpt_gn_accumulate): GroupNorm(gamma, beta, eps) is applied from
                                 them -- no statistics pass over the tensor, no reduction in this kernel */
+  int raw_planes;            /* format of `raw`: 0 = as `out` (split3), 1 = one fp16 plane, 2 = [hi | lo] planes. A ResBlock's skip 1x1 GEMM
+                                (openaimodel.py:241) runs error-compensated on the raw copy while conv1 may take a single-plane operand */
 } upgpt_prep_args;
 int upgpt_prep_operand(const upgpt_prep_args* args, void* stream);
 /* Adds the per-(image, group) moments of x [B][HW][C] (channels choff .. choff + C of a GroupNorm over `groups` groups of `cpg` channels)

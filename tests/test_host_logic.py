@@ -206,7 +206,7 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
             a = args[0]._obj
             fmt[a.out] = bool(a.split3)
             if a.raw:
-                fmt[a.raw] = bool(a.split3)
+                fmt[a.raw] = bool(a.split3) if a.raw_planes == 0 else a.raw_planes == 2
         elif fn in (L.upgpt_layernorm, L.upgpt_layernorm_split3):
             assert args[0] and args[4] and args[5] and args[7]
             fmt[args[7]] = fn is L.upgpt_layernorm_split3
@@ -232,6 +232,29 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     else:   # mixed: the 4x4 level entirely, the 8x8 level except skip / proj_in / proj_out and the convs sharing operands with a skip
         assert n_plain == 64 and eng.mixed
         assert eng.use_x3("conv", 1024) and not eng.use_x3("resid1x1", 16) and eng.use_x3("resid1x1", 64) and not eng.use_x3("tf", 64)
+    if precision == "mixed":
+        # calibrated plan deep+tf1 (upgpt_b200/precision.py): additionally every attention / feed-forward GEMM and the 8x8-level ResBlock
+        # convs whose input also feeds a skip 1x1 GEMM on single planes; that GEMM keeps [hi | lo] planes of its own (raw_planes = 2)
+        eng2 = UNetEngine(unet, 1, 32, 32, 87, precision="mixed", dry=True, plan=dict(mixed_hw=(64, 16), tf_x1=True, skip_x1=True, name="deep+tf1"))
+        fmt2, plain2, mixed_raw = {}, 0, 0
+        for fn, args in eng2.prog.kernel_calls():
+            if fn in (L.upgpt_prep_operand, L.upgpt_groupnorm_prep):
+                a = args[0]._obj
+                fmt2[a.out] = bool(a.split3)
+                if a.raw:
+                    fmt2[a.raw] = bool(a.split3) if a.raw_planes == 0 else a.raw_planes == 2
+                    mixed_raw += fmt2[a.raw] != fmt2[a.out]
+            elif fn is L.upgpt_attention:
+                fmt2[args[0]._obj.out] = bool(args[0]._obj.split3_out)
+            elif fn is L.upgpt_gemm:
+                a = args[0]._obj
+                x3 = bool(a.flags & _C.GEMM_F_X3)
+                plain2 += not x3
+                if a.a in fmt2:
+                    assert fmt2[a.a] == x3, "operand planes do not match the GEMM's precision flag (calibrated plan)"
+                if a.out16:
+                    fmt2[a.out16] = bool(a.flags & _C.GEMM_F_SPLIT3OUT)
+        assert mixed_raw == 4 and plain2 > n_plain + 4, (mixed_raw, plain2, n_plain)
     with pytest.raises(_C.UpgptError):
         eng.run()
     # an architecture without a probed profile keeps fp16x3 everywhere in "mixed" (the probe shows its deep levels are not cheap in error)

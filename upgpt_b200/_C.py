@@ -80,7 +80,7 @@ class PrepArgs(C.Structure):
         ("stats", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
         ("silu", C.c_int), ("layout", C.c_int), ("split3", C.c_int),
         ("out", C.c_void_p), ("ldo", C.c_int), ("raw", C.c_void_p), ("ldraw", C.c_int), ("scale_shift", C.c_void_p),
-        ("gn_acc", C.c_void_p),
+        ("gn_acc", C.c_void_p), ("raw_planes", C.c_int),
     ]
 
 

@@ -187,6 +187,7 @@ struct PrepParams {
   int split3;              // output channels = 2C: [hi | lo]
   __half* out; int ldo;    // elements per output pixel (>= C or 3C)
   __half* raw; int ldraw;  // optional un-normalised fp16 copy (layout 0)
+  int raw_split3;          // the raw copy carries [hi | lo] planes (may differ from split3: the skip GEMM runs fp16x3, conv1 need not)
   int B;
 };
 
@@ -201,7 +202,7 @@ __device__ __forceinline__ void prep_emit(const PrepParams& p, int b, int pp, in
       __half2 r0 = __floats2half2_rn(v.x, v.y), r1 = __floats2half2_rn(v.z, v.w);
       uint2 pk = make_uint2(*(uint32_t*)&r0, *(uint32_t*)&r1);
       *(uint2*)(p.raw + row * p.ldraw + c) = pk;
-      if (p.split3) {   // the un-normalised copy feeds the skip 1x1 GEMM: same [hi | lo] planes
+      if (p.raw_split3) {   // the un-normalised copy feeds the skip 1x1 GEMM: [hi | lo] planes when that GEMM runs fp16x3
         const float2 f0 = __half22float2(r0), f1 = __half22float2(r1);
         __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
         *(uint2*)(p.raw + row * p.ldraw + C + c) = make_uint2(*(uint32_t*)&l0, *(uint32_t*)&l1);
@@ -774,7 +775,8 @@ extern "C" int upgpt_prep_operand(const upgpt_prep_args* a, void* stream_) {
   p.groups = a->groups; p.stats = a->stats; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
   p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
-  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
+  p.raw_split3 = a->raw_planes == 0 ? a->split3 : (a->raw_planes == 2);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (p.raw_split3 ? 2 * C : C);
   UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "prep_operand: ld must be a multiple of 4");
   const int HW = a->H * a->W;
   p.chunk = pick_chunk(HW, a->B);
@@ -809,7 +811,8 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
       p.groups = a->groups; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
       p.layout = a->layout; p.split3 = a->split3;
       p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
-      p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
+      p.raw_split3 = a->raw_planes == 0 ? a->split3 : (a->raw_planes == 2);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (p.raw_split3 ? 2 * C : C);
       UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "groupnorm_prep: ld must be a multiple of 4");
       const FastDiv fd_ip = make_fastdiv(cpg), fd_cpg = make_fastdiv(cpg);      // items per pixel = 4 cpg / 4 = cpg
       const dim3 grid(a->groups / kGroupG, a->B), block(kGroupThreads);
@@ -887,7 +890,8 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
   p.groups = a->groups; p.gamma = a->gamma; p.beta = a->beta; p.eps = a->eps; p.silu = a->silu;
   p.layout = a->layout; p.split3 = a->split3;
   p.out = (__half*)a->out; p.ldo = a->ldo > 0 ? a->ldo : (a->split3 ? 2 * C : C);
-  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (a->split3 ? 2 * C : C);
+  p.raw_split3 = a->raw_planes == 0 ? a->split3 : (a->raw_planes == 2);
+  p.raw = (__half*)a->raw; p.ldraw = a->ldraw > 0 ? a->ldraw : (p.raw_split3 ? 2 * C : C);
   UPGPT_REQUIRE(p.ldo % 4 == 0 && p.ldraw % 4 == 0, "groupnorm_prep: ld must be a multiple of 4");
   UPGPT_REQUIRE((((uintptr_t)a->x1) & 15) == 0 && (!a->x2 || (((uintptr_t)a->x2) & 15) == 0), "groupnorm_prep: inputs must be 16-byte aligned");
   cudaLaunchConfig_t cfg{};

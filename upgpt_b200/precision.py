@@ -7,7 +7,8 @@ At the first engine request after the weights changed, the module therefore meas
 synthetic latent / context -- the eps of each candidate plan against the fp16x3 eps of the same weights and keeps the FASTEST
 candidate whose deviation stays under `LIMIT`:
 
-    deep+tf1 : single plane in the two deepest levels (weight-bandwidth bound) and in every attention projection / feed-forward GEMM
+    deep+tf1 : single plane in the two deepest levels (weight-bandwidth bound; incl. the ResBlock convs whose input also feeds a skip 1x1 GEMM
+               -- that GEMM keeps [hi | lo] planes of its own) and in every attention projection / feed-forward GEMM
     deep+tf1s: the same, but the attention / feed-forward GEMMs of the full-resolution level (the most sensitive ones:
                profiles/r01_precision_sensitivity.txt) keep [hi | lo] planes
     deep     : single plane in the two deepest levels only (the round-1 plan)
@@ -31,8 +32,8 @@ def candidates(H, W, n_levels):
     deep = (max(hw0 // 16, 1), max(hw0 // 64, 1)) if n_levels >= 3 else None
     out = []
     if deep is not None:
-        out.append(("deep+tf1", dict(mixed_hw=deep, tf_x1=True)))
-        out.append(("deep+tf1s", dict(mixed_hw=deep, tf_x1=True, tf_hw=max(hw0 // 4, 1))))
+        out.append(("deep+tf1", dict(mixed_hw=deep, tf_x1=True, skip_x1=True)))
+        out.append(("deep+tf1s", dict(mixed_hw=deep, tf_x1=True, skip_x1=True, tf_hw=max(hw0 // 4, 1))))
         out.append(("deep", dict(mixed_hw=deep, tf_x1=False)))
         out.append(("deepest", dict(mixed_hw=(deep[1], deep[1]), tf_x1=False)))
     else:

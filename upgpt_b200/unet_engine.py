@@ -269,12 +269,13 @@ class EngineBase:
         self.prog.add(self.L.upgpt_groupnorm_affine, self.p(x1), C1, self.p(x2), C2, B, HW, 32, self.p(stats), self.p(gamma), self.p(beta),
                       eps, self.p(ss))
 
-    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, ss=None, gn_acc=0):
+    def e_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, ss=None, gn_acc=0, raw_split3=None):
         if self._sizing:
             return
         a = _C.PrepArgs()
         a.scale_shift = self.p(ss)
         a.gn_acc = gn_acc
+        a.raw_planes = 0 if raw_split3 is None else (2 if raw_split3 else 1)
         a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
         a.B, a.H, a.W, a.groups = B, H, W, 32
         a.stats, a.gamma, a.beta, a.eps = self.p(stats), self.p(gamma), self.p(beta), eps
@@ -282,10 +283,11 @@ class EngineBase:
         a.out, a.ldo, a.raw, a.ldraw = self.p(out), 0, self.p(raw), 0
         self.prog.add_struct(self.L.upgpt_prep_operand, a)
 
-    def e_gn_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False):
+    def e_gn_prep(self, x1, C1, x2, C2, B, H, W, stats, gamma, beta, eps, silu, layout, out, raw=None, split3=False, raw_split3=None):
         if self._sizing:
             return
         a = _C.PrepArgs()
+        a.raw_planes = 0 if raw_split3 is None else (2 if raw_split3 else 1)
         a.x1, a.C1, a.x2, a.C2 = self.p(x1), C1, self.p(x2), C2
         a.B, a.H, a.W, a.groups = B, H, W, 32
         a.stats, a.scale_shift = 0, 0
@@ -403,12 +405,15 @@ class EngineBase:
         self.prog.add_struct(self.L.upgpt_attention, a)
 
     # GroupNorm(+SiLU) -> fp16 operand of the (possibly concatenated) input; returns (operand, raw16)
-    def norm_operand(self, x1, C1, x2, C2, B, H, W, gname, eps, silu, want_raw=False, layout=0, split3=False):
+    def norm_operand(self, x1, C1, x2, C2, B, H, W, gname, eps, silu, want_raw=False, layout=0, split3=False, raw_split3=None):
+        """raw_split3: plane format of the un-normalised copy (None = as the operand's): the skip GEMM that reads it may run fp16x3
+        while the convolution on the normalised operand takes a single plane."""
         Cc = C1 + C2
         stats = self.buf("gn_stats", (B, 32, 2), torch.float64)
         mult = 4 if layout == 1 else 1
+        rs3 = split3 if raw_split3 is None else raw_split3
         op = self.scratch("op16", B * H * W * mult * Cc * (2 if split3 else 1), torch.float16)
-        raw = self.scratch("raw16", B * H * W * Cc * (2 if split3 else 1), torch.float16) if want_raw else None
+        raw = self.scratch("raw16", B * H * W * Cc * (2 if rs3 else 1), torch.float16) if want_raw else None
         if gname is not None:
             acc = None
             if not self._sizing:
@@ -416,13 +421,13 @@ class EngineBase:
             if acc is not None:
                 # the moments come from the epilogues of the launches that produced x1 / x2: GroupNorm(+SiLU) + cast is apply-only
                 self.e_prep(x1, C1, x2, C2, B, H, W, None, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
-                            raw, split3, gn_acc=acc)
+                            raw, split3, gn_acc=acc, raw_split3=raw_split3)
             else:
                 # GroupNorm(+SiLU) + cast: one fused cluster launch per GroupNorm (two launches internally for VAE-sized images)
                 self.e_gn_prep(x1, C1, x2, C2, B, H, W, stats, self.w.get(gname + ".weight"), self.w.get(gname + ".bias"), eps, silu, layout, op,
-                               raw, split3)
+                               raw, split3, raw_split3=raw_split3)
         else:
-            self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3)
+            self.e_prep(x1, C1, x2, C2, B, H, W, None, None, None, 0.0, False, layout, op, raw, split3, raw_split3=raw_split3)
         return op, raw
 
 
@@ -458,6 +463,7 @@ class UNetEngine(EngineBase):
             self.mixed_hw, tf_x1 = plan["mixed_hw"], bool(plan["tf_x1"])
         # tf_hw: the attention / feed-forward GEMMs run on single planes up to this many tokens per image (None = every level)
         self.tf_hw = (plan or {}).get("tf_hw") if self.precision == "mixed" else None
+        self.skip_x1 = bool((plan or {}).get("skip_x1", os.environ.get("UPGPT_SKIP_X1", "0") == "1")) and self.precision == "mixed"
         self.mixed = self.mixed_hw is not None
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and tf_x1
@@ -510,7 +516,9 @@ class UNetEngine(EngineBase):
         if hw <= full_hw or (kind == "tf" and self.tf_x1 and (self.tf_hw is None or hw <= self.tf_hw)):
             return False
         if hw <= deep_hw:
-            return kind in ("resid1x1", "conv_skipshared")
+            # conv_skipshared: the un-normalised copy that feeds the skip GEMM keeps its own [hi | lo] planes (raw_planes), so the 3x3 conv
+            # on the normalised operand need not follow the skip GEMM's format (skip_x1, plans deep+tf1 / deep+tf1s)
+            return kind == "resid1x1" or (kind == "conv_skipshared" and not self.skip_x1)
         return True
 
     # ------------------------------------------------------------------------------------------------ weights
@@ -524,7 +532,7 @@ class UNetEngine(EngineBase):
 
     def plan_signature(self):
         if getattr(self, "_plan_sig", None) is None:
-            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.ln_fold,
+            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.skip_x1, self.ln_fold,
                               tuple(sorted(self.layer_hw.items())) if self.mixed else None)
         return self._plan_sig
 
@@ -549,7 +557,8 @@ class UNetEngine(EngineBase):
                 p = name
                 hw = self.layer_hw[p]
                 has_skip = (p + ".skip_connection.weight") in sd
-                x3a = self.use_x3("conv_skipshared" if has_skip else "conv", hw)     # conv1 and the skip GEMM read the same operand planes
+                x3a = self.use_x3("conv_skipshared" if has_skip else "conv", hw)     # conv1
+                x3s = x3a or self.use_x3("resid1x1", hw)                             # the skip GEMM (on the un-normalised copy's planes)
                 for g in (".in_layers.0", ".out_layers.0"):
                     put(p + g + ".weight", sd[p + g + ".weight"]); put(p + g + ".bias", sd[p + g + ".bias"])
                 put(p + ".conv1.weight", self._conv_w(sd[p + ".in_layers.2.weight"], x3a)); put(p + ".conv1.bias", sd[p + ".in_layers.2.bias"])
@@ -557,7 +566,7 @@ class UNetEngine(EngineBase):
                 put(p + ".conv2.bias", sd[p + ".out_layers.3.bias"])
                 if has_skip:
                     ws = sd[p + ".skip_connection.weight"]
-                    put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]), x3a)); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
+                    put(p + ".skip.weight", self._w16(ws.reshape(ws.shape[0], ws.shape[1]), x3s)); put(p + ".skip.bias", sd[p + ".skip_connection.bias"])
                 emb_w.append(sd[p + ".emb_layers.1.weight"]); emb_b.append(sd[p + ".emb_layers.1.bias"])
             elif isinstance(mod, (om.Downsample, om.Upsample)):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
@@ -635,10 +644,11 @@ class UNetEngine(EngineBase):
         Cin, Cout = C1 + C2, mod.out_channels
         HW = H * W
         has_skip = (p + ".skip.weight") in self.w
-        x3a = self.use_x3("conv_skipshared" if has_skip else "conv", HW)     # conv1 (+ the skip GEMM on the same operand planes)
+        x3a = self.use_x3("conv_skipshared" if has_skip else "conv", HW)     # conv1
+        x3s = x3a or self.use_x3("resid1x1", HW)                             # the skip GEMM, on the un-normalised copy's own planes
         x3b = self.use_x3("conv", HW)                                        # conv2
-        fa, fb = (_C.GEMM_F_X3 if x3a else 0), (_C.GEMM_F_X3 if x3b else 0)
-        op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=x3a)
+        fa, fb, fs = (_C.GEMM_F_X3 if x3a else 0), (_C.GEMM_F_X3 if x3b else 0), (_C.GEMM_F_X3 if x3s else 0)
+        op, raw = self.norm_operand(x1, C1, x2, C2, B, H, W, p + ".in_layers.0", 1e-5, True, want_raw=has_skip, split3=x3a, raw_split3=x3s)
         h32 = self.scratch("res_h", B * HW * Cout, torch.float32)
         emb = None if self._sizing else self.bufs["emb_all"][:, self.emb_off[p]:]
         par_skip = has_skip and self.par_skip and not self._sizing
@@ -650,7 +660,7 @@ class UNetEngine(EngineBase):
             self.prog.fork(0)
             self.prog.aux = 0
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
-                        bias=self.w.get(p + ".skip.bias"), flags=fa)
+                        bias=self.w.get(p + ".skip.bias"), flags=fs)
             self.prog.aux = None
         self.e_gemm(a=op, w=self.w.get(p + ".conv1.weight"), mode=_C.GEMM_CONV3X3, N=Cout, K=Cin, n_imgs=B, H=H, W=W,
                     out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=fa)
@@ -660,7 +670,7 @@ class UNetEngine(EngineBase):
             res = skip32
         elif has_skip:
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
-                        bias=self.w.get(p + ".skip.bias"), flags=fa)
+                        bias=self.w.get(p + ".skip.bias"), flags=fs)
             res = skip32
         else:
             assert x2 is None or self._sizing or C2 == 0
