@@ -695,13 +695,9 @@ def gpu_arm(args, rank, world):
 def dtype_string(precision, plan_name):
     if precision != "mixed" or plan_name in ("static", None):
         return PRECISION_NOTES[precision][0]
-    where = {"deep+tf1": "single f16 plane in the weight-bound 8x8 / 4x4 levels and in every attention projection / feed-forward GEMM",
-             "tf1": "single f16 plane in every attention projection / feed-forward GEMM",
-             "deep": "single f16 plane in the weight-bound 8x8 / 4x4 levels", "deepest": "single f16 plane in the deepest level",
-             "fp16x3": "everywhere"}.get(plan_name, plan_name)
-    return ("f16 hi+lo operand planes (3 MMAs per product) on the 3x3 convs and residual-path 1x1s of the 32x32 / 16x16 levels, %s "
-            "(plan '%s', calibrated on these weights against fp16x3 at load: upgpt_b200/precision.py); f32 accumulate / residual / statistics"
-            % (where, plan_name))
+    from upgpt_b200.precision import DESCRIPTIONS
+    return ("f16 hi+lo operand planes (3 MMAs per product) except: %s (plan '%s', calibrated on these weights against fp16x3 at load: "
+            "upgpt_b200/precision.py); f32 accumulate / residual / statistics" % (DESCRIPTIONS.get(plan_name, plan_name), plan_name))
 
 
 PRECISION_NOTES = {

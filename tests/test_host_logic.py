@@ -235,7 +235,10 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
     if precision == "mixed":
         # calibrated plan deep+tf1 (upgpt_b200/precision.py): additionally every attention / feed-forward GEMM and the 8x8-level ResBlock
         # convs whose input also feeds a skip 1x1 GEMM on single planes; that GEMM keeps [hi | lo] planes of its own (raw_planes = 2)
-        eng2 = UNetEngine(unet, 1, 32, 32, 87, precision="mixed", dry=True, plan=dict(mixed_hw=(64, 16), tf_x1=True, skip_x1=True, name="deep+tf1"))
+        from upgpt_b200 import precision as P
+        cands = dict(P.candidates(32, 32, 4))
+        assert list(cands)[0] == "deep+tf1C" and list(cands)[-1] == "fp16x3" and set(cands) <= set(P.DESCRIPTIONS)
+        eng2 = UNetEngine(unet, 1, 32, 32, 87, precision="mixed", dry=True, plan=dict(cands["deep+tf1C"], name="deep+tf1C"))
         fmt2, plain2, mixed_raw = {}, 0, 0
         for fn, args in eng2.prog.kernel_calls():
             if fn in (L.upgpt_prep_operand, L.upgpt_groupnorm_prep):
@@ -254,7 +257,8 @@ def test_unet_program_operand_formats_are_consistent(precision, monkeypatch):
                     assert fmt2[a.a] == x3, "operand planes do not match the GEMM's precision flag (calibrated plan)"
                 if a.out16:
                     fmt2[a.out16] = bool(a.flags & _C.GEMM_F_SPLIT3OUT)
-        assert mixed_raw == 4 and plain2 > n_plain + 4, (mixed_raw, plain2, n_plain)
+        # raw copy in [hi | lo] planes beside a single-plane operand: the skip-connected ResBlocks of the 8x8 level (4) + every decoder block above it (6)
+        assert mixed_raw == 10 and plain2 > n_plain + 4, (mixed_raw, plain2, n_plain)
     with pytest.raises(_C.UpgptError):
         eng.run()
     # an architecture without a probed profile keeps fp16x3 everywhere in "mixed" (the probe shows its deep levels are not cheap in error)

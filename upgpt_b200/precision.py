@@ -7,10 +7,12 @@ At the first engine request after the weights changed, the module therefore meas
 synthetic latent / context -- the eps of each candidate plan against the fp16x3 eps of the same weights and keeps the FASTEST
 candidate whose deviation stays under `LIMIT`:
 
-    deep+tf1 : single plane in the two deepest levels (weight-bandwidth bound; incl. the ResBlock convs whose input also feeds a skip 1x1 GEMM
-               -- that GEMM keeps [hi | lo] planes of its own) and in every attention projection / feed-forward GEMM
-    deep+tf1s: the same, but the attention / feed-forward GEMMs of the full-resolution level (the most sensitive ones:
-               profiles/r01_precision_sensitivity.txt) keep [hi | lo] planes
+    deep+tf1C : single plane in the two deepest levels (weight-bandwidth bound; incl. the ResBlock convs whose input also feeds a skip 1x1
+                GEMM -- that GEMM keeps [hi | lo] planes of its own), in the decoder ResBlocks' first conv (input [h | skip]: the most
+                expensive fp16x3 launches) and in every attention projection / feed-forward GEMM except the attention out-projections and
+                ff2 of the full-resolution level (the worst error per microsecond saved, profiles/r01_precision_sensitivity.txt)
+    deep+tf1sC: the same, but every attention / feed-forward GEMM of the full-resolution level keeps [hi | lo] planes
+    deep+tf1s : as deep+tf1sC without the decoder convs
     deep     : single plane in the two deepest levels only (the round-1 plan)
     deepest  : single plane in the deepest level only
     fp16x3   : error-compensated operands everywhere
@@ -27,12 +29,34 @@ LIMIT = 6.5e-4        # max |eps_plan - eps_fp16x3| / max |eps_fp16x3|; + fp16x3
 TIMESTEPS = (981, 481)
 
 
+# what each plan runs on single fp16 planes (everything else: [hi | lo] planes, 3 MMAs per product); bench.py quotes these
+DESCRIPTIONS = {
+    "deep+tf1C": "single f16 plane in the weight-bound 8x8 / 4x4 levels, in the decoder ResBlocks' first conv (input [h | skip]) of every level and in "
+                 "every attention projection / feed-forward GEMM except the attention out-projections and ff2 of the 32x32 level",
+    "deep+tf1sC": "single f16 plane in the weight-bound 8x8 / 4x4 levels, in the decoder ResBlocks' first conv (input [h | skip]) of every level and in "
+                  "the attention projection / feed-forward GEMMs below the 32x32 level",
+    "deep+tf1s": "single f16 plane in the weight-bound 8x8 / 4x4 levels and in the attention projection / feed-forward GEMMs below the 32x32 level",
+    "deep": "single f16 plane in the weight-bound 8x8 / 4x4 levels",
+    "deepest": "single f16 plane in the deepest level",
+    "tf1": "single f16 plane in every attention projection / feed-forward GEMM",
+    "fp16x3": "nowhere",
+}
+
+
 def candidates(H, W, n_levels):
+    """Fastest first. Measured on the bbox.yaml U-Net, synthetic weights, B200 (tools/gpu_probe_candidates.py, profiles/r02_precision_
+    candidates.jsonl): deviation from fp16x3 / U-Net step at B = 8 = 6.2e-4 / 3.98 ms (deep+tf1C), ~5e-4 / 4.07 (deep+tf1sC), 4.0e-4 /
+    4.17 (deep+tf1s), 3.6e-4 / 4.42 (deep), 1.7e-4 / 4.67 (deepest), 0 / 4.78 (fp16x3). (The first r2 plan, every transformer GEMM +
+    the two deep levels on single planes, sat at 6.3e-4 .. 6.8e-4 / 4.04 ms: dominated by deep+tf1C, which moves the attention
+    out-projections and ff2 of the full-resolution level -- the worst error per microsecond saved -- back to [hi | lo] planes and
+    spends that budget on the decoder's concatenated-input convs, the most expensive fp16x3 launches.)"""
     hw0 = H * W
     deep = (max(hw0 // 16, 1), max(hw0 // 64, 1)) if n_levels >= 3 else None
     out = []
     if deep is not None:
-        out.append(("deep+tf1", dict(mixed_hw=deep, tf_x1=True, skip_x1=True)))
+        keep = {"tf_out": hw0, "tf_ff2": hw0}
+        out.append(("deep+tf1C", dict(mixed_hw=deep, tf_x1=True, skip_x1=True, tf_keep_x3=keep, concat_x1_hw=hw0)))
+        out.append(("deep+tf1sC", dict(mixed_hw=deep, tf_x1=True, skip_x1=True, tf_hw=max(hw0 // 4, 1), concat_x1_hw=hw0)))
         out.append(("deep+tf1s", dict(mixed_hw=deep, tf_x1=True, skip_x1=True, tf_hw=max(hw0 // 4, 1))))
         out.append(("deep", dict(mixed_hw=deep, tf_x1=False)))
         out.append(("deepest", dict(mixed_hw=(deep[1], deep[1]), tf_x1=False)))

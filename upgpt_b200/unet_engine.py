@@ -464,6 +464,12 @@ class UNetEngine(EngineBase):
         # tf_hw: the attention / feed-forward GEMMs run on single planes up to this many tokens per image (None = every level)
         self.tf_hw = (plan or {}).get("tf_hw") if self.precision == "mixed" else None
         self.skip_x1 = bool((plan or {}).get("skip_x1", os.environ.get("UPGPT_SKIP_X1", "0") == "1")) and self.precision == "mixed"
+        # finer allocation of the eps budget (precision.py, plans deep+tf1c*): concat_x1_hw = the decoder ResBlocks' first conv (input =
+        # [h | skip], K = 9 (C1 + C2): the most expensive fp16x3 launches) takes single planes up to this many tokens per image;
+        # tf_keep_x3 = {sub-kind: hw}: attention out-projections ("tf_out") / ff2 ("tf_ff2") keep [hi | lo] planes from that resolution up
+        # (their error per microsecond saved is the worst of the transformer GEMMs, profiles/r01_precision_sensitivity.txt)
+        self.concat_x1_hw = int((plan or {}).get("concat_x1_hw", 0)) if self.precision == "mixed" else 0
+        self.tf_keep_x3 = dict((plan or {}).get("tf_keep_x3", {})) if self.precision == "mixed" else {}
         self.mixed = self.mixed_hw is not None
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and tf_x1
@@ -513,6 +519,14 @@ class UNetEngine(EngineBase):
         if not self.mixed:
             return self.split3
         deep_hw, full_hw = self.mixed_hw
+        if kind in ("tf_out", "tf_ff2"):       # sub-kinds of "tf" that a plan may keep error-compensated at the high resolutions
+            if hw > full_hw and kind in self.tf_keep_x3 and hw >= self.tf_keep_x3[kind]:
+                return True
+            kind = "tf"
+        if kind == "conv_concat":              # a decoder ResBlock's first conv (always with a skip connection)
+            if hw <= self.concat_x1_hw:
+                return False
+            kind = "conv_skipshared"
         if hw <= full_hw or (kind == "tf" and self.tf_x1 and (self.tf_hw is None or hw <= self.tf_hw)):
             return False
         if hw <= deep_hw:
@@ -520,6 +534,13 @@ class UNetEngine(EngineBase):
             # on the normalised operand need not follow the skip GEMM's format (skip_x1, plans deep+tf1 / deep+tf1s)
             return kind == "resid1x1" or (kind == "conv_skipshared" and not self.skip_x1)
         return True
+
+    @staticmethod
+    def _conv1_kind(path, has_skip):
+        """Precision-plan kind of a ResBlock's first conv: output_blocks.N.0 reads the concatenation [h | skip] (openaimodel.py:736)."""
+        if path.startswith("output_blocks.") and has_skip:
+            return "conv_concat"
+        return "conv_skipshared" if has_skip else "conv"
 
     # ------------------------------------------------------------------------------------------------ weights
     def _w16(self, w, x3=None):
@@ -532,7 +553,8 @@ class UNetEngine(EngineBase):
 
     def plan_signature(self):
         if getattr(self, "_plan_sig", None) is None:
-            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.skip_x1, self.ln_fold,
+            self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.skip_x1, self.concat_x1_hw,
+                              tuple(sorted(self.tf_keep_x3.items())), self.ln_fold,
                               tuple(sorted(self.layer_hw.items())) if self.mixed else None)
         return self._plan_sig
 
@@ -557,7 +579,7 @@ class UNetEngine(EngineBase):
                 p = name
                 hw = self.layer_hw[p]
                 has_skip = (p + ".skip_connection.weight") in sd
-                x3a = self.use_x3("conv_skipshared" if has_skip else "conv", hw)     # conv1
+                x3a = self.use_x3(self._conv1_kind(p, has_skip), hw)                 # conv1
                 x3s = x3a or self.use_x3("resid1x1", hw)                             # the skip GEMM (on the un-normalised copy's planes)
                 for g in (".in_layers.0", ".out_layers.0"):
                     put(p + g + ".weight", sd[p + g + ".weight"]); put(p + g + ".bias", sd[p + g + ".bias"])
@@ -581,6 +603,7 @@ class UNetEngine(EngineBase):
                 Cc, Hh, d = mod.in_channels, mod.n_heads, mod.d_head
                 dpad = head_pad(d, Hh)
                 x3p, x3t = self.use_x3("resid1x1", self.layer_hw[p]), self.use_x3("tf", self.layer_hw[p])
+                x3o, x3f = self.use_x3("tf_out", self.layer_hw[p]), self.use_x3("tf_ff2", self.layer_hw[p])    # attention out-projections ; ff2
                 put(p + ".norm.weight", sd[p + ".norm.weight"]); put(p + ".norm.bias", sd[p + ".norm.bias"])
                 wpi = sd[p + ".proj_in.weight"]
                 put(p + ".proj_in.weight", self._w16(wpi.reshape(wpi.shape[0], wpi.shape[1]), x3p)); put(p + ".proj_in.bias", sd[p + ".proj_in.bias"])
@@ -600,12 +623,12 @@ class UNetEngine(EngineBase):
                         wqkv = self._put_ln_folded(q + ".attn1.qkv", wqkv, None, sd[q + ".norm1.weight"], sd[q + ".norm1.bias"], x3t)
                         wq2 = self._put_ln_folded(q + ".attn2.q", wq2, None, sd[q + ".norm2.weight"], sd[q + ".norm2.bias"], x3t)
                     put(q + ".attn1.qkv.weight", self._w16(wqkv, x3t))
-                    put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad), x3t))
+                    put(q + ".attn1.out.weight", self._w16(pad_heads_cols(sd[q + ".attn1.to_out.0.weight"], Hh, d, dpad), x3o))
                     put(q + ".attn1.out.bias", sd[q + ".attn1.to_out.0.bias"])
                     put(q + ".attn2.q.weight", self._w16(wq2, x3t))
                     put(q + ".attn2.kv.weight", self._w16(torch.cat([pad_heads_rows(sd[q + ".attn2.to_k.weight"], Hh, d, dpad),
                                                                      pad_heads_rows(sd[q + ".attn2.to_v.weight"], Hh, d, dpad)], 0)))
-                    put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad), x3t))
+                    put(q + ".attn2.out.weight", self._w16(pad_heads_cols(sd[q + ".attn2.to_out.0.weight"], Hh, d, dpad), x3o))
                     put(q + ".attn2.out.bias", sd[q + ".attn2.to_out.0.bias"])
                     inner = sd[q + ".ff.net.2.weight"].shape[1]
                     half = geglu_half(inner, x3t)
@@ -618,7 +641,7 @@ class UNetEngine(EngineBase):
                     put(q + ".ff1.weight", self._w16(w1, x3t)); put(q + ".ff1.bias", b1)
                     if self.ln_fold:
                         put(q + ".ff1.colsum", self.w[q + ".ff1.weight"].double().sum(-1).float())
-                    put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"], x3t)); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
+                    put(q + ".ff2.weight", self._w16(sd[q + ".ff.net.2.weight"], x3f)); put(q + ".ff2.bias", sd[q + ".ff.net.2.bias"])
         from .ops import timestep_freqs
         put("temb.freqs", timestep_freqs(self.mc))
         put("emb_all.weight", torch.cat(emb_w, 0)); put("emb_all.bias", torch.cat(emb_b, 0))
@@ -644,7 +667,7 @@ class UNetEngine(EngineBase):
         Cin, Cout = C1 + C2, mod.out_channels
         HW = H * W
         has_skip = (p + ".skip.weight") in self.w
-        x3a = self.use_x3("conv_skipshared" if has_skip else "conv", HW)     # conv1
+        x3a = self.use_x3(self._conv1_kind(p, has_skip), HW)                 # conv1
         x3s = x3a or self.use_x3("resid1x1", HW)                             # the skip GEMM, on the un-normalised copy's own planes
         x3b = self.use_x3("conv", HW)                                        # conv2
         fa, fb, fs = (_C.GEMM_F_X3 if x3a else 0), (_C.GEMM_F_X3 if x3b else 0), (_C.GEMM_F_X3 if x3s else 0)
@@ -685,9 +708,13 @@ class UNetEngine(EngineBase):
         HD = Hh * dpad
         L, Lp = self.ctx_len, _round_up(self.ctx_len, 8)
         x3p, x3t = self.use_x3("resid1x1", HW), self.use_x3("tf", HW)    # proj_in / proj_out ; attention projections + feed-forward
-        kx = 2 if (x3p or x3t) else 1          # operand planes [hi | lo] of an error-compensated operand (scratch sizing)
+        x3o, x3f = self.use_x3("tf_out", HW), self.use_x3("tf_ff2", HW)  # the attention out-projections / ff2 may keep [hi | lo] planes
+        kx = 2 if (x3p or x3t or x3o) else 1   # operand planes [hi | lo] of an error-compensated operand (scratch sizing)
         kxt = 2 if x3t else 1
+        kxo, kxf = (2 if x3o else 1), (2 if x3f else 1)
         x3 = _C.GEMM_F_X3 if x3t else 0
+        fo, ff_ = (_C.GEMM_F_X3 if x3o else 0), (_C.GEMM_F_X3 if x3f else 0)
+        s3f = _C.GEMM_F_SPLIT3OUT if x3f else 0
         fp = _C.GEMM_F_X3 if x3p else 0
         s3 = _C.GEMM_F_SPLIT3OUT if x3t else 0
         op, _ = self.norm_operand(x, Cc, None, 0, B, H, W, p + ".norm", 1e-6, False, split3=x3p)
@@ -709,7 +736,7 @@ class UNetEngine(EngineBase):
             q = f"{p}.transformer_blocks.{bi}"
             g = lambda n: self.w.get(q + n)
             inner = mod.transformer_blocks[bi].ff.net[2].in_features
-            ff16 = self.scratch("ff16", M * inner * kxt, torch.float16)
+            ff16 = self.scratch("ff16", M * inner * kxf, torch.float16)
             last = bi == len(mod.transformer_blocks) - 1
             assert slots <= 16
             # --- self attention ---
@@ -721,10 +748,10 @@ class UNetEngine(EngineBase):
             kptr = None if self._sizing else qkv16[HD:]
             vptr = None if self._sizing else qkv16[2 * HD:]
             self.e_attention(q=qkv16, ldq=3 * HD, k=kptr, ldk=3 * HD, k_batch_stride=HW * 3 * HD, vt=vptr, ldvt=3 * HD, v_rowmajor=1,
-                             v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
-                             scale=float(d) ** -0.5, split3_out=int(x3t))
+                             v_batch_stride=HW * 3 * HD, out=att16, ldo=HD * kxo, B=B, H=Hh, Nq=HW, Nk=HW, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(x3o))
             slots = self.e_gemm(a=att16, w=g(".attn1.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
-                                bias=g(".attn1.out.bias"), res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
+                                bias=g(".attn1.out.bias"), res32=cur, flags=fo | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
             # --- cross attention over the cached context K / V^T ---
             if not fold:
@@ -734,25 +761,25 @@ class UNetEngine(EngineBase):
             kvc = self.buf(q + ".ctx_kv", (B * L, 2 * HD), torch.float16)       # cond-cache: K | V of the context, row-major
             vcp = None if self._sizing else kvc.reshape(-1)[HD:]
             self.e_attention(q=qkv16, ldq=HD, k=kvc, ldk=2 * HD, k_batch_stride=L * 2 * HD, vt=vcp, ldvt=2 * HD, v_rowmajor=1,
-                             v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kxt, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
-                             scale=float(d) ** -0.5, split3_out=int(x3t))
+                             v_batch_stride=L * 2 * HD, out=att16, ldo=HD * kxo, B=B, H=Hh, Nq=HW, Nk=L, dpad=dpad,
+                             scale=float(d) ** -0.5, split3_out=int(x3o))
             slots = self.e_gemm(a=att16, w=g(".attn2.out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=HD, out32=nxt,
-                                bias=g(".attn2.out.bias"), res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
+                                bias=g(".attn2.out.bias"), res32=cur, flags=fo | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
             # --- GEGLU feed-forward ---
             if not fold:
                 self.e_layernorm(cur, M, Cc, g(".norm3.weight"), g(".norm3.bias"), tok16, x3t)
             self.e_gemm(a=tok16, w=g(".ff1.weight"), mode=_C.GEMM_PLAIN, M=M, N=2 * inner, K=Cc, block_n=2 * geglu_half(inner, x3t),
-                        out16=ff16, flags=_C.GEMM_F_GEGLU | s3 | x3,
+                        out16=ff16, flags=_C.GEMM_F_GEGLU | s3f | x3,
                         **(lnkw(q + ".ff1", slots) if fold else dict(bias=g(".ff1.bias"))))
             # the last block's feed-forward also emits the fp16 operand of proj_out, in proj_out's operand format; an inner block's emits
             # the raw planes + row statistics of the next block's first LayerNorm
             if last:
                 self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
-                            res32=cur, out16=tok16, flags=(_C.GEMM_F_SPLIT3OUT if x3p else 0) | x3)
+                            res32=cur, out16=tok16, flags=(_C.GEMM_F_SPLIT3OUT if x3p else 0) | ff_)
             else:
                 slots = self.e_gemm(a=ff16, w=g(".ff2.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=inner, out32=nxt, bias=g(".ff2.bias"),
-                                    res32=cur, flags=x3 | (s3 if fold else 0), **rawkw())
+                                    res32=cur, flags=ff_ | (s3 if fold else 0), **rawkw())
             cur, nxt = nxt, cur
         self.e_gemm(a=tok16, w=self.w.get(p + ".proj_out.weight"), mode=_C.GEMM_PLAIN, M=M, N=Cc, K=Cc, out32=out,
                     bias=self.w.get(p + ".proj_out.bias"), res32=x, flags=fp)
