@@ -17,6 +17,11 @@ m = UNetModel(**kw); m.load_state_dict(synth.synth_state_dict(m.state_dict(), in
 x1, mask1, ctx1 = synth.synth_inputs(1, 32, 32, 87, 768, 0)
 x8, mask8, ctx8 = synth.synth_inputs(8, 32, 32, 87, 768, 3)
 cands = P.candidates(32, 32, len(m.channel_mult))
+if os.environ.get("EXTRA_PLANS"):
+    # experiments: JSON {name: {"base": candidate name, ...plan keys to override / add}}
+    base = dict(cands)
+    extra = json.loads(os.environ["EXTRA_PLANS"])
+    cands = [(n, dict(base[v.pop("base")], **v)) for n, v in extra.items()] + [cands[-1]]
 ref = None
 with torch.no_grad():
     for name, plan in reversed(cands):

@@ -470,6 +470,8 @@ class UNetEngine(EngineBase):
         # (their error per microsecond saved is the worst of the transformer GEMMs, profiles/r01_precision_sensitivity.txt)
         self.concat_x1_hw = int((plan or {}).get("concat_x1_hw", 0)) if self.precision == "mixed" else 0
         self.tf_keep_x3 = dict((plan or {}).get("tf_keep_x3", {})) if self.precision == "mixed" else {}
+        self.force_x1 = frozenset((k, int(h)) for k, h in (plan or {}).get("x1", ())) if self.precision == "mixed" else frozenset()
+        self.force_x3 = frozenset((k, int(h)) for k, h in (plan or {}).get("x3", ())) if self.precision == "mixed" else frozenset()
         self.mixed = self.mixed_hw is not None
         # "mixed" only: attention projections + feed-forward GEMMs of every level on single fp16 planes (see default_precision)
         self.tf_x1 = self.mixed and tf_x1
@@ -519,6 +521,11 @@ class UNetEngine(EngineBase):
         if not self.mixed:
             return self.split3
         deep_hw, full_hw = self.mixed_hw
+        # explicit per-(kind, tokens per image) overrides of a plan: {"x1": [[kind, hw], ...], "x3": [...]} (the sub-kind first, then its parent)
+        if (kind, hw) in self.force_x1:
+            return False
+        if (kind, hw) in self.force_x3:
+            return True
         if kind in ("tf_out", "tf_ff2"):       # sub-kinds of "tf" that a plan may keep error-compensated at the high resolutions
             if hw > full_hw and kind in self.tf_keep_x3 and hw >= self.tf_keep_x3[kind]:
                 return True
@@ -527,6 +534,12 @@ class UNetEngine(EngineBase):
             if hw <= self.concat_x1_hw:
                 return False
             kind = "conv_skipshared"
+        if kind == "conv_updown":              # Downsample / Upsample convs
+            kind = "conv"
+        if (kind, hw) in self.force_x1:
+            return False
+        if (kind, hw) in self.force_x3:
+            return True
         if hw <= full_hw or (kind == "tf" and self.tf_x1 and (self.tf_hw is None or hw <= self.tf_hw)):
             return False
         if hw <= deep_hw:
@@ -554,7 +567,7 @@ class UNetEngine(EngineBase):
     def plan_signature(self):
         if getattr(self, "_plan_sig", None) is None:
             self._plan_sig = (type(self).__name__, self.precision, self.mixed_hw, self.tf_x1, self.tf_hw, self.skip_x1, self.concat_x1_hw,
-                              tuple(sorted(self.tf_keep_x3.items())), self.ln_fold,
+                              tuple(sorted(self.tf_keep_x3.items())), tuple(sorted(self.force_x1)), tuple(sorted(self.force_x3)), self.ln_fold,
                               tuple(sorted(self.layer_hw.items())) if self.mixed else None)
         return self._plan_sig
 
@@ -594,9 +607,9 @@ class UNetEngine(EngineBase):
                 sub = ".op" if isinstance(mod, om.Downsample) else ".conv"
                 w = sd[name + sub + ".weight"]
                 if isinstance(mod, om.Upsample) and UP2_FOLD:
-                    put(name + ".weight", self._w16(up2_conv_w(w), self.use_x3("conv", self.layer_hw[name])))
+                    put(name + ".weight", self._w16(up2_conv_w(w), self.use_x3("conv_updown", self.layer_hw[name])))
                 else:
-                    put(name + ".weight", self._conv_w(w, self.use_x3("conv", self.layer_hw[name])))
+                    put(name + ".weight", self._conv_w(w, self.use_x3("conv_updown", self.layer_hw[name])))
                 put(name + ".bias", sd[name + sub + ".bias"])
             elif isinstance(mod, SpatialTransformer):
                 p = name
@@ -841,7 +854,7 @@ class UNetEngine(EngineBase):
                     self._transformer(p, mod, h, ch, B, hh, ww, out)
                     h = out
                 elif isinstance(mod, om.Downsample):
-                    x3c = self.use_x3("conv", (hh // 2) * (ww // 2))
+                    x3c = self.use_x3("conv_updown", (hh // 2) * (ww // 2))
                     op, _ = self.norm_operand(h, ch, None, 0, B, hh, ww, None, 0.0, False, layout=2, split3=x3c)
                     hh, ww = hh // 2, ww // 2
                     out = self.buf(p + ".out", (B, hh * ww, mod.out_channels))
@@ -849,7 +862,7 @@ class UNetEngine(EngineBase):
                                 H=hh, W=ww, out32=out, bias=self.w.get(p + ".bias"), flags=_C.GEMM_F_X3 if x3c else 0)
                     h, ch = out, mod.out_channels
                 elif isinstance(mod, om.Upsample):
-                    x3c = self.use_x3("conv", hh * ww * 4)
+                    x3c = self.use_x3("conv_updown", hh * ww * 4)
                     out = self.buf(p + ".out", (B, hh * ww * 4, mod.out_channels))
                     if UP2_FOLD:
                         # the x2 replicate is never materialised: four parity-wise 2x2 convolutions over the low-resolution operand
