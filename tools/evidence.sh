@@ -13,5 +13,5 @@ tail -3 gpurun_out/${T}_ncu.log
 python tools/ncu_summary.py gpurun_out/${T}_conv224_x3.ncu-rep gpurun_out/${T}_conv_deep.ncu-rep gpurun_out/${T}_conv_up2.ncu-rep gpurun_out/${T}_attn_self.ncu-rep gpurun_out/${T}_attn_cross.ncu-rep gpurun_out/${T}_gn_fused.ncu-rep gpurun_out/${T}_prep.ncu-rep > gpurun_out/${T}_ncu_set_full_summary.txt 2>&1
 head -60 gpurun_out/${T}_ncu_set_full_summary.txt
 # launch list of the default bench step (cold caches, serialised: shares)
-UPGPT_CALIBRATE=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tc_gemm|attention_kernel|prep_kernel|gn_stats|gn_prep_fused|layernorm|linear_small|conv_small|timestep_emb|softmax_rows" --csv --log-file gpurun_out/${T}_launches.csv python tools/prof_hot_path.py > gpurun_out/${T}_prof.log 2>&1
+UPGPT_CALIBRATE=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tc_gemm|attention_kernel|prep_kernel|gn_stats|gn_prep_fused|gn_group|layernorm|linear_small|conv_small|timestep_emb|softmax_rows" --csv --log-file gpurun_out/${T}_launches.csv python tools/prof_hot_path.py > gpurun_out/${T}_prof.log 2>&1
 tail -1 gpurun_out/${T}_prof.log
