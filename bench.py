@@ -295,7 +295,7 @@ def facade_arm(dev, precision, eta, steps):
 
 def _traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` capture of the kernel
-    (profiles/r02_roofline_traffic.json <- profiles/r02b_ncu_set_full_summary.txt, tools/evidence.sh); None when no capture of this case is committed."""
+    (profiles/r02_roofline_traffic.json <- profiles/r02c_ncu_set_full_summary.txt, tools/evidence.sh); None when no capture of this case is committed."""
     for name in ("r02_roofline_traffic.json", "r01_roofline_traffic.json"):
         tp = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tp):

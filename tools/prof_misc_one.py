@@ -12,6 +12,13 @@ if which == "gn_fused":
     st = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64); out = torch.zeros(B * H * W * 2 * C, device=dev, dtype=torch.half)
     fn = lambda: ops.groupnorm_prep(st, x1=x, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, gamma=gamma, beta=beta, eps=1e-5, silu=1, layout=0,
                                     split3=1, out=out, raw=None)
+elif which == "gn_group":
+    # the one-CTA-per-(image, 4 groups) form at the 8x8 level (896 channels, B = 8)
+    B, H, W, C = 8, 8, 8, 896
+    x = torch.randn(B, H * W, C, device=dev); gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
+    st = torch.zeros(B, 32, 2, device=dev, dtype=torch.float64); out = torch.zeros(B * H * W * C, device=dev, dtype=torch.half)
+    fn = lambda: ops.groupnorm_prep(st, x1=x, C1=C, x2=None, C2=0, B=B, H=H, W=W, groups=32, gamma=gamma, beta=beta, eps=1e-5, silu=1, layout=0,
+                                    split3=0, out=out, raw=None)
 elif which == "prep":
     # GroupNorm apply + swish + fp16 cast at the VAE decoder's 256x256x128 level, B = 8 (bench.py's roofline_hbm kernel)
     B, H, W, C = 8, 256, 256, 128
