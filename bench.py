@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json workload: c2 = configs[1] (headline), c4 = configs[3], c5 = configs[4]")
     ap.add_argument("--full", action="store_true", help="--impl reference: time ONE complete 50-step + decode job (minutes) instead of bounded samples")
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("UPGPT_LANES", "3")),
+                    help="independent batches in flight per GPU (upgpt_b200/lanes.py): consecutive bench steps go to lanes round-robin; "
+                         "1 = one batch after the other")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline (outside the timed region)")
     return ap.parse_args()
 
@@ -549,10 +552,14 @@ def gpu_arm(args, rank, world):
     x_pin, ctx_pin, mask_kf_pin = x_T.pin_memory(), ctx.pin_memory(), mask_kf.pin_memory()
     smpl_kf_pin = None if smpl_kf is None else smpl_kf.pin_memory()
     out_pin = torch.empty(KF, B, px, px, 3, dtype=torch.uint8).pin_memory()
-    sampler = DDIMSampler(model)
+    from upgpt_b200 import lanes
+    n_lanes = max(1, min(args.lanes, lanes.MAX_LANES))
+    samplers = [DDIMSampler(model) for _ in range(n_lanes)]
+    out_pins = [out_pin] + [torch.empty_like(out_pin).pin_memory() for _ in range(n_lanes - 1)]
 
     def hot_path(xT, m, c):
         cond = {"c_crossattn": c, "c_concat": [m]}
+        sampler = samplers[lanes.current()]
         z, _ = sampler.sample(DDIM_STEPS, B, (4, lat, lat), conditioning=cond, eta=args.eta, x_T=xT, verbose=False, log_every_t=1000)
         img = model.decode_first_stage(z)
         frames = ops.to_uint8_nhwc(img)
@@ -569,14 +576,24 @@ def gpu_arm(args, rank, world):
             if sink is not None:
                 sink[k].copy_(frames, non_blocking=True)
 
-    def step_resident():
-        sequence(x_dev, ctx_dev, mask_kf_dev, smpl_kf_dev)
+    # bench step i runs on lane i % n_lanes: with n_lanes > 1 consecutive batches are in flight side by side (every batch is sampled and
+    # decoded exactly as with one lane -- same engines' programs, bit-identical results -- only the schedule on the GPU differs)
+    lane_of = lambda i: i % cur_lanes[0]
+    cur_lanes = [n_lanes]
 
-    def step_e2e():
-        xd = x_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True); md = mask_kf_pin.to(dev, non_blocking=True)
-        sd = None if smpl_kf_pin is None else smpl_kf_pin.to(dev, non_blocking=True)
-        sequence(xd, cd, md, sd, out_pin)
-        torch.cuda.current_stream().synchronize()
+    def step_resident(i=0):
+        with lanes.lane(lane_of(i)):
+            sequence(x_dev, ctx_dev, mask_kf_dev, smpl_kf_dev)
+
+    def step_e2e(i=0):
+        with lanes.lane(lane_of(i)) as s:
+            # the host reads a lane's previous result (its D2H copy has landed) before it feeds the lane again: one step per lane in flight
+            s.synchronize()
+            xd = x_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True); md = mask_kf_pin.to(dev, non_blocking=True)
+            sd = None if smpl_kf_pin is None else smpl_kf_pin.to(dev, non_blocking=True)
+            sequence(xd, cd, md, sd, out_pins[lane_of(i)])
+            if cur_lanes[0] == 1:
+                s.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -584,16 +601,23 @@ def gpu_arm(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, warmup, steps):
-        for _ in range(warmup):
-            fn()
+    def timed(fn, warmup, steps, use_lanes=None):
+        cur_lanes[0] = n_lanes if use_lanes is None else use_lanes
+        for i in range(max(warmup, cur_lanes[0] if warmup else 0)):       # every lane builds its engines / graphs before the clock starts
+            fn(i)
         barrier()
         l0 = L.upgpt_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        main = torch.cuda.current_stream()
+        lane_streams = [lanes.stream(l) for l in range(1, cur_lanes[0])]
         t_wall = time.perf_counter()
         e0.record()
-        for _ in range(steps):
-            fn()
+        for ls in lane_streams:                 # the lanes start after the start event ...
+            ls.wait_event(e0)
+        for i in range(steps):
+            fn(i)
+        for ls in lane_streams:                 # ... and the stop event waits for every lane
+            ev = torch.cuda.Event(); ev.record(ls); main.wait_event(ev)
         e1.record()
         barrier()
         wall = time.perf_counter() - t_wall
@@ -614,6 +638,11 @@ def gpu_arm(args, rank, world):
     n_img = world * B * KF * args.steps
     value = n_img / (ms * 1e-3)
     e2e_val = n_img / (ms_e2e * 1e-3)
+    single_lane = None
+    if n_lanes > 1:      # the same K steps one after the other (one batch in flight), for the record
+        ms_1, _, _ = timed(step_resident, 1, args.steps, use_lanes=1)
+        single_lane = {"value": n_img / (ms_1 * 1e-3), "unit": UNIT, "ms_per_step": ms_1 / args.steps,
+                       "note": "one batch in flight (--lanes 1): the per-batch latency; `value` has %d batches of %d in flight" % (n_lanes, B)}
     cond_cache = None
     if KF > 1:
         eng0 = next(iter(model.model.diffusion_model._engines.values()))
@@ -653,6 +682,10 @@ def gpu_arm(args, rank, world):
                 "config": {"workload": workload_string(args.config, args.eta),
                            "global_batch": world * B, "images_per_step": world * B * KF,
                            "parallelism": "batch-sharded x%d, one NCCL all-gather of frames" % world,
+                           "lanes": n_lanes,
+                           "schedule": ("%d independent batches of %d in flight per GPU (lanes: one CUDA stream + one captured step graph per batch, "
+                                        "bench step i on lane i %% %d; every batch is sampled exactly as with one lane, bit-identical results)"
+                                        % (n_lanes, B, n_lanes)) if n_lanes > 1 else "one batch at a time",
                            "l2_policy": "inputs+weights (>= 1.9 GB per U-Net pass) exceed the 126 MB L2; no explicit flush",
                            "kernels_per_unet_step": eng.launches_per_step - eng.n_emb_calls + 3, "precision_mode": args.precision,
                            "precision_plan": {"name": eng.plan_name, "calibration": next((v[2] for v in getattr(model.model.diffusion_model, "_plans", {}).values()), None)},
@@ -667,6 +700,8 @@ def gpu_arm(args, rank, world):
                 "whole_step": {"algorithmic_tflop_per_step": alg_tf_per_step, "achieved_tflops": alg_tf_per_step / (ms / args.steps * 1e-3),
                                "frac_of_sustained_peak": alg_tf_per_step / (ms / args.steps * 1e-3) / pk["tf_sustained"]},
                 "fast_mode": fast}
+        if single_lane is not None:
+            line["single_lane"] = single_lane
         if cond_cache is not None:
             line["cond_cache"] = cond_cache
         if world == 1 and not args.no_cpu_baseline:
@@ -677,7 +712,7 @@ def gpu_arm(args, rank, world):
             line["cpu_baseline"] = None
         if world == 1 and not args.no_eager_baseline and args.config == "c2":
             try:
-                del model, sampler
+                del model, samplers
                 torch.cuda.empty_cache()
                 line["facade"] = facade_arm(dev, args.precision, args.eta, max(2, args.steps // 2))
             except Exception as e:

@@ -671,3 +671,52 @@ def test_upscale_model_full_size_and_kl_f4(dev):
     with torch.no_grad():
         rec_ref = O.decode_first_stage(vsd, UPSCALE_VAE_KW, m_ref[:, :3], 1.0)
     assert tuple(rec.shape) == (1, 3, 128, 96) and relerr(rec, rec_ref) < 1e-2
+
+
+def test_lanes_two_batches_in_flight_are_bit_identical(dev):
+    """upgpt_b200/lanes.py: two independent batches sampled + decoded side by side (own stream, engines, step graphs and library scratch
+    slot per lane; shared packed weights) give exactly the results of running them one after the other, on the tiny model and -- the
+    cluster split-K / fork-join paths of the benchmarked configuration -- on the bbox U-Net at B = 8."""
+    from ldm.models.diffusion.ddim import DDIMSampler
+    from upgpt_b200 import lanes
+    model, sd = _tiny_ldm(dev)
+    S = 10
+    ins = []
+    for seed in (0, 1):
+        x, mask, ctx = synth.synth_inputs(2, 16, 16, 87, 128, seed)
+        noises = torch.randn(S, *x.shape, generator=torch.Generator().manual_seed(50 + seed))
+        ins.append((x.to(dev), {"c_crossattn": ctx.to(dev), "c_concat": [mask.to(dev)]}, noises.to(dev)))
+
+    def run(i):
+        x, cond, noises = ins[i]
+        z, _ = DDIMSampler(model).sample(S, 2, (4, 16, 16), conditioning=cond, eta=1.0, x_T=x, verbose=False, log_every_t=1000, x_noise=noises)
+        return z, model.decode_first_stage(z)
+    seq = [run(0), run(1)]                       # one after the other, lane 0
+    torch.cuda.synchronize()
+    outs = {}
+    for rep in range(2):                         # first round builds lane 1's engines / graphs, second round is pure replay
+        with lanes.lane(0):
+            outs[0] = run(0)
+        with lanes.lane(1):
+            outs[1] = run(1)                     # enqueued while lane 0's batch is still running
+        torch.cuda.synchronize()
+        for i in (0, 1):
+            assert torch.equal(outs[i][0], seq[i][0]) and torch.equal(outs[i][1], seq[i][1]), "lane %d, round %d" % (i, rep)
+    unet = model.model.diffusion_model
+    assert {k[-1] for k in unet._engines} == {0, 1} and len({id(e.w) for e in unet._engines.values()}) >= 1
+    assert lanes.current() == 0
+    # bbox U-Net at B = 8: one step per lane, concurrently, vs sequentially
+    m, _ = _unet(BBOX_UNET_KW, 0, dev)
+    xs = []
+    for seed in (3, 5, 7):
+        x, mask, ctx = synth.synth_inputs(8, 32, 32, 87, 768, seed)
+        xs.append((torch.cat([x, mask], 1).to(dev), torch.full((8,), 481, dtype=torch.long, device=dev), ctx.to(dev)))
+    ref = [m(*xs[i]).clone() for i in range(3)]
+    torch.cuda.synchronize()
+    for rep in range(2):
+        ys = []
+        for i in range(3):                       # three batches in flight (bench.py's default schedule)
+            with lanes.lane(i):
+                ys.append(m(*xs[i]))
+        torch.cuda.synchronize()
+        assert all(torch.equal(ys[i], ref[i]) for i in range(3)), "bbox U-Net, round %d" % rep

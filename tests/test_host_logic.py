@@ -312,15 +312,24 @@ def test_engine_cache_is_lru_bounded_and_shares_packed_weights(monkeypatch):
     monkeypatch.setenv("UPGPT_MAX_ENGINES", "3")
     h = Host()
     engs = [h._engine_get((b,), lambda: Eng(h)) for b in range(5)]
-    assert len(h._engines) == 3 and list(h._engines)[0] == (2, "raw")
+    assert len(h._engines) == 3 and list(h._engines)[0] == (2, "raw", 0)      # (key, weights tag, lane)
     assert h._engine_get((4,), lambda: None) is engs[4] and engs[4].packs == 1
     h.mark_weights_changed()
     assert h._engine_get((4,), lambda: None).packs == 2          # re-pack on a version change only
     h.use_weights_tag("ema")
     e_ema = h._engine_get((4,), lambda: Eng(h))
-    assert e_ema is not engs[4] and list(h._engines)[-1] == (4, "ema")
+    assert e_ema is not engs[4] and list(h._engines)[-1] == (4, "ema", 0)
     h.use_weights_tag("raw")
     assert h._engine_get((4,), lambda: None) is engs[4] and engs[4].packs == 2, "leaving the EMA scope costs no re-pack"
+    # a second batch in flight (upgpt_b200/lanes.py) gets its own engine -- buffers, programs, graphs -- for the same key
+    from upgpt_b200 import lanes
+    assert lanes.current() == 0 and lanes.branch_aux(0) == 0 and lanes.branch_aux(1) == 3
+    lanes._current = 1
+    try:
+        e_l1 = h._engine_get((4,), lambda: Eng(h))
+    finally:
+        lanes._current = 0
+    assert e_l1 is not engs[4] and list(h._engines)[-1] == (4, "raw", 1) and h._engine_get((4,), lambda: None) is engs[4]
     st = WeightStore()
     a = st.put("w", "raw", torch.ones(4), "cpu")
     b = st.put("w", "raw", torch.full((4,), 2.0), "cpu")

@@ -38,7 +38,12 @@ int make_tmap(CUtensorMap* out, int elem_bytes, const void* base, int rank, cons
               const uint32_t* box, bool swizzle128);
 
 bool pdl_enabled();   // programmatic dependent launch (UPGPT_PDL=0 disables)
-bool is_aux_stream(cudaStream_t s);   // one of the library's auxiliary (parallel-branch) streams of the current device
+bool is_aux_stream(cudaStream_t s);   // one of the library's auxiliary (parallel-branch / lane) streams of the current device
+// Scratch slot of a stream: 0 = any stream the library does not own, 1 + i = its auxiliary stream i. Library-owned scratch (split-K
+// workspace, GroupNorm partials / scale-shift) exists once per slot, so launches on different streams of the library never share it:
+// a forked branch beside its main chain, or several independent batches in flight ("lanes", upgpt_b200/lanes.py).
+static constexpr int kStreamSlots = 9;
+int stream_slot(cudaStream_t s);
 
 #ifdef __CUDACC__
 // Launches `k` with the programmatic-stream-serialization attribute: the kernel may begin (and run its prologue) while its

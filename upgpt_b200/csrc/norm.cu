@@ -696,9 +696,10 @@ static constexpr int kGnMaxBatch = 4096;
 static constexpr size_t kFusedSsFloats = (size_t)1 << 20;
 static constexpr int kNormMaxDevices = 64;
 struct NormDev {
-  double* gn_partials = nullptr;   // [B][chunks][2*groups] per-chunk partial moments (graph-stable address)
-  int* gn_counters = nullptr;
-  float* fused_ss = nullptr;       // scale/shift scratch of the two-launch fallback
+  // per stream slot (common.cuh: stream_slot), allocated on the slot's first use, then fixed (graph-stable addresses):
+  double* gn_partials[kStreamSlots] = {};   // [B][chunks][2*groups] per-chunk partial moments
+  int* gn_counters[kStreamSlots] = {};
+  float* fused_ss[kStreamSlots] = {};       // scale/shift scratch of the two-launch fallback
   int fused_max_cl = -1;
   int fused_n16 = 0;               // co-resident 16-CTA clusters (occupancy API, full shared-memory carve-out)
   int fused_smem_optin = 0;
@@ -718,16 +719,17 @@ static int groupnorm_stats_impl(const float* x1, int C1, const float* x2, int C2
   UPGPT_REQUIRE(C <= 2048 && B <= kGnMaxBatch, "groupnorm_stats: C=%d > 2048 or B=%d too large", C, B);
   NormDev* nd = norm_dev();
   UPGPT_REQUIRE(nd, "groupnorm_stats: no current CUDA device");
+  const int slot = stream_slot(stream);
   {
     std::lock_guard<std::mutex> lk(g_norm_mu);
-    if (!nd->gn_partials) {
-      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_partials, kGnPartialDoubles * sizeof(double)));
-      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_counters, kGnMaxBatch * sizeof(int)));
-      UPGPT_CHECK_CUDA(cudaMemset(nd->gn_counters, 0, kGnMaxBatch * sizeof(int)));
+    if (!nd->gn_partials[slot]) {
+      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_partials[slot], kGnPartialDoubles * sizeof(double)));
+      UPGPT_CHECK_CUDA(cudaMalloc(&nd->gn_counters[slot], kGnMaxBatch * sizeof(int)));
+      UPGPT_CHECK_CUDA(cudaMemset(nd->gn_counters[slot], 0, kGnMaxBatch * sizeof(int)));
     }
   }
-  double* g_gn_partials = nd->gn_partials;
-  int* g_gn_counters = nd->gn_counters;
+  double* g_gn_partials = nd->gn_partials[slot];
+  int* g_gn_counters = nd->gn_counters[slot];
   // ~2 CTAs per SM in total, at least 8 pixels per CTA, at most 256 chunks per image (cross-chunk reduction cost)
   int per_img = (4 * 148 + B - 1) / B;
   if (per_img > 256) per_img = 256;
@@ -833,14 +835,14 @@ extern "C" int upgpt_groupnorm_prep(const upgpt_prep_args* a, double* stats, voi
   int& g_fused_max_cl = nd->fused_max_cl;
   int& g_fused_n16 = nd->fused_n16;
   int& g_fused_smem_optin = nd->fused_smem_optin;
-  float*& g_fused_ss = nd->fused_ss;
+  float*& g_fused_ss = nd->fused_ss[stream_slot(stream)];
+  if (!g_fused_ss) UPGPT_CHECK_CUDA(cudaMalloc(&g_fused_ss, kFusedSsFloats * sizeof(float)));
   if (g_fused_max_cl < 0) {
     int dev = 0;
     UPGPT_CHECK_CUDA(cudaGetDevice(&dev));
     UPGPT_CHECK_CUDA(cudaDeviceGetAttribute(&g_fused_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     UPGPT_CHECK_CUDA(cudaFuncSetAttribute(gn_prep_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_fused_smem_optin));
     UPGPT_CHECK_CUDA(cudaFuncSetAttribute(gn_prep_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    UPGPT_CHECK_CUDA(cudaMalloc(&g_fused_ss, kFusedSsFloats * sizeof(float)));
     // can a 16-CTA cluster with the full shared-memory carve-out be scheduled on this part at all?
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(16, 8); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = g_fused_smem_optin;

@@ -97,7 +97,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // One non-blocking stream per (device, index); fork / join are event edges, so they are captured into CUDA graphs as plain
 // dependencies. Events come from a small per-process ring (an event only carries the dependency between its record and the wait
 // issued right after it).
-static constexpr int kAuxStreams = 2, kAuxDevices = 64, kEventRing = 64;
+static constexpr int kAuxStreams = kStreamSlots - 1, kAuxDevices = 64, kEventRing = 64;
 static cudaStream_t g_aux[kAuxDevices][kAuxStreams] = {};
 static cudaEvent_t g_events[kAuxDevices][kEventRing] = {};
 static int g_event_next[kAuxDevices] = {};
@@ -117,6 +117,14 @@ bool is_aux_stream(cudaStream_t s) {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDevices) return false;
   for (int i = 0; i < kAuxStreams; ++i) if (g_aux[dev][i] == s) return true;
   return false;
+}
+
+int stream_slot(cudaStream_t s) {
+  if (!s) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kAuxDevices) return 0;
+  for (int i = 0; i < kAuxStreams; ++i) if (g_aux[dev][i] == s) return 1 + i;
+  return 0;
 }
 
 static int edge(cudaStream_t from, cudaStream_t to) {

@@ -1155,9 +1155,10 @@ struct GemmDev {
   bool ready = false;
   int num_sms = 0, smem_optin = 0;
   int max_clusters[9] = {0};         // co-resident clusters of size S (S CTAs must share a GPC), from the occupancy API
-  float* ws[2] = {nullptr, nullptr}; // split-K partial-tile workspaces (allocated once: graph-stable addresses)
+  float* ws[kStreamSlots] = {};      // split-K partial-tile workspaces per stream slot (allocated on a slot's first use, then fixed:
+                                     // graph-stable addresses; the engines run every program once eagerly before they capture it)
   size_t ws_bytes = 0;
-  int* counters[2] = {nullptr, nullptr};
+  int* counters[kStreamSlots] = {};
 };
 static GemmDev g_gdev[kMaxDevices];
 static std::mutex g_gemm_mu;
@@ -1186,12 +1187,17 @@ static int gemm_device_setup(GemmDev** out) {
     d.max_clusters[S] = n;
   }
   d.ws_bytes = (size_t)96 << 20;
-  for (int i = 0; i < 2; ++i) {
-    UPGPT_CHECK_CUDA(cudaMalloc(&d.ws[i], d.ws_bytes));
-    UPGPT_CHECK_CUDA(cudaMalloc(&d.counters[i], kMaxCounters * sizeof(int)));
-    UPGPT_CHECK_CUDA(cudaMemset(d.counters[i], 0, kMaxCounters * sizeof(int)));
-  }
   d.ready = true;
+  return 0;
+}
+
+// split-K workspace + arrival counters of one stream slot (global-workspace fallback of the split-K reduction)
+static int gemm_slot_workspace(GemmDev* d, int slot) {
+  std::lock_guard<std::mutex> lk(g_gemm_mu);
+  if (d->ws[slot]) return 0;
+  UPGPT_CHECK_CUDA(cudaMalloc(&d->ws[slot], d->ws_bytes));
+  UPGPT_CHECK_CUDA(cudaMalloc(&d->counters[slot], kMaxCounters * sizeof(int)));
+  UPGPT_CHECK_CUDA(cudaMemset(d->counters[slot], 0, kMaxCounters * sizeof(int)));
   return 0;
 }
 
@@ -1245,7 +1251,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
   const int g_num_sms = gd->num_sms, g_smem_optin = gd->smem_optin;
   const int* g_max_clusters = gd->max_clusters;
   const size_t g_ws_bytes = gd->ws_bytes;
-  const int ws_slot = is_aux_stream(stream) ? 1 : 0;
+  const int ws_slot = stream_slot(stream);
   UPGPT_REQUIRE(a && (dry || (a->a && a->w)), "upgpt_gemm: null operand");
   UPGPT_REQUIRE(a->out32 || a->out16, "upgpt_gemm: no output");
   UPGPT_REQUIRE(!((a->flags & UPGPT_GEMM_F_SPLIT3OUT) && (a->flags & UPGPT_GEMM_F_CHW)), "upgpt_gemm: SPLIT3OUT is not available with channel-major stores");
@@ -1405,6 +1411,11 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
       while (splits > 1 && ((size_t)splits * p.ws_rows * p.ws_ld * sizeof(float) > g_ws_bytes || n_ctr > kMaxCounters)) --splits;
       while (splits > 1 && (splits - 1) * ((k_iters + splits - 1) / splits) >= k_iters) --splits;
       p.num_splits = splits;
+    }
+    if (!dry) {
+      // (only the global-workspace fallback reads these; the cluster reduction keeps its partials in shared memory)
+      const int rc = gemm_slot_workspace(gd, ws_slot);
+      if (rc) return rc;
     }
     p.ws = gd->ws[ws_slot];
     p.counters = gd->counters[ws_slot];

@@ -8,7 +8,7 @@
 * weights tag: `ema_scope` (ddpm.py:179-192) swaps EMA weights into the module for the duration of a sampling call. The packed copy
   of the EMA weights lives under its own tag ("ema") beside the training weights ("raw"), so entering / leaving the scope switches
   between two resident packed sets instead of re-packing 425 M parameters (and re-capturing the step graph) twice per request.
-* engine cache: LRU-bounded (UPGPT_MAX_ENGINES, default 6) -- a long-running service with many distinct shapes cannot grow without bound.
+* engine cache: LRU-bounded (UPGPT_MAX_ENGINES, default 8) -- a long-running service with many distinct shapes cannot grow without bound.
 """
 import os
 from collections import OrderedDict
@@ -62,10 +62,11 @@ class EngineHostMixin:
         self.mark_weights_changed()
 
     def _engine_get(self, key, make):
-        key = tuple(key) + (self._weights_tag,)
+        from . import lanes
+        key = tuple(key) + (self._weights_tag, lanes.current())      # engines (buffers, programs, graphs) exist per lane; weights are shared
         eng = self._engines.get(key)
         if eng is None:
-            cap = max(1, int(os.environ.get("UPGPT_MAX_ENGINES", "6")))
+            cap = max(1, int(os.environ.get("UPGPT_MAX_ENGINES", "8")))
             while len(self._engines) >= cap:
                 self._engines.popitem(last=False)          # least recently used: its activation buffers / graphs are freed
             eng = make()

@@ -178,7 +178,10 @@ class Graph:
         """Captures the upgpt_* calls made by fn() (on torch's current stream) into an executable graph.
         The legacy default stream cannot be captured, so the capture happens on a side stream."""
         torch.cuda.synchronize()
-        side = torch.cuda.Stream()
+        # lane 0: any side stream (scratch slot 0, like the caller's own stream). Lane i > 0: the lane's own library stream, so the
+        # captured nodes bake that lane's scratch slot (common.cuh: stream_slot) -- graphs of different lanes replay side by side
+        from . import lanes
+        side = torch.cuda.Stream() if lanes.current() == 0 else lanes.stream(lanes.current())
         with torch.cuda.stream(side):
             _C.check(_C.lib().upgpt_capture_begin(C.c_void_p(side.cuda_stream)), "capture_begin")
             try:

@@ -204,6 +204,9 @@ class EngineBase:
         self._scratch = {}
         self._sizing = True
         self.prog = _Program()
+        from . import lanes
+        self.lane = lanes.current()                       # the lane (upgpt_b200/lanes.py) this engine's buffers and programs belong to
+        self.branch_aux = lanes.branch_aux(self.lane)     # auxiliary stream of its forked branches
         # GroupNorm statistics from the producing GEMM's epilogue (include/upgpt_b200.h: gn_acc): out32 pointer -> recorded args struct of
         # the launch that produces the tensor; accumulator slots of [B][32][2] int64 from one pool that the program zeroes first
         self.gn_epi = os.environ.get("UPGPT_GN_EPILOGUE", "0") != "0"
@@ -693,8 +696,8 @@ class UNetEngine(EngineBase):
         if par_skip:
             # the skip 1x1 (openaimodel.py:241) only needs the un-normalised operand planes: it runs on an auxiliary stream beside
             # conv1 and the second GroupNorm and is joined in front of conv2, which consumes it as its residual
-            self.prog.fork(0)
-            self.prog.aux = 0
+            self.prog.fork(self.branch_aux)
+            self.prog.aux = self.branch_aux
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
                         bias=self.w.get(p + ".skip.bias"), flags=fs)
             self.prog.aux = None
@@ -702,7 +705,7 @@ class UNetEngine(EngineBase):
                     out32=h32, bias=self.w.get(p + ".conv1.bias"), rowvec=emb, ld_rowvec=self.emb_total, flags=fa)
         op2, _ = self.norm_operand(h32, Cout, None, 0, B, H, W, p + ".out_layers.0", 1e-5, True, split3=x3b)
         if par_skip:
-            self.prog.join(0)
+            self.prog.join(self.branch_aux)
             res = skip32
         elif has_skip:
             self.e_gemm(a=raw, w=self.w.get(p + ".skip.weight"), mode=_C.GEMM_PLAIN, M=B * HW, N=Cout, K=Cin, out32=skip32,
