@@ -9,6 +9,11 @@ configs[1]), synthetic 32x32x4 latents / (B, 87, 768) context / bbox person mask
 
 One "step" = one full pass of the hot path over one batch: 50 DDIM steps through the U-Net (one CUDA graph replay per
 step) + the VAE decode of the batch.  Prints ONE JSON line (rank 0).
+
+Schedule: bench step i runs on lane i % --lanes (default 3, upgpt_b200/lanes.py): consecutive batches are in flight side by side on
+one GPU, each on its own stream with its own engines and step graphs (shared weights); every batch is sampled and decoded exactly as
+with one lane (bit-identical results, tests/test_gpu_hotpath.py). `value` / `e2e` are the throughput of that schedule over the K
+timed steps; `single_lane` in the same line is the same K steps with one batch in flight (--lanes 1).
 """
 import argparse
 import json
