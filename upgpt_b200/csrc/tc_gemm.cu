@@ -1432,10 +1432,12 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
 
   p.debug_ts = g_debug_ts;
   {
-    // UPGPT_GEMM_WPREFETCH: 0 = off, 1 = operand ring only (default), n > 1 = ring + L2 prefetch of up to n further k-blocks.
-    // Measured on the bbox.yaml step at B = 8 (gpurun_out/r2r_probe.jsonl): 4.32 / 4.29 / 4.36 ms for 0 / 1 / 64 -- inside the run-to-run
-    // noise: the chain is not bound by the weight stream (the CTA that starts last has no lead time to use).
-    static const int wp_env = getenv("UPGPT_GEMM_WPREFETCH") ? atoi(getenv("UPGPT_GEMM_WPREFETCH")) : 1;
+    // UPGPT_GEMM_WPREFETCH: 0 = off (default), 1 = operand ring only, n > 1 = ring + L2 prefetch of up to n further k-blocks.
+    // Measured on the bbox.yaml step at B = 8 (profiles/r02_probe_weight_prefetch.jsonl): 4.32 / 4.29 / 4.36 ms for 0 / 1 / 64 -- inside
+    // the run-to-run noise: the chain is not bound by the weight stream (the CTA that starts last has no lead time to use). With
+    // three batches in flight (lanes) "off" is 1 % faster (49.1 vs 48.5 images/s, profiles/r02_knobs_under_lanes.txt): an early CTA
+    // that sits on filled ring slots keeps a neighbour lane's CTA off the SM.
+    static const int wp_env = getenv("UPGPT_GEMM_WPREFETCH") ? atoi(getenv("UPGPT_GEMM_WPREFETCH")) : 0;
     p.w_prefetch = (a->flags & UPGPT_GEMM_F_W_STATIC) ? wp_env : 0;
   }
   p.rowstats = a->rowstats_out;
