@@ -16,6 +16,7 @@ with one lane (bit-identical results, tests/test_gpu_hotpath.py). `value` / `e2e
 timed steps; `single_lane` in the same line is the same K steps with one batch in flight (--lanes 1).
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -572,14 +573,18 @@ def gpu_arm(args, rank, world):
             gather_frames(frames, sizes=[B] * world)
         return frames
 
-    def sequence(xT, c, masks, smpls, sink=None):
+    def sequence(xT, c, masks, smpls, sink=None, base=0):
         """One bench step: KF keyframes (1 except configs[3]); per keyframe the SMPL token is projected on the device (LinearProject,
-        poses.py:3-9) and replaces context row 86 -- the cond-cache refreshes that row of the 16 K | V caches only."""
+        poses.py:3-9) and replaces context row 86 -- the cond-cache refreshes that row of the 16 K | V caches only. With several lanes
+        the keyframes of a sequence (independent samplings) go to the lanes round-robin: a whole 16-keyframe sequence is ~1300 queued
+        launches, more than one stream's launch queue holds, so lanes fed sequence by sequence would run one after the other."""
         for k in range(KF):
-            ck = c if smpls is None else torch.cat([c[:, :CTX_LEN - 1], model.extra_cond_models[1](smpls[k])], 1)
-            frames = hot_path(xT, masks[k], ck)
-            if sink is not None:
-                sink[k].copy_(frames, non_blocking=True)
+            cm = lanes.lane((base + k) % cur_lanes[0]) if (KF > 1 and cur_lanes[0] > 1) else contextlib.nullcontext()
+            with cm:
+                ck = c if smpls is None else torch.cat([c[:, :CTX_LEN - 1], model.extra_cond_models[1](smpls[k])], 1)
+                frames = hot_path(xT, masks[k], ck)
+                if sink is not None:
+                    sink[k].copy_(frames, non_blocking=True)
 
     # bench step i runs on lane i % n_lanes: with n_lanes > 1 consecutive batches are in flight side by side (every batch is sampled and
     # decoded exactly as with one lane -- same engines' programs, bit-identical results -- only the schedule on the GPU differs)
@@ -587,10 +592,22 @@ def gpu_arm(args, rank, world):
     cur_lanes = [n_lanes]
 
     def step_resident(i=0):
+        if KF > 1:
+            return sequence(x_dev, ctx_dev, mask_kf_dev, smpl_kf_dev, base=i * KF)
         with lanes.lane(lane_of(i)):
             sequence(x_dev, ctx_dev, mask_kf_dev, smpl_kf_dev)
 
     def step_e2e(i=0):
+        if KF > 1:
+            # one sequence in flight: its keyframes are spread over the lanes; the inputs land before any lane reads them
+            torch.cuda.synchronize()
+            xd = x_pin.to(dev, non_blocking=True); cd = ctx_pin.to(dev, non_blocking=True); md = mask_kf_pin.to(dev, non_blocking=True)
+            sd = smpl_kf_pin.to(dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            sequence(xd, cd, md, sd, out_pins[0], base=i * KF)
+            if cur_lanes[0] == 1:
+                torch.cuda.current_stream().synchronize()
+            return
         with lanes.lane(lane_of(i)) as s:
             # the host reads a lane's previous result (its D2H copy has landed) before it feeds the lane again: one step per lane in flight
             s.synchronize()
