@@ -1224,7 +1224,14 @@ static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_
     const double us_per_iter = ingest_us > mma_us ? ingest_us : mma_us;
     const double epi = 0.6 * ((bn + chunk_cols - 1) / chunk_cols);
     // split-K = the CTAs of one cluster (<= 8): partial tiles stay in shared memory and are reduced over DSMEM
-    const int max_splits = allow_split ? (k_iters / 2 < 8 ? k_iters / 2 : 8) : 1;
+    // Cap of the split-K factor. The cost model above minimises the latency of ONE launch that has the GPU to itself: 6 - 8 splits for the
+    // small-M layers. With several batches in flight (upgpt_b200/lanes.py) the objective is SM time -- every extra CTA pays its own
+    // prologue, drain and DSMEM reduction while another lane's kernel waits for the SM: measured with 3 lanes 49.0 / 50.1 / 50.85 /
+    // 49.0 images/s for a cap of 8 / 5 / 4 / 3 (one batch in flight: 38.6 / 38.3 / 38.1 / 36.4), profiles/r02_split_cap_under_lanes.txt.
+    // UPGPT_GEMM_MAX_SPLITS=8 restores the latency-optimal choice.
+    static const int split_cap = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 4;
+    int max_splits = allow_split ? (k_iters / 2 < 8 ? k_iters / 2 : 8) : 1;
+    if (max_splits > split_cap) max_splits = split_cap < 1 ? 1 : split_cap;
     for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
       const int ctas = base * sp;
       const int capacity = sp == 1 ? num_sms : g_max_clusters[sp] * sp;   // CTAs of size-sp clusters that fit at once
@@ -1384,6 +1391,10 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
         splits = g_num_sms / base;
         if (splits > k_iters / 2) splits = k_iters / 2;
         if (splits > 8) splits = 8;
+        {
+          static const int split_cap2 = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 4;
+          if (splits > split_cap2) splits = split_cap2 < 1 ? 1 : split_cap2;
+        }
         while (splits > 1 && base * splits > g_max_clusters[splits] * splits) --splits;
         if (splits < 1) splits = 1;
       }
