@@ -66,7 +66,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json workload: c2 = configs[1] (headline), c4 = configs[3], c5 = configs[4]")
     ap.add_argument("--full", action="store_true", help="--impl reference: time ONE complete 50-step + decode job (minutes) instead of bounded samples")
-    ap.add_argument("--lanes", type=int, default=int(os.environ.get("UPGPT_LANES", "3")),
+    ap.add_argument("--lanes", type=int, default=int(os.environ.get("UPGPT_LANES", "4")),
                     help="independent batches in flight per GPU (upgpt_b200/lanes.py): consecutive bench steps go to lanes round-robin; "
                          "1 = one batch after the other")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline (outside the timed region)")
@@ -560,6 +560,8 @@ def gpu_arm(args, rank, world):
     out_pin = torch.empty(KF, B, px, px, 3, dtype=torch.uint8).pin_memory()
     from upgpt_b200 import lanes
     n_lanes = max(1, min(args.lanes, lanes.MAX_LANES))
+    if n_lanes > 1 and os.environ.get("UPGPT_GEMM_SM_WEIGHT") is None:
+        lanes.set_throughput_mode(True)       # before any engine is built: the GEMM tiler counts SM time, not only latency
     samplers = [DDIMSampler(model) for _ in range(n_lanes)]
     out_pins = [out_pin] + [torch.empty_like(out_pin).pin_memory() for _ in range(n_lanes - 1)]
 
@@ -664,7 +666,9 @@ def gpu_arm(args, rank, world):
     if n_lanes > 1:      # the same K steps one after the other (one batch in flight), for the record
         ms_1, _, _ = timed(step_resident, 1, args.steps, use_lanes=1)
         single_lane = {"value": n_img / (ms_1 * 1e-3), "unit": UNIT, "ms_per_step": ms_1 / args.steps,
-                       "note": "one batch in flight (--lanes 1): the per-batch latency; `value` has %d batches of %d in flight" % (n_lanes, B)}
+                       "note": "one batch in flight with the SAME engines (throughput-mode tiling, upgpt_b200/lanes.py: SM time in the GEMM "
+                               "tiler's objective); `value` has %d batches of %d in flight. `python bench.py --lanes 1` builds the "
+                               "latency-optimal tiling instead: 38.9 images/s (profiles/r02_bench_c2_lanes1.json.log)" % (n_lanes, B)}
     cond_cache = None
     if KF > 1:
         eng0 = next(iter(model.model.diffusion_model._engines.values()))
@@ -736,6 +740,7 @@ def gpu_arm(args, rank, world):
             try:
                 del model, samplers
                 torch.cuda.empty_cache()
+                lanes.set_throughput_mode(False)      # the facade arm is ONE request at a time: latency-optimal tiling for its engines
                 line["facade"] = facade_arm(dev, args.precision, args.eta, max(2, args.steps // 2))
             except Exception as e:
                 line["facade"] = {"error": repr(e)[:300]}

@@ -110,6 +110,10 @@ int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
  * (N tiles = rowstats slots per row), plan[2] = split-K factor, plan[3] = pipeline stages, plan[4] = epilogue path (1 TMA-store,
  * 2 cluster split-K reduction, 0 other: only 1 and 2 can emit rowstats_out / gn_acc), plan[5..7] reserved */
 int upgpt_gemm_plan(const upgpt_gemm_args* args, int plan[8]);
+/* Tiling objective of every following upgpt_gemm / upgpt_gemm_plan of the process: 0 (default) = the latency of one launch that has the
+ * GPU to itself; w > 0 = latency x (1 + w x CTAs / SMs): SM time counts, for several independent batches in flight on one GPU
+ * (upgpt_b200/lanes.py sets 8). Set it before programs are recorded / graphs captured: a captured graph keeps the tiling it was built with. */
+int upgpt_gemm_set_sm_weight(double w);
 /* bring-up instrumentation: CTA c of every following upgpt_gemm stamps %globaltimer (ns) into buf[c*16 + slot]; NULL = off */
 int upgpt_debug_set_gemm_timestamps(long long* buf);
 /* bring-up instrumentation: launch trace inside dependent chains / graph replays. buf (device memory, 8-byte words): buf[0] = counter

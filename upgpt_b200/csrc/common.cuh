@@ -42,7 +42,7 @@ bool is_aux_stream(cudaStream_t s);   // one of the library's auxiliary (paralle
 // Scratch slot of a stream: 0 = any stream the library does not own, 1 + i = its auxiliary stream i. Library-owned scratch (split-K
 // workspace, GroupNorm partials / scale-shift) exists once per slot, so launches on different streams of the library never share it:
 // a forked branch beside its main chain, or several independent batches in flight ("lanes", upgpt_b200/lanes.py).
-static constexpr int kStreamSlots = 9;
+static constexpr int kStreamSlots = 17;
 int stream_slot(cudaStream_t s);
 
 #ifdef __CUDACC__

@@ -1207,6 +1207,7 @@ static int gemm_slot_workspace(GemmDev* d, int slot) {
 // and a split-K tile additionally writes + re-reads its fp32 partial tile and synchronises (~2.5 us + 0.9 us per chunk).
 // Wide tiles minimise A re-reads; split-K supplies the parallelism that small-M layers lack.
 struct TileChoice { int bn; int splits; };
+static double g_sm_weight = getenv("UPGPT_GEMM_SM_WEIGHT") ? atof(getenv("UPGPT_GEMM_SM_WEIGHT")) : 0.0;
 static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_batch, int k_iters, int num_sms, int gran, bool must_divide,
                                 bool allow_split, int chunk_cols, bool x3) {
   TileChoice best{gran, 1};
@@ -1224,12 +1225,9 @@ static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_
     const double us_per_iter = ingest_us > mma_us ? ingest_us : mma_us;
     const double epi = 0.6 * ((bn + chunk_cols - 1) / chunk_cols);
     // split-K = the CTAs of one cluster (<= 8): partial tiles stay in shared memory and are reduced over DSMEM
-    // Cap of the split-K factor. The cost model above minimises the latency of ONE launch that has the GPU to itself: 6 - 8 splits for the
-    // small-M layers. With several batches in flight (upgpt_b200/lanes.py) the objective is SM time -- every extra CTA pays its own
-    // prologue, drain and DSMEM reduction while another lane's kernel waits for the SM: measured with 3 lanes 49.0 / 50.1 / 50.85 /
-    // 49.0 images/s for a cap of 8 / 5 / 4 / 3 (one batch in flight: 38.6 / 38.3 / 38.1 / 36.4), profiles/r02_split_cap_under_lanes.txt.
-    // UPGPT_GEMM_MAX_SPLITS=8 restores the latency-optimal choice.
-    static const int split_cap = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 4;
+    // UPGPT_GEMM_MAX_SPLITS: cap of the split-K factor (experiments; a cap of 4 was the first form of the throughput mode: 49.0 -> 50.85
+    // images/s with 3 lanes, profiles/r02_split_cap_under_lanes.txt; the SM-time weight above does the same job per shape)
+    static const int split_cap = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 8;
     int max_splits = allow_split ? (k_iters / 2 < 8 ? k_iters / 2 : 8) : 1;
     if (max_splits > split_cap) max_splits = split_cap < 1 ? 1 : split_cap;
     for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
@@ -1241,6 +1239,10 @@ static TileChoice choose_tiling(const int* g_max_clusters, int N, int m_tiles_x_
       double t = waves * (2.5 + iters * us_per_iter + (sp == 1 ? epi : 0.3 * ((bn + 31) / 32)));
       // DSMEM reduction: every CTA pulls (sp-1)/sp of a [128][bn] fp32 tile from its siblings at ~35 GB/s, + 2 cluster barriers
       if (sp > 1) t += 1.2 + 512.0 * bn * (sp - 1) / sp / 35e3;
+      // throughput mode (upgpt_gemm_set_sm_weight): SM time in the objective, cost = latency x (1 + w x CTAs / SMs). With one batch in
+      // flight a small layer should spread over as many SMs as its latency gains from; with several batches in flight (lanes) every
+      // CTA beyond the necessary ones takes an SM from another batch's kernel and pays its own prologue / drain / reduction.
+      if (g_sm_weight > 0.0) t *= 1.0 + g_sm_weight * (double)(ctas < num_sms ? ctas : num_sms) / (double)num_sms;
       if (t < best_t - 1e-9) { best_t = t; best = {bn, sp}; }
     }
   }
@@ -1392,7 +1394,7 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
         if (splits > k_iters / 2) splits = k_iters / 2;
         if (splits > 8) splits = 8;
         {
-          static const int split_cap2 = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 4;
+          static const int split_cap2 = getenv("UPGPT_GEMM_MAX_SPLITS") ? atoi(getenv("UPGPT_GEMM_MAX_SPLITS")) : 8;
           if (splits > split_cap2) splits = split_cap2 < 1 ? 1 : split_cap2;
         }
         while (splits > 1 && base * splits > g_max_clusters[splits] * splits) --splits;
@@ -1642,6 +1644,12 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
 }
 
 extern "C" int upgpt_gemm(const upgpt_gemm_args* a, void* stream_) { return gemm_run(a, (cudaStream_t)stream_, nullptr); }
+
+extern "C" int upgpt_gemm_set_sm_weight(double w) {
+  UPGPT_REQUIRE(w >= 0.0 && w <= 1000.0, "upgpt_gemm_set_sm_weight: weight %f out of range", w);
+  g_sm_weight = w;
+  return 0;
+}
 
 extern "C" int upgpt_gemm_plan(const upgpt_gemm_args* a, int plan[8]) {
   UPGPT_REQUIRE(plan, "upgpt_gemm_plan: null plan");

@@ -17,8 +17,20 @@ Single host thread: the lanes are fed one after the other, asynchronously; nothi
 import contextlib
 import ctypes as C
 
-MAX_LANES = 4
+MAX_LANES = 8
+THROUGHPUT_SM_WEIGHT = 8.0
 _current = 0
+
+
+def set_throughput_mode(on=True, sm_weight=None):
+    """Tiling objective of the GEMM library for several batches in flight: SM time counts (upgpt_gemm_set_sm_weight), so that a small
+    layer takes the SMs it needs instead of all it can use. Call it before engines are built (recorded programs and captured graphs keep
+    the tiling they were built with). Measured on the bbox.yaml path, B = 8 (profiles/r02_throughput_mode.txt): 6 lanes 65.6 images/s
+    (one batch in flight: 31.9) vs the latency objective's 49.0 with 3 lanes (38.9 with one)."""
+    from . import _C
+    w = (THROUGHPUT_SM_WEIGHT if sm_weight is None else float(sm_weight)) if on else 0.0
+    _C.check(_C.lib().upgpt_gemm_set_sm_weight(C.c_double(w)), "upgpt_gemm_set_sm_weight")
+    return w
 
 
 def current():
