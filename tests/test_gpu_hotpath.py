@@ -720,3 +720,32 @@ def test_lanes_two_batches_in_flight_are_bit_identical(dev):
                 ys.append(m(*xs[i]))
         torch.cuda.synchronize()
         assert all(torch.equal(ys[i], ref[i]) for i in range(3)), "bbox U-Net, round %d" % rep
+
+
+def test_throughput_mode_tiling_keeps_eps_parity(dev, golden):
+    """lanes.set_throughput_mode(): the GEMM tiler counts SM time (upgpt_gemm_set_sm_weight), so small layers take fewer CTAs / split-K
+    slices -- a different summation split, the same result within the tolerance; the tiling really changes; the mode is process-global and
+    is switched back."""
+    import ctypes as C_
+    from upgpt_b200 import lanes, _C
+    L = _C.lib()
+
+    def plan_of(M, N, K):
+        a = _C.GemmArgs(); a.mode, a.M, a.N, a.K = _C.GEMM_PLAIN, M, N, K
+        a.out32 = 16       # (any non-null value: the plan only looks at shapes and flags)
+        p = (C_.c_int * 8)()
+        _C.check(L.upgpt_gemm_plan(C_.byref(a), C_.byref(p)), "plan")
+        return int(p[0]), int(p[2])
+    lat = plan_of(128, 896, 1792)
+    try:
+        assert lanes.set_throughput_mode(True) == lanes.THROUGHPUT_SM_WEIGHT
+        thr = plan_of(128, 896, 1792)
+        assert thr != lat and thr[1] <= lat[1], (lat, thr)
+        m, _ = _unet(BBOX_UNET_KW, 0, dev)
+        x, mask, ctx = synth.synth_inputs(1, 32, 32, 87, 768, 0)
+        for t in (981, 481):
+            y = m(torch.cat([x, mask], 1).to(dev), torch.full((1,), t, dtype=torch.long, device=dev), ctx.to(dev))
+            assert relerr(y, torch.from_numpy(golden[f"bbox_eps_t{t}"])) < 1e-3
+    finally:
+        lanes.set_throughput_mode(False)
+    assert plan_of(128, 896, 1792) == lat
