@@ -114,6 +114,10 @@ int upgpt_gemm_plan(const upgpt_gemm_args* args, int plan[8]);
  * GPU to itself; w > 0 = latency x (1 + w x CTAs / SMs): SM time counts, for several independent batches in flight on one GPU
  * (upgpt_b200/lanes.py sets 8). Set it before programs are recorded / graphs captured: a captured graph keeps the tiling it was built with. */
 int upgpt_gemm_set_sm_weight(double w);
+/* Programmatic dependent launch of every following launch of the library (default on; UPGPT_PDL=0): a successor's CTAs become resident
+ * while their predecessor drains -- good for one chain's latency, but with several batches in flight those waiting CTAs hold SMs another
+ * batch's kernel could use (throughput mode switches it off: +1.8 %). Captured graphs keep what they were built with. */
+int upgpt_set_pdl(int on);
 /* bring-up instrumentation: CTA c of every following upgpt_gemm stamps %globaltimer (ns) into buf[c*16 + slot]; NULL = off */
 int upgpt_debug_set_gemm_timestamps(long long* buf);
 /* bring-up instrumentation: launch trace inside dependent chains / graph replays. buf (device memory, 8-byte words): buf[0] = counter

@@ -98,6 +98,7 @@ _PROTOS = {
     "upgpt_gemm": [C.POINTER(GemmArgs), _vp],
     "upgpt_gemm_plan": [C.POINTER(GemmArgs), C.POINTER(C.c_int * 8)],
     "upgpt_gemm_set_sm_weight": [C.c_double],
+    "upgpt_set_pdl": [C.c_int],
     "upgpt_debug_set_gemm_timestamps": [_vp],
     "upgpt_trace_set": [_vp],
     "upgpt_groupnorm_stats": [_vp, _i, _vp, _i, _i, _i, _i, _vp, _vp],

@@ -13,10 +13,10 @@ namespace upgpt {
 static thread_local char g_err[1024] = "";
 std::atomic<long long> g_launches{0};
 
+static int g_pdl = -1;      // -1: not decided yet (UPGPT_PDL=0 disables; upgpt_set_pdl overrides)
 bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("UPGPT_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v != 0;
+  if (g_pdl < 0) { const char* e = getenv("UPGPT_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+  return g_pdl != 0;
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -161,6 +161,7 @@ extern "C" int upgpt_stream_join(void* main_stream, int aux_idx) {
 namespace upgpt {
 }  // namespace upgpt
 
+extern "C" int upgpt_set_pdl(int on) { upgpt::g_pdl = on ? 1 : 0; return 0; }
 extern "C" const char* upgpt_last_error(void) { return upgpt::g_err; }
 extern "C" int upgpt_abi_version(void) { return 1; }
 extern "C" long long upgpt_launch_count(void) { return upgpt::g_launches.load(); }

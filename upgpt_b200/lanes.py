@@ -23,13 +23,18 @@ _current = 0
 
 
 def set_throughput_mode(on=True, sm_weight=None):
-    """Tiling objective of the GEMM library for several batches in flight: SM time counts (upgpt_gemm_set_sm_weight), so that a small
-    layer takes the SMs it needs instead of all it can use. Call it before engines are built (recorded programs and captured graphs keep
+    """Library settings for several batches in flight: the GEMM tiler counts SM time (upgpt_gemm_set_sm_weight), so that a small layer
+    takes the SMs it needs instead of all it can use, and launches go without programmatic dependent launch (upgpt_set_pdl). Call it before engines are built (recorded programs and captured graphs keep
     the tiling they were built with). Measured on the bbox.yaml path, B = 8 (profiles/r02_throughput_mode.txt): 6 lanes 65.6 images/s
     (one batch in flight: 31.9) vs the latency objective's 49.0 with 3 lanes (38.9 with one)."""
+    import os
     from . import _C
     w = (THROUGHPUT_SM_WEIGHT if sm_weight is None else float(sm_weight)) if on else 0.0
     _C.check(_C.lib().upgpt_gemm_set_sm_weight(C.c_double(w)), "upgpt_gemm_set_sm_weight")
+    # programmatic dependent launch makes a successor's CTAs resident while the predecessor drains: they wait on SMs that another lane's
+    # kernel could use (63.8 -> 64.9 images/s without it, 4 lanes; profiles/r02_knobs_under_lanes.txt). One batch alone wants it on.
+    if os.environ.get("UPGPT_PDL") is None:
+        _C.check(_C.lib().upgpt_set_pdl(0 if on else 1), "upgpt_set_pdl")
     return w
 
 
