@@ -688,6 +688,12 @@ def gpu_arm(args, rank, world):
         fast = {"precision": "fp16", "value": n_img / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / args.steps,
                 "eps_max_rel_vs_reference": "1.3e-3 .. 1.7e-3 (tests/test_gpu_hotpath.py)"}
     if rank == 0:
+        # live parity of the benchmarked engine first: its recorded program (LayerNorm row-statistic slots = N tiles of the producing GEMM)
+        # belongs to the settings it was built with, so it is checked before those change
+        parity = parity_spot_check(model, dev) if (world == 1 and not args.no_cpu_baseline and args.config == "c2") else None
+        # the roofline kernels are timed ALONE: latency-optimal settings (the throughput mode of the benchmarked step trades a kernel's own
+        # latency for SM time -- fewer CTAs per small layer, no programmatic dependent launch -- which is the wrong yardstick for one kernel)
+        lanes.set_throughput_mode(False)
         roof = roofline_dominant_kernel(dev, pk, args.precision)
         roof_hbm = roofline_hbm_kernel(dev, pk)
         try:
@@ -732,8 +738,8 @@ def gpu_arm(args, rank, world):
             line["cond_cache"] = cond_cache
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_quick(args.config)
-            if args.config == "c2":
-                line["parity"] = parity_spot_check(model, dev)
+            if parity is not None:
+                line["parity"] = parity
         else:
             line["cpu_baseline"] = None
         if world == 1 and not args.no_eager_baseline and args.config == "c2":

@@ -24,9 +24,11 @@ _current = 0
 
 def set_throughput_mode(on=True, sm_weight=None):
     """Library settings for several batches in flight: the GEMM tiler counts SM time (upgpt_gemm_set_sm_weight), so that a small layer
-    takes the SMs it needs instead of all it can use, and launches go without programmatic dependent launch (upgpt_set_pdl). Call it before engines are built (recorded programs and captured graphs keep
-    the tiling they were built with). Measured on the bbox.yaml path, B = 8 (profiles/r02_throughput_mode.txt): 6 lanes 65.6 images/s
-    (one batch in flight: 31.9) vs the latency objective's 49.0 with 3 lanes (38.9 with one)."""
+    takes the SMs it needs instead of all it can use, and launches go without programmatic dependent launch (upgpt_set_pdl).
+    Call it before engines are built, and do not switch it while engines built under the other setting are still in use: captured
+    graphs keep the tiling they were built with, but an EAGER replay of a recorded program re-plans its GEMMs, and the folded
+    LayerNorm's row-statistic slots (= N tiles of the producing GEMM) were sized at record time. Measured on the bbox.yaml path, B = 8 (profiles/r02_throughput_mode.txt): 4 lanes 65.9 images/s
+    (one batch in flight: 31) vs the latency objective's 49.0 with 3 lanes (38.9 with one)."""
     import os
     from . import _C
     w = (THROUGHPUT_SM_WEIGHT if sm_weight is None else float(sm_weight)) if on else 0.0
