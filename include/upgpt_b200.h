@@ -104,6 +104,9 @@ typedef struct upgpt_gemm_args {
   int gn_groups, gn_cpg, gn_choff;
   long long* gn_acc2;
   int gn_cpg2, gn_choff2;
+  int rowstats_slots;       /* 0, or the number of N tiles (= partial slots per row of rowstats_out) the caller sized its consumers for: the
+                               launch fails if the tiling picked now differs (e.g. the process-wide tiling objective was switched after the
+                               program was recorded) instead of feeding a consumer the wrong number of partials */
 } upgpt_gemm_args;
 int upgpt_gemm(const upgpt_gemm_args* args, void* stream);
 /* the tiling upgpt_gemm picks for these arguments on the current device, without launching: plan[0] = block_n, plan[1] = n_tiles

@@ -749,3 +749,12 @@ def test_throughput_mode_tiling_keeps_eps_parity(dev, golden):
     finally:
         lanes.set_throughput_mode(False)
     assert plan_of(128, 896, 1792) == lat
+    # the engine above was recorded under the throughput tiling. An eager replay re-plans every GEMM under the settings of the moment:
+    # either the LayerNorm producers keep their N tiling (then the result is still right) or the launch fails loudly -- never garbage
+    eng = m.engine(1, 32, 32, 87)
+    eng.stage_inputs(torch.cat([x, mask], 1).to(dev), torch.full((1,), 481, dtype=torch.long, device=dev))
+    try:
+        y = eng.run(use_graph=False)
+        assert relerr(y, torch.from_numpy(golden["bbox_eps_t481"])) < 1e-3
+    except _C.UpgptError as ex:
+        assert "rebuild the engine" in str(ex)

@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("rowstats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_eps", C.c_float), ("ln_colsum", C.c_void_p),
         ("gn_acc", C.c_void_p), ("gn_groups", C.c_int), ("gn_cpg", C.c_int), ("gn_choff", C.c_int),
         ("gn_acc2", C.c_void_p), ("gn_cpg2", C.c_int), ("gn_choff2", C.c_int),
+        ("rowstats_slots", C.c_int),
     ]
 
 

@@ -1601,6 +1601,11 @@ static int gemm_run(const upgpt_gemm_args* a, cudaStream_t stream, int* plan_out
     UPGPT_REQUIRE(p.num_splits == 1 || p.cluster_reduce, "upgpt_gemm: folded LayerNorm needs the cluster split-K reduction (splits=%d)", p.num_splits);
   if (p.rowstats)
     UPGPT_REQUIRE(p.cluster_reduce || p.epi_mode == 1, "upgpt_gemm: rowstats_out needs the TMA-store epilogue (16-byte aligned fp32 rows)");
+  if (p.rowstats && a->rowstats_slots > 0 && !dry)
+    UPGPT_REQUIRE(p.num_n_tiles == a->rowstats_slots,
+                  "upgpt_gemm: rowstats_out: this launch is tiled into %d N tiles but its consumers were sized for %d partial slots per row "
+                  "(the tiling objective / UPGPT_GEMM_* settings changed since the program was recorded: rebuild the engine)",
+                  p.num_n_tiles, a->rowstats_slots);
   const int epi_path = (p.num_splits == 1 && p.epi_mode == 1) ? 1 : (p.cluster_reduce ? 2 : 0);
   if (p.gn_acc[0]) {
     UPGPT_REQUIRE(epi_path != 0, "upgpt_gemm: gn_acc needs the TMA-store epilogue or the cluster split-K reduction (block_n=%d splits=%d)", p.block_n, p.num_splits);

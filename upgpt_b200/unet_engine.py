@@ -318,6 +318,7 @@ class EngineBase:
                 a.splits = 1        # the row statistics need the TMA-store or the cluster split-K epilogue: drop split-K if the pick has neither
                 _C.check(self.L.upgpt_gemm_plan(C.byref(a), C.byref(plan)), "upgpt_gemm_plan")
             n_tiles = int(plan[1])
+            a.rowstats_slots = n_tiles      # a later launch that would tile differently fails loudly instead of mis-feeding the consumers
         self.prog.add_struct(self.L.upgpt_gemm, a)
         if a.out32:
             self._producers[a.out32] = a
