@@ -55,8 +55,8 @@ def workload_string(cfg, eta):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--eta", type=float, default=1.0, help="DDIM eta (reference default in log_images is 1.0)")
     ap.add_argument("--precision", default=None,
